@@ -1,0 +1,164 @@
+/*
+ * rdfc_b200.h -- C ABI of librdfc_b200.so, the sm_100a implementation of the RDF-GAN / RDFC-GAN generator hot path.
+ *
+ * Plain pointers and sizes only (no torch / ATen types).  Every pointer is a DEVICE pointer unless its name ends in
+ * `_host`.  Every entry point enqueues work on `stream` (a cudaStream_t passed as void*, NULL = legacy default
+ * stream), never synchronises, and returns 0 on success or a negative rdfc_status; rdfc_last_error() then returns a
+ * thread-local message.  Nothing here falls back to the CPU: without an sm_100 device the calls fail.
+ *
+ * Reference interfaces replaced (paths are relative to
+ * /root/reference/RDFC-GAN/lib/models/generator/rdf_generator/ ; D = nlspn/deformconv):
+ *
+ *   rdfc_dcn_forward / rdfc_dcn_backward
+ *       D/src/vision.cpp:7-12 -- pybind module `DCN`: deform_conv_forward/backward (mask == NULL) and
+ *       modulated_deform_conv_forward/backward; dispatch D/src/modulated_deform_conv.h:10-44,46-86 and
+ *       D/src/deform_conv.h; CUDA bodies D/src/cuda/modulated_deform_conv_cuda.cu:19-121,124-280.
+ *   rdfc_nlspn_affinity_forward
+ *       nlspn/nlspn_model.py:68-138  NLPSN._get_offset_affinity (conv_offset_aff + 8 confidence gathers + normalisation).
+ *   rdfc_nlspn_propagate_forward
+ *       nlspn/nlspn_model.py:140-144,157-173  the prop_time x ModulatedDeformConvFunction loop (C = 1, ones weight).
+ *   rdfc_fuse_depth_forward
+ *       rdf_generator.py:401-406  clamp + 2-way confidence softmax + weighted sum.
+ *   rdfc_conv_forward
+ *       encoder_decoder/common.py:29-61 conv_bn_relu / convt_bn_relu, torchvision BasicBlock convs
+ *       (encoder_decoder/encoder_decoder.py:39-59), decode heads (rdf_generator.py:68-102) and the per-pixel
+ *       EqualLinear of W-AdaIN (model_utils.py:39-50,72-75): NHWC implicit GEMM with a fused
+ *       scale/shift (+residual) + activation epilogue.  `path` selects the tcgen05 bf16 kernel or the fp32 SIMT kernel.
+ *   rdfc_instnorm_stats / rdfc_adain_apply
+ *       model_utils.py:53-90 (AdaptiveInstanceNorm = W-AdaIN), :92-116 (AdaIN), :119-129 (IN).
+ */
+#ifndef RDFC_B200_H
+#define RDFC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDFC_ABI_VERSION 1
+
+typedef enum {
+    RDFC_OK = 0,
+    RDFC_ERR_INVALID = -1,   /* bad argument (shape / divisibility / null pointer): the reference's AT_ASSERTM cases */
+    RDFC_ERR_CUDA = -2,      /* CUDA runtime error (message carries cudaGetErrorString) */
+    RDFC_ERR_UNSUPPORTED = -3
+} rdfc_status;
+
+typedef enum { RDFC_F32 = 0, RDFC_F64 = 1, RDFC_BF16 = 2 } rdfc_dtype;
+
+int rdfc_abi_version(void);
+const char *rdfc_last_error(void);
+/* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
+uint64_t rdfc_launch_count(void);
+
+/* ------------------------------------------------------------------ DCN boundary ------------------------------ */
+/* Shapes follow D/src/cuda/modulated_deform_conv_cuda.cu:47-76.
+ *   input (B,Cin,H,W)  weight (Cout,Cin/group,kh,kw)  bias (Cout)  offset (B,dg*2*kh*kw,Ho,Wo)  mask (B,dg*kh*kw,Ho,Wo)
+ *   output (B,Cout,Ho,Wo) contiguous NCHW, Ho = (H + 2 ph - (dh (kh-1) + 1)) / sh + 1.
+ * `im2col_step` is validated exactly like the reference (B % min(B, im2col_step) == 0) and otherwise ignored. */
+typedef struct {
+    int B, Cin, H, W, Cout;
+    int kh, kw, sh, sw, ph, pw, dh, dw;
+    int group, deformable_group, im2col_step;
+} rdfc_dcn_shape;
+
+int rdfc_dcn_out_size(const rdfc_dcn_shape *s, int *Ho, int *Wo);
+
+/* mask == NULL => DCN v1 (deform_conv_forward).  dtype: RDFC_F32 or RDFC_F64. */
+int rdfc_dcn_forward(const void *input, const void *weight, const void *bias, const void *offset, const void *mask,
+                     void *output, const rdfc_dcn_shape *s, int dtype, void *stream);
+
+/* Any grad_* may be NULL (skipped).  grad_input is zero-filled by the callee before the scatter.
+ * mask == NULL => DCN v1 (grad_mask must be NULL). */
+int rdfc_dcn_backward(const void *input, const void *weight, const void *offset, const void *mask,
+                      const void *grad_output, void *grad_input, void *grad_offset, void *grad_mask,
+                      void *grad_weight, void *grad_bias, const rdfc_dcn_shape *s, int dtype, void *stream);
+
+/* ------------------------------------------------------------------ NLSPN ------------------------------------- */
+typedef enum { RDFC_AFF_AS = 0, RDFC_AFF_ASS = 1, RDFC_AFF_TC = 2, RDFC_AFF_TGASS = 3 } rdfc_affinity;
+
+/* guidance (B,8,H,W) fp32 NCHW; confidence (B,1,H,W) or NULL when conf_prop == 0;
+ * conv_w (24,8,3,3), conv_b (24) = conv_offset_aff; aff_scale = aff_scale_const (device pointer to 1 float).
+ * Writes offset (B,18,H,W) and aff (B,9,H,W) in the reference layout (centre tap inserted at index 4). k_f = 3 only. */
+int rdfc_nlspn_affinity_forward(const float *guidance, const float *confidence, const float *conv_w,
+                                const float *conv_b, const float *aff_scale, int affinity, int conf_prop,
+                                float *offset, float *aff, int B, int H, int W, void *stream);
+
+/* feat_init (B,1,H,W); offset (B,18,H,W); aff (B,9,H,W); feat_fix (B,1,H,W) or NULL; out (B,1,H,W);
+ * scratch: B*H*W floats (ping-pong buffer, may not alias anything else);
+ * inter: NULL or prop_time*B*H*W floats receiving every iteration's result (the reference's list_feat).
+ * clamp_out != 0 additionally clamps the final result to [-1,1] (rdf_generator.py:401). */
+int rdfc_nlspn_propagate_forward(const float *feat_init, const float *offset, const float *aff,
+                                 const float *feat_fix, int preserve_input, float *out, float *scratch,
+                                 float *inter, int B, int H, int W, int prop_time, int clamp_out, void *stream);
+
+/* pred = softmax([c1,c2]) . [d1, clamp(d2)] ; d2_clamped receives clamp(d2,-1,1) (may alias d2). n = B*H*W. */
+int rdfc_fuse_depth_forward(const float *d1, const float *c1, const float *d2, const float *c2, float *d2_clamped,
+                            float *pred, size_t n, void *stream);
+
+/* ------------------------------------------------------------------ dense part (NHWC) ------------------------- */
+typedef enum { RDFC_ACT_NONE = 0, RDFC_ACT_RELU = 1, RDFC_ACT_LEAKY02 = 2, RDFC_ACT_TANH = 3, RDFC_ACT_SIGMOID = 4 }
+    rdfc_act;
+typedef enum { RDFC_PATH_SIMT_F32 = 0, RDFC_PATH_UMMA_BF16 = 1 } rdfc_conv_path;
+
+/* A view of an NHWC tensor: element (b,y,x,c) lives at ptr[((b*H + y)*W + x)*pix_stride + c].
+ * nchw != 0 switches to (B,C,H,W) contiguous addressing (pix_stride ignored) -- SIMT path only. */
+typedef struct {
+    void *ptr;
+    int dtype;       /* RDFC_F32 or RDFC_BF16 */
+    int C;           /* channels of the view */
+    int pix_stride;  /* elements between consecutive pixels (>= C; lets a view be a channel slice of a concat buffer) */
+    int nchw;
+} rdfc_view;
+
+typedef struct {
+    int B, Hi, Wi;          /* input spatial size */
+    int Ho, Wo;             /* output spatial size actually written (ConvTranspose: may be cropped, rdf_generator.py:249-256) */
+    int kh, kw, stride, pad;
+    int transposed;         /* 1 = ConvTranspose2d(k3,s2,p1,op1) gather form; weights packed accordingly */
+    int act;                /* rdfc_act */
+    int path;               /* rdfc_conv_path */
+    rdfc_view in;           /* Cin = in.C */
+    rdfc_view in2;          /* optional second source concatenated after `in` along C (ptr == NULL: unused); SIMT only */
+    rdfc_view out;          /* Cout = out.C */
+    rdfc_view residual;     /* optional (ptr == NULL: none): added after scale/shift, before the activation */
+    const void *weight;     /* packed by rdfc_gan_b200.engine: SIMT: fp32 [kh*kw][Cin][Cout]; UMMA: see rdfc_umma_pack_size */
+    const float *scale;     /* per-Cout multiplier (folded BN gamma/sqrt(var+eps)) or NULL (= 1) */
+    const float *shift;     /* per-Cout addend (folded BN beta - mean*scale, or the conv bias) or NULL (= 0) */
+} rdfc_conv_desc;
+
+int rdfc_conv_forward(const rdfc_conv_desc *d, void *stream);
+
+/* UMMA weight image: bytes needed for a (Cout, Cin, kh, kw) filter bank, and the host-side packer
+ * (src_host: fp32 [Cout][kh*kw][Cin] gather-form; dst_host: bf16 image to be copied to the device verbatim). */
+size_t rdfc_umma_pack_size(int Cout, int Cin, int ntaps);
+int rdfc_umma_pack_weights_host(const float *src_host, void *dst_host, int Cout, int Cin, int ntaps);
+
+/* per-(b,c) mean and 1/sqrt(var+eps) over the pixels of an NHWC view.  unbiased != 0 divides by (n-1) (AdaIN,
+ * model_utils.py:98) and returns sqrt(var+eps) in `rstd` instead of its reciprocal when want_std != 0.
+ * partial: workspace of B*nchunk*C*2 floats with nchunk = rdfc_instnorm_nchunk(H*W). mean/rstd: (B,C) fp32. */
+int rdfc_instnorm_nchunk(int npix);
+int rdfc_instnorm_stats(const rdfc_view *x, int B, int H, int W, float eps, int unbiased, int want_std,
+                        float *partial, float *mean, float *rstd, void *stream);
+
+/* W-AdaIN apply (model_utils.py:76-88): out[p,c] = gw*gamma*(x-mean)*rstd + bw*beta with
+ * gamma = gb[p, c], beta = gb[p, C + c]  (gb = EqualLinear output, NHWC view with 2C channels) and optional
+ * gw/bw = gamma/beta_weight_layer(x) views (ptr NULL = 1). */
+int rdfc_wadain_apply(const rdfc_view *x, const rdfc_view *gb, const rdfc_view *gw, const rdfc_view *bw,
+                      const float *mean, const float *rstd, const rdfc_view *out, int B, int H, int W, void *stream);
+
+/* AdaIN apply (model_utils.py:102-116): out = (x - cmean)/cstd * sstd + smean, all (B,C) statistics. */
+int rdfc_adain_apply(const rdfc_view *x, const float *cmean, const float *cstd, const float *smean,
+                     const float *sstd, const rdfc_view *out, int B, int H, int W, void *stream);
+
+/* plain per-channel affine normalise (IN fuse, model_utils.py:119-129): out = (x - mean) * rstd, written into `out`
+ * (a channel slice of the concat buffer that feeds down_channel). */
+int rdfc_norm_apply(const rdfc_view *x, const float *mean, const float *rstd, const rdfc_view *out, int B, int H,
+                    int W, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDFC_B200_H */

@@ -1,0 +1,441 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), bf16 x bf16 -> fp32.
+//
+// One kernel covers every GEMM-shaped layer of the generator (encoder_decoder/common.py:29-61, the torchvision
+// BasicBlock convs, the decode heads rdf_generator.py:68-102 and the per-pixel EqualLinear of W-AdaIN
+// model_utils.py:72-75): 3x3 / 1x1, stride 1 / 2, and ConvTranspose2d(k3,s2,p1,op1) as four sub-pixel phases.
+//
+// GEMM view (per CTA):  D[128*NACC pixels, BN couts] += A[pixels, 32 cin] * B[couts, 32 cin]^T
+//   * the CTA owns a 16 x (8*NACC) pixel tile of one image; accumulator j (128 TMEM lanes x BN fp32 columns) holds
+//     the 16 x 8 sub-tile j, MMA row m = 8*r + c.
+//   * A: the input HALO of the tile (all pixels any tap can touch) is staged ONCE per 32-channel block by the four
+//     producer warps with 16-byte cp.async (zero-fill outside the image = the conv padding), in the UMMA
+//     no-swizzle K-major layout [cin/8][pixel][8]: a core matrix is 8 consecutive pixels of a row (128 contiguous
+//     bytes), SBO = the plane's row pitch, LBO = the cin-chunk pitch.  Every filter tap is then just a different
+//     start address into the same staged plane, so the input is read from L2 ~1.2x instead of 9x.
+//     Stride-2 layers stage the four input-parity planes; transposed layers run one launch with the four output
+//     phases in blockIdx.z, each a 1/2/2/4-tap convolution over the input grid.
+//   * B: filters are pre-packed on the host as [tap][cin/8][cout][8]; warp 5 streams one (tap, 32-cin) block per
+//     stage with cp.async.bulk (TMA 1-D) onto an mbarrier.
+//   * warp 4 / lane 0 issues tcgen05.mma (M=128, N=BN, K=16) and releases stages with tcgen05.commit.
+//   * epilogue (warps 0-3): tcgen05.ld 32 lanes x 16 columns, y = act(acc*scale + shift + residual), bf16, 32-byte
+//     vector stores into the NHWC channel slice (this is how every torch.cat of the reference disappears).
+#include "common.cuh"
+
+namespace rdfc {
+namespace {
+
+constexpr int BK = 32;            // input channels per A stage (2 MMAs of K=16)
+constexpr int KCH = BK / 8;       // 16-byte cin chunks per stage
+constexpr int TH = 16;            // tile rows (= 8-row groups of one M=128 MMA)
+constexpr int NPROD = 128;        // producer / epilogue threads (warps 0-3)
+constexpr int NTHREADS = 192;     // + warp 4 (MMA) + warp 5 (B loader)
+constexpr int MAX_PLANES = 4, MAX_TAPS = 9;
+
+struct Plane {
+    int ystep, yoff, xstep, xoff;  // input pixel = (ystep*(ty0+r) + yoff, xstep*(tx0+c) + xoff)
+    int rows, cols, base;          // extent and first pixel slot of the plane inside a stage
+};
+struct Tap {
+    int plane, sy, sx, wtap;       // staged plane, shift inside it, index of the filter tap in the packed weights
+};
+struct Phase {                     // one sub-pixel phase of a transposed conv (or the single phase of a conv)
+    int ntaps;
+    Tap taps[MAX_TAPS];
+    int oyo, oxo;                  // output pixel = (oys*(ty0+r) + oyo, oxs*(tx0+c) + oxo)
+};
+struct Params {
+    const __nv_bfloat16 *in;
+    int in_stride, B, Hi, Wi;
+    int Ht, Wt, tiles_y, tiles_x;  // tile space
+    const __nv_bfloat16 *w;
+    int CoutP, cin_chunks, nkb;    // padded Cout, Cin/8, Cin/BK
+    __nv_bfloat16 *out;
+    int out_stride, Cout, Ho, Wo, oys, oxs;
+    const __nv_bfloat16 *res;
+    int res_stride;
+    const float *scale, *shift;
+    int act, nacc, bn, sa, sb, npix_pad, nplanes, tmem_cols;
+    Plane planes[MAX_PLANES];
+    Phase phases[4];
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps after ~4 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 8000000000ll) {
+            printf("rdfc conv_umma: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+                   threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// no-swizzle K-major shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);
+}
+
+__global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_constant__ Params P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a_stage_bytes = KCH * P.npix_pad * 16, b_stage_bytes = KCH * P.bn * 16;
+    unsigned char *sA = smem;
+    unsigned char *sB = sA + (size_t)P.sa * a_stage_bytes;
+    int *pix_off = reinterpret_cast<int *>(sB + (size_t)P.sb * b_stage_bytes);
+    float *s_scale = reinterpret_cast<float *>(pix_off + P.npix_pad);
+    float *s_shift = s_scale + P.bn;
+    uint64_t *bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(s_shift + P.bn) + 7) & ~uintptr_t(7));
+    // barrier map: [0,sa) a_full, [sa,2sa) a_empty, [2sa,2sa+sb) b_full, [2sa+sb,2sa+2sb) b_empty, then acc_full
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    const int A_FULL = 0, A_EMPTY = P.sa, B_FULL = 2 * P.sa, B_EMPTY = 2 * P.sa + P.sb, ACC_FULL = 2 * P.sa + 2 * P.sb;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + ACC_FULL + 1);
+
+    // ---- tile decode
+    const Phase &ph = P.phases[blockIdx.z];
+    int t = blockIdx.x;
+    const int txi = t % P.tiles_x; t /= P.tiles_x;
+    const int tyi = t % P.tiles_y; t /= P.tiles_y;
+    const int b = t;
+    const int ty0 = tyi * TH, tx0 = txi * 8 * P.nacc;
+    const int n0 = blockIdx.y * P.bn;
+
+    // ---- one-time setup
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.sa; ++i) { mbar_init(BAR(A_FULL + i), NPROD); mbar_init(BAR(A_EMPTY + i), 1); }
+        for (int i = 0; i < P.sb; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+        mbar_init(BAR(ACC_FULL), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)P.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // gather table: element offset of every staged pixel (or -1 outside the image)
+    for (int e = threadIdx.x; e < P.npix_pad; e += NTHREADS) {
+        int off = -1;
+        for (int pl = 0; pl < P.nplanes; ++pl) {
+            const Plane &q = P.planes[pl];
+            const int rel = e - q.base;
+            if (rel >= 0 && rel < q.rows * q.cols) {
+                const int iy = q.ystep * (ty0 + rel / q.cols) + q.yoff, ix = q.xstep * (tx0 + rel % q.cols) + q.xoff;
+                if (iy >= 0 && iy < P.Hi && ix >= 0 && ix < P.Wi) off = ((b * P.Hi + iy) * P.Wi + ix);
+            }
+        }
+        pix_off[e] = off;
+    }
+    for (int e = threadIdx.x; e < P.bn; e += NTHREADS) {
+        const int co = n0 + e;
+        s_scale[e] = (P.scale && co < P.Cout) ? P.scale[co] : 1.f;
+        s_shift[e] = (P.shift && co < P.Cout) ? P.shift[co] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ================= A producers: stage the halo planes of each 32-channel block =================
+        const int nelem = P.npix_pad * KCH;
+        for (int i = 0; i < P.nkb; ++i) {
+            const int s = i % P.sa;
+            mbar_wait(BAR(A_EMPTY + s), ((i / P.sa) & 1) ^ 1);
+            const uint32_t dst0 = smem_u32(sA + (size_t)s * a_stage_bytes);
+            const __nv_bfloat16 *src0 = P.in + i * BK;
+            for (int e = threadIdx.x; e < nelem; e += NPROD) {
+                const int pixel = e / KCH, ch = e % KCH;
+                const int off = pix_off[pixel];
+                const __nv_bfloat16 *src = off >= 0 ? src0 + (long long)off * P.in_stride + ch * 8 : P.in;
+                cp_async16(dst0 + (uint32_t)(ch * P.npix_pad + pixel) * 16u, src, off >= 0 ? 16u : 0u);
+            }
+            cp_async_commit();
+            if (i >= 1) {
+                cp_async_wait<1>();
+                fence_proxy_async();
+                mbar_arrive(BAR(A_FULL + (i - 1) % P.sa));
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        mbar_arrive(BAR(A_FULL + (P.nkb - 1) % P.sa));
+
+        // ================= epilogue =================
+        mbar_wait(BAR(ACC_FULL), 0);
+        tc_fence_after();
+        const int r = 4 * warp + (lane >> 3), c = lane & 7;   // MMA row m = 32*warp + lane = 8*r + c
+        for (int j = 0; j < P.nacc; ++j) {
+            const int yy = ty0 + r, xx = tx0 + 8 * j + c;
+            const int oy = P.oys * yy + ph.oyo, ox = P.oxs * xx + ph.oxo;
+            const bool ok = yy < P.Ht && xx < P.Wt && oy < P.Ho && ox < P.Wo;
+            const long long opix = ((long long)b * P.Ho + oy) * P.Wo + ox;
+            for (int n = 0; n < P.bn; n += 16) {
+                uint32_t v[16];
+                tc_ld16(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)(j * P.bn + n), v);   // warp-collective
+                if (!ok || n0 + n >= P.Cout) continue;
+                float f[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]) * s_scale[n + q] + s_shift[n + q];
+                if (P.res) {
+                    const uint4 *rp = reinterpret_cast<const uint4 *>(P.res + opix * P.res_stride + n0 + n);
+                    const uint4 r0 = rp[0], r1 = rp[1];
+                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float2 p2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr[q]));
+                        f[2 * q] += p2.x;
+                        f[2 * q + 1] += p2.y;
+                    }
+                }
+                uint32_t o[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(apply_act(f[2 * q], P.act), apply_act(f[2 * q + 1], P.act));
+                    o[q] = *reinterpret_cast<const uint32_t *>(&h2);
+                }
+                __nv_bfloat16 *op = P.out + opix * P.out_stride + n0 + n;
+                if (n0 + n + 16 <= P.Cout) {
+                    uint4 *o4 = reinterpret_cast<uint4 *>(op);
+                    o4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                    o4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                } else {
+                    const __nv_bfloat16 *oh = reinterpret_cast<const __nv_bfloat16 *>(o);
+                    for (int q = 0; q < P.Cout - n0 - n; ++q) op[q] = oh[q];
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | (8u << 24);
+            const uint32_t a_lbo = (uint32_t)P.npix_pad * 16u, b_lbo = (uint32_t)P.bn * 16u;
+            int bi = 0;   // running B-stage counter
+            for (int i = 0; i < P.nkb; ++i) {
+                const int s = i % P.sa;
+                mbar_wait(BAR(A_FULL + s), (i / P.sa) & 1);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(sA + (size_t)s * a_stage_bytes);
+                for (int tp = 0; tp < ph.ntaps; ++tp, ++bi) {
+                    const int sb = bi % P.sb;
+                    mbar_wait(BAR(B_FULL + sb), (bi / P.sb) & 1);
+                    tc_fence_after();
+                    const Tap &tap = ph.taps[tp];
+                    const Plane &q = P.planes[tap.plane];
+                    const uint32_t b_base = smem_u32(sB + (size_t)sb * b_stage_bytes);
+                    const uint32_t a_tap = a_base + (uint32_t)(q.base + tap.sy * q.cols + tap.sx) * 16u;
+                    for (int j = 0; j < P.nacc; ++j)
+#pragma unroll
+                        for (int k2 = 0; k2 < BK / 16; ++k2) {
+                            const uint64_t da = make_desc(a_tap + (uint32_t)j * 128u + (uint32_t)k2 * 2u * a_lbo, a_lbo,
+                                                          (uint32_t)q.cols * 16u);
+                            const uint64_t db = make_desc(b_base + (uint32_t)k2 * 2u * b_lbo, b_lbo, 128u);
+                            tc_mma(tmem_base + (uint32_t)(j * P.bn), da, db, idesc, (i | tp | k2) ? 1u : 0u);
+                        }
+                    tc_commit(BAR(B_EMPTY + sb));
+                }
+                tc_commit(BAR(A_EMPTY + s));
+            }
+            tc_commit(BAR(ACC_FULL));
+        }
+        __syncwarp();
+    } else {
+        // ================= B loader (TMA 1-D bulk copies of pre-packed filter blocks) =================
+        if (lane == 0) {
+            int bi = 0;
+            const uint32_t piece = (uint32_t)P.bn * 16u;
+            for (int i = 0; i < P.nkb; ++i)
+                for (int tp = 0; tp < ph.ntaps; ++tp, ++bi) {
+                    const int sb = bi % P.sb;
+                    mbar_wait(BAR(B_EMPTY + sb), ((bi / P.sb) & 1) ^ 1);
+                    mbar_expect_tx(BAR(B_FULL + sb), piece * KCH);
+                    const uint32_t dst = smem_u32(sB + (size_t)sb * b_stage_bytes);
+                    const int wt = ph.taps[tp].wtap;
+#pragma unroll
+                    for (int ch = 0; ch < KCH; ++ch) {
+                        const __nv_bfloat16 *src =
+                            P.w + (((long long)wt * P.cin_chunks + (i * KCH + ch)) * P.CoutP + n0) * 8;
+                        bulk_g2s(dst + (uint32_t)ch * piece, src, piece, BAR(B_FULL + sb));
+                    }
+                }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols)
+                     : "memory");
+    }
+}
+
+int next_pow2_cols(int c) {
+    int p = 32;
+    while (p < c) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+// Host-side planning: planes, taps, tile shape, stage counts.
+int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st) {
+    RDFC_REQUIRE(d->in.dtype == RDFC_BF16 && d->out.dtype == RDFC_BF16, "UMMA conv: bf16 in/out only");
+    RDFC_REQUIRE(!d->in.nchw && !d->out.nchw && !d->in2.ptr, "UMMA conv: single NHWC source / NHWC output only");
+    RDFC_REQUIRE(d->in.C % BK == 0, "UMMA conv: Cin (%d) must be a multiple of %d", d->in.C, BK);
+    RDFC_REQUIRE(d->in.pix_stride % 8 == 0 && d->out.pix_stride % 8 == 0 && ((uintptr_t)d->in.ptr % 16) == 0 &&
+                     ((uintptr_t)d->out.ptr % 16) == 0 && ((uintptr_t)d->weight % 16) == 0,
+                 "UMMA conv: views must be 16-byte aligned with pixel strides that are multiples of 8 elements");
+    RDFC_REQUIRE(!d->residual.ptr || (d->residual.dtype == RDFC_BF16 && d->residual.pix_stride % 8 == 0 &&
+                                      ((uintptr_t)d->residual.ptr % 16) == 0),
+                 "UMMA conv: residual must be an aligned bf16 NHWC view");
+    const bool k3 = d->kh == 3 && d->kw == 3, k1 = d->kh == 1 && d->kw == 1;
+    RDFC_REQUIRE(k3 || k1, "UMMA conv: 3x3 or 1x1 kernels only");
+    RDFC_REQUIRE(d->stride == 1 || d->stride == 2, "UMMA conv: stride 1 or 2");
+    RDFC_REQUIRE(!d->transposed || (k3 && d->stride == 2 && d->pad == 1), "UMMA conv: transposed = k3 s2 p1 op1 only");
+    RDFC_REQUIRE(d->transposed || d->pad == (k3 ? 1 : 0), "UMMA conv: padding must be (k-1)/2");
+
+    Params P{};
+    P.in = (const __nv_bfloat16 *)d->in.ptr; P.in_stride = d->in.pix_stride;
+    P.B = d->B; P.Hi = d->Hi; P.Wi = d->Wi;
+    P.w = (const __nv_bfloat16 *)d->weight;
+    P.Cout = d->out.C; P.CoutP = (P.Cout + 15) / 16 * 16;
+    P.cin_chunks = d->in.C / 8; P.nkb = d->in.C / BK;
+    P.out = (__nv_bfloat16 *)d->out.ptr; P.out_stride = d->out.pix_stride; P.Ho = d->Ho; P.Wo = d->Wo;
+    P.res = (const __nv_bfloat16 *)d->residual.ptr; P.res_stride = d->residual.pix_stride;
+    P.scale = d->scale; P.shift = d->shift; P.act = d->act;
+
+    // tile space: output grid for convs, input grid for the sub-pixel phases of a transposed conv
+    P.Ht = d->transposed ? d->Hi : d->Ho;
+    P.Wt = d->transposed ? d->Wi : d->Wo;
+    P.oys = P.oxs = d->transposed ? 2 : 1;
+    P.bn = P.CoutP < 128 ? P.CoutP : 128;
+    while (P.CoutP % P.bn) P.bn -= 16;   // largest multiple of 16 <= 128 dividing the padded Cout
+    // accumulators per CTA: wide tiles amortise the filter stream; small problems need more CTAs
+    const long long pixels = (long long)P.B * P.Ht * P.Wt;
+    P.nacc = 4;
+    while (P.nacc > 1 && (P.Wt <= 8 * (P.nacc / 2) || pixels / (128 * P.nacc) * (P.CoutP / P.bn) < 2 * sm_count())) P.nacc /= 2;
+    if (d->stride == 2 && !d->transposed && k3 && P.nacc > 2) P.nacc = 2;   // four parity planes: keep the stage small
+    const int TW = 8 * P.nacc;
+    P.tiles_y = cdiv(P.Ht, TH); P.tiles_x = cdiv(P.Wt, TW);
+
+    int nphases = 1, base = 0;
+    auto add_plane = [&](int ystep, int yoff, int xstep, int xoff, int rows, int cols) {
+        P.planes[P.nplanes] = Plane{ystep, yoff, xstep, xoff, rows, cols, base};
+        base += rows * cols;
+        return P.nplanes++;
+    };
+    if (d->transposed) {
+        // oy = 2*iy - 1 + ky: even rows take ky = 1 (iy = y); odd rows take ky = 0 (iy = y + 1) and ky = 2 (iy = y)
+        const int pl = add_plane(1, 0, 1, 0, TH + 1, TW + 1);
+        nphases = 4;
+        for (int a = 0; a < 2; ++a)
+            for (int bq = 0; bq < 2; ++bq) {
+                Phase &ph = P.phases[a * 2 + bq];
+                ph.oyo = a; ph.oxo = bq; ph.ntaps = 0;
+                for (int ky = 0; ky < 3; ++ky)
+                    for (int kx = 0; kx < 3; ++kx) {
+                        if ((ky % 2 == 1) != (a == 0) || (kx % 2 == 1) != (bq == 0)) continue;
+                        ph.taps[ph.ntaps++] = Tap{pl, ky == 0 ? 1 : 0, kx == 0 ? 1 : 0, ky * 3 + kx};
+                    }
+            }
+    } else if (d->stride == 1) {
+        const int pl = add_plane(1, -d->pad, 1, -d->pad, TH + d->kh - 1, TW + d->kw - 1);
+        Phase &ph = P.phases[0];
+        for (int ky = 0; ky < d->kh; ++ky)
+            for (int kx = 0; kx < d->kw; ++kx) ph.taps[ph.ntaps++] = Tap{pl, ky, kx, ky * d->kw + kx};
+    } else if (k1) {
+        const int pl = add_plane(2, 0, 2, 0, TH, TW);
+        P.phases[0].taps[P.phases[0].ntaps++] = Tap{pl, 0, 0, 0};
+    } else {
+        // iy = 2*oy - 1 + ky: ky = 1 reads the even-row plane; ky = 0 / 2 read the odd-row plane (rows oy-1 / oy)
+        int pl[2][2];
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px)
+                pl[py][px] = add_plane(2, py ? -1 : 0, 2, px ? -1 : 0, TH + py, TW + px);
+        Phase &ph = P.phases[0];
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx)
+                ph.taps[ph.ntaps++] = Tap{pl[ky != 1][kx != 1], ky == 2 ? 1 : 0, kx == 2 ? 1 : 0, ky * 3 + kx};
+    }
+    P.npix_pad = (base + 7) / 8 * 8;
+    P.tmem_cols = next_pow2_cols(P.nacc * P.bn);
+    RDFC_REQUIRE(P.tmem_cols <= 512, "UMMA conv: accumulators exceed TMEM");
+
+    const int a_stage = KCH * P.npix_pad * 16, b_stage = KCH * P.bn * 16;
+    const int fixed = P.npix_pad * 4 + 2 * P.bn * 4 + 8 + (2 * 4 + 2 * 8 + 2) * 8 + 16 + 128;
+    const int budget = 200 * 1024;
+    P.sb = 4;
+    P.sa = (budget - fixed - P.sb * b_stage) / a_stage;
+    if (P.sa > 4) P.sa = 4;
+    if (P.sa > P.nkb) P.sa = P.nkb < 1 ? 1 : P.nkb;
+    RDFC_REQUIRE(P.sa >= 1, "UMMA conv: tile does not fit shared memory");
+    const size_t smem = (size_t)P.sa * a_stage + (size_t)P.sb * b_stage + fixed;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(P.tiles_x * P.tiles_y * P.B, P.CoutP / P.bn, nphases);
+    RDFC_REQUIRE(grid.y <= 65535, "UMMA conv: too many Cout tiles");
+    conv_umma_kernel<<<grid, NTHREADS, smem, st>>>(P);
+    RDFC_CHECK_LAUNCH("conv_umma_kernel");
+    return 0;
+}
+
+}  // namespace rdfc

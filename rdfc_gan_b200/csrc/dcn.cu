@@ -1,0 +1,369 @@
+// General deformable convolution (DCN v1 / modulated v2), forward and backward, fp32 / fp64, NCHW.
+//
+// This is the drop-in for the reference's pybind module `DCN`
+// (nlspn/deformconv/src/vision.cpp:7-12; semantics restated in SURVEY.md Appendix C).  Unlike the reference there is
+// no `columns` buffer and no per-im2col_step chunking: a CTA samples a strip of output pixels once into shared
+// memory and contracts it against the filter bank in registers.  The NLSPN-shaped calls (Cin = Cout = 1) never come
+// here from the generator -- they run in nlspn.cu -- but the Function / Module API does.
+#include "common.cuh"
+
+namespace rdfc {
+namespace {
+
+constexpr int TP = 32;        // output pixels per CTA strip (one warp lane per pixel in the contraction)
+constexpr int NT = 256;       // threads per CTA
+constexpr int CHUNK = 64;     // (ci,k) rows sampled per pass
+constexpr int RMAX = 16;      // output channels per thread per pass (8 warps x 16 = 128 per pass)
+
+struct Geo {
+    int B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, group, dg, Ho, Wo;
+};
+
+template <typename T>
+__device__ __forceinline__ T ld(const T *p) { return __ldg(p); }
+
+// value at (y,x) with the reference's validity rule and per-corner zeroing
+// (modulated_deform_im2col_cuda.cuh:25-54,180)
+template <typename T>
+__device__ __forceinline__ T sample(const T *im, int H, int W, T y, T x) {
+    if (!(y > (T)-1 && x > (T)-1 && y < (T)H && x < (T)W)) return (T)0;
+    const int yl = (int)floor(y), xl = (int)floor(x);
+    const int yh = yl + 1, xh = xl + 1;
+    const T ly = y - yl, lx = x - xl, hy = (T)1 - ly, hx = (T)1 - lx;
+    const T v1 = (yl >= 0 && xl >= 0) ? ld(im + (size_t)yl * W + xl) : (T)0;
+    const T v2 = (yl >= 0 && xh <= W - 1) ? ld(im + (size_t)yl * W + xh) : (T)0;
+    const T v3 = (yh <= H - 1 && xl >= 0) ? ld(im + (size_t)yh * W + xl) : (T)0;
+    const T v4 = (yh <= H - 1 && xh <= W - 1) ? ld(im + (size_t)yh * W + xh) : (T)0;
+    return hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
+}
+
+// d val / d y and d val / d x (modulated_deform_im2col_cuda.cuh:84-125)
+template <typename T>
+__device__ __forceinline__ void sample_grad(const T *im, int H, int W, T y, T x, T &val, T &gy, T &gx) {
+    val = gy = gx = (T)0;
+    if (y <= (T)-1 || y >= (T)H || x <= (T)-1 || x >= (T)W) return;
+    const int yl = (int)floor(y), xl = (int)floor(x);
+    const int yh = yl + 1, xh = xl + 1;
+    const T ly = y - yl, lx = x - xl, hy = (T)1 - ly, hx = (T)1 - lx;
+    const T v1 = (yl >= 0 && xl >= 0) ? ld(im + (size_t)yl * W + xl) : (T)0;
+    const T v2 = (yl >= 0 && xh <= W - 1) ? ld(im + (size_t)yl * W + xh) : (T)0;
+    const T v3 = (yh <= H - 1 && xl >= 0) ? ld(im + (size_t)yh * W + xl) : (T)0;
+    const T v4 = (yh <= H - 1 && xh <= W - 1) ? ld(im + (size_t)yh * W + xh) : (T)0;
+    val = hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
+    gy = hx * (v3 - v1) + lx * (v4 - v2);
+    gx = hy * (v2 - v1) + ly * (v4 - v3);
+}
+
+// ---------------------------------------------------------------- forward -------------------------------------
+// grid: (ceil(Ho*Wo / TP), B, group).  Each CTA: TP pixels of image b, all Cout/group outputs of group g.
+template <typename T, bool kMask>
+__global__ void __launch_bounds__(NT) dcn_fwd_kernel(const T *__restrict__ input, const T *__restrict__ weight,
+                                                      const T *__restrict__ bias, const T *__restrict__ offset,
+                                                      const T *__restrict__ mask, T *__restrict__ output, Geo g) {
+    __shared__ T col[CHUNK][TP + 1];
+    const int K = g.kh * g.kw, P = g.Ho * g.Wo;
+    const int cpg = g.Cin / g.group, opg = g.Cout / g.group, cpdg = g.Cin / g.dg;
+    const int pix0 = blockIdx.x * TP, b = blockIdx.y, grp = blockIdx.z;
+    const int lane = threadIdx.x % TP, wrp = threadIdx.x / TP;  // wrp in [0,8)
+    const int rows = cpg * K;                                    // contraction length of this group
+
+    for (int co0 = 0; co0 < opg; co0 += (NT / TP) * RMAX) {
+        T acc[RMAX];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) acc[r] = (T)0;
+        for (int q0 = 0; q0 < rows; q0 += CHUNK) {
+            __syncthreads();
+            // phase 1: sample CHUNK x TP values
+            for (int e = threadIdx.x; e < CHUNK * TP; e += NT) {
+                const int qq = e / TP, pl = e % TP, q = q0 + qq, pix = pix0 + pl;
+                T v = (T)0;
+                if (q < rows && pix < P) {
+                    const int ci = grp * cpg + q / K, k = q % K, i = k / g.kw, j = k % g.kw;
+                    const int ho = pix / g.Wo, wo = pix % g.Wo, gd = ci / cpdg;
+                    const T *off = offset + ((size_t)(b * g.dg + gd) * 2 * K) * P;
+                    const T y = (T)(ho * g.sh - g.ph + i * g.dh) + ld(off + (size_t)(2 * k) * P + pix);
+                    const T x = (T)(wo * g.sw - g.pw + j * g.dw) + ld(off + (size_t)(2 * k + 1) * P + pix);
+                    v = sample(input + ((size_t)b * g.Cin + ci) * g.H * g.W, g.H, g.W, y, x);
+                    if (kMask) v *= ld(mask + ((size_t)(b * g.dg + gd) * K + k) * P + pix);
+                }
+                col[qq][pl] = v;
+            }
+            __syncthreads();
+            // phase 2: contract against the filters; weight address is warp-uniform (broadcast load)
+            const int qn = min(CHUNK, rows - q0);
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const int col_o = co0 + wrp + r * (NT / TP);
+                if (col_o < opg) {
+                    const T *wrow = weight + (size_t)(grp * opg + col_o) * rows + q0;
+                    T a = acc[r];
+                    for (int qq = 0; qq < qn; ++qq) a += ld(wrow + qq) * col[qq][lane];
+                    acc[r] = a;
+                }
+            }
+        }
+        const int pix = pix0 + lane;
+        if (pix < P) {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const int col_o = co0 + wrp + r * (NT / TP);
+                if (col_o < opg) {
+                    const int co = grp * opg + col_o;
+                    output[((size_t)b * g.Cout + co) * P + pix] = acc[r] + (bias ? ld(bias + co) : (T)0);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- backward: data ------------------------------
+// One thread per (b, gd, k, pixel): loops the channels of the deformable group, forms
+// gcol = sum_co W[co,ci,k] * gout[b,co,pix]  (modulated_deform_conv_cuda.cu:217-222), then
+// grad_mask / grad_offset (col2im_coord, cuh:257-328) and the grad_input scatter (col2im, cuh:197-254).
+template <typename T, bool kMask>
+__global__ void __launch_bounds__(NT) dcn_bwd_data_kernel(const T *__restrict__ input, const T *__restrict__ weight,
+                                                           const T *__restrict__ offset, const T *__restrict__ mask,
+                                                           const T *__restrict__ gout, T *__restrict__ gin,
+                                                           T *__restrict__ goff, T *__restrict__ gmask, Geo g) {
+    const int K = g.kh * g.kw, P = g.Ho * g.Wo;
+    const int cpg = g.Cin / g.group, opg = g.Cout / g.group, cpdg = g.Cin / g.dg;
+    const long long total = (long long)g.B * g.dg * K * P;
+    for (long long idx = (long long)blockIdx.x * NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
+        const int pix = (int)(idx % P);
+        const int k = (int)((idx / P) % K);
+        const int gd = (int)((idx / P / K) % g.dg);
+        const int b = (int)(idx / P / K / g.dg);
+        const int i = k / g.kw, j = k % g.kw, ho = pix / g.Wo, wo = pix % g.Wo;
+        const T *off = offset + ((size_t)(b * g.dg + gd) * 2 * K) * P;
+        const T y = (T)(ho * g.sh - g.ph + i * g.dh) + ld(off + (size_t)(2 * k) * P + pix);
+        const T x = (T)(wo * g.sw - g.pw + j * g.dw) + ld(off + (size_t)(2 * k + 1) * P + pix);
+        const T m = kMask ? ld(mask + ((size_t)(b * g.dg + gd) * K + k) * P + pix) : (T)1;
+        const bool valid = (y > (T)-1 && x > (T)-1 && y < (T)g.H && x < (T)g.W);
+        const int yl = (int)floor(y), xl = (int)floor(x);
+        const T ly = y - yl, lx = x - xl;
+        T s_mask = (T)0, s_y = (T)0, s_x = (T)0;
+        for (int c = 0; c < cpdg; ++c) {
+            const int ci = gd * cpdg + c, grp = ci / cpg, cil = ci % cpg;
+            T gcol = (T)0;
+            for (int o = 0; o < opg; ++o) {
+                const int co = grp * opg + o;
+                gcol += ld(weight + ((size_t)co * cpg + cil) * K + k) * ld(gout + ((size_t)b * g.Cout + co) * P + pix);
+            }
+            const T *im = input + ((size_t)b * g.Cin + ci) * g.H * g.W;
+            T val, gy, gx;
+            sample_grad(im, g.H, g.W, y, x, val, gy, gx);
+            s_mask += gcol * val;
+            s_y += gcol * m * gy;
+            s_x += gcol * m * gx;
+            if (gin && valid) {
+                T *gim = gin + ((size_t)b * g.Cin + ci) * g.H * g.W;
+                const T top = gcol * m;
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        const int yy = yl + a, xx = xl + c2;
+                        if (yy >= 0 && yy <= g.H - 1 && xx >= 0 && xx <= g.W - 1) {
+                            const T wgt = (a ? ly : (T)1 - ly) * (c2 ? lx : (T)1 - lx);
+                            atomicAdd(gim + (size_t)yy * g.W + xx, wgt * top);
+                        }
+                    }
+            }
+        }
+        if (goff) {
+            T *go = goff + ((size_t)(b * g.dg + gd) * 2 * K) * P;
+            go[(size_t)(2 * k) * P + pix] = s_y;
+            go[(size_t)(2 * k + 1) * P + pix] = s_x;
+        }
+        if (kMask && gmask) gmask[((size_t)(b * g.dg + gd) * K + k) * P + pix] = s_mask;
+    }
+}
+
+// ---------------------------------------------------------------- backward: filters ---------------------------
+// grid: (Cin * K).  grad_weight[co, cil, k] = sum_{b,pix} gout[b,co,pix] * col(ci,k,b,pix)   (cu:248-272).
+// Deterministic: fixed tile order, warp-shuffle reduction, one owner per output element.
+template <typename T, bool kMask>
+__global__ void __launch_bounds__(NT) dcn_bwd_weight_kernel(const T *__restrict__ input,
+                                                             const T *__restrict__ offset,
+                                                             const T *__restrict__ mask, const T *__restrict__ gout,
+                                                             T *__restrict__ gweight, Geo g) {
+    extern __shared__ unsigned char smem_raw[];
+    T *colv = reinterpret_cast<T *>(smem_raw);          // NT
+    T *acc_s = colv + NT;                               // opg
+    const int K = g.kh * g.kw, P = g.Ho * g.Wo;
+    const int cpg = g.Cin / g.group, opg = g.Cout / g.group, cpdg = g.Cin / g.dg;
+    const int ci = blockIdx.x / K, k = blockIdx.x % K;
+    const int grp = ci / cpg, cil = ci % cpg, gd = ci / cpdg, i = k / g.kw, j = k % g.kw;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    for (int o = threadIdx.x; o < opg; o += NT) acc_s[o] = (T)0;
+    const long long total = (long long)g.B * P;
+    for (long long t0 = 0; t0 < total; t0 += NT) {
+        __syncthreads();
+        const long long p = t0 + threadIdx.x;
+        T v = (T)0;
+        if (p < total) {
+            const int b = (int)(p / P), pix = (int)(p % P), ho = pix / g.Wo, wo = pix % g.Wo;
+            const T *off = offset + ((size_t)(b * g.dg + gd) * 2 * K) * P;
+            const T y = (T)(ho * g.sh - g.ph + i * g.dh) + ld(off + (size_t)(2 * k) * P + pix);
+            const T x = (T)(wo * g.sw - g.pw + j * g.dw) + ld(off + (size_t)(2 * k + 1) * P + pix);
+            v = sample(input + ((size_t)b * g.Cin + ci) * g.H * g.W, g.H, g.W, y, x);
+            if (kMask) v *= ld(mask + ((size_t)(b * g.dg + gd) * K + k) * P + pix);
+        }
+        colv[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = wrp; o < opg; o += NT / 32) {
+            const int co = grp * opg + o;
+            T part = (T)0;
+#pragma unroll
+            for (int jj = 0; jj < NT / 32; ++jj) {
+                const long long pp = t0 + lane + 32 * jj;
+                if (pp < total) {
+                    const int b = (int)(pp / P), pix = (int)(pp % P);
+                    part += ld(gout + ((size_t)b * g.Cout + co) * P + pix) * colv[lane + 32 * jj];
+                }
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(0xffffffffu, part, s);
+            if (lane == 0) acc_s[o] += part;
+        }
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < opg; o += NT)
+        gweight[((size_t)(grp * opg + o) * cpg + cil) * K + k] = acc_s[o];
+}
+
+// grid: (Cout).  grad_bias[co] = sum gout[:,co,:]  (cu:271-273)
+template <typename T>
+__global__ void __launch_bounds__(NT) dcn_bwd_bias_kernel(const T *__restrict__ gout, T *__restrict__ gbias, int B,
+                                                           int Cout, int P) {
+    __shared__ T red[NT / 32];
+    const int co = blockIdx.x;
+    T s = (T)0;
+    for (long long p = threadIdx.x; p < (long long)B * P; p += NT)
+        s += ld(gout + ((size_t)(p / P) * Cout + co) * P + (p % P));
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T t = (T)0;
+        for (int w = 0; w < NT / 32; ++w) t += red[w];
+        gbias[co] = t;
+    }
+}
+
+int check_shape(const rdfc_dcn_shape *s, Geo &g) {
+    RDFC_REQUIRE(s != nullptr, "shape is NULL");
+    RDFC_REQUIRE(s->B > 0 && s->Cin > 0 && s->Cout > 0 && s->H > 0 && s->W > 0, "empty tensor dimension");
+    RDFC_REQUIRE(s->kh > 0 && s->kw > 0 && s->sh > 0 && s->sw > 0 && s->dh > 0 && s->dw > 0 && s->ph >= 0 &&
+                     s->pw >= 0,
+                 "bad kernel/stride/dilation/padding");
+    RDFC_REQUIRE(s->group > 0 && s->deformable_group > 0, "group and deformable_group must be positive");
+    // modulated_deform_conv_cuda.cu:56-63
+    const int step = s->im2col_step < s->B ? s->im2col_step : s->B;
+    RDFC_REQUIRE(step > 0 && s->B % step == 0, "batch(%d) must divide im2col_step(%d)", s->B, step);
+    RDFC_REQUIRE(s->Cin % s->group == 0 && s->Cout % s->group == 0,
+                 "channels(%d) and channels_out(%d) must divide group(%d)", s->Cin, s->Cout, s->group);
+    RDFC_REQUIRE(s->Cin % s->deformable_group == 0, "channels(%d) must divide deformable_group(%d)", s->Cin,
+                 s->deformable_group);
+    g = Geo{s->B, s->Cin, s->H, s->W, s->Cout, s->kh, s->kw, s->sh, s->sw, s->ph, s->pw, s->dh, s->dw,
+            s->group, s->deformable_group, 0, 0};
+    g.Ho = (s->H + 2 * s->ph - (s->dh * (s->kh - 1) + 1)) / s->sh + 1;
+    g.Wo = (s->W + 2 * s->pw - (s->dw * (s->kw - 1) + 1)) / s->sw + 1;
+    RDFC_REQUIRE(g.Ho > 0 && g.Wo > 0, "empty output (%d x %d)", g.Ho, g.Wo);
+    RDFC_REQUIRE(s->B <= 65535 && s->group <= 65535, "batch / group exceed grid limits");
+    return 0;
+}
+
+template <typename T>
+int fwd(const void *input, const void *weight, const void *bias, const void *offset, const void *mask, void *output,
+        const Geo &g, cudaStream_t st) {
+    dim3 grid(cdiv(g.Ho * g.Wo, TP), g.B, g.group);
+    if (mask)
+        dcn_fwd_kernel<T, true><<<grid, NT, 0, st>>>((const T *)input, (const T *)weight, (const T *)bias,
+                                                     (const T *)offset, (const T *)mask, (T *)output, g);
+    else
+        dcn_fwd_kernel<T, false><<<grid, NT, 0, st>>>((const T *)input, (const T *)weight, (const T *)bias,
+                                                      (const T *)offset, nullptr, (T *)output, g);
+    RDFC_CHECK_LAUNCH("dcn_fwd_kernel");
+    return 0;
+}
+
+template <typename T>
+int bwd(const void *input, const void *weight, const void *offset, const void *mask, const void *gout, void *gin,
+        void *goff, void *gmask, void *gw, void *gb, const Geo &g, cudaStream_t st) {
+    const int K = g.kh * g.kw, P = g.Ho * g.Wo;
+    if (gin) RDFC_CUDA(cudaMemsetAsync(gin, 0, sizeof(T) * (size_t)g.B * g.Cin * g.H * g.W, st));
+    if (gin || goff || gmask) {
+        const long long total = (long long)g.B * g.dg * K * P;
+        const int blocks = (int)min((long long)cdiv(total, NT), (long long)sm_count() * 16);
+        if (mask)
+            dcn_bwd_data_kernel<T, true><<<blocks, NT, 0, st>>>((const T *)input, (const T *)weight,
+                                                                (const T *)offset, (const T *)mask, (const T *)gout,
+                                                                (T *)gin, (T *)goff, (T *)gmask, g);
+        else
+            dcn_bwd_data_kernel<T, false><<<blocks, NT, 0, st>>>((const T *)input, (const T *)weight,
+                                                                 (const T *)offset, nullptr, (const T *)gout,
+                                                                 (T *)gin, (T *)goff, nullptr, g);
+        RDFC_CHECK_LAUNCH("dcn_bwd_data_kernel");
+    }
+    if (gw) {
+        const size_t smem = sizeof(T) * (NT + g.Cout / g.group);
+        RDFC_REQUIRE(smem <= 48 * 1024, "Cout/group too large for the filter-gradient kernel");
+        if (mask)
+            dcn_bwd_weight_kernel<T, true><<<g.Cin * K, NT, smem, st>>>((const T *)input, (const T *)offset,
+                                                                        (const T *)mask, (const T *)gout, (T *)gw, g);
+        else
+            dcn_bwd_weight_kernel<T, false><<<g.Cin * K, NT, smem, st>>>((const T *)input, (const T *)offset, nullptr,
+                                                                         (const T *)gout, (T *)gw, g);
+        RDFC_CHECK_LAUNCH("dcn_bwd_weight_kernel");
+    }
+    if (gb) {
+        dcn_bwd_bias_kernel<T><<<g.Cout, NT, 0, st>>>((const T *)gout, (T *)gb, g.B, g.Cout, P);
+        RDFC_CHECK_LAUNCH("dcn_bwd_bias_kernel");
+    }
+    return 0;
+}
+
+}  // namespace
+}  // namespace rdfc
+
+using namespace rdfc;
+
+extern "C" int rdfc_dcn_out_size(const rdfc_dcn_shape *s, int *Ho, int *Wo) {
+    Geo g;
+    if (int rc = check_shape(s, g)) return rc;
+    if (Ho) *Ho = g.Ho;
+    if (Wo) *Wo = g.Wo;
+    return 0;
+}
+
+extern "C" int rdfc_dcn_forward(const void *input, const void *weight, const void *bias, const void *offset,
+                                const void *mask, void *output, const rdfc_dcn_shape *s, int dtype, void *stream) {
+    Geo g;
+    if (int rc = check_shape(s, g)) return rc;
+    RDFC_REQUIRE(input && weight && offset && output, "input / weight / offset / output must not be NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == RDFC_F32) return fwd<float>(input, weight, bias, offset, mask, output, g, st);
+    if (dtype == RDFC_F64) return fwd<double>(input, weight, bias, offset, mask, output, g, st);
+    return fail(RDFC_ERR_UNSUPPORTED, "rdfc_dcn_forward: dtype %d not supported (fp32 / fp64 only, as the reference)",
+                dtype);
+}
+
+extern "C" int rdfc_dcn_backward(const void *input, const void *weight, const void *offset, const void *mask,
+                                 const void *grad_output, void *grad_input, void *grad_offset, void *grad_mask,
+                                 void *grad_weight, void *grad_bias, const rdfc_dcn_shape *s, int dtype,
+                                 void *stream) {
+    Geo g;
+    if (int rc = check_shape(s, g)) return rc;
+    RDFC_REQUIRE(input && weight && offset && grad_output, "input / weight / offset / grad_output must not be NULL");
+    RDFC_REQUIRE(mask || !grad_mask, "grad_mask requested without a mask (DCN v1 has none)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == RDFC_F32)
+        return bwd<float>(input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask, grad_weight,
+                          grad_bias, g, st);
+    if (dtype == RDFC_F64)
+        return bwd<double>(input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask, grad_weight,
+                           grad_bias, g, st);
+    return fail(RDFC_ERR_UNSUPPORTED, "rdfc_dcn_backward: dtype %d not supported", dtype);
+}

@@ -1,0 +1,255 @@
+// NLSPN: fused offset/affinity stage and the propagation loop (fp32, NCHW, channels_f == 1, k_f == 3).
+//
+// Replaces nlspn/nlspn_model.py:68-138 (NLPSN._get_offset_affinity: a 3x3 conv, 8 ModulatedDeformConvFunction calls
+// with a 1x1 kernel and ~25 small ATen kernels) by ONE kernel, and nlspn_model.py:140-144,166-173 (prop_time x
+// {columns alloc, im2col, addmm(K=9,N=1), permute+contiguous}) by one gather kernel per iteration with no
+// intermediate buffer.  The propagation is HBM / L2 bound: per pixel and iteration it streams 16 offsets + 9
+// affinities (the centre tap's offsets are identically zero and are not read), gathers 36 feature corners through
+// L1, and writes one float.  The host wrapper walks the batch in L2-sized image groups so that iterations 2..T of a
+// group find their offset/affinity planes in the 126 MB L2 instead of HBM.
+#include "common.cuh"
+
+namespace rdfc {
+namespace {
+
+constexpr int TX = 32, TY = 8;   // pixel tile of a CTA (one warp = one 32-pixel row segment -> coalesced planes)
+
+// streaming load: read-only, do not allocate in L1 (keeps L1 for the gathered feature map)
+__device__ __forceinline__ float ld_stream(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// bilinear sample with the DCN validity rule and per-corner zeroing (deformconv/src/cuda/modulated_deform_im2col_cuda.cuh:25-54,180)
+__device__ __forceinline__ float bilinear(const float *__restrict__ im, int H, int W, float y, float x) {
+    if (!(y > -1.f && x > -1.f && y < (float)H && x < (float)W)) return 0.f;
+    const float fy = floorf(y), fx = floorf(x);
+    const int yl = (int)fy, xl = (int)fx;
+    const float ly = y - fy, lx = x - fx, hy = 1.f - ly, hx = 1.f - lx;
+    const bool y0 = yl >= 0, y1 = yl + 1 <= H - 1, x0 = xl >= 0, x1 = xl + 1 <= W - 1;
+    const float *r0 = im + (long long)yl * W + xl;
+    const float v1 = (y0 && x0) ? __ldg(r0) : 0.f;
+    const float v2 = (y0 && x1) ? __ldg(r0 + 1) : 0.f;
+    const float v3 = (y1 && x0) ? __ldg(r0 + W) : 0.f;
+    const float v4 = (y1 && x1) ? __ldg(r0 + W + 1) : 0.f;
+    return hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Offset / affinity stage.  grid (ceil(W/TX), ceil(H/TY), B), block TX*TY.
+//   1. conv_offset_aff: 8 -> 24 channels, 3x3, pad 1 (guidance tile + halo staged in shared memory, weights too)
+//   2. offsets: tap j (of the 8 non-centre taps) takes conv channels (2j, 2j+1) as (dy, dx)   (nlspn_model.py:76)
+//   3. affinity: AS/ASS raw, TC tanh/scale, TGASS tanh/(scale+1e-8)                           (:82-87)
+//   4. conf_prop: aff_j *= bilinear(confidence, h + dy_j, w + dx_j)  (1x1 kernel, pad 0)       (:96-119)
+//   5. normalise by max(sum|aff| + 1e-4, 1) (ASS/TGASS) or sum|aff| + 1e-4 (AS); aff_ref = 1 - sum  (:122-136)
+__global__ void __launch_bounds__(TX *TY) nlspn_affinity_kernel(const float *__restrict__ guidance,
+                                                                const float *__restrict__ confidence,
+                                                                const float *__restrict__ conv_w,
+                                                                const float *__restrict__ conv_b,
+                                                                const float *__restrict__ aff_scale, int affinity,
+                                                                int conf_prop, float *__restrict__ offset,
+                                                                float *__restrict__ aff, int H, int W) {
+    __shared__ float s_w[24 * 72];
+    __shared__ float s_b[24];
+    __shared__ float s_g[8][TY + 2][TX + 2];
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    const int b = blockIdx.z, x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const long long P = (long long)H * W;
+    for (int e = tid; e < 24 * 72; e += TX * TY) s_w[e] = conv_w[e];
+    if (tid < 24) s_b[tid] = conv_b[tid];
+    for (int e = tid; e < 8 * (TY + 2) * (TX + 2); e += TX * TY) {
+        const int c = e / ((TY + 2) * (TX + 2)), r = e % ((TY + 2) * (TX + 2));
+        const int yy = y0 + r / (TX + 2) - 1, xx = x0 + r % (TX + 2) - 1;
+        s_g[c][r / (TX + 2)][r % (TX + 2)] =
+            (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(guidance + ((long long)b * 8 + c) * P + (long long)yy * W + xx) : 0.f;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+
+    float o[24];
+#pragma unroll
+    for (int c = 0; c < 24; ++c) o[c] = s_b[c];
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float g = s_g[ci][threadIdx.y + t / 3][threadIdx.x + t % 3];
+#pragma unroll
+            for (int c = 0; c < 24; ++c) o[c] = fmaf(s_w[c * 72 + ci * 9 + t], g, o[c]);
+        }
+
+    const float scale = __ldg(aff_scale);
+    float a[8];
+    float abs_sum = 0.f;
+    const float *conf = confidence + (long long)b * P;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float v = o[16 + j];
+        if (affinity == RDFC_AFF_TC) v = tanhf(v) / scale;
+        else if (affinity == RDFC_AFF_TGASS) v = tanhf(v) / (scale + 1e-8f);
+        if (conf_prop) v *= bilinear(conf, H, W, (float)y + o[2 * j], (float)x + o[2 * j + 1]);
+        a[j] = v;
+        abs_sum += fabsf(v);
+    }
+    abs_sum += 1e-4f;
+    if (affinity == RDFC_AFF_ASS || affinity == RDFC_AFF_TGASS) abs_sum = abs_sum < 1.f ? 1.f : abs_sum;
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (affinity != RDFC_AFF_TC) a[j] = a[j] / abs_sum;
+        sum += a[j];
+    }
+    const long long pix = (long long)y * W + x;
+    float *offp = offset + (long long)b * 18 * P + pix;
+    float *affp = aff + (long long)b * 9 * P + pix;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = j < 4 ? j : j + 1;   // centre tap inserted at index 4
+        offp[(long long)(2 * k) * P] = o[2 * j];
+        offp[(long long)(2 * k + 1) * P] = o[2 * j + 1];
+        affp[(long long)k * P] = a[j];
+    }
+    offp[8 * P] = 0.f;
+    offp[9 * P] = 0.f;
+    affp[4 * P] = 1.f - sum;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// One propagation iteration over images [0, nb) of the pointers given.  grid (ceil(W/TX), ceil(H/TY), nb).
+//   out(h,w) = sum_k aff_k(h,w) * bilinear(in, h - 1 + k/3 + dy_k, w - 1 + k%3 + dx_k)
+template <bool kClamp>
+__global__ void __launch_bounds__(TX *TY) nlspn_prop_kernel(const float *__restrict__ in,
+                                                            const float *__restrict__ offset,
+                                                            const float *__restrict__ aff, float *__restrict__ out,
+                                                            float *__restrict__ inter, int H, int W) {
+    const int x = blockIdx.x * TX + threadIdx.x, y = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+    if (x >= W || y >= H) return;
+    const long long P = (long long)H * W, pix = (long long)y * W + x;
+    const float *offp = offset + (long long)b * 18 * P + pix;
+    const float *affp = aff + (long long)b * 9 * P + pix;
+    const float *im = in + (long long)b * P;
+
+    // issue all streaming loads first (25 independent requests in flight per thread)
+    float dy[9], dx[9], a[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        a[k] = ld_stream(affp + (long long)k * P);
+        if (k == 4) {
+            dy[k] = 0.f;
+            dx[k] = 0.f;
+        } else {
+            dy[k] = ld_stream(offp + (long long)(2 * k) * P);
+            dx[k] = ld_stream(offp + (long long)(2 * k + 1) * P);
+        }
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+        acc = fmaf(a[k], bilinear(im, H, W, (float)(y - 1 + k / 3) + dy[k], (float)(x - 1 + k % 3) + dx[k]), acc);
+    if (kClamp) acc = fminf(fmaxf(acc, -1.f), 1.f);
+    out[(long long)b * P + pix] = acc;
+    if (inter) inter[(long long)b * P + pix] = acc;
+}
+
+// feat = (1 - m) * feat + m * fix, m = fix > 0   (nlspn_model.py:159-160,169)
+__global__ void nlspn_preserve_kernel(const float *__restrict__ in, const float *__restrict__ fix,
+                                      float *__restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float f = __ldg(fix + i);
+        const float m = f > 0.f ? 1.f : 0.f;
+        out[i] = (1.f - m) * in[i] + m * f;
+    }
+}
+
+__global__ void fuse_depth_kernel(const float *__restrict__ d1, const float *__restrict__ c1,
+                                  const float *__restrict__ d2, const float *__restrict__ c2,
+                                  float *__restrict__ d2c, float *__restrict__ pred, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v2 = fminf(fmaxf(d2[i], -1.f), 1.f);
+        const float a = c1[i], b = c2[i], m = fmaxf(a, b);
+        const float e1 = expf(a - m), e2 = expf(b - m), inv = 1.f / (e1 + e2);
+        if (d2c) d2c[i] = v2;
+        pred[i] = d1[i] * (e1 * inv) + v2 * (e2 * inv);
+    }
+}
+
+}  // namespace
+}  // namespace rdfc
+
+using namespace rdfc;
+
+extern "C" int rdfc_nlspn_affinity_forward(const float *guidance, const float *confidence, const float *conv_w,
+                                           const float *conv_b, const float *aff_scale, int affinity, int conf_prop,
+                                           float *offset, float *aff, int B, int H, int W, void *stream) {
+    RDFC_REQUIRE(guidance && conv_w && conv_b && aff_scale && offset && aff, "NULL pointer argument");
+    RDFC_REQUIRE(!conf_prop || confidence, "conf_prop requires a confidence map (nlspn_model.py:150-151)");
+    RDFC_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "bad shape (%d,%d,%d)", B, H, W);
+    RDFC_REQUIRE(affinity >= RDFC_AFF_AS && affinity <= RDFC_AFF_TGASS, "unknown affinity mode %d", affinity);
+    dim3 grid(cdiv(W, TX), cdiv(H, TY), B), block(TX, TY);
+    nlspn_affinity_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(guidance, confidence, conv_w, conv_b, aff_scale,
+                                                                     affinity, conf_prop, offset, aff, H, W);
+    RDFC_CHECK_LAUNCH("nlspn_affinity_kernel");
+    return 0;
+}
+
+extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float *offset, const float *aff,
+                                            const float *feat_fix, int preserve_input, float *out, float *scratch,
+                                            float *inter, int B, int H, int W, int prop_time, int clamp_out,
+                                            void *stream) {
+    RDFC_REQUIRE(feat_init && offset && aff && out && scratch, "NULL pointer argument");
+    RDFC_REQUIRE(!preserve_input || feat_fix, "preserve_input requires feat_fix (nlspn_model.py:157-158)");
+    RDFC_REQUIRE(B > 0 && H > 0 && W > 0 && prop_time >= 0, "bad shape (%d,%d,%d) x %d", B, H, W, prop_time);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long P = (long long)H * W;
+    if (prop_time == 0) {
+        RDFC_CUDA(cudaMemcpyAsync(out, feat_init, sizeof(float) * B * P, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    // L2 blocking: offset+aff of a group (27 planes, 25 read) should stay L2 resident across the iterations.
+    const long long bytes_per_img = 27 * P * 4;
+    long long gsz = (64ll << 20) / bytes_per_img;
+    if (gsz < 1) gsz = 1;
+    if (gsz > 65535) gsz = 65535;
+    // extra buffer for preserve_input (blend result); reuse: blend writes into the buffer not being read
+    for (long long b0 = 0; b0 < B; b0 += gsz) {
+        const int nb = (int)((B - b0) < gsz ? (B - b0) : gsz);
+        dim3 grid(cdiv(W, TX), cdiv(H, TY), nb), block(TX, TY);
+        const float *off_g = offset + b0 * 18 * P, *aff_g = aff + b0 * 9 * P;
+        const float *fix_g = feat_fix ? feat_fix + b0 * P : nullptr;
+        float *bufs[2] = {scratch + b0 * P, out + b0 * P};
+        // choose ping-pong parity so that the last iteration lands in `out`
+        const float *cur = feat_init + b0 * P;
+        for (int t = 0; t < prop_time; ++t) {
+            float *dst = bufs[(prop_time - 1 - t) % 2 == 0 ? 1 : 0];
+            if (preserve_input) {
+                // blend into dst's sibling is unsafe (cur may live there); blend in place needs cur writable:
+                // iteration 0 reads feat_init (const) -> blend into the other buffer first.
+                float *tmp = (dst == bufs[0]) ? bufs[1] : bufs[0];
+                const int nblk = (int)min((long long)cdiv(nb * P, 256), (long long)sm_count() * 8);
+                nlspn_preserve_kernel<<<nblk, 256, 0, st>>>(cur, fix_g, tmp, nb * P);
+                RDFC_CHECK_LAUNCH("nlspn_preserve_kernel");
+                cur = tmp;
+            }
+            float *it = inter ? inter + ((long long)t * B + b0) * P : nullptr;
+            if (clamp_out && t == prop_time - 1)
+                nlspn_prop_kernel<true><<<grid, block, 0, st>>>(cur, off_g, aff_g, dst, it, H, W);
+            else
+                nlspn_prop_kernel<false><<<grid, block, 0, st>>>(cur, off_g, aff_g, dst, it, H, W);
+            RDFC_CHECK_LAUNCH("nlspn_prop_kernel");
+            cur = dst;
+        }
+    }
+    return 0;
+}
+
+extern "C" int rdfc_fuse_depth_forward(const float *d1, const float *c1, const float *d2, const float *c2,
+                                       float *d2_clamped, float *pred, size_t n, void *stream) {
+    RDFC_REQUIRE(d1 && c1 && d2 && c2 && pred, "NULL pointer argument");
+    if (n == 0) return 0;
+    const int nblk = (int)min((long long)cdiv((long long)n, 256), (long long)sm_count() * 8);
+    fuse_depth_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(d1, c1, d2, c2, d2_clamped, pred, n);
+    RDFC_CHECK_LAUNCH("fuse_depth_kernel");
+    return 0;
+}

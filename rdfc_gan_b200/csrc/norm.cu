@@ -1,0 +1,175 @@
+// Instance-norm statistics and the RGB<-depth fusion epilogues (W-AdaIN / AdaIN / IN) on NHWC views.
+// Reference: model_utils.py:53-90 (AdaptiveInstanceNorm), :92-116 (AdaIN, unbiased variance), :119-129 (IN).
+#include "common.cuh"
+
+namespace rdfc {
+namespace {
+
+constexpr int CHUNK_PIX = 256;
+
+// Pass 1: per (b, pixel chunk, c) shifted sums -> (mean, M2) partials.  grid (nchunk, B), block 256 (threads over c).
+template <typename T>
+__global__ void __launch_bounds__(256) in_partial_kernel(const T *__restrict__ x, int C, int stride, int npix,
+                                                         float *__restrict__ partial, int nchunk) {
+    const int chunk = blockIdx.x, b = blockIdx.y;
+    const int p0 = chunk * CHUNK_PIX, p1 = min(npix, p0 + CHUNK_PIX), n = p1 - p0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const T *px = x + ((long long)b * npix + p0) * stride + c;
+        const float pivot = ldf(px);
+        float s = 0.f, ss = 0.f;
+        for (int p = 0; p < n; ++p) {
+            const float d = ldf(px + (long long)p * stride) - pivot;
+            s += d;
+            ss = fmaf(d, d, ss);
+        }
+        const float mean = pivot + s / n, m2 = fmaxf(ss - s * s / n, 0.f);
+        float *o = partial + (((long long)b * nchunk + chunk) * C + c) * 2;
+        o[0] = mean;
+        o[1] = m2;
+    }
+}
+
+// Pass 2: Chan combination in chunk order (deterministic).  grid (B), threads over c.
+__global__ void __launch_bounds__(256) in_final_kernel(const float *__restrict__ partial, int C, int npix, int nchunk,
+                                                       float eps, int unbiased, int want_std,
+                                                       float *__restrict__ mean_o, float *__restrict__ rstd_o) {
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float mean = 0.f, m2 = 0.f, n = 0.f;
+        for (int k = 0; k < nchunk; ++k) {
+            const float *p = partial + (((long long)b * nchunk + k) * C + c) * 2;
+            const float nb = (float)min(CHUNK_PIX, npix - k * CHUNK_PIX);
+            const float delta = p[0] - mean, nn = n + nb;
+            mean += delta * nb / nn;
+            m2 += p[1] + delta * delta * n * nb / nn;
+            n = nn;
+        }
+        const float var = m2 / (unbiased ? (n - 1.f) : n) + eps;
+        mean_o[(long long)b * C + c] = mean;
+        rstd_o[(long long)b * C + c] = want_std ? sqrtf(var) : rsqrtf(var);
+    }
+}
+
+struct V {
+    const void *ptr;
+    int stride;
+};
+
+template <typename TX, typename TG, typename TO>
+__global__ void __launch_bounds__(256) wadain_kernel(V x, V gb, V gw, V bw, const float *__restrict__ mean,
+                                                     const float *__restrict__ rstd, void *out, int out_stride,
+                                                     int C, long long npix_total, int npix) {
+    const long long total = npix_total * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / C;
+        const int c = (int)(i % C), b = (int)(p / npix);
+        const float xv = ldf((const TX *)x.ptr + p * x.stride + c);
+        float gamma = ldf((const TG *)gb.ptr + p * gb.stride + c);
+        float beta = ldf((const TG *)gb.ptr + p * gb.stride + C + c);
+        if (gw.ptr) gamma *= ldf((const TG *)gw.ptr + p * gw.stride + c);
+        if (bw.ptr) beta *= ldf((const TG *)bw.ptr + p * bw.stride + c);
+        const float nrm = (xv - mean[(long long)b * C + c]) * rstd[(long long)b * C + c];
+        stf((TO *)out + p * out_stride + c, gamma * nrm + beta);
+    }
+}
+
+// out = (x - m0) * r0 * s1 + m1   (s1/m1 NULL -> plain normalise)
+template <typename TX, typename TO>
+__global__ void __launch_bounds__(256) affine_norm_kernel(V x, const float *__restrict__ m0,
+                                                          const float *__restrict__ r0, const float *__restrict__ m1,
+                                                          const float *__restrict__ s1, int divide, void *out,
+                                                          int out_stride, int C, long long npix_total, int npix) {
+    const long long total = npix_total * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / C;
+        const int c = (int)(i % C), b = (int)(p / npix);
+        const long long bc = (long long)b * C + c;
+        float v = ldf((const TX *)x.ptr + p * x.stride + c) - m0[bc];
+        v = divide ? v / r0[bc] : v * r0[bc];
+        if (s1) v = v * s1[bc] + m1[bc];
+        stf((TO *)out + p * out_stride + c, v);
+    }
+}
+
+int grid_for(long long total) { return (int)min((long long)cdiv(total, 256), (long long)sm_count() * 16); }
+
+}  // namespace
+}  // namespace rdfc
+
+using namespace rdfc;
+
+extern "C" int rdfc_instnorm_nchunk(int npix) { return cdiv(npix, CHUNK_PIX); }
+
+extern "C" int rdfc_instnorm_stats(const rdfc_view *x, int B, int H, int W, float eps, int unbiased, int want_std,
+                                   float *partial, float *mean, float *rstd, void *stream) {
+    RDFC_REQUIRE(x && x->ptr && partial && mean && rstd, "NULL pointer argument");
+    RDFC_REQUIRE(!x->nchw, "instnorm_stats expects an NHWC view");
+    RDFC_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "bad shape");
+    const int npix = H * W, nchunk = cdiv(npix, CHUNK_PIX);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(nchunk, B);
+    if (x->dtype == RDFC_F32)
+        in_partial_kernel<float><<<grid, 256, 0, st>>>((const float *)x->ptr, x->C, x->pix_stride, npix, partial, nchunk);
+    else if (x->dtype == RDFC_BF16)
+        in_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x->ptr, x->C, x->pix_stride, npix,
+                                                               partial, nchunk);
+    else
+        return fail(RDFC_ERR_UNSUPPORTED, "instnorm_stats: dtype %d", x->dtype);
+    RDFC_CHECK_LAUNCH("in_partial_kernel");
+    in_final_kernel<<<B, 256, 0, st>>>(partial, x->C, npix, nchunk, eps, unbiased, want_std, mean, rstd);
+    RDFC_CHECK_LAUNCH("in_final_kernel");
+    return 0;
+}
+
+extern "C" int rdfc_wadain_apply(const rdfc_view *x, const rdfc_view *gb, const rdfc_view *gw, const rdfc_view *bw,
+                                 const float *mean, const float *rstd, const rdfc_view *out, int B, int H, int W,
+                                 void *stream) {
+    RDFC_REQUIRE(x && gb && out && x->ptr && gb->ptr && out->ptr && mean && rstd, "NULL pointer argument");
+    RDFC_REQUIRE(gb->C == 2 * x->C && out->C == x->C, "wadain: channel mismatch (x %d, gb %d, out %d)", x->C, gb->C, out->C);
+    RDFC_REQUIRE(x->dtype == out->dtype && gb->dtype == x->dtype, "wadain: x, gb and out must share a dtype");
+    const V vx{x->ptr, x->pix_stride}, vg{gb->ptr, gb->pix_stride};
+    const V vgw{gw ? gw->ptr : nullptr, gw ? gw->pix_stride : 0}, vbw{bw ? bw->ptr : nullptr, bw ? bw->pix_stride : 0};
+    RDFC_REQUIRE((!gw || gw->dtype == x->dtype) && (!bw || bw->dtype == x->dtype), "wadain: weighting dtype mismatch");
+    const long long np = (long long)B * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = grid_for(np * x->C);
+    if (x->dtype == RDFC_F32)
+        wadain_kernel<float, float, float><<<g, 256, 0, st>>>(vx, vg, vgw, vbw, mean, rstd, out->ptr, out->pix_stride, x->C, np, H * W);
+    else if (x->dtype == RDFC_BF16)
+        wadain_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(vx, vg, vgw, vbw, mean, rstd, out->ptr,
+                                                                                     out->pix_stride, x->C, np, H * W);
+    else
+        return fail(RDFC_ERR_UNSUPPORTED, "wadain: dtype %d", x->dtype);
+    RDFC_CHECK_LAUNCH("wadain_kernel");
+    return 0;
+}
+
+static int affine_norm(const rdfc_view *x, const float *m0, const float *r0, const float *m1, const float *s1,
+                       int divide, const rdfc_view *out, int B, int H, int W, void *stream) {
+    RDFC_REQUIRE(x && out && x->ptr && out->ptr && m0 && r0, "NULL pointer argument");
+    RDFC_REQUIRE(out->C == x->C && x->dtype == out->dtype, "norm apply: view mismatch");
+    const V vx{x->ptr, x->pix_stride};
+    const long long np = (long long)B * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = grid_for(np * x->C);
+    if (x->dtype == RDFC_F32)
+        affine_norm_kernel<float, float><<<g, 256, 0, st>>>(vx, m0, r0, m1, s1, divide, out->ptr, out->pix_stride, x->C, np, H * W);
+    else if (x->dtype == RDFC_BF16)
+        affine_norm_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(vx, m0, r0, m1, s1, divide, out->ptr,
+                                                                           out->pix_stride, x->C, np, H * W);
+    else
+        return fail(RDFC_ERR_UNSUPPORTED, "norm apply: dtype %d", x->dtype);
+    RDFC_CHECK_LAUNCH("affine_norm_kernel");
+    return 0;
+}
+
+extern "C" int rdfc_adain_apply(const rdfc_view *x, const float *cmean, const float *cstd, const float *smean,
+                                const float *sstd, const rdfc_view *out, int B, int H, int W, void *stream) {
+    RDFC_REQUIRE(smean && sstd, "NULL style statistics");
+    return affine_norm(x, cmean, cstd, smean, sstd, 1, out, B, H, W, stream);
+}
+
+extern "C" int rdfc_norm_apply(const rdfc_view *x, const float *mean, const float *rstd, const rdfc_view *out, int B,
+                               int H, int W, void *stream) {
+    return affine_norm(x, mean, rstd, nullptr, nullptr, 0, out, B, H, W, stream);
+}
