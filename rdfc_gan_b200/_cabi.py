@@ -1,0 +1,115 @@
+"""ctypes binding of librdfc_b200.so (include/rdfc_b200.h).  There is no fallback: if the library is missing the
+import fails, and every call raises RuntimeError with rdfc_last_error() on a non-zero status -- the same exception
+type the reference's AT_ASSERTM / AT_ERROR surface in Python (deformconv/src/modulated_deform_conv.h:43)."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librdfc_b200.so")
+
+F32, F64, BF16 = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH, ACT_SIGMOID = range(5)
+PATH_SIMT_F32, PATH_UMMA_BF16 = 0, 1
+AFFINITY = {"AS": 0, "ASS": 1, "TC": 2, "TGASS": 3}
+_DT = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
+
+c_int, c_void_p, c_float = ctypes.c_int, ctypes.c_void_p, ctypes.c_float
+
+
+class DcnShape(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in ("B", "Cin", "H", "W", "Cout", "kh", "kw", "sh", "sw", "ph", "pw", "dh", "dw",
+                                     "group", "deformable_group", "im2col_step")]
+
+
+class View(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("dtype", c_int), ("C", c_int), ("pix_stride", c_int), ("nchw", c_int)]
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [("B", c_int), ("Hi", c_int), ("Wi", c_int), ("Ho", c_int), ("Wo", c_int), ("kh", c_int), ("kw", c_int),
+                ("stride", c_int), ("pad", c_int), ("transposed", c_int), ("act", c_int), ("path", c_int),
+                ("inp", View), ("in2", View), ("out", View), ("residual", View), ("weight", c_void_p),
+                ("scale", c_void_p), ("shift", c_void_p)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m rdfc_gan_b200.build` (nvcc, sm_100a). "
+            "rdfc_gan_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.rdfc_last_error.restype = ctypes.c_char_p
+    lib.rdfc_launch_count.restype = ctypes.c_uint64
+    lib.rdfc_fuse_depth_forward.argtypes = [c_void_p] * 6 + [ctypes.c_size_t, c_void_p]
+    lib.rdfc_dcn_forward.argtypes = [c_void_p] * 6 + [ctypes.POINTER(DcnShape), c_int, c_void_p]
+    lib.rdfc_dcn_backward.argtypes = [c_void_p] * 10 + [ctypes.POINTER(DcnShape), c_int, c_void_p]
+    lib.rdfc_dcn_out_size.argtypes = [ctypes.POINTER(DcnShape), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
+    lib.rdfc_nlspn_affinity_forward.argtypes = [c_void_p] * 5 + [c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                                                c_void_p]
+    lib.rdfc_nlspn_propagate_forward.argtypes = [c_void_p] * 4 + [c_int] + [c_void_p] * 3 + [c_int] * 5 + [c_void_p]
+    lib.rdfc_conv_forward.argtypes = [ctypes.POINTER(ConvDesc), c_void_p]
+    lib.rdfc_instnorm_stats.argtypes = [ctypes.POINTER(View), c_int, c_int, c_int, c_float, c_int, c_int, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]
+    lib.rdfc_wadain_apply.argtypes = [ctypes.POINTER(View)] * 4 + [c_void_p, c_void_p, ctypes.POINTER(View), c_int,
+                                                                  c_int, c_int, c_void_p]
+    lib.rdfc_adain_apply.argtypes = [ctypes.POINTER(View)] + [c_void_p] * 4 + [ctypes.POINTER(View), c_int, c_int,
+                                                                              c_int, c_void_p]
+    lib.rdfc_norm_apply.argtypes = [ctypes.POINTER(View), c_void_p, c_void_p, ctypes.POINTER(View), c_int, c_int,
+                                    c_int, c_void_p]
+    lib.rdfc_instnorm_nchunk.argtypes = [c_int]
+    return lib
+
+
+lib = _load()
+
+EXPORTS = ["rdfc_abi_version", "rdfc_last_error", "rdfc_launch_count", "rdfc_dcn_out_size", "rdfc_dcn_forward",
+           "rdfc_dcn_backward", "rdfc_nlspn_affinity_forward", "rdfc_nlspn_propagate_forward",
+           "rdfc_fuse_depth_forward", "rdfc_conv_forward", "rdfc_instnorm_nchunk", "rdfc_instnorm_stats",
+           "rdfc_wadain_apply", "rdfc_adain_apply", "rdfc_norm_apply"]
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(lib.rdfc_last_error().decode("utf-8", "replace"))
+
+
+def launch_count():
+    return int(lib.rdfc_launch_count())
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def dtype_code(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"rdfc_gan_b200: unsupported dtype {t.dtype}") from None
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            # deformconv/src/modulated_deform_conv.h:43
+            raise RuntimeError("Not implemented on the CPU")
+
+
+def view(t, C=None, c0=0, nchw=False):
+    """View over an NHWC tensor (B,H,W,Ctot) selecting channels [c0, c0+C); or over a contiguous NCHW tensor."""
+    if t is None:
+        return View(None, 0, 0, 0, 0)
+    if nchw:
+        assert t.is_contiguous()
+        return View(t.data_ptr(), dtype_code(t), t.shape[1], 0, 1)
+    assert t.is_contiguous() and t.dim() == 4
+    ctot = t.shape[3]
+    C = ctot - c0 if C is None else C
+    assert 0 <= c0 and c0 + C <= ctot
+    return View(t.data_ptr() + c0 * t.element_size(), dtype_code(t), C, ctot, 0)

@@ -1,0 +1,378 @@
+"""Execution engine of the generator forward pass (rdf_generator.py:280-414) on the sm_100a kernels.
+
+The engine turns the module tree (parameter containers) into
+  * packed weights: filters in GEMM form ([tap][cin][cout] fp32 for the CUDA-core path, [tap][cin/8][cout][8] bf16
+    for the tcgen05 path), eval-mode BatchNorm folded into a per-channel (scale, shift) epilogue, EqualLR applied;
+  * a Plan per input shape: NHWC activation buffers laid out so that every ``torch.cat`` of the reference is a
+    channel slice of a preallocated buffer, and a flat list of C-ABI calls with fixed pointers, captured in a CUDA
+    graph and replayed.
+
+HBM layout (per image, C channels innermost; bf16 in 'bf16' mode, fp32 in 'fp32' mode):
+    head_r  (H, W, 160)  = [rgb_pred_dec1 64 | rgb_conf_dec1 32 | rgb_fe1 64]
+    head_d  (H, W, 224)  = [id_dec1 64 | cf_dec1 32 | gd_dec1 64 | depth_fe1 64]
+    cat2_x  (H, W, 128)  = [de2 64 | fe2 64]          cat3_x (H/2, W/2, 192) = [de3 64 | fe3 128]
+    cat4_x  (H/4,W/4,384)= [de4 128 | fe4 256]        cat5_x (H/8, W/8, 768) = [de5 256 | fe5 512]     fe6_x (H/16, W/16, 512)
+NLSPN tensors stay fp32 NCHW as in the reference (guide (B,8,H,W), offset (B,18,H,W), aff (B,9,H,W)).
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _cabi as C
+
+
+def _down(n):
+    return (n - 1) // 2 + 1      # conv k3 s2 p1 (and 1x1 s2 p0)
+
+
+class _Packed:
+    """Persistent device storage for one (possibly fused) conv layer's packed filters and epilogue vectors."""
+
+    def __init__(self):
+        self.weight = self.scale = self.shift = None
+
+    def store(self, weight, scale, shift):
+        for name, val in (("weight", weight), ("scale", scale), ("shift", shift)):
+            cur = getattr(self, name)
+            if val is None:
+                setattr(self, name, None)
+            elif cur is None or cur.shape != val.shape or cur.dtype != val.dtype:
+                setattr(self, name, val.contiguous().clone())
+            else:
+                cur.copy_(val)
+
+
+class Plan:
+    def __init__(self):
+        self.steps = []          # callables taking the stream pointer
+        self.keep = []           # ctypes structs / tensors that must outlive the plan
+        self.graph = None
+        self.n_launch = 0
+
+    def run_eager(self):
+        s = C.stream_ptr()
+        for f in self.steps:
+            f(s)
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.run_eager()
+
+
+class GeneratorEngine:
+    def __init__(self, gen):
+        self.gen = gen
+        self.precision = 'fp32'
+        self.use_cuda_graph = True
+        self._plans = {}
+        self._packed = {}        # (precision, layer name) -> _Packed
+        self._wver = {}          # precision -> parameter version stamp
+        self._recipes = {}       # (precision, layer name) -> (sources, umma, transposed) for in-place re-packing
+
+    # ------------------------------------------------------------------------------------------- weights --------
+    def _stamp(self):
+        g = self.gen
+        return tuple((t.data_ptr(), t._version) for t in list(g.parameters()) + list(g.buffers()))
+
+    @staticmethod
+    def _bn_fold(bn):
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        return scale, bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+
+    def _pack(self, name, sources, precision, umma, transposed=False):
+        """sources: list of (weight (Cout,Cin,kh,kw) or ConvT (Cin,Cout,kh,kw), bn module or None, bias or None),
+        fused along Cout."""
+        self._recipes[(precision, name)] = (sources, umma, transposed)
+        ws, scs, shs = [], [], []
+        for w, bn, bias in sources:
+            w = (w() if callable(w) else w).detach().float()
+            if transposed:
+                w = w.permute(1, 0, 2, 3)                # -> (Cout, Cin, kh, kw), scatter-form taps kept
+            ws.append(w)
+            if bn is not None:
+                sc, sh = self._bn_fold(bn)
+            else:
+                sc = torch.ones(w.shape[0], device=w.device)
+                sh = bias.detach().float() if bias is not None else torch.zeros(w.shape[0], device=w.device)
+            scs.append(sc)
+            shs.append(sh)
+        w = torch.cat(ws, 0)
+        Cout, Cin, kh, kw = w.shape
+        g = w.permute(0, 2, 3, 1).reshape(Cout, kh * kw, Cin)          # [cout][tap][cin]
+        if umma:
+            CoutP = (Cout + 15) // 16 * 16
+            if CoutP != Cout:
+                g = torch.cat([g, g.new_zeros(CoutP - Cout, kh * kw, Cin)], 0)
+            packed = g.reshape(CoutP, kh * kw, Cin // 8, 8).permute(1, 2, 0, 3).contiguous().to(torch.bfloat16)
+        else:
+            packed = g.permute(1, 2, 0).contiguous()                    # [tap][cin][cout] fp32
+        p = self._packed.setdefault((precision, name), _Packed())
+        p.store(packed, torch.cat(scs).contiguous(), torch.cat(shs).contiguous())
+        return p
+
+    def _pack_nlspn(self, precision):
+        pl = self.gen.nlspn_refine_module.prop_layer
+        pw = self._packed.setdefault((precision, 'nlspn'), _Packed())
+        pw.store(pl.conv_offset_aff.weight.detach().float(), pl.aff_scale_const.detach().float(),
+                 pl.conv_offset_aff.bias.detach().float())
+        return pw
+
+    def _repack(self, precision):
+        """Refresh every packed tensor of this precision in place (pointers, plans and CUDA graphs stay valid)."""
+        for (prec, name), (sources, umma, transposed) in list(self._recipes.items()):
+            if prec == precision:
+                self._pack(name, sources, precision, umma, transposed)
+        if (precision, 'nlspn') in self._packed:
+            self._pack_nlspn(precision)
+
+    # ------------------------------------------------------------------------------------------- plan -----------
+    def _build_plan(self, B, H, W, Cs, device, precision):
+        g = self.gen
+        bf16 = precision == 'bf16'
+        adt = torch.bfloat16 if bf16 else torch.float32
+        plan = Plan()
+        plan.precision = precision
+        new = lambda *shape, dtype=adt: torch.empty(shape, dtype=dtype, device=device)
+        f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+
+        Hs = [None, H, H, _down(H)]
+        Ws = [None, W, W, _down(W)]
+        for _ in range(3):
+            Hs.append(_down(Hs[-1]))
+            Ws.append(_down(Ws[-1]))            # index = encoder level 1..6
+        chan = {2: 64, 3: 128, 4: 256, 5: 512}
+        dchan = {5: 256, 4: 128, 3: 64, 2: 64}
+        has_gd = g.use_nlspn_refine
+        if has_gd and g.nlspn_refine_module.prop_layer.k_f != 3:
+            raise NotImplementedError("the fused NLSPN kernels support prop_kernel == 3 (the reference's only setting)")
+
+        plan.stem_in = f32(B, Cs, H, W)
+        plan.depth = f32(B, 1, H, W)
+        head = {'r': new(B, H, W, 160), 'd': new(B, H, W, 224 if has_gd else 160)}
+        fe1 = {'r': (head['r'], 96, 64), 'd': (head['d'], 160 if has_gd else 96, 64)}
+        cat = {x: {l: new(B, Hs[l], Ws[l], dchan[l] + chan[l]) for l in (2, 3, 4, 5)} for x in 'rd'}
+        fe6 = {x: new(B, Hs[6], Ws[6], 512) for x in 'rd'}
+        tmp = {l: [new(B, Hs[l], Ws[l], chan[l]) for _ in range(4)] for l in (2, 3, 4, 5)}   # t1, ya, yb, downsample
+
+        def conv(name, sources, inp, out, k, stride=1, pad=None, act=C.ACT_NONE, transposed=False, residual=None,
+                 in2=None, hin=None, hout=None, out_nchw=False, in_nchw=False):
+            """inp/out/residual/in2: (tensor, c0, C) NHWC slices, or NCHW tensors when *_nchw."""
+            pad = (k - 1) // 2 if pad is None else pad
+            vin = C.view(inp, nchw=True) if in_nchw else C.view(inp[0], inp[2], inp[1])
+            vin2 = C.view(None) if in2 is None else C.view(in2[0], in2[2], in2[1])
+            vout = C.view(out, nchw=True) if out_nchw else C.view(out[0], out[2], out[1])
+            vres = C.view(None) if residual is None else C.view(residual[0], residual[2], residual[1])
+            cin = vin.C + (vin2.C if in2 is not None else 0)
+            umma = (bf16 and not in_nchw and not out_nchw and in2 is None and cin % 32 == 0 and vout.C >= 16 and
+                    vin.dtype == C.BF16 and vout.dtype == C.BF16)
+            pk = self._pack(name, sources, precision, umma, transposed)
+            d = C.ConvDesc()
+            d.B, (d.Hi, d.Wi), (d.Ho, d.Wo) = B, hin, hout
+            d.kh = d.kw = k
+            d.stride, d.pad, d.transposed, d.act = stride, pad, int(transposed), act
+            d.path = C.PATH_UMMA_BF16 if umma else C.PATH_SIMT_F32
+            d.inp, d.in2, d.out, d.residual = vin, vin2, vout, vres
+            d.weight, d.scale, d.shift = pk.weight.data_ptr(), pk.scale.data_ptr(), pk.shift.data_ptr()
+            plan.keep.append((d, pk))
+            plan.steps.append(lambda s, d=d: C.check(C.lib.rdfc_conv_forward(ctypes.byref(d), s)))
+            plan.n_launch += 1
+
+        def seq_src(mod):           # conv_bn_relu / convt_bn_relu Sequential -> (weight, bn, bias)
+            bn = mod[1] if len(mod) > 1 and isinstance(mod[1], torch.nn.BatchNorm2d) else None
+            return (mod[0].weight, bn, mod[0].bias)
+
+        # ---- stems (rdf_generator.py:286-292): NCHW fp32 in, NHWC slice out
+        L = C.ACT_LEAKY02
+        full = (H, W)
+        conv('rgb_branch_en1', [seq_src(g.rgb_branch_en1)], plan.stem_in, fe1['r'], 3, act=L, in_nchw=True, hin=full, hout=full)
+        conv('depth_branch_en1_rgb', [seq_src(g.depth_branch_en1_rgb)], plan.stem_in, (fe1['d'][0], fe1['d'][1], 48), 3,
+             act=L, in_nchw=True, hin=full, hout=full)
+        conv('depth_branch_en1_depth', [seq_src(g.depth_branch_en1_depth)], plan.depth,
+             (fe1['d'][0], fe1['d'][1] + 48, 16), 3, act=L, in_nchw=True, hin=full, hout=full)
+
+        # ---- encoders (rdf_generator.py:295-312)
+        feat = {}
+        for x, ed in (('r', g.rgb_branch_encoder_decoder), ('d', g.depth_branch_encoder_decoder)):
+            cur, hw_cur = fe1[x], full
+            for l in (2, 3, 4, 5):
+                layer = getattr(ed, f'en{l}')
+                hw = (Hs[l], Ws[l])
+                t1, ya, yb, ds = tmp[l]
+                for bi, blk in enumerate(layer):
+                    last = bi == len(layer) - 1
+                    dst = (cat[x][l], dchan[l], chan[l]) if last else ((ya if bi % 2 == 0 else yb), 0, chan[l])
+                    nm = f'{x}.en{l}.{bi}'
+                    stride = blk.stride
+                    if blk.downsample is not None:
+                        conv(nm + '.ds', [(blk.downsample[0].weight, blk.downsample[1], None)], cur, (ds, 0, chan[l]), 1,
+                             stride=stride, hin=hw_cur, hout=hw)
+                        ident = (ds, 0, chan[l])
+                    else:
+                        ident = cur
+                    conv(nm + '.c1', [(blk.conv1.weight, blk.bn1, None)], cur, (t1, 0, chan[l]), 3, stride=stride,
+                         act=C.ACT_RELU, hin=hw_cur, hout=hw)
+                    conv(nm + '.c2', [(blk.conv2.weight, blk.bn2, None)], (t1, 0, chan[l]), dst, 3, act=C.ACT_RELU,
+                         residual=ident, hin=hw, hout=hw)
+                    cur, hw_cur = dst, hw
+                feat[(x, l)] = cur
+            conv(f'{x}.en6', [seq_src(ed.en6)], cur, (fe6[x], 0, 512), 3, stride=2, act=L, hin=hw_cur, hout=(Hs[6], Ws[6]))
+
+        # ---- decoders with RGB<-depth fusion (rdf_generator.py:315-368)
+        xr, xd = (fe6['r'], 0, 512), (fe6['d'], 0, 512)
+        lvl_in = 6
+        for n, l in enumerate((5, 4, 3, 2), start=1):
+            hw_in, hw_out = (Hs[lvl_in], Ws[lvl_in]), (Hs[l], Ws[l])      # ConvT output cropped to the skip's size
+            fz = self._plan_fuse(plan, conv, new, f32, getattr(g, f'fuse_layer{n}'), n, xr, xd, B, hw_in, precision)
+            conv(f'r.de{l}', [seq_src(getattr(g.rgb_branch_encoder_decoder, f'de{l}'))], fz, (cat['r'][l], 0, dchan[l]), 3,
+                 stride=2, pad=1, act=L, transposed=True, hin=hw_in, hout=hw_out)
+            conv(f'd.de{l}', [seq_src(getattr(g.depth_branch_encoder_decoder, f'de{l}'))], xd, (cat['d'][l], 0, dchan[l]), 3,
+                 stride=2, pad=1, act=L, transposed=True, hin=hw_in, hout=hw_out)
+            xr, xd = (cat['r'][l], 0, dchan[l] + chan[l]), (cat['d'][l], 0, dchan[l] + chan[l])
+            lvl_in = l
+
+        # ---- decode heads (rdf_generator.py:372-398); the *_dec1 convs that share an input run as ONE conv
+        conv('r.dec1', [seq_src(g.rgb_pred_dec1), seq_src(g.rgb_conf_dec1)], xr, (head['r'], 0, 96), 3, act=L, hin=full, hout=full)
+        d_srcs = [seq_src(g.id_dec1), seq_src(g.cf_dec1)] + ([seq_src(g.gd_dec1)] if has_gd else [])
+        conv('d.dec1', d_srcs, xd, (head['d'], 0, 160 if has_gd else 96), 3, act=L, hin=full, hout=full)
+        plan.d1, plan.c1, plan.pred_init, plan.conf = f32(B, 1, H, W), f32(B, 1, H, W), f32(B, 1, H, W), f32(B, 1, H, W)
+        conv('rgb_pred_dec0', [seq_src(g.rgb_pred_dec0)], (head['r'], 0, 64), plan.d1, 3, act=C.ACT_TANH, in2=fe1['r'],
+             out_nchw=True, hin=full, hout=full)
+        conv('rgb_conf_dec0', [(g.rgb_conf_dec0[0].weight, None, g.rgb_conf_dec0[0].bias)], (head['r'], 64, 96), plan.c1, 3,
+             act=C.ACT_SIGMOID, out_nchw=True, hin=full, hout=full)
+        conv('id_dec0', [seq_src(g.id_dec0)], (head['d'], 0, 64), plan.pred_init, 3, act=C.ACT_TANH, in2=fe1['d'],
+             out_nchw=True, hin=full, hout=full)
+        conv('cf_dec0', [(g.cf_dec0[0].weight, None, g.cf_dec0[0].bias)], (head['d'], 64, 32), plan.conf, 3,
+             act=C.ACT_SIGMOID, in2=fe1['d'], out_nchw=True, hin=full, hout=full)
+
+        # ---- NLSPN + output fusion (rdf_generator.py:400-406)
+        plan.d2, plan.pred = f32(B, 1, H, W), f32(B, 1, H, W)
+        n = B * H * W
+        if has_gd:
+            pl = g.nlspn_refine_module.prop_layer
+            plan.guide = f32(B, 8, H, W)
+            conv('gd_dec0', [seq_src(g.gd_dec0)], (head['d'], 96, 128), plan.guide, 3, out_nchw=True, hin=full, hout=full)
+            plan.offset, plan.aff, plan.scratch, plan.d2raw = f32(B, 18, H, W), f32(B, 9, H, W), f32(B, 1, H, W), f32(B, 1, H, W)
+            pw = self._pack_nlspn(precision)
+            plan.keep.append(pw)
+            aff_mode, conf_prop, preserve, T = C.AFFINITY[pl.affinity], int(bool(pl.conf_prop)), int(bool(pl.preserve_input)), pl.prop_time
+            plan.steps.append(lambda s: C.check(C.lib.rdfc_nlspn_affinity_forward(
+                C.ptr(plan.guide), C.ptr(plan.conf), C.ptr(pw.weight), C.ptr(pw.shift), C.ptr(pw.scale), aff_mode, conf_prop,
+                C.ptr(plan.offset), C.ptr(plan.aff), B, H, W, s)))
+            plan.steps.append(lambda s: C.check(C.lib.rdfc_nlspn_propagate_forward(
+                C.ptr(plan.pred_init), C.ptr(plan.offset), C.ptr(plan.aff), C.ptr(plan.depth) if preserve else None, preserve,
+                C.ptr(plan.d2raw), C.ptr(plan.scratch), None, B, H, W, T, 0, s)))
+            plan.n_launch += 1 + T * (2 if preserve else 1)
+            d2src = plan.d2raw
+        else:
+            d2src = plan.pred_init
+        plan.steps.append(lambda s: C.check(C.lib.rdfc_fuse_depth_forward(
+            C.ptr(plan.d1), C.ptr(plan.c1), C.ptr(d2src), C.ptr(plan.conf), C.ptr(plan.d2), C.ptr(plan.pred), n, s)))
+        plan.n_launch += 1
+        plan.outputs = (plan.d1, plan.c1, plan.d2, plan.conf, plan.pred)
+        return plan
+
+    def _plan_fuse(self, plan, conv, new, f32, layer, n, xr, xd, B, hw, precision):
+        """fuse_layer{n}(rgb feature xr, depth feature xd) -> NHWC slice (tensor, 0, C).  model_utils.py:53-129."""
+        from .model_utils import IN, AdaIN, AdaptiveInstanceNorm
+        Hh, Ww = hw
+        Cx, Cd = xr[2], xd[2]
+        nchunk = C.lib.rdfc_instnorm_nchunk(Hh * Ww)
+        out = new(B, Hh, Ww, Cx)
+        vx, vd, vout = C.view(xr[0], xr[2], xr[1]), C.view(xd[0], xd[2], xd[1]), C.view(out)
+        plan.keep += [vx, vd, vout]
+
+        def stats(v, Cc, unbiased, want_std):
+            part, mean, rstd = f32(B, nchunk, Cc, 2), f32(B, Cc), f32(B, Cc)
+            plan.keep += [part, mean, rstd]
+            plan.steps.append(lambda s: C.check(C.lib.rdfc_instnorm_stats(
+                ctypes.byref(v), B, Hh, Ww, 1e-5, unbiased, want_std, C.ptr(part), C.ptr(mean), C.ptr(rstd), s)))
+            plan.n_launch += 2
+            return mean, rstd
+
+        if isinstance(layer, AdaptiveInstanceNorm):
+            lin = layer.style.linear
+            gb = new(B, Hh, Ww, 2 * Cx)
+            w = lambda lin=lin: lin.effective_weight().detach().reshape(lin.out_features, lin.in_features, 1, 1)
+            conv(f'fuse{n}.style', [(w, None, lin.bias)], xd, (gb, 0, 2 * Cx), 1, hin=hw, hout=hw)
+            mean, rstd = stats(vx, Cx, 0, 0)
+            vgb = C.view(gb)
+            vgw = vbw = None
+            if layer.weighting:
+                gwbw = new(B, Hh, Ww, 2 * Cx)
+                conv(f'fuse{n}.weighting', [(layer.gamma_weight_layer.weight, None, layer.gamma_weight_layer.bias),
+                                            (layer.beta_weight_layer.weight, None, layer.beta_weight_layer.bias)],
+                     xr, (gwbw, 0, 2 * Cx), 1, hin=hw, hout=hw)
+                vgw, vbw = C.view(gwbw, Cx, 0), C.view(gwbw, Cx, Cx)
+            plan.keep += [vgb, vgw, vbw, gb]
+            plan.steps.append(lambda s: C.check(C.lib.rdfc_wadain_apply(
+                ctypes.byref(vx), ctypes.byref(vgb), ctypes.byref(vgw) if vgw is not None else None,
+                ctypes.byref(vbw) if vbw is not None else None, C.ptr(mean), C.ptr(rstd), ctypes.byref(vout), B, Hh, Ww, s)))
+            plan.n_launch += 1
+        elif isinstance(layer, AdaIN):
+            assert Cx == Cd, "AdaIN needs equal channel counts (model_utils.py:107)"
+            cm, cs = stats(vx, Cx, 1, 1)
+            sm, ss = stats(vd, Cd, 1, 1)
+            plan.steps.append(lambda s: C.check(C.lib.rdfc_adain_apply(
+                ctypes.byref(vx), C.ptr(cm), C.ptr(cs), C.ptr(sm), C.ptr(ss), ctypes.byref(vout), B, Hh, Ww, s)))
+            plan.n_launch += 1
+        elif isinstance(layer, IN):
+            both = new(B, Hh, Ww, Cx + Cd)
+            for v, c0, Cc in ((vx, 0, Cx), (vd, Cx, Cd)):
+                mean, rstd = stats(v, Cc, 0, 0)
+                vo = C.view(both, Cc, c0)
+                plan.keep.append(vo)
+                plan.steps.append(lambda s, v=v, mean=mean, rstd=rstd, vo=vo: C.check(C.lib.rdfc_norm_apply(
+                    ctypes.byref(v), C.ptr(mean), C.ptr(rstd), ctypes.byref(vo), B, Hh, Ww, s)))
+                plan.n_launch += 1
+            conv(f'fuse{n}.down', [(layer.down_channel.weight, None, layer.down_channel.bias)], (both, 0, Cx + Cd),
+                 (out, 0, Cx), 1, hin=hw, hout=hw)
+        else:
+            raise NotImplementedError(type(layer))
+        return (out, 0, Cx)
+
+    # ------------------------------------------------------------------------------------------- run ------------
+    def forward(self, stem_in, depth):
+        g = self.gen
+        B, Cs, H, W = stem_in.shape
+        if Cs != g.semantic_channels_in:
+            raise RuntimeError(f"stem input has {Cs} channels, the generator was built for {g.semantic_channels_in}")
+        if tuple(depth.shape) != (B, 1, H, W):
+            raise RuntimeError(f"depth must be ({B},1,{H},{W}), got {tuple(depth.shape)}")
+        if H < 16 or W < 16:
+            raise RuntimeError("inputs smaller than 16x16 do not survive the four stride-2 stages")
+        dev = stem_in.device
+        key = (B, H, W, Cs, dev, self.precision)
+        with torch.cuda.device(dev), torch.no_grad():
+            stamp = self._stamp()
+            plan = self._plans.get(key)
+            if plan is None:
+                plan = self._plans[key] = self._build_plan(B, H, W, Cs, dev, self.precision)   # packs the weights too
+                self._wver[self.precision] = stamp
+                plan.stem_in.copy_(stem_in)
+                plan.depth.copy_(depth)
+                if self.use_cuda_graph:
+                    self._capture(plan)
+            elif self._wver.get(self.precision) != stamp:
+                self._repack(self.precision)
+                self._wver[self.precision] = stamp
+            plan.stem_in.copy_(stem_in)
+            plan.depth.copy_(depth)
+            plan.run()
+            return tuple(t.clone() for t in plan.outputs)
+
+    @staticmethod
+    def _capture(plan):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            plan.run_eager()            # warm-up: lazy cudaFuncSetAttribute calls happen outside the capture
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            plan.run_eager()
+        plan.graph = graph

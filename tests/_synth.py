@@ -1,0 +1,153 @@
+"""Deterministic synthetic weights and inputs shared by the golden-vector generator, the tests, smoke() and bench.py.
+
+Everything is drawn from numpy PCG64 streams keyed by (seed, crc32(name)), so the build container (where the golden
+files are produced from the reference) and the GPU box regenerate bit-identical tensors without shipping 137 MB of
+weights.  Recipes:
+
+* ``init``    the reference's "random init": init_weights (C/lib/models/init_weights.py:5-33) -- Conv / ConvT weights
+              N(0, 0.02), biases 0, BatchNorm weight N(1, 0.02), bias 0, running stats (0, 1); EqualLinear keeps its
+              N(0,1) ``weight_orig`` and (1..,0..) bias because init_weights skips it.
+* ``scaled``  fan-in scaled weights and non-trivial BatchNorm statistics, so that activations stay O(1) through the
+              40-layer stack and the parity check exercises every layer (with ``init`` the signal decays to ~1e-3).
+* ``nlspn_stress=True`` overrides conv_offset_aff as in SURVEY 8d: offsets sigma ~ 2.3 px, positive affinities.
+"""
+import zlib
+
+import numpy as np
+import torch
+
+
+def _rng(seed, name):
+    return np.random.Generator(np.random.PCG64([seed, zlib.crc32(name.encode())]))
+
+
+def synth_state_dict(module, seed=0, recipe="init", nlspn_stress=False):
+    sd = module.state_dict()
+    bn_prefixes = {k[:-len(".running_mean")] for k in sd if k.endswith(".running_mean")}
+    out = {}
+    for key, t in sd.items():
+        r = _rng(seed, key)
+        shape = tuple(t.shape)
+        prefix, _, leaf = key.rpartition(".")
+        n = lambda std=1.0, mean=0.0: (mean + std * r.standard_normal(shape)).astype(np.float32)
+        u = lambda lo, hi: r.uniform(lo, hi, shape).astype(np.float32)
+        if leaf == "num_batches_tracked":
+            v = np.zeros(shape, np.int64)
+        elif prefix in bn_prefixes:
+            if recipe == "init":
+                v = {"weight": n(0.02, 1.0), "bias": np.zeros(shape, np.float32),
+                     "running_mean": np.zeros(shape, np.float32), "running_var": np.ones(shape, np.float32)}[leaf]
+            else:
+                v = {"weight": u(0.8, 1.2), "bias": n(0.1), "running_mean": n(0.1), "running_var": u(0.6, 1.4)}[leaf]
+        elif leaf == "weight_orig":
+            v = n(1.0 if recipe == "init" else 0.35)
+        elif "_weight_layer." in key and recipe != "init":
+            # W-AdaIN weighting convs (model_utils.py:64-67): keep the multiplicative gates near 1
+            v = n(float(np.sqrt(0.003 / shape[1]))) if len(shape) == 4 else n(0.05, 1.0)
+        elif key.endswith("style.linear.bias"):
+            c = shape[0] // 2
+            v = np.concatenate([np.ones(c, np.float32), np.zeros(c, np.float32)])
+            if recipe != "init":
+                v = v + 0.1 * r.standard_normal(shape).astype(np.float32)
+        elif ".prop_layer." in key and leaf in ("w", "b", "w_conf", "aff_scale_const"):
+            v = t.detach().cpu().numpy().copy()         # frozen dummies / gamma*8 keep their constructor values
+        elif len(shape) == 4:
+            if recipe == "init":
+                v = n(0.02)
+            else:
+                # Conv2d (Cout,Cin,k,k): fan_in = Cin k^2.  ConvTranspose2d (Cin,Cout,k,k) with stride 2: each output
+                # pixel sees ~k^2/4 taps of Cin channels.
+                transposed = ".de" in key
+                fan_in = shape[0] * shape[2] * shape[3] / 4 if transposed else shape[1] * shape[2] * shape[3]
+                gain = 0.4 if "_dec0." in key else 1.3      # keep tanh / sigmoid heads out of saturation
+                v = n(float(np.sqrt(gain / fan_in)))
+        elif len(shape) == 1:
+            v = np.zeros(shape, np.float32) if recipe == "init" else n(0.05)
+        else:
+            raise KeyError(f"no synthetic recipe for {key} {shape}")
+        out[key] = torch.from_numpy(np.ascontiguousarray(v))
+    if nlspn_stress:
+        kw, kb = [k for k in out if k.endswith("conv_offset_aff.weight")], [k for k in out if k.endswith("conv_offset_aff.bias")]
+        for k in kw:
+            r = _rng(seed, k + "#stress")
+            w = out[k].numpy().copy()
+            w[:16] = 0.25 * r.standard_normal(w[:16].shape)
+            w[16:] = 0.02 * r.standard_normal(w[16:].shape)
+            out[k] = torch.from_numpy(w.astype(np.float32))
+        for k in kb:
+            r = _rng(seed, k + "#stress")
+            b = out[k].numpy().copy()
+            b[:16] = r.uniform(-1.5, 1.5, 16)
+            b[16:] = r.uniform(0.3, 2.0, b[16:].shape)
+            out[k] = torch.from_numpy(b.astype(np.float32))
+    return out
+
+
+def state_dict_digest(sd):
+    """Order-independent checksum used to prove that the GPU box regenerated the weights the goldens were made with."""
+    h = 0
+    for k in sorted(sd):
+        h = zlib.crc32(sd[k].detach().cpu().contiguous().numpy().tobytes(), zlib.crc32(k.encode(), h))
+    return h
+
+
+def synth_inputs(B, H, W, seed=0, Cs=3, n_samples=500):
+    """rgb U(-1,1); stem input: unit normals (Cs == 3, C/helper.py:404-408) or N(0,1) feature maps; sparse depth:
+    ``n_samples`` random pixels of a smooth 0.5..9.5 m field, normalised (d-5)/5, exact zeros elsewhere
+    (F/lib/dataset/nyuv2/nyuv2_sparse_to_dense_dataset.py:146-154,221-240)."""
+    r = _rng(seed, f"inputs{B}x{H}x{W}x{Cs}")
+    rgb = r.uniform(-1, 1, (B, 3, H, W)).astype(np.float32)
+    stem = r.standard_normal((B, Cs, H, W)).astype(np.float32)
+    if Cs == 3:
+        stem = stem / np.sqrt((stem ** 2).sum(1, keepdims=True) + 1e-12).astype(np.float32)
+    coarse = torch.from_numpy(r.uniform(0.5, 9.5, (B, 1, 8, 10)).astype(np.float32))
+    dense = torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=True).numpy()
+    depth = np.zeros((B, 1, H, W), np.float32)
+    k = min(n_samples, max(1, H * W // 8))
+    for b in range(B):
+        idx = r.permutation(H * W)[:k]
+        depth[b, 0].reshape(-1)[idx] = ((dense[b, 0].reshape(-1)[idx] - 5.0) / 5.0)
+    return torch.from_numpy(rgb), torch.from_numpy(stem.astype(np.float32)), torch.from_numpy(depth)
+
+
+def nlspn_stress_inputs(B, H, W, seed=0):
+    """Stand-alone NLSPN fixture inputs: guidance N(0,1), confidence U(0,1), pred_init U(-1,1), sparse depth."""
+    r = _rng(seed, f"nlspn{B}x{H}x{W}")
+    guidance = r.standard_normal((B, 8, H, W)).astype(np.float32)
+    confidence = r.uniform(0, 1, (B, 1, H, W)).astype(np.float32)
+    pred_init = r.uniform(-1, 1, (B, 1, H, W)).astype(np.float32)
+    fix = np.zeros((B, 1, H, W), np.float32)
+    k = max(1, H * W // 8)
+    for b in range(B):
+        idx = r.permutation(H * W)[:k]
+        fix[b, 0].reshape(-1)[idx] = r.uniform(-0.9, 0.9, k)
+    conv_w = np.concatenate([0.25 * r.standard_normal((16, 8, 3, 3)), 0.02 * r.standard_normal((8, 8, 3, 3))]).astype(np.float32)
+    conv_b = np.concatenate([r.uniform(-1.5, 1.5, 16), r.uniform(0.3, 2.0, 8)]).astype(np.float32)
+    return dict(guidance=guidance, confidence=confidence, pred_init=pred_init, feat_fix=fix, conv_w=conv_w, conv_b=conv_b)
+
+
+def dcn_case_inputs(case, seed=0, dtype=np.float32):
+    """Random tensors for one DCN boundary case (dict with B,Cin,Cout,H,W,k,s,p,d,g,dg,mask,off_std)."""
+    r = _rng(seed, "dcn" + repr(sorted(case.items())))
+    B, Cin, Cout, H, W, k = case["B"], case["Cin"], case["Cout"], case["H"], case["W"], case["k"]
+    s, p, d, g, dg = case["s"], case["p"], case["d"], case["g"], case["dg"]
+    Ho = (H + 2 * p - (d * (k - 1) + 1)) // s + 1
+    Wo = (W + 2 * p - (d * (k - 1) + 1)) // s + 1
+    t = dict(input=r.standard_normal((B, Cin, H, W)), weight=0.3 * r.standard_normal((Cout, Cin // g, k, k)),
+             bias=0.1 * r.standard_normal(Cout), offset=case["off_std"] * r.standard_normal((B, dg * 2 * k * k, Ho, Wo)),
+             grad_output=r.standard_normal((B, Cout, Ho, Wo)))
+    if case["mask"]:
+        t["mask"] = r.uniform(0, 1, (B, dg * k * k, Ho, Wo))
+    return {n: np.ascontiguousarray(v.astype(dtype)) for n, v in t.items()}
+
+
+DCN_CASES = {
+    # the shape of deformconv/test.py:16-19 (N=2, C=4, 4x4, k3, groups 2)
+    "ref_test_shape": dict(B=2, Cin=4, Cout=4, H=4, W=4, k=3, s=1, p=1, d=1, g=2, dg=1, mask=True, off_std=2.0),
+    "nlspn_prop": dict(B=2, Cin=1, Cout=1, H=10, W=12, k=3, s=1, p=1, d=1, g=1, dg=1, mask=True, off_std=3.0),
+    "nlspn_conf": dict(B=2, Cin=1, Cout=1, H=10, W=12, k=1, s=1, p=0, d=1, g=1, dg=1, mask=True, off_std=5.0),
+    "strided_groups": dict(B=2, Cin=8, Cout=12, H=9, W=11, k=3, s=2, p=1, d=1, g=2, dg=2, mask=True, off_std=1.5),
+    "dilated": dict(B=1, Cin=6, Cout=5, H=12, W=10, k=3, s=1, p=2, d=2, g=1, dg=3, mask=True, off_std=1.0),
+    "v1_plain": dict(B=2, Cin=4, Cout=6, H=7, W=8, k=3, s=1, p=1, d=1, g=1, dg=1, mask=False, off_std=2.0),
+    "wide": dict(B=1, Cin=16, Cout=140, H=6, W=37, k=3, s=1, p=1, d=1, g=1, dg=2, mask=True, off_std=1.0),
+}

@@ -1,0 +1,175 @@
+"""-m gpu: rdfc_conv_forward (CUDA-core fp32 kernel and the tcgen05 bf16 kernel) and the norm/fusion kernels against CPU
+torch.nn.functional restatements of the reference layers (encoder_decoder/common.py:29-61, model_utils.py:53-129)."""
+import ctypes
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_conv(x_nchw, w, scale, shift, *, stride=1, pad=1, act=0, transposed=False, residual=None, bf16=False, crop=None,
+              in_pad=0, out_pad=0):
+    """x (B,Cin,H,W) fp32 cpu; w conv (Cout,Cin,k,k) or convT (Cin,Cout,k,k).  Returns NCHW fp32 cpu result."""
+    from rdfc_gan_b200 import _cabi as C
+    B, Cin, H, W = x_nchw.shape
+    k = w.shape[-1]
+    wg = (w.permute(1, 0, 2, 3) if transposed else w).float()
+    Cout = wg.shape[0]
+    if transposed:
+        Ho, Wo = crop if crop else (2 * H, 2 * W)
+    else:
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    dt = torch.bfloat16 if bf16 else torch.float32
+    xin = torch.zeros(B, H, W, Cin + in_pad, dtype=dt, device="cuda")
+    xin[..., in_pad:] = x_nchw.permute(0, 2, 3, 1).to(dt).cuda()
+    out = torch.full((B, Ho, Wo, Cout + out_pad), 7.0, dtype=dt, device="cuda")
+    g = wg.permute(0, 2, 3, 1).reshape(Cout, k * k, Cin)
+    if bf16:
+        CoutP = (Cout + 15) // 16 * 16
+        g = torch.cat([g, g.new_zeros(CoutP - Cout, k * k, Cin)], 0)
+        packed = g.reshape(CoutP, k * k, Cin // 8, 8).permute(1, 2, 0, 3).contiguous().to(torch.bfloat16).cuda()
+    else:
+        packed = g.permute(1, 2, 0).contiguous().cuda()
+    d = C.ConvDesc()
+    d.B, d.Hi, d.Wi, d.Ho, d.Wo = B, H, W, Ho, Wo
+    d.kh = d.kw = k
+    d.stride, d.pad, d.transposed, d.act = stride, pad, int(transposed), act
+    d.path = C.PATH_UMMA_BF16 if bf16 else C.PATH_SIMT_F32
+    d.inp, d.in2, d.out = C.view(xin, Cin, in_pad), C.view(None), C.view(out, Cout, out_pad)
+    res_t = None
+    if residual is not None:
+        res_t = residual.permute(0, 2, 3, 1).to(dt).contiguous().cuda()
+        d.residual = C.view(res_t)
+    else:
+        d.residual = C.view(None)
+    sc, sh = scale.float().cuda(), shift.float().cuda()
+    d.weight, d.scale, d.shift = packed.data_ptr(), sc.data_ptr(), sh.data_ptr()
+    C.check(C.lib.rdfc_conv_forward(ctypes.byref(d), C.stream_ptr()))
+    torch.cuda.synchronize()
+    if out_pad:
+        assert (out[..., :out_pad].float() == 7.0).all(), "wrote outside its channel slice"
+    return out[..., out_pad:].float().permute(0, 3, 1, 2).cpu()
+
+
+def _ref_conv(x, w, scale, shift, *, stride=1, pad=1, act=0, transposed=False, residual=None, crop=None, bf16=False):
+    if bf16:    # the kernel sees bf16-rounded inputs / weights / residual and accumulates in fp32
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+        residual = None if residual is None else residual.bfloat16().float()
+    if transposed:
+        y = F.conv_transpose2d(x.double(), w.double(), None, stride=2, padding=1, output_padding=1)
+        if crop:
+            y = y[:, :, :crop[0], :crop[1]]
+    else:
+        y = F.conv2d(x.double(), w.double(), None, stride, pad)
+    y = y * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+    if residual is not None:
+        y = y + residual.double()
+    y = [lambda v: v, F.relu, lambda v: F.leaky_relu(v, 0.2), torch.tanh, torch.sigmoid][act](y)
+    return y.float()
+
+
+CASES = [
+    # B, Cin, Cout, H, W, k, stride, transposed, act, residual, crop
+    (2, 64, 64, 20, 27, 3, 1, False, 1, True, None),
+    (1, 128, 96, 17, 35, 3, 1, False, 2, False, None),
+    (2, 64, 128, 21, 30, 3, 2, False, 1, False, None),
+    (2, 64, 128, 21, 30, 1, 2, False, 0, False, None),
+    (1, 192, 384, 9, 13, 1, 1, False, 0, False, None),
+    (2, 96, 64, 7, 10, 3, 2, True, 2, False, (13, 20)),
+    (1, 256, 160, 33, 18, 3, 1, False, 2, False, None),
+    (1, 512, 512, 8, 10, 3, 1, False, 1, True, None),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("bf16", [False, True])
+def test_conv_paths(case, bf16):
+    B, Cin, Cout, H, W, k, stride, transposed, act, use_res, crop = case
+    gen = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(B, Cin, H, W, generator=gen)
+    wshape = (Cin, Cout, k, k) if transposed else (Cout, Cin, k, k)
+    w = torch.randn(wshape, generator=gen) / math.sqrt(Cin * k * k)
+    scale = 0.5 + torch.rand(Cout, generator=gen)
+    shift = 0.2 * torch.randn(Cout, generator=gen)
+    pad = (k - 1) // 2
+    kw = dict(stride=stride, pad=pad, act=act, transposed=transposed, crop=crop)
+    ref0 = _ref_conv(x, w, scale, shift, **kw)
+    res = torch.randn(ref0.shape, generator=gen) if use_res else None
+    ref = _ref_conv(x, w, scale, shift, residual=res, bf16=bf16, **kw)
+    got = _run_conv(x, w, scale, shift, residual=res, bf16=bf16, in_pad=32, out_pad=16, **kw)
+    assert got.shape == ref.shape
+    err = (got - ref).abs().max().item()
+    # fp32 path: accumulation order only.  bf16 path: inputs are pre-rounded in the reference, the only extra error
+    # is the bf16 rounding of the OUTPUT (rel 2^-9) plus fp32 accumulation order.
+    tol = 2e-5 * max(1.0, ref.abs().max().item()) if not bf16 else 2.0 ** -8 * max(1.0, ref.abs().max().item())
+    assert err <= tol, (err, tol)
+
+
+def test_small_cout_and_stem_kernels():
+    """Cout <= 8 heads with two concatenated sources and NCHW output; 3-channel NCHW stem (rdf_generator.py:60-102)."""
+    from rdfc_gan_b200 import _cabi as C
+    gen = torch.Generator().manual_seed(5)
+    B, H, W = 2, 19, 23
+    a, b2 = torch.randn(B, 64, H, W, generator=gen), torch.randn(B, 64, H, W, generator=gen)
+    for Cout, act in ((1, 3), (8, 0), (1, 4)):
+        w = torch.randn(Cout, 128, 3, 3, generator=gen) / 30
+        bias = torch.randn(Cout, generator=gen)
+        ref = [None, None, None, torch.tanh, torch.sigmoid][act](F.conv2d(torch.cat([a, b2], 1).double(), w.double(), bias.double(), 1, 1)) \
+            if act else F.conv2d(torch.cat([a, b2], 1).double(), w.double(), bias.double(), 1, 1)
+        buf = torch.zeros(B, H, W, 160, device="cuda")
+        buf[..., 0:64] = a.permute(0, 2, 3, 1).cuda()
+        buf[..., 96:160] = b2.permute(0, 2, 3, 1).cuda()
+        out = torch.empty(B, Cout, H, W, device="cuda")
+        packed = w.permute(0, 2, 3, 1).reshape(Cout, 9, 128).permute(1, 2, 0).contiguous().cuda()
+        d = C.ConvDesc()
+        d.B, d.Hi, d.Wi, d.Ho, d.Wo, d.kh, d.kw, d.stride, d.pad, d.act, d.path = B, H, W, H, W, 3, 3, 1, 1, act, 0
+        d.inp, d.in2, d.out, d.residual = C.view(buf, 64, 0), C.view(buf, 64, 96), C.view(out, nchw=True), C.view(None)
+        bc = bias.cuda()
+        d.weight, d.scale, d.shift = packed.data_ptr(), None, bc.data_ptr()
+        C.check(C.lib.rdfc_conv_forward(ctypes.byref(d), C.stream_ptr()))
+        assert (out.cpu().double() - ref).abs().max() < 2e-5
+    x = torch.randn(B, 3, H, W, generator=gen)
+    w = torch.randn(48, 3, 3, 3, generator=gen) / 5
+    bias = torch.randn(48, generator=gen)
+    ref = F.leaky_relu(F.conv2d(x.double(), w.double(), bias.double(), 1, 1), 0.2)
+    xc = x.cuda()
+    out = torch.zeros(B, H, W, 64, device="cuda")
+    packed = w.permute(0, 2, 3, 1).reshape(48, 9, 3).permute(1, 2, 0).contiguous().cuda()
+    d = C.ConvDesc()
+    d.B, d.Hi, d.Wi, d.Ho, d.Wo, d.kh, d.kw, d.stride, d.pad, d.act, d.path = B, H, W, H, W, 3, 3, 1, 1, 2, 0
+    d.inp, d.in2, d.out, d.residual = C.view(xc, nchw=True), C.view(None), C.view(out, 48, 0), C.view(None)
+    bc = bias.cuda()
+    d.weight, d.scale, d.shift = packed.data_ptr(), None, bc.data_ptr()
+    C.check(C.lib.rdfc_conv_forward(ctypes.byref(d), C.stream_ptr()))
+    assert (out[..., :48].permute(0, 3, 1, 2).cpu().double() - ref).abs().max() < 2e-5
+    assert (out[..., 48:] == 0).all()
+
+
+def test_instnorm_and_wadain():
+    from rdfc_gan_b200 import _cabi as C
+    gen = torch.Generator().manual_seed(9)
+    B, Cc, H, W = 2, 192, 29, 38
+    x = 3 + 2 * torch.randn(B, Cc, H, W, generator=gen)
+    gb = torch.randn(B, 2 * Cc, H, W, generator=gen)
+    xn = x.permute(0, 2, 3, 1).contiguous().cuda()
+    gbn = gb.permute(0, 2, 3, 1).contiguous().cuda()
+    nchunk = C.lib.rdfc_instnorm_nchunk(H * W)
+    part = torch.empty(B, nchunk, Cc, 2, device="cuda")
+    mean, rstd = torch.empty(B, Cc, device="cuda"), torch.empty(B, Cc, device="cuda")
+    vx, vgb = C.view(xn), C.view(gbn)
+    C.check(C.lib.rdfc_instnorm_stats(ctypes.byref(vx), B, H, W, 1e-5, 0, 0, C.ptr(part), C.ptr(mean), C.ptr(rstd), C.stream_ptr()))
+    xd = x.double()
+    assert (mean.cpu().double() - xd.mean((2, 3))).abs().max() < 1e-5
+    assert (rstd.cpu().double() - 1 / torch.sqrt(xd.var((2, 3), unbiased=False) + 1e-5)).abs().max() < 1e-5
+    out = torch.empty_like(xn)
+    vo = C.view(out)
+    C.check(C.lib.rdfc_wadain_apply(ctypes.byref(vx), ctypes.byref(vgb), None, None, C.ptr(mean), C.ptr(rstd), ctypes.byref(vo),
+                                    B, H, W, C.stream_ptr()))
+    ref = gb[:, :Cc].double() * F.instance_norm(xd, eps=1e-5) + gb[:, Cc:].double()
+    assert (out.permute(0, 3, 1, 2).cpu().double() - ref).abs().max() < 2e-5
+    # AdaIN statistics: unbiased variance, std returned
+    C.check(C.lib.rdfc_instnorm_stats(ctypes.byref(vx), B, H, W, 1e-5, 1, 1, C.ptr(part), C.ptr(mean), C.ptr(rstd), C.stream_ptr()))
+    assert (rstd.cpu().double() - torch.sqrt(xd.var((2, 3), unbiased=True) + 1e-5)).abs().max() < 1e-5
