@@ -124,17 +124,12 @@ typedef struct {
     rdfc_view in2;          /* optional second source concatenated after `in` along C (ptr == NULL: unused); SIMT only */
     rdfc_view out;          /* Cout = out.C */
     rdfc_view residual;     /* optional (ptr == NULL: none): added after scale/shift, before the activation */
-    const void *weight;     /* packed by rdfc_gan_b200.engine: SIMT: fp32 [kh*kw][Cin][Cout]; UMMA: see rdfc_umma_pack_size */
+    const void *weight;     /* packed by rdfc_gan_b200.engine: SIMT: fp32 [kh*kw][Cin][Cout]; UMMA: bf16 [kh*kw][Cin/8][Cout padded to 16][8] */
     const float *scale;     /* per-Cout multiplier (folded BN gamma/sqrt(var+eps)) or NULL (= 1) */
     const float *shift;     /* per-Cout addend (folded BN beta - mean*scale, or the conv bias) or NULL (= 0) */
 } rdfc_conv_desc;
 
 int rdfc_conv_forward(const rdfc_conv_desc *d, void *stream);
-
-/* UMMA weight image: bytes needed for a (Cout, Cin, kh, kw) filter bank, and the host-side packer
- * (src_host: fp32 [Cout][kh*kw][Cin] gather-form; dst_host: bf16 image to be copied to the device verbatim). */
-size_t rdfc_umma_pack_size(int Cout, int Cin, int ntaps);
-int rdfc_umma_pack_weights_host(const float *src_host, void *dst_host, int Cout, int Cin, int ntaps);
 
 /* per-(b,c) mean and 1/sqrt(var+eps) over the pixels of an NHWC view.  unbiased != 0 divides by (n-1) (AdaIN,
  * model_utils.py:98) and returns sqrt(var+eps) in `rstd` instead of its reciprocal when want_std != 0.

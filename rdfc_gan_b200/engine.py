@@ -135,8 +135,13 @@ class GeneratorEngine:
         adt = torch.bfloat16 if bf16 else torch.float32
         plan = Plan()
         plan.precision = precision
-        new = lambda *shape, dtype=adt: torch.empty(shape, dtype=dtype, device=device)
-        f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+        def new(*shape, dtype=adt):
+            t = torch.empty(shape, dtype=dtype, device=device)
+            plan.keep.append(t)          # descriptors hold raw pointers: every buffer must live as long as the plan
+            return t
+
+        def f32(*shape):
+            return new(*shape, dtype=torch.float32)
 
         Hs = [None, H, H, _down(H)]
         Ws = [None, W, W, _down(W)]

@@ -1,0 +1,91 @@
+"""CPU: pins the oracle (oracle/) to the golden vectors that tests/golden/make_golden.py produced from the
+reference's own Python -- every oracle function the GPU parity tests rely on is checked here first."""
+import numpy as np
+import pytest
+import torch
+
+from _synth import (DCN_CASES, dcn_case_inputs, nlspn_stress_inputs, state_dict_digest, synth_inputs,
+                    synth_state_dict)
+from make_golden import GEN_CASES, NLSPN_CASES, NLSPN_SHAPE
+
+
+@pytest.mark.parametrize("name", list(DCN_CASES))
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+def test_dcn_oracle_matches_reference(name, dtype, tol, golden_dir):
+    from oracle import dcn as odcn
+    case = DCN_CASES[name]
+    t = dcn_case_inputs(case, dtype=dtype)
+    gold = np.load(f"{golden_dir}/dcn_{name}.npz")
+    k, s, p, d, g, dg = (case[x] for x in ("k", "s", "p", "d", "g", "dg"))
+    geo = (k, k, s, s, p, p, d, d, g, dg)
+    out = odcn.modulated_deform_conv_forward(t["input"], t["weight"], t["bias"], t["offset"], t.get("mask"), *geo)
+    grads = odcn.modulated_deform_conv_backward(t["input"], t["weight"], t["bias"], t["offset"], t.get("mask"),
+                                                t["grad_output"], *geo)
+    assert out.dtype == dtype
+    assert np.abs(out - gold["output"]).max() <= tol * max(1, np.abs(gold["output"]).max())
+    for n, gr in zip(("grad_input", "grad_offset", "grad_mask", "grad_weight", "grad_bias"), grads):
+        if gr is None:
+            assert n == "grad_mask" and not case["mask"]
+            continue
+        assert np.abs(gr - gold[n]).max() <= tol * max(1, np.abs(gold[n]).max()), n
+
+
+def test_dcn_oracle_known_answers():
+    """deformconv/test.py:69-110,142-181: zero offsets (+ mask 1) == Conv2d; identity filters with mask 0.5 halve."""
+    from oracle import dcn as odcn
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 4, 4, 4))
+    w = rng.standard_normal((4, 2, 3, 3))
+    b = rng.standard_normal(4)
+    off = np.zeros((2, 18, 4, 4))
+    out = odcn.modulated_deform_conv_forward(x, w, b, off, np.ones((2, 9, 4, 4)), 3, 3, 1, 1, 1, 1, 1, 1, 2, 1)
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), 1, 1, 1, 2).numpy()
+    assert np.abs(out - ref).max() < 1e-12
+    wi = np.zeros((4, 2, 3, 3))
+    for q in range(4):
+        wi[q, q % 2, 1, 1] = 1.0
+    out = odcn.modulated_deform_conv_forward(x, wi, np.zeros(4), off, np.full((2, 9, 4, 4), 0.5), 3, 3, 1, 1, 1, 1, 1, 1, 2, 1)
+    assert np.abs(2 * out - x).max() < 1e-12
+    assert np.abs(odcn.deform_conv_forward(x, wi, np.zeros(4), off, 3, 3, 1, 1, 1, 1, 1, 1, 2, 1) - x).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", list(NLSPN_CASES))
+def test_nlspn_oracle_matches_reference(name, golden_dir):
+    from oracle import nlspn as onl
+    cfg = NLSPN_CASES[name]
+    x = nlspn_stress_inputs(*NLSPN_SHAPE, cfg["seed"])
+    gold = np.load(f"{golden_dir}/nlspn_{name}.npz")
+    y, off, aff, inter = onl.nlspn_forward(x["pred_init"], x["guidance"], x["confidence"], x["feat_fix"], x["conv_w"],
+                                           x["conv_b"], gold["aff_scale"], prop_time=cfg["prop_time"],
+                                           affinity=cfg["affinity"], conf_prop=cfg["conf_prop"],
+                                           preserve_input=cfg["preserve_input"], return_inter=True)
+    y_fast, _, _ = onl.nlspn_forward(x["pred_init"], x["guidance"], x["confidence"], x["feat_fix"], x["conv_w"],
+                                     x["conv_b"], gold["aff_scale"], prop_time=cfg["prop_time"], affinity=cfg["affinity"],
+                                     conf_prop=cfg["conf_prop"], preserve_input=cfg["preserve_input"])
+    assert np.abs(off - gold["offset"]).max() <= 1e-6
+    assert np.abs(aff - gold["aff"]).max() <= 5e-6
+    assert np.abs(inter[0] - gold["first"]).max() <= 5e-6
+    assert np.abs(y - gold["y"]).max() <= 5e-6
+    assert np.abs(y_fast - y).max() <= 1e-6          # the fused C loop == the call-per-iteration restatement
+    # structure the reference guarantees (nlspn_model.py:77-80,131-136)
+    assert np.all(off[:, 8:10] == 0) and np.abs(aff.sum(1) - 1).max() < 1e-5
+
+
+@pytest.mark.parametrize("name", [n for n in GEN_CASES if "full" not in n] + ["rdfc_full_init"])
+def test_generator_oracle_matches_reference(name, golden_dir):
+    from oracle import generator as ogen
+    from rdfc_gan_b200.generator import RDFGenerator
+    kw, B, H, W, Cs, recipe, stress, seed = GEN_CASES[name]
+    G = RDFGenerator(pretrained_on_imagenet=False, **kw).eval()
+    sd = synth_state_dict(G, seed=seed, recipe=recipe, nlspn_stress=stress)
+    gold = np.load(f"{golden_dir}/generator_{name}.npz")
+    assert state_dict_digest(sd) == int(gold["digest"][0])
+    rgb, stem, depth = synth_inputs(B, H, W, seed=seed, Cs=Cs)
+    out = ogen.generator_forward(sd, stem, depth, fuse=kw.get("fuse_depth_in_rgb_decoder", "WAdaIN"),
+                                 adain_weighting=kw.get("adain_weighting", False), use_nlspn_refine=kw["use_nlspn_refine"],
+                                 nlspn_configs=kw.get("nlspn_configs"))
+    for k in ("depth_map_1", "confidence_map_1", "depth_map_2", "confidence_map_2", "pred_depth"):
+        v, g = out[k].numpy(), gold[k]
+        if v.shape != g.shape:
+            v = v[:, :, ::4, ::4]
+        assert np.abs(v - g).max() <= 2e-5, k
