@@ -19,6 +19,8 @@
 //   * warp 4 / lane 0 issues tcgen05.mma (M=128, N=BN, K=16) and releases stages with tcgen05.commit.
 //   * epilogue (warps 0-3): tcgen05.ld 32 lanes x 16 columns, y = act(acc*scale + shift + residual), bf16, 32-byte
 //     vector stores into the NHWC channel slice (this is how every torch.cat of the reference disappears).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rdfc {
@@ -371,6 +373,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st) {
     P.nacc = 4;
     while (P.nacc > 1 && (P.Wt <= 8 * (P.nacc / 2) || pixels / (128 * P.nacc) * (P.CoutP / P.bn) < 2 * sm_count())) P.nacc /= 2;
     if (d->stride == 2 && !d->transposed && k3 && P.nacc > 2) P.nacc = 2;   // four parity planes: keep the stage small
+    if (const char *e = getenv("RDFC_UMMA_NACC")) P.nacc = atoi(e);      // development knob
     const int TW = 8 * P.nacc;
     P.tiles_y = cdiv(P.Ht, TH); P.tiles_x = cdiv(P.Wt, TW);
 
@@ -421,8 +424,10 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st) {
     const int fixed = P.npix_pad * 4 + 2 * P.bn * 4 + 8 + (2 * 4 + 2 * 8 + 2) * 8 + 16 + 128;
     const int budget = 200 * 1024;
     P.sb = 4;
+    if (const char *e = getenv("RDFC_UMMA_SB")) P.sb = atoi(e);          // development knob (<= 8)
     P.sa = (budget - fixed - P.sb * b_stage) / a_stage;
     if (P.sa > 4) P.sa = 4;
+    if (const char *e = getenv("RDFC_UMMA_SA")) P.sa = atoi(e) < P.sa ? atoi(e) : P.sa;
     if (P.sa > P.nkb) P.sa = P.nkb < 1 ? 1 : P.nkb;
     RDFC_REQUIRE(P.sa >= 1, "UMMA conv: tile does not fit shared memory");
     const size_t smem = (size_t)P.sa * a_stage + (size_t)P.sb * b_stage + fixed;

@@ -7,6 +7,8 @@
 // affinities (the centre tap's offsets are identically zero and are not read), gathers 36 feature corners through
 // L1, and writes one float.  The host wrapper walks the batch in L2-sized image groups so that iterations 2..T of a
 // group find their offset/affinity planes in the 126 MB L2 instead of HBM.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rdfc {
@@ -209,7 +211,9 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
     }
     // L2 blocking: offset+aff of a group (27 planes, 25 read) should stay L2 resident across the iterations.
     const long long bytes_per_img = 27 * P * 4;
-    long long gsz = (64ll << 20) / bytes_per_img;
+    long long budget = 64ll << 20;
+    if (const char *e = getenv("RDFC_NLSPN_GROUP_MB")) budget = (long long)atoi(e) << 20;   // development knob
+    long long gsz = budget / bytes_per_img;
     if (gsz < 1) gsz = 1;
     if (gsz > 65535) gsz = 65535;
     // extra buffer for preserve_input (blend result); reuse: blend writes into the buffer not being read
