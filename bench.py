@@ -233,7 +233,7 @@ def main():
     # ---------------- roofline: NLSPN propagation kernel alone (18 launches per image group)
     T = NLSPN_CFG["prop_time"]
     P = H * W
-    group = max(1, min(B, (64 << 20) // (27 * P * 4)))
+    group = B          # one launch per iteration over the whole batch (see nlspn.cu)
     n_groups = (B + group - 1) // group
     s = C.stream_ptr()
 

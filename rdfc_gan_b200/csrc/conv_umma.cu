@@ -57,6 +57,7 @@ struct Params {
     int res_stride;
     const float *scale, *shift;
     int act, nacc, bn, sa, sb, npix_pad, nplanes, tmem_cols;
+    long long *dbg;                // development: per-CTA %globaltimer stamps (8 per CTA) or NULL
     Plane planes[MAX_PLANES];
     Phase phases[4];
 };
@@ -126,6 +127,13 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define STAMP(i) do { if (P.dbg && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 4096) P.dbg[blockIdx.x * 8 + (i)] = gtime(); } while (0)
+
 // no-swizzle K-major shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
@@ -159,6 +167,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
+        STAMP(0);
         for (int i = 0; i < P.sa; ++i) { mbar_init(BAR(A_FULL + i), NPROD); mbar_init(BAR(A_EMPTY + i), 1); }
         for (int i = 0; i < P.sb; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
         mbar_init(BAR(ACC_FULL), 1);
@@ -192,6 +201,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) STAMP(1);
 
     if (warp < 4) {
         // ================= A producers: stage the halo planes of each 32-channel block =================
@@ -208,6 +218,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
                 cp_async16(dst0 + (uint32_t)(ch * P.npix_pad + pixel) * 16u, src, off >= 0 ? 16u : 0u);
             }
             cp_async_commit();
+            if (i == 0 && threadIdx.x == 0) STAMP(2);
             if (i >= 1) {
                 cp_async_wait<1>();
                 fence_proxy_async();
@@ -221,6 +232,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
         // ================= epilogue =================
         mbar_wait(BAR(ACC_FULL), 0);
         tc_fence_after();
+        if (threadIdx.x == 0) STAMP(6);
         const int r = 4 * warp + (lane >> 3), c = lane & 7;   // MMA row m = 32*warp + lane = 8*r + c
         for (int j = 0; j < P.nacc; ++j) {
             const int yy = ty0 + r, xx = tx0 + 8 * j + c;
@@ -263,6 +275,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
             }
         }
         tc_fence_before();
+        if (threadIdx.x == 0) STAMP(7);
     } else if (warp == 4) {
         // ================= MMA issuer =================
         if (lane == 0) {
@@ -273,18 +286,20 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
                 const int s = i % P.sa;
                 mbar_wait(BAR(A_FULL + s), (i / P.sa) & 1);
                 tc_fence_after();
+                if (i == 0) STAMP(3);
                 const uint32_t a_base = smem_u32(sA + (size_t)s * a_stage_bytes);
                 for (int tp = 0; tp < ph.ntaps; ++tp, ++bi) {
                     const int sb = bi % P.sb;
                     mbar_wait(BAR(B_FULL + sb), (bi / P.sb) & 1);
                     tc_fence_after();
+                    if (bi == 0) STAMP(4);
                     const Tap &tap = ph.taps[tp];
                     const Plane &q = P.planes[tap.plane];
                     const uint32_t b_base = smem_u32(sB + (size_t)sb * b_stage_bytes);
                     const uint32_t a_tap = a_base + (uint32_t)(q.base + tap.sy * q.cols + tap.sx) * 16u;
-                    for (int j = 0; j < P.nacc; ++j)
 #pragma unroll
-                        for (int k2 = 0; k2 < BK / 16; ++k2) {
+                    for (int k2 = 0; k2 < BK / 16; ++k2)
+                        for (int j = 0; j < P.nacc; ++j) {
                             const uint64_t da = make_desc(a_tap + (uint32_t)j * 128u + (uint32_t)k2 * 2u * a_lbo, a_lbo,
                                                           (uint32_t)q.cols * 16u);
                             const uint64_t db = make_desc(b_base + (uint32_t)k2 * 2u * b_lbo, b_lbo, 128u);
@@ -295,6 +310,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
                 tc_commit(BAR(A_EMPTY + s));
             }
             tc_commit(BAR(ACC_FULL));
+            STAMP(5);
         }
         __syncwarp();
     } else {
@@ -326,6 +342,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
                      : "memory");
     }
 }
+
+long long *g_umma_dbg = nullptr;
 
 int next_pow2_cols(int c) {
     int p = 32;
@@ -361,16 +379,26 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st) {
     P.out = (__nv_bfloat16 *)d->out.ptr; P.out_stride = d->out.pix_stride; P.Ho = d->Ho; P.Wo = d->Wo;
     P.res = (const __nv_bfloat16 *)d->residual.ptr; P.res_stride = d->residual.pix_stride;
     P.scale = d->scale; P.shift = d->shift; P.act = d->act;
+    {
+        static long long *dbg = nullptr;
+        if (getenv("RDFC_UMMA_DBG") && !dbg) cudaMalloc(&dbg, 4096 * 8 * sizeof(long long));
+        P.dbg = getenv("RDFC_UMMA_DBG") ? dbg : nullptr;
+        g_umma_dbg = dbg;
+    }
 
     // tile space: output grid for convs, input grid for the sub-pixel phases of a transposed conv
     P.Ht = d->transposed ? d->Hi : d->Ho;
     P.Wt = d->transposed ? d->Wi : d->Wo;
     P.oys = P.oxs = d->transposed ? 2 : 1;
-    P.bn = P.CoutP < 128 ? P.CoutP : 128;
-    while (P.CoutP % P.bn) P.bn -= 16;   // largest multiple of 16 <= 128 dividing the padded Cout
+    // one tcgen05.mma (M=128,K=16) costs max(~76, N/2) cycles (measured, scripts/umma_rate.cu): use the widest N
+    int bn_max = 256;
+    if (const char *e = getenv("RDFC_UMMA_BN")) bn_max = atoi(e);        // development knob
+    P.bn = P.CoutP < bn_max ? P.CoutP : bn_max;
+    while (P.CoutP % P.bn) P.bn -= 16;   // largest multiple of 16 <= bn_max dividing the padded Cout
     // accumulators per CTA: wide tiles amortise the filter stream; small problems need more CTAs
     const long long pixels = (long long)P.B * P.Ht * P.Wt;
     P.nacc = 4;
+    while (P.nacc * P.bn > 512) P.nacc /= 2;   // TMEM: 512 fp32 columns
     while (P.nacc > 1 && (P.Wt <= 8 * (P.nacc / 2) || pixels / (128 * P.nacc) * (P.CoutP / P.bn) < 2 * sm_count())) P.nacc /= 2;
     if (d->stride == 2 && !d->transposed && k3 && P.nacc > 2) P.nacc = 2;   // four parity planes: keep the stage small
     if (const char *e = getenv("RDFC_UMMA_NACC")) P.nacc = atoi(e);      // development knob
@@ -444,3 +472,9 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st) {
 }
 
 }  // namespace rdfc
+
+// development aid (not in the public header): copies the per-CTA timestamps of the last instrumented launch
+extern "C" int rdfc_dev_umma_stamps(long long *host, int n_ctas) {
+    if (!rdfc::g_umma_dbg) return -1;
+    return (int)cudaMemcpy(host, rdfc::g_umma_dbg, sizeof(long long) * 8 * n_ctas, cudaMemcpyDeviceToHost);
+}

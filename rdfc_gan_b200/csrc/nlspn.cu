@@ -211,8 +211,11 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
     }
     // L2 blocking: offset+aff of a group (27 planes, 25 read) should stay L2 resident across the iterations.
     const long long bytes_per_img = 27 * P * 4;
-    long long budget = 64ll << 20;
-    if (const char *e = getenv("RDFC_NLSPN_GROUP_MB")) budget = (long long)atoi(e) << 20;   // development knob
+    // Measured on B200 (profiles/): walking the batch in L2-sized groups does NOT pay -- a 60 MB group still misses
+    // L2 (21 % hit rate, LRU thrash) and small launches lose more to launch/tail effects -- so the default is one
+    // launch per iteration over the whole batch.  RDFC_NLSPN_GROUP_MB re-enables grouping for experiments.
+    long long budget = 1ll << 40;
+    if (const char *e = getenv("RDFC_NLSPN_GROUP_MB")) budget = (long long)atoi(e) << 20;
     long long gsz = budget / bytes_per_img;
     if (gsz < 1) gsz = 1;
     if (gsz > 65535) gsz = 65535;
