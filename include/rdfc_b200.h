@@ -24,6 +24,8 @@
  *       (encoder_decoder/encoder_decoder.py:39-59), decode heads (rdf_generator.py:68-102) and the per-pixel
  *       EqualLinear of W-AdaIN (model_utils.py:39-50,72-75): NHWC implicit GEMM with a fused
  *       scale/shift (+residual) + activation epilogue.  `path` selects the tcgen05 bf16 kernel or the fp32 SIMT kernel.
+ *   rdfc_heads_forward
+ *       rdf_generator.py:374-398  the five Cout<=8 *_dec0 heads (+tanh / sigmoid), fused per branch.
  *   rdfc_instnorm_stats / rdfc_adain_apply
  *       model_utils.py:53-90 (AdaptiveInstanceNorm = W-AdaIN), :92-116 (AdaIN), :119-129 (IN).
  */
@@ -130,6 +132,24 @@ typedef struct {
 } rdfc_conv_desc;
 
 int rdfc_conv_forward(const rdfc_conv_desc *d, void *stream);
+
+/* Fused decode heads (rdf_generator.py:372-398): ONE 3x3 / stride-1 / pad-1 tensor-core convolution over an NHWC
+ * bf16 view whose <= 16 output columns are the *_dec0 heads that read it (block-sparse filter bank packed like any
+ * UMMA weight with Cout = 16).  Column q gets bias shift[q], activation act[q] and is written as an fp32 plane:
+ * out[q][b * out_bstride[q] + y * W + x]  -- so depth / confidence maps and the NCHW guidance tensor the NLSPN
+ * kernels read come straight out of the epilogue. */
+typedef struct {
+    int B, H, W;
+    rdfc_view in;                /* bf16 NHWC, C % 32 == 0 */
+    const void *weight;          /* bf16 [9][C/8][16][8] */
+    const float *shift;          /* device, 16 floats (bias per column; unused columns 0) */
+    int ncols;                   /* 1..16 */
+    int act[16];                 /* rdfc_act per column */
+    float *out[16];              /* device plane base pointers */
+    long long out_bstride[16];   /* elements between consecutive images of a plane */
+} rdfc_heads_desc;
+
+int rdfc_heads_forward(const rdfc_heads_desc *d, void *stream);
 
 /* per-(b,c) mean and 1/sqrt(var+eps) over the pixels of an NHWC view.  unbiased != 0 divides by (n-1) (AdaIN,
  * model_utils.py:98) and returns sqrt(var+eps) in `rstd` instead of its reciprocal when want_std != 0.

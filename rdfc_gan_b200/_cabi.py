@@ -34,6 +34,11 @@ class ConvDesc(ctypes.Structure):
                 ("scale", c_void_p), ("shift", c_void_p)]
 
 
+class HeadsDesc(ctypes.Structure):
+    _fields_ = [("B", c_int), ("H", c_int), ("W", c_int), ("inp", View), ("weight", c_void_p), ("shift", c_void_p),
+                ("ncols", c_int), ("act", c_int * 16), ("out", c_void_p * 16), ("out_bstride", ctypes.c_longlong * 16)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -50,6 +55,7 @@ def _load():
                                                                 c_void_p]
     lib.rdfc_nlspn_propagate_forward.argtypes = [c_void_p] * 4 + [c_int] + [c_void_p] * 3 + [c_int] * 5 + [c_void_p]
     lib.rdfc_conv_forward.argtypes = [ctypes.POINTER(ConvDesc), c_void_p]
+    lib.rdfc_heads_forward.argtypes = [ctypes.POINTER(HeadsDesc), c_void_p]
     lib.rdfc_instnorm_stats.argtypes = [ctypes.POINTER(View), c_int, c_int, c_int, c_float, c_int, c_int, c_void_p,
                                         c_void_p, c_void_p, c_void_p]
     lib.rdfc_wadain_apply.argtypes = [ctypes.POINTER(View)] * 4 + [c_void_p, c_void_p, ctypes.POINTER(View), c_int,
@@ -66,7 +72,7 @@ lib = _load()
 
 EXPORTS = ["rdfc_abi_version", "rdfc_last_error", "rdfc_launch_count", "rdfc_dcn_out_size", "rdfc_dcn_forward",
            "rdfc_dcn_backward", "rdfc_nlspn_affinity_forward", "rdfc_nlspn_propagate_forward",
-           "rdfc_fuse_depth_forward", "rdfc_conv_forward", "rdfc_instnorm_nchunk", "rdfc_instnorm_stats",
+           "rdfc_fuse_depth_forward", "rdfc_conv_forward", "rdfc_heads_forward", "rdfc_instnorm_nchunk", "rdfc_instnorm_stats",
            "rdfc_wadain_apply", "rdfc_adain_apply", "rdfc_norm_apply"]
 
 

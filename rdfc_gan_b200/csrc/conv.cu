@@ -3,7 +3,7 @@
 
 namespace rdfc {
 int conv_simt_forward(const rdfc_conv_desc *d, cudaStream_t st);
-int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st);
+int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads);
 }  // namespace rdfc
 
 using namespace rdfc;
@@ -23,7 +23,21 @@ extern "C" int rdfc_conv_forward(const rdfc_conv_desc *d, void *stream) {
     RDFC_REQUIRE(d->in.nchw || d->in.pix_stride >= d->in.C, "conv: input pixel stride smaller than its channel count");
     RDFC_REQUIRE(d->out.nchw || d->out.pix_stride >= d->out.C, "conv: output pixel stride smaller than its channel count");
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->path == RDFC_PATH_UMMA_BF16) return conv_umma_forward(d, st);
+    if (d->path == RDFC_PATH_UMMA_BF16) return conv_umma_forward(d, st, nullptr);
     if (d->path == RDFC_PATH_SIMT_F32) return conv_simt_forward(d, st);
     return fail(RDFC_ERR_INVALID, "conv: unknown path %d", d->path);
+}
+
+extern "C" int rdfc_heads_forward(const rdfc_heads_desc *h, void *stream) {
+    RDFC_REQUIRE(h != nullptr && h->in.ptr && h->weight && h->shift, "heads: NULL argument");
+    RDFC_REQUIRE(h->ncols >= 1 && h->ncols <= 16, "heads: ncols must be 1..16");
+    RDFC_REQUIRE(h->B > 0 && h->H > 0 && h->W > 0, "heads: empty dimension");
+    for (int q = 0; q < h->ncols; ++q) RDFC_REQUIRE(h->out[q] != nullptr, "heads: output plane %d is NULL", q);
+    rdfc_conv_desc d{};
+    d.B = h->B; d.Hi = d.Ho = h->H; d.Wi = d.Wo = h->W;
+    d.kh = d.kw = 3; d.stride = 1; d.pad = 1; d.act = RDFC_ACT_NONE; d.path = RDFC_PATH_UMMA_BF16;
+    d.in = h->in;
+    d.out.ptr = h->out[0]; d.out.dtype = RDFC_F32; d.out.C = 16; d.out.pix_stride = 16;
+    d.weight = h->weight; d.scale = nullptr; d.shift = h->shift;
+    return conv_umma_forward(&d, (cudaStream_t)stream, h);
 }

@@ -4,6 +4,8 @@
 //     (memory bound; a warp per output pixel).
 // Epilogue (both kernels): y = act(acc * scale[co] + shift[co] + residual), written into an NHWC channel slice or an
 // NCHW tensor.  Reference layers: encoder_decoder/common.py:29-61, rdf_generator.py:60-102.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace rdfc {
@@ -191,8 +193,81 @@ __global__ void __launch_bounds__(256) conv_smallc_kernel(ConvGeo g) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stem kernel: NCHW fp32 input with <= 4 channels (normal map / sparse depth, rdf_generator.py:60-61,77-80), 3x3,
+// stride 1, pad 1.  CTA = 32x8 pixels; the input tile + halo and the whole filter bank sit in shared memory; a thread
+// produces one pixel x 16 output channels per pass and writes them as one 32/64-byte NHWC vector.
+constexpr int ST_TX = 32, ST_TY = 8, ST_MAXC = 4;
+
+template <typename TOut>
+__global__ void __launch_bounds__(ST_TX *ST_TY) conv_stem_kernel(ConvGeo g) {
+    extern __shared__ float st_smem[];
+    float *s_in = st_smem;                                           // [Cin][ST_TY+2][ST_TX+2]
+    float *s_w = s_in + ST_MAXC * (ST_TY + 2) * (ST_TX + 2);        // [Cin*9][CoutP]  (CoutP = Cout rounded up to 16)
+    const int Cin = g.in.C, CoutP = (g.Cout + 15) / 16 * 16;
+    const int tid = threadIdx.y * ST_TX + threadIdx.x;
+    const int b = blockIdx.z, x0 = blockIdx.x * ST_TX, y0 = blockIdx.y * ST_TY;
+    const float *in = (const float *)g.in.ptr;
+    for (int e = tid; e < Cin * (ST_TY + 2) * (ST_TX + 2); e += ST_TX * ST_TY) {
+        const int c = e / ((ST_TY + 2) * (ST_TX + 2)), r = e % ((ST_TY + 2) * (ST_TX + 2));
+        const int yy = y0 + r / (ST_TX + 2) - 1, xx = x0 + r % (ST_TX + 2) - 1;
+        s_in[e] = (yy >= 0 && yy < g.Hi && xx >= 0 && xx < g.Wi) ? __ldg(in + (((long long)b * Cin + c) * g.Hi + yy) * g.Wi + xx) : 0.f;
+    }
+    // packed SIMT weights are [tap][cin][cout]; re-index to [(cin*9+tap)][coutP]
+    for (int e = tid; e < Cin * 9 * CoutP; e += ST_TX * ST_TY) {
+        const int co = e % CoutP, q = e / CoutP, ci = q / 9, t = q % 9;
+        s_w[e] = co < g.Cout ? __ldg(g.weight + ((long long)t * Cin + ci) * g.Cout + co) : 0.f;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= g.Wi || y >= g.Hi) return;
+    float v[ST_MAXC * 9];
+    for (int ci = 0; ci < Cin; ++ci)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[ci * 9 + t] = s_in[(ci * (ST_TY + 2) + threadIdx.y + t / 3) * (ST_TX + 2) + threadIdx.x + t % 3];
+    const long long pix = ((long long)b * g.Ho + y) * g.Wo + x;
+    TOut *op = (TOut *)g.out + pix * g.out_stride;
+    for (int c0 = 0; c0 < g.Cout; c0 += 16) {
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        for (int q = 0; q < Cin * 9; ++q) {
+            const float4 *w4 = reinterpret_cast<const float4 *>(s_w + q * CoutP + c0);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 w = w4[j4];
+                acc[4 * j4 + 0] = fmaf(v[q], w.x, acc[4 * j4 + 0]);
+                acc[4 * j4 + 1] = fmaf(v[q], w.y, acc[4 * j4 + 1]);
+                acc[4 * j4 + 2] = fmaf(v[q], w.z, acc[4 * j4 + 2]);
+                acc[4 * j4 + 3] = fmaf(v[q], w.w, acc[4 * j4 + 3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int co = c0 + j;
+            if (co < g.Cout) {
+                const float r = acc[j] * (g.scale ? __ldg(g.scale + co) : 1.f) + (g.shift ? __ldg(g.shift + co) : 0.f);
+                stf(op + co, apply_act(r, g.act));
+            }
+        }
+    }
+}
+
 template <typename TIn, typename TOut>
 int launch(const ConvGeo &g, cudaStream_t st) {
+    if constexpr (std::is_same<TIn, float>::value) {
+        if (g.in.nchw && !g.in2.ptr && g.in.C <= ST_MAXC && g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 &&
+            !g.transposed && !g.res && !g.out_nchw && g.Cout <= 256) {
+            const int CoutP = (g.Cout + 15) / 16 * 16;
+            const size_t smem = sizeof(float) * (ST_MAXC * (ST_TY + 2) * (ST_TX + 2) + g.in.C * 9 * CoutP);
+            dim3 grid(cdiv(g.Wi, ST_TX), cdiv(g.Hi, ST_TY), g.B), block(ST_TX, ST_TY);
+            RDFC_REQUIRE(g.B <= 65535 && smem <= 48 * 1024, "stem conv: batch / filter bank too large");
+            conv_stem_kernel<TOut><<<grid, block, smem, st>>>(g);
+            RDFC_CHECK_LAUNCH("conv_stem_kernel");
+            return 0;
+        }
+    }
     const long long M = (long long)g.B * g.Ho * g.Wo;
     if (g.Cout <= SC_MAX && g.CinT >= 32) {
         const size_t smem = sizeof(float) * g.kh * g.kw * g.CinT * (g.Cout <= 1 ? 1 : (g.Cout <= 2 ? 2 : (g.Cout <= 4 ? 4 : 8)));

@@ -30,7 +30,7 @@ constexpr int BK = 32;            // input channels per A stage (2 MMAs of K=16)
 constexpr int KCH = BK / 8;       // 16-byte cin chunks per stage
 constexpr int TH = 16;            // tile rows (= 8-row groups of one M=128 MMA)
 constexpr int NPROD = 128;        // producer / epilogue threads (warps 0-3)
-constexpr int NTHREADS = 192;     // + warp 4 (MMA) + warp 5 (B loader)
+constexpr int NTHREADS = 256;     // + warp 4 (MMA) + warp 5 (B loader) + warps 6-7; warps 4-7 form the 2nd epilogue group
 constexpr int MAX_PLANES = 4, MAX_TAPS = 9;
 
 struct Plane {
@@ -58,6 +58,10 @@ struct Params {
     const float *scale, *shift;
     int act, nacc, bn, sa, sb, npix_pad, nplanes, tmem_cols;
     long long *dbg;                // development: per-CTA %globaltimer stamps (8 per CTA) or NULL
+    int planar, ncols;             // planar != 0: fp32 output planes, one per output column (fused decode heads)
+    float *plane[16];
+    long long plane_bstride[16];
+    int act_col[16];
     Plane planes[MAX_PLANES];
     Phase phases[4];
 };
@@ -75,6 +79,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug traps after ~4 s instead of hanging the GPU.
+template <bool kBackoff = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     for (;;) {
@@ -87,6 +92,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (ok) return;
+        if (kBackoff) __nanosleep(256);      // long waits (accumulator ready): do not steal issue slots from the MMA warp
         if (clock64() - t0 > 8000000000ll) {
             printf("rdfc conv_umma: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
                    threadIdx.x);
@@ -205,17 +211,30 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
 
     if (warp < 4) {
         // ================= A producers: stage the halo planes of each 32-channel block =================
+        // Four independent cp.async chains per loop trip: one producer warp per scheduler has nobody to hide the
+        // LDS -> address -> LDGSTS latency behind, so the ILP has to come from unrolling.
         const int nelem = P.npix_pad * KCH;
+        const int in_stride = P.in_stride, npix_pad = P.npix_pad;
         for (int i = 0; i < P.nkb; ++i) {
             const int s = i % P.sa;
             mbar_wait(BAR(A_EMPTY + s), ((i / P.sa) & 1) ^ 1);
             const uint32_t dst0 = smem_u32(sA + (size_t)s * a_stage_bytes);
             const __nv_bfloat16 *src0 = P.in + i * BK;
-            for (int e = threadIdx.x; e < nelem; e += NPROD) {
-                const int pixel = e / KCH, ch = e % KCH;
-                const int off = pix_off[pixel];
-                const __nv_bfloat16 *src = off >= 0 ? src0 + (long long)off * P.in_stride + ch * 8 : P.in;
-                cp_async16(dst0 + (uint32_t)(ch * P.npix_pad + pixel) * 16u, src, off >= 0 ? 16u : 0u);
+            for (int e0 = threadIdx.x; e0 < nelem; e0 += 4 * NPROD) {
+                int off[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * NPROD;
+                    off[u] = e < nelem ? pix_off[e / KCH] : -2;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * NPROD, pixel = e / KCH, ch = e % KCH;
+                    if (off[u] != -2) {
+                        const __nv_bfloat16 *src = off[u] >= 0 ? src0 + (long long)off[u] * in_stride + ch * 8 : P.in;
+                        cp_async16(dst0 + (uint32_t)(ch * npix_pad + pixel) * 16u, src, off[u] >= 0 ? 16u : 0u);
+                    }
+                }
             }
             cp_async_commit();
             if (i == 0 && threadIdx.x == 0) STAMP(2);
@@ -228,59 +247,12 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
         cp_async_wait<0>();
         fence_proxy_async();
         mbar_arrive(BAR(A_FULL + (P.nkb - 1) % P.sa));
-
-        // ================= epilogue =================
-        mbar_wait(BAR(ACC_FULL), 0);
-        tc_fence_after();
-        if (threadIdx.x == 0) STAMP(6);
-        const int r = 4 * warp + (lane >> 3), c = lane & 7;   // MMA row m = 32*warp + lane = 8*r + c
-        for (int j = 0; j < P.nacc; ++j) {
-            const int yy = ty0 + r, xx = tx0 + 8 * j + c;
-            const int oy = P.oys * yy + ph.oyo, ox = P.oxs * xx + ph.oxo;
-            const bool ok = yy < P.Ht && xx < P.Wt && oy < P.Ho && ox < P.Wo;
-            const long long opix = ((long long)b * P.Ho + oy) * P.Wo + ox;
-            for (int n = 0; n < P.bn; n += 16) {
-                uint32_t v[16];
-                tc_ld16(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)(j * P.bn + n), v);   // warp-collective
-                if (!ok || n0 + n >= P.Cout) continue;
-                float f[16];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]) * s_scale[n + q] + s_shift[n + q];
-                if (P.res) {
-                    const uint4 *rp = reinterpret_cast<const uint4 *>(P.res + opix * P.res_stride + n0 + n);
-                    const uint4 r0 = rp[0], r1 = rp[1];
-                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float2 p2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr[q]));
-                        f[2 * q] += p2.x;
-                        f[2 * q + 1] += p2.y;
-                    }
-                }
-                uint32_t o[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(apply_act(f[2 * q], P.act), apply_act(f[2 * q + 1], P.act));
-                    o[q] = *reinterpret_cast<const uint32_t *>(&h2);
-                }
-                __nv_bfloat16 *op = P.out + opix * P.out_stride + n0 + n;
-                if (n0 + n + 16 <= P.Cout) {
-                    uint4 *o4 = reinterpret_cast<uint4 *>(op);
-                    o4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                    o4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                } else {
-                    const __nv_bfloat16 *oh = reinterpret_cast<const __nv_bfloat16 *>(o);
-                    for (int q = 0; q < P.Cout - n0 - n; ++q) op[q] = oh[q];
-                }
-            }
-        }
-        tc_fence_before();
-        if (threadIdx.x == 0) STAMP(7);
     } else if (warp == 4) {
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | (8u << 24);
             const uint32_t a_lbo = (uint32_t)P.npix_pad * 16u, b_lbo = (uint32_t)P.bn * 16u;
+            const int nacc = P.nacc, bn = P.bn;
             int bi = 0;   // running B-stage counter
             for (int i = 0; i < P.nkb; ++i) {
                 const int s = i % P.sa;
@@ -297,14 +269,15 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
                     const Plane &q = P.planes[tap.plane];
                     const uint32_t b_base = smem_u32(sB + (size_t)sb * b_stage_bytes);
                     const uint32_t a_tap = a_base + (uint32_t)(q.base + tap.sy * q.cols + tap.sx) * 16u;
+                    const uint32_t a_sbo = (uint32_t)q.cols * 16u;
 #pragma unroll
-                    for (int k2 = 0; k2 < BK / 16; ++k2)
-                        for (int j = 0; j < P.nacc; ++j) {
-                            const uint64_t da = make_desc(a_tap + (uint32_t)j * 128u + (uint32_t)k2 * 2u * a_lbo, a_lbo,
-                                                          (uint32_t)q.cols * 16u);
-                            const uint64_t db = make_desc(b_base + (uint32_t)k2 * 2u * b_lbo, b_lbo, 128u);
-                            tc_mma(tmem_base + (uint32_t)(j * P.bn), da, db, idesc, (i | tp | k2) ? 1u : 0u);
+                    for (int k2 = 0; k2 < BK / 16; ++k2) {
+                        const uint64_t db = make_desc(b_base + (uint32_t)k2 * 2u * b_lbo, b_lbo, 128u);
+                        for (int j = 0; j < nacc; ++j) {     // consecutive MMAs target different accumulators
+                            const uint64_t da = make_desc(a_tap + (uint32_t)j * 128u + (uint32_t)k2 * 2u * a_lbo, a_lbo, a_sbo);
+                            tc_mma(tmem_base + (uint32_t)(j * bn), da, db, idesc, (i | tp | k2) ? 1u : 0u);
                         }
+                    }
                     tc_commit(BAR(B_EMPTY + sb));
                 }
                 tc_commit(BAR(A_EMPTY + s));
@@ -313,7 +286,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
             STAMP(5);
         }
         __syncwarp();
-    } else {
+    } else if (warp == 5) {
         // ================= B loader (TMA 1-D bulk copies of pre-packed filter blocks) =================
         if (lane == 0) {
             int bi = 0;
@@ -335,6 +308,93 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
         }
         __syncwarp();
     }
+
+    // ================= epilogue: all 8 warps; warp w reads TMEM lanes 32*(w%4).., group w/4 takes every other
+    // accumulator.  y = act(acc*scale + shift + residual) -> bf16 NHWC slice, or fp32 planes (fused decode heads).
+    {
+        mbar_wait<true>(BAR(ACC_FULL), 0);
+        tc_fence_after();
+        if (threadIdx.x == 0) STAMP(6);
+        const int wq = warp & 3, grp = warp >> 2;
+        const int r = 4 * wq + (lane >> 3), c = lane & 7;     // MMA row m = 32*wq + lane = 8*r + c
+        const int bn = P.bn, Cout = P.Cout, out_stride = P.out_stride, res_stride = P.res_stride, act = P.act;
+        const float slope = act == RDFC_ACT_RELU ? 0.f : (act == RDFC_ACT_LEAKY02 ? 0.2f : 1.f);
+        const __nv_bfloat16 *res = P.res;
+        for (int j = grp; j < P.nacc; j += 2) {
+            const int yy = ty0 + r, xx = tx0 + 8 * j + c;
+            const int oy = P.oys * yy + ph.oyo, ox = P.oxs * xx + ph.oxo;
+            const bool ok = yy < P.Ht && xx < P.Wt && oy < P.Ho && ox < P.Wo;
+            const long long opix = ((long long)b * P.Ho + oy) * P.Wo + ox;
+            const uint32_t trow = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(j * bn);
+            for (int n = 0; n < bn; n += 16) {
+                uint32_t v[16];
+                tc_ld16(trow + (uint32_t)n, v);   // warp-collective
+                if (!ok || n0 + n >= Cout) continue;
+                float f[16];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 sc = *reinterpret_cast<const float4 *>(s_scale + n + 4 * q4);
+                    const float4 sh = *reinterpret_cast<const float4 *>(s_shift + n + 4 * q4);
+                    f[4 * q4 + 0] = fmaf(__uint_as_float(v[4 * q4 + 0]), sc.x, sh.x);
+                    f[4 * q4 + 1] = fmaf(__uint_as_float(v[4 * q4 + 1]), sc.y, sh.y);
+                    f[4 * q4 + 2] = fmaf(__uint_as_float(v[4 * q4 + 2]), sc.z, sh.z);
+                    f[4 * q4 + 3] = fmaf(__uint_as_float(v[4 * q4 + 3]), sc.w, sh.w);
+                }
+                if (P.planar) {
+                    // fused decode heads: column q -> its own fp32 plane with its own activation
+                    const long long pp = (long long)oy * P.Wo + ox;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        if (q < P.ncols) {
+                            const int a = P.act_col[q];
+                            float y = f[q];
+                            if (a == RDFC_ACT_TANH) y = tanhf(y);
+                            else if (a == RDFC_ACT_SIGMOID) y = 1.f / (1.f + expf(-y));
+                            P.plane[q][(long long)b * P.plane_bstride[q] + pp] = y;
+                        }
+                    }
+                    continue;
+                }
+                if (res) {
+                    const uint4 *rp = reinterpret_cast<const uint4 *>(res + opix * res_stride + n0 + n);
+                    const uint4 r0 = rp[0], r1 = rp[1];
+                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float2 p2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr[q]));
+                        f[2 * q] += p2.x;
+                        f[2 * q + 1] += p2.y;
+                    }
+                }
+                if (act <= RDFC_ACT_LEAKY02) {         // none / relu / leaky in one branch-free form: max(v, slope*v)
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) f[q] = fmaxf(f[q], slope * f[q]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) f[q] = act == RDFC_ACT_TANH ? tanhf(f[q]) : 1.f / (1.f + expf(-f[q]));
+                }
+                uint32_t o[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+                    o[q] = *reinterpret_cast<const uint32_t *>(&h2);
+                }
+                __nv_bfloat16 *op = P.out + opix * out_stride + n0 + n;
+                if (n0 + n + 16 <= Cout) {
+                    uint4 *o4 = reinterpret_cast<uint4 *>(op);
+                    o4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                    o4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                } else {
+                    const int nvalid = Cout - n0 - n;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        if (q < nvalid) op[q] = __float2bfloat16_rn(f[q]);
+                }
+            }
+        }
+        tc_fence_before();
+        if (threadIdx.x == 0) STAMP(7);
+    }
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
@@ -354,12 +414,12 @@ int next_pow2_cols(int c) {
 }  // namespace
 
 // Host-side planning: planes, taps, tile shape, stage counts.
-int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st) {
-    RDFC_REQUIRE(d->in.dtype == RDFC_BF16 && d->out.dtype == RDFC_BF16, "UMMA conv: bf16 in/out only");
+int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads) {
+    RDFC_REQUIRE(d->in.dtype == RDFC_BF16 && (heads || d->out.dtype == RDFC_BF16), "UMMA conv: bf16 in/out only");
     RDFC_REQUIRE(!d->in.nchw && !d->out.nchw && !d->in2.ptr, "UMMA conv: single NHWC source / NHWC output only");
     RDFC_REQUIRE(d->in.C % BK == 0, "UMMA conv: Cin (%d) must be a multiple of %d", d->in.C, BK);
-    RDFC_REQUIRE(d->in.pix_stride % 8 == 0 && d->out.pix_stride % 8 == 0 && ((uintptr_t)d->in.ptr % 16) == 0 &&
-                     ((uintptr_t)d->out.ptr % 16) == 0 && ((uintptr_t)d->weight % 16) == 0,
+    RDFC_REQUIRE(d->in.pix_stride % 8 == 0 && ((uintptr_t)d->in.ptr % 16) == 0 && ((uintptr_t)d->weight % 16) == 0 &&
+                     (heads || (d->out.pix_stride % 8 == 0 && ((uintptr_t)d->out.ptr % 16) == 0)),
                  "UMMA conv: views must be 16-byte aligned with pixel strides that are multiples of 8 elements");
     RDFC_REQUIRE(!d->residual.ptr || (d->residual.dtype == RDFC_BF16 && d->residual.pix_stride % 8 == 0 &&
                                       ((uintptr_t)d->residual.ptr % 16) == 0),
@@ -379,6 +439,12 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st) {
     P.out = (__nv_bfloat16 *)d->out.ptr; P.out_stride = d->out.pix_stride; P.Ho = d->Ho; P.Wo = d->Wo;
     P.res = (const __nv_bfloat16 *)d->residual.ptr; P.res_stride = d->residual.pix_stride;
     P.scale = d->scale; P.shift = d->shift; P.act = d->act;
+    if (heads) {
+        P.planar = 1; P.ncols = heads->ncols;
+        for (int q = 0; q < 16; ++q) {
+            P.plane[q] = heads->out[q]; P.plane_bstride[q] = heads->out_bstride[q]; P.act_col[q] = heads->act[q];
+        }
+    }
     {
         static long long *dbg = nullptr;
         if (getenv("RDFC_UMMA_DBG") && !dbg) cudaMalloc(&dbg, 4096 * 8 * sizeof(long long));

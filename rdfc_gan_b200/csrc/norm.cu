@@ -7,25 +7,75 @@ namespace {
 
 constexpr int CHUNK_PIX = 256;
 
-// Pass 1: per (b, pixel chunk, c) shifted sums -> (mean, M2) partials.  grid (nchunk, B), block 256 (threads over c).
+// Pass 1: per (b, pixel chunk, c) shifted sums -> (mean, M2) partials.
+// grid (nchunk, B, ceil(C/64)), block 256 = 8 channel groups (8 channels = one 16/32-byte vector) x 32 pixel lanes;
+// each thread strides over the chunk's pixels, then the 32 lanes are reduced through shared memory.
+template <typename T>
+__device__ __forceinline__ void load8(const T *p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float *p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16 *p, float (&v)[8]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p));
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w[q]));
+        v[2 * q] = f.x;
+        v[2 * q + 1] = f.y;
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) in_partial_kernel(const T *__restrict__ x, int C, int stride, int npix,
                                                          float *__restrict__ partial, int nchunk) {
+    __shared__ float red[32][8][17];
     const int chunk = blockIdx.x, b = blockIdx.y;
+    const int cg = threadIdx.x & 7, lane = threadIdx.x >> 3;            // 8 channel groups x 32 pixel lanes
+    const int c0 = blockIdx.z * 64 + cg * 8;
     const int p0 = chunk * CHUNK_PIX, p1 = min(npix, p0 + CHUNK_PIX), n = p1 - p0;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const T *px = x + ((long long)b * npix + p0) * stride + c;
-        const float pivot = ldf(px);
-        float s = 0.f, ss = 0.f;
-        for (int p = 0; p < n; ++p) {
-            const float d = ldf(px + (long long)p * stride) - pivot;
-            s += d;
-            ss = fmaf(d, d, ss);
+    float s[8], ss[8], pivot[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] = ss[q] = pivot[q] = 0.f;
+    const bool active = c0 < C;                                          // C is a multiple of 8 (checked on the host)
+    if (active) {
+        const T *base = x + ((long long)b * npix + p0) * stride + c0;
+        load8<T>(base, pivot);
+        for (int p = lane; p < n; p += 32) {
+            float v[8];
+            load8<T>(base + (long long)p * stride, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float d = v[q] - pivot[q];
+                s[q] += d;
+                ss[q] = fmaf(d, d, ss[q]);
+            }
         }
-        const float mean = pivot + s / n, m2 = fmaxf(ss - s * s / n, 0.f);
-        float *o = partial + (((long long)b * nchunk + chunk) * C + c) * 2;
-        o[0] = mean;
-        o[1] = m2;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        red[lane][cg][q] = s[q];
+        red[lane][cg][8 + q] = ss[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int g2 = threadIdx.x >> 3, q = threadIdx.x & 7, c = blockIdx.z * 64 + g2 * 8 + q;
+        if (c < C) {
+            float ts = 0.f, tss = 0.f;
+            for (int l = 0; l < 32; ++l) {
+                ts += red[l][g2][q];
+                tss += red[l][g2][8 + q];
+            }
+            // every lane used the same pivot (pixel p0 of the chunk)
+            const float pv = ldf(x + ((long long)b * npix + p0) * stride + c);
+            const float mean = pv + ts / n, m2 = fmaxf(tss - ts * ts / n, 0.f);
+            float *o = partial + (((long long)b * nchunk + chunk) * C + c) * 2;
+            o[0] = mean;
+            o[1] = m2;
+        }
     }
 }
 
@@ -107,7 +157,9 @@ extern "C" int rdfc_instnorm_stats(const rdfc_view *x, int B, int H, int W, floa
     RDFC_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "bad shape");
     const int npix = H * W, nchunk = cdiv(npix, CHUNK_PIX);
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(nchunk, B);
+    RDFC_REQUIRE(x->C % 8 == 0 && x->pix_stride % 8 == 0 && ((uintptr_t)x->ptr % 32) == 0,
+                 "instnorm_stats: channels / pixel stride must be multiples of 8 and the view 32-byte aligned");
+    dim3 grid(nchunk, B, cdiv(x->C, 64));
     if (x->dtype == RDFC_F32)
         in_partial_kernel<float><<<grid, 256, 0, st>>>((const float *)x->ptr, x->C, x->pix_stride, npix, partial, nchunk);
     else if (x->dtype == RDFC_BF16)

@@ -96,6 +96,7 @@ class GeneratorEngine:
                 sc, sh = self._bn_fold(bn)
             else:
                 sc = torch.ones(w.shape[0], device=w.device)
+                bias = bias() if callable(bias) else bias
                 sh = bias.detach().float() if bias is not None else torch.zeros(w.shape[0], device=w.device)
             scs.append(sc)
             shs.append(sh)
@@ -243,22 +244,38 @@ class GeneratorEngine:
         d_srcs = [seq_src(g.id_dec1), seq_src(g.cf_dec1)] + ([seq_src(g.gd_dec1)] if has_gd else [])
         conv('d.dec1', d_srcs, xd, (head['d'], 0, 160 if has_gd else 96), 3, act=L, hin=full, hout=full)
         plan.d1, plan.c1, plan.pred_init, plan.conf = f32(B, 1, H, W), f32(B, 1, H, W), f32(B, 1, H, W), f32(B, 1, H, W)
-        conv('rgb_pred_dec0', [seq_src(g.rgb_pred_dec0)], (head['r'], 0, 64), plan.d1, 3, act=C.ACT_TANH, in2=fe1['r'],
-             out_nchw=True, hin=full, hout=full)
-        conv('rgb_conf_dec0', [(g.rgb_conf_dec0[0].weight, None, g.rgb_conf_dec0[0].bias)], (head['r'], 64, 96), plan.c1, 3,
-             act=C.ACT_SIGMOID, out_nchw=True, hin=full, hout=full)
-        conv('id_dec0', [seq_src(g.id_dec0)], (head['d'], 0, 64), plan.pred_init, 3, act=C.ACT_TANH, in2=fe1['d'],
-             out_nchw=True, hin=full, hout=full)
-        conv('cf_dec0', [(g.cf_dec0[0].weight, None, g.cf_dec0[0].bias)], (head['d'], 64, 32), plan.conf, 3,
-             act=C.ACT_SIGMOID, in2=fe1['d'], out_nchw=True, hin=full, hout=full)
+        if has_gd:
+            plan.guide = f32(B, 8, H, W)
+        P_ = H * W
+        if bf16:
+            # all *_dec0 heads of a branch as ONE tensor-core conv over the whole head buffer (block-sparse filters)
+            self._plan_heads(plan, 'r.dec0', head['r'], B, H, W, [
+                dict(mod=g.rgb_pred_dec0[0], act=C.ACT_TANH, segs=[(0, 64, 0), (64, 64, 96)], out=[(plan.d1, 0, P_)]),
+                dict(mod=g.rgb_conf_dec0[0], act=C.ACT_SIGMOID, segs=[(0, 32, 64), (32, 64, 96)], out=[(plan.c1, 0, P_)])])
+            fe = 160 if has_gd else 96
+            cols = [dict(mod=g.id_dec0[0], act=C.ACT_TANH, segs=[(0, 64, 0), (64, 64, fe)], out=[(plan.pred_init, 0, P_)]),
+                    dict(mod=g.cf_dec0[0], act=C.ACT_SIGMOID, segs=[(0, 32, 64), (32, 64, fe)], out=[(plan.conf, 0, P_)])]
+            if has_gd:
+                cols.append(dict(mod=g.gd_dec0[0], act=C.ACT_NONE, segs=[(0, 64, 96), (64, 64, fe)],
+                                 out=[(plan.guide, k * P_, 8 * P_) for k in range(8)]))
+            self._plan_heads(plan, 'd.dec0', head['d'], B, H, W, cols)
+        else:
+            conv('rgb_pred_dec0', [seq_src(g.rgb_pred_dec0)], (head['r'], 0, 64), plan.d1, 3, act=C.ACT_TANH, in2=fe1['r'],
+                 out_nchw=True, hin=full, hout=full)
+            conv('rgb_conf_dec0', [(g.rgb_conf_dec0[0].weight, None, g.rgb_conf_dec0[0].bias)], (head['r'], 64, 96), plan.c1, 3,
+                 act=C.ACT_SIGMOID, out_nchw=True, hin=full, hout=full)
+            conv('id_dec0', [seq_src(g.id_dec0)], (head['d'], 0, 64), plan.pred_init, 3, act=C.ACT_TANH, in2=fe1['d'],
+                 out_nchw=True, hin=full, hout=full)
+            conv('cf_dec0', [(g.cf_dec0[0].weight, None, g.cf_dec0[0].bias)], (head['d'], 64, 32), plan.conf, 3,
+                 act=C.ACT_SIGMOID, in2=fe1['d'], out_nchw=True, hin=full, hout=full)
+            if has_gd:
+                conv('gd_dec0', [seq_src(g.gd_dec0)], (head['d'], 96, 128), plan.guide, 3, out_nchw=True, hin=full, hout=full)
 
         # ---- NLSPN + output fusion (rdf_generator.py:400-406)
         plan.d2, plan.pred = f32(B, 1, H, W), f32(B, 1, H, W)
         n = B * H * W
         if has_gd:
             pl = g.nlspn_refine_module.prop_layer
-            plan.guide = f32(B, 8, H, W)
-            conv('gd_dec0', [seq_src(g.gd_dec0)], (head['d'], 96, 128), plan.guide, 3, out_nchw=True, hin=full, hout=full)
             plan.offset, plan.aff, plan.scratch, plan.d2raw = f32(B, 18, H, W), f32(B, 9, H, W), f32(B, 1, H, W), f32(B, 1, H, W)
             pw = self._pack_nlspn(precision)
             plan.keep.append(pw)
@@ -278,6 +295,43 @@ class GeneratorEngine:
         plan.n_launch += 1
         plan.outputs = (plan.d1, plan.c1, plan.d2, plan.conf, plan.pred)
         return plan
+
+    def _plan_heads(self, plan, name, buf, B, H, W, cols):
+        """One rdfc_heads_forward over the NHWC head buffer `buf`.  cols: dicts with the head's conv module, activation,
+        channel segments (src_c0, n, dst_c0) mapping the conv's input channels onto buffer channels, and output planes
+        (tensor, element offset, batch stride)."""
+        Ctot = buf.shape[3]
+
+        def fused_weight():
+            w16 = torch.zeros(16, Ctot, 3, 3, device=buf.device)
+            q = 0
+            for c in cols:
+                w = c['mod'].weight.detach().float()
+                for s0, n, d0 in c['segs']:
+                    w16[q:q + w.shape[0], d0:d0 + n] = w[:, s0:s0 + n]
+                q += w.shape[0]
+            return w16
+
+        def fused_bias():
+            return torch.cat([c['mod'].bias.detach().float() for c in cols] +
+                             [torch.zeros(16 - sum(c['mod'].weight.shape[0] for c in cols), device=buf.device)])
+
+        pk = self._pack(name, [(fused_weight, None, fused_bias)], 'bf16', True)
+        d = C.HeadsDesc()
+        d.B, d.H, d.W = B, H, W
+        d.inp = C.view(buf)
+        d.weight, d.shift = pk.weight.data_ptr(), pk.shift.data_ptr()
+        q = 0
+        for c in cols:
+            for t, off, bstride in c['out']:
+                d.act[q] = c['act']
+                d.out[q] = t.data_ptr() + 4 * off
+                d.out_bstride[q] = bstride
+                q += 1
+        d.ncols = q
+        plan.keep.append((d, pk))
+        plan.steps.append(lambda s, d=d: C.check(C.lib.rdfc_heads_forward(ctypes.byref(d), s)))
+        plan.n_launch += 1
 
     def _plan_fuse(self, plan, conv, new, f32, layer, n, xr, xd, B, hw, precision):
         """fuse_layer{n}(rgb feature xr, depth feature xd) -> NHWC slice (tensor, 0, C).  model_utils.py:53-129."""
