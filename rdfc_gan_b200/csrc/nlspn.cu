@@ -155,6 +155,100 @@ __global__ void __launch_bounds__(TX *TY) nlspn_prop_kernel(const float *__restr
     if (inter) inter[(long long)b * P + pix] = acc;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Row-streaming propagation kernel (the default when W % 4 == 0): persistent CTAs, one image row per trip, one
+// thread per pixel.  The 25 offset/affinity planes of a row are staged in shared memory by TMA 1-D bulk copies
+// (cp.async.bulk, W*4 bytes each) onto an mbarrier, `stages` rows ahead of the compute, so HBM requests stay in
+// flight while the warps gather feature corners through L1.  A CTA owns a contiguous band of rows: the feature
+// rows its taps touch stay L1-resident from one trip to the next.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 8000000000ll) __trap();      // protocol bug: fail loudly instead of hanging the GPU
+    }
+}
+
+template <bool kClamp>
+__global__ void __launch_bounds__(1024) nlspn_prop_rows_kernel(const float *__restrict__ in,
+                                                               const float *__restrict__ offset,
+                                                               const float *__restrict__ aff, float *__restrict__ out,
+                                                               float *__restrict__ inter, int B, int H, int W,
+                                                               int stages, int rows_per_cta) {
+    extern __shared__ __align__(128) unsigned char nl_smem[];
+    float *stage_base = reinterpret_cast<float *>(nl_smem);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(nl_smem + (size_t)stages * 25 * W * sizeof(float));
+    const long long total = (long long)B * H, P = (long long)H * W;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = r0 + rows_per_cta < total ? r0 + rows_per_cta : total;
+    if (r0 >= r1) return;
+    const int x = threadIdx.x;
+    if (x == 0) {
+        for (int s = 0; s < stages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t row_bytes = (uint32_t)W * 4u;
+    auto issue = [&](long long row, int s) {          // thread 0: 25 bulk copies of one row
+        const int b = (int)(row / H), y = (int)(row % H);
+        const uint32_t bar = smem_u32(bars + s);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(25u * row_bytes) : "memory");
+        const uint32_t dst = smem_u32(stage_base + (size_t)s * 25 * W);
+        const float *offp = offset + (long long)b * 18 * P + (long long)y * W;
+        const float *affp = aff + (long long)b * 9 * P + (long long)y * W;
+        int slot = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            if (k == 4) continue;                     // the centre tap's offsets are identically zero
+            bulk_g2s(dst + (uint32_t)(slot++) * row_bytes, offp + (long long)(2 * k) * P, row_bytes, bar);
+            bulk_g2s(dst + (uint32_t)(slot++) * row_bytes, offp + (long long)(2 * k + 1) * P, row_bytes, bar);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) bulk_g2s(dst + (uint32_t)(16 + k) * row_bytes, affp + (long long)k * P, row_bytes, bar);
+    };
+    if (x == 0)
+        for (int s = 0; s < stages; ++s)
+            if (r0 + s < r1) issue(r0 + s, s);
+
+    int it = 0;
+    for (long long row = r0; row < r1; ++row, ++it) {
+        const int s = it % stages;
+        mbar_wait_parity(smem_u32(bars + s), (uint32_t)((it / stages) & 1));
+        if (x < W) {
+            const int b = (int)(row / H), y = (int)(row % H);
+            const float *st = stage_base + (size_t)s * 25 * W + x;
+            const float *im = in + (long long)b * P;
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int j = k < 4 ? k : k - 1;
+                const float dy = k == 4 ? 0.f : st[(2 * j) * W], dx = k == 4 ? 0.f : st[(2 * j + 1) * W];
+                acc = fmaf(st[(16 + k) * W], bilinear(im, H, W, (float)(y - 1 + k / 3) + dy, (float)(x - 1 + k % 3) + dx), acc);
+            }
+            if (kClamp) acc = fminf(fmaxf(acc, -1.f), 1.f);
+            const long long o = (long long)b * P + (long long)y * W + x;
+            out[o] = acc;
+            if (inter) inter[o] = acc;
+        }
+        __syncthreads();                               // everyone is done reading stage s
+        if (x == 0 && row + stages < r1) issue(row + stages, s);
+    }
+}
+
 // feat = (1 - m) * feat + m * fix, m = fix > 0   (nlspn_model.py:159-160,169)
 __global__ void nlspn_preserve_kernel(const float *__restrict__ in, const float *__restrict__ fix,
                                       float *__restrict__ out, long long n) {
@@ -240,11 +334,44 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
                 cur = tmp;
             }
             float *it = inter ? inter + ((long long)t * B + b0) * P : nullptr;
-            if (clamp_out && t == prop_time - 1)
-                nlspn_prop_kernel<true><<<grid, block, 0, st>>>(cur, off_g, aff_g, dst, it, H, W);
-            else
-                nlspn_prop_kernel<false><<<grid, block, 0, st>>>(cur, off_g, aff_g, dst, it, H, W);
-            RDFC_CHECK_LAUNCH("nlspn_prop_kernel");
+            const bool clamp = clamp_out && t == prop_time - 1;
+            // row-streaming kernel: needs 16-byte row granularity for the bulk copies
+            const size_t stage_bytes = (size_t)25 * W * sizeof(float);
+            int stages = 3;
+            while (stages > 1 && stages * stage_bytes + 64 > 100 * 1024) --stages;
+            const bool rows_ok = !getenv("RDFC_NLSPN_SIMPLE") && W % 4 == 0 && W <= 1024 &&
+                                 stages * stage_bytes + 64 <= 200 * 1024 && ((uintptr_t)off_g % 16) == 0 &&
+                                 ((uintptr_t)aff_g % 16) == 0;
+            if (rows_ok) {
+                const size_t smem = stages * stage_bytes + 64;
+                static bool attr = false;
+                if (!attr) {
+                    RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    attr = true;
+                }
+                const int nt = (W + 31) / 32 * 32;
+                int per_sm = (int)((220 * 1024) / (smem + 1024));
+                if (per_sm * nt > 2048) per_sm = 2048 / nt;
+                if (per_sm < 1) per_sm = 1;
+                if (const char *e = getenv("RDFC_NLSPN_CTAS_PER_SM")) per_sm = atoi(e);
+                const long long total_rows = (long long)nb * H;
+                long long nctas = (long long)sm_count() * per_sm;
+                if (nctas > total_rows) nctas = total_rows;
+                const int rpc = (int)((total_rows + nctas - 1) / nctas);
+                nctas = (total_rows + rpc - 1) / rpc;
+                if (clamp)
+                    nlspn_prop_rows_kernel<true><<<(int)nctas, nt, smem, st>>>(cur, off_g, aff_g, dst, it, nb, H, W, stages, rpc);
+                else
+                    nlspn_prop_rows_kernel<false><<<(int)nctas, nt, smem, st>>>(cur, off_g, aff_g, dst, it, nb, H, W, stages, rpc);
+                RDFC_CHECK_LAUNCH("nlspn_prop_rows_kernel");
+            } else {
+                if (clamp)
+                    nlspn_prop_kernel<true><<<grid, block, 0, st>>>(cur, off_g, aff_g, dst, it, H, W);
+                else
+                    nlspn_prop_kernel<false><<<grid, block, 0, st>>>(cur, off_g, aff_g, dst, it, H, W);
+                RDFC_CHECK_LAUNCH("nlspn_prop_kernel");
+            }
             cur = dst;
         }
     }

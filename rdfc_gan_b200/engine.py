@@ -46,6 +46,7 @@ class _Packed:
 class Plan:
     def __init__(self):
         self.steps = []          # callables taking the stream pointer
+        self.names = []          # debug: one label per step
         self.keep = []           # ctypes structs / tensors that must outlive the plan
         self.graph = None
         self.n_launch = 0
@@ -183,6 +184,7 @@ class GeneratorEngine:
             d.inp, d.in2, d.out, d.residual = vin, vin2, vout, vres
             d.weight, d.scale, d.shift = pk.weight.data_ptr(), pk.scale.data_ptr(), pk.shift.data_ptr()
             plan.keep.append((d, pk))
+            plan.names.append(f"conv {name} k{k} s{stride} T{int(transposed)} {vin.C}->{vout.C} {hin}->{hout} {'umma' if umma else 'simt'}")
             plan.steps.append(lambda s, d=d: C.check(C.lib.rdfc_conv_forward(ctypes.byref(d), s)))
             plan.n_launch += 1
 
