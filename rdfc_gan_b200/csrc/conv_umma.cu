@@ -238,15 +238,21 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
             }
             cp_async_commit();
             if (i == 0 && threadIdx.x == 0) STAMP(2);
-            if (i >= 1) {
+            if (P.sa == 1) {                  // single-stage ring: publish at once (nothing to overlap with)
+                cp_async_wait<0>();
+                fence_proxy_async();
+                mbar_arrive(BAR(A_FULL));
+            } else if (i >= 1) {              // publish stage i-1 while stage i is in flight
                 cp_async_wait<1>();
                 fence_proxy_async();
                 mbar_arrive(BAR(A_FULL + (i - 1) % P.sa));
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        mbar_arrive(BAR(A_FULL + (P.nkb - 1) % P.sa));
+        if (P.sa > 1) {
+            cp_async_wait<0>();
+            fence_proxy_async();
+            mbar_arrive(BAR(A_FULL + (P.nkb - 1) % P.sa));
+        }
     } else if (warp == 4) {
         // ================= MMA issuer =================
         if (lane == 0) {
@@ -517,8 +523,12 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     const int a_stage = KCH * P.npix_pad * 16, b_stage = KCH * P.bn * 16;
     const int fixed = P.npix_pad * 4 + 2 * P.bn * 4 + 8 + (2 * 4 + 2 * 8 + 2) * 8 + 16 + 128;
     const int budget = 200 * 1024;
+    // A ring first (>= 2 stages whenever there are >= 2 channel blocks: the producers publish stage i while filling
+    // stage i+1), then as many B stages as fit (2..4).
+    const int sa_want = P.nkb < 2 ? 1 : 2;
     P.sb = 4;
     if (const char *e = getenv("RDFC_UMMA_SB")) P.sb = atoi(e);          // development knob (<= 8)
+    while (P.sb > 2 && sa_want * a_stage + P.sb * b_stage + fixed > budget) --P.sb;
     P.sa = (budget - fixed - P.sb * b_stage) / a_stage;
     if (P.sa > 4) P.sa = 4;
     if (const char *e = getenv("RDFC_UMMA_SA")) P.sa = atoi(e) < P.sa ? atoi(e) : P.sa;

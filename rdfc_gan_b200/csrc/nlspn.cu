@@ -182,8 +182,8 @@ __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) 
     }
 }
 
-template <bool kClamp>
-__global__ void __launch_bounds__(1024) nlspn_prop_rows_kernel(const float *__restrict__ in,
+template <bool kClamp, int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) nlspn_prop_rows_kernel(const float *__restrict__ in,
                                                                const float *__restrict__ offset,
                                                                const float *__restrict__ aff, float *__restrict__ out,
                                                                float *__restrict__ inter, int B, int H, int W,
@@ -337,22 +337,18 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
             const bool clamp = clamp_out && t == prop_time - 1;
             // row-streaming kernel: needs 16-byte row granularity for the bulk copies
             const size_t stage_bytes = (size_t)25 * W * sizeof(float);
-            int stages = 3;
-            while (stages > 1 && stages * stage_bytes + 64 > 100 * 1024) --stages;
-            const bool rows_ok = !getenv("RDFC_NLSPN_SIMPLE") && W % 4 == 0 && W <= 1024 &&
-                                 stages * stage_bytes + 64 <= 200 * 1024 && ((uintptr_t)off_g % 16) == 0 &&
-                                 ((uintptr_t)aff_g % 16) == 0;
+            const int nt = (W + 31) / 32 * 32;
+            // many small CTAs per SM (1 stage each) hide the bulk-copy latency by interleaving; wide rows get 2 stages
+            int stages = nt <= 320 ? 1 : 2;
+            if (const char *e = getenv("RDFC_NLSPN_STAGES")) stages = atoi(e);
+            while (stages > 1 && stages * stage_bytes + 64 > 200 * 1024) --stages;
+            const size_t smem = stages * stage_bytes + 64;
+            const bool rows_ok = !getenv("RDFC_NLSPN_SIMPLE") && W % 4 == 0 && W <= 1024 && smem <= 200 * 1024 &&
+                                 ((uintptr_t)off_g % 16) == 0 && ((uintptr_t)aff_g % 16) == 0;
             if (rows_ok) {
-                const size_t smem = stages * stage_bytes + 64;
-                static bool attr = false;
-                if (!attr) {
-                    RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    attr = true;
-                }
-                const int nt = (W + 31) / 32 * 32;
-                int per_sm = (int)((220 * 1024) / (smem + 1024));
+                int per_sm = (int)((226 * 1024) / (smem + 1024));
                 if (per_sm * nt > 2048) per_sm = 2048 / nt;
+                if (nt <= 320 && per_sm > 4) per_sm = 4;       // register budget of the <320,4> instantiation
                 if (per_sm < 1) per_sm = 1;
                 if (const char *e = getenv("RDFC_NLSPN_CTAS_PER_SM")) per_sm = atoi(e);
                 const long long total_rows = (long long)nb * H;
@@ -360,10 +356,18 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
                 if (nctas > total_rows) nctas = total_rows;
                 const int rpc = (int)((total_rows + nctas - 1) / nctas);
                 nctas = (total_rows + rpc - 1) / rpc;
-                if (clamp)
-                    nlspn_prop_rows_kernel<true><<<(int)nctas, nt, smem, st>>>(cur, off_g, aff_g, dst, it, nb, H, W, stages, rpc);
-                else
-                    nlspn_prop_rows_kernel<false><<<(int)nctas, nt, smem, st>>>(cur, off_g, aff_g, dst, it, nb, H, W, stages, rpc);
+#define RDFC_ROWS(CL, MT, MB)                                                                                        \
+    do {                                                                                                             \
+        RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_rows_kernel<CL, MT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       200 * 1024));                                                                 \
+        nlspn_prop_rows_kernel<CL, MT, MB><<<(int)nctas, nt, smem, st>>>(cur, off_g, aff_g, dst, it, nb, H, W, stages, rpc); \
+    } while (0)
+                if (nt <= 320) {
+                    if (clamp) RDFC_ROWS(true, 320, 4); else RDFC_ROWS(false, 320, 4);
+                } else {
+                    if (clamp) RDFC_ROWS(true, 1024, 1); else RDFC_ROWS(false, 1024, 1);
+                }
+#undef RDFC_ROWS
                 RDFC_CHECK_LAUNCH("nlspn_prop_rows_kernel");
             } else {
                 if (clamp)

@@ -81,6 +81,11 @@ CASES = [
     (2, 96, 64, 7, 10, 3, 2, True, 2, False, (13, 20)),
     (1, 256, 160, 33, 18, 3, 1, False, 2, False, None),
     (1, 512, 512, 8, 10, 3, 1, False, 1, True, None),
+    # large-grid configurations (wide tiles, N = 256, two accumulators, four parity planes): the shapes bench.py runs
+    (6, 128, 256, 114, 152, 3, 2, False, 1, False, None),
+    (8, 256, 256, 57, 76, 3, 1, False, 1, True, None),
+    (4, 64, 64, 228, 304, 3, 1, False, 1, True, None),
+    (2, 192, 64, 114, 152, 3, 2, True, 2, False, None),
 ]
 
 
