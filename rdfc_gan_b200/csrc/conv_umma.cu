@@ -138,7 +138,7 @@ __device__ __forceinline__ long long gtime() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-#define STAMP(i) do { if (P.dbg && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 4096) P.dbg[blockIdx.x * 8 + (i)] = gtime(); } while (0)
+#define STAMP(i) do { if (P.dbg && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 4096) P.dbg[blockIdx.x * 16 + (i)] = gtime(); } while (0)
 
 // no-swizzle K-major shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -260,15 +260,20 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
             const uint32_t a_lbo = (uint32_t)P.npix_pad * 16u, b_lbo = (uint32_t)P.bn * 16u;
             const int nacc = P.nacc, bn = P.bn;
             int bi = 0;   // running B-stage counter
+            long long wait_a = 0, wait_b = 0;
             for (int i = 0; i < P.nkb; ++i) {
                 const int s = i % P.sa;
+                long long tw = P.dbg ? clock64() : 0;
                 mbar_wait(BAR(A_FULL + s), (i / P.sa) & 1);
+                if (P.dbg) wait_a += clock64() - tw;
                 tc_fence_after();
                 if (i == 0) STAMP(3);
                 const uint32_t a_base = smem_u32(sA + (size_t)s * a_stage_bytes);
                 for (int tp = 0; tp < ph.ntaps; ++tp, ++bi) {
                     const int sb = bi % P.sb;
+                    tw = P.dbg ? clock64() : 0;
                     mbar_wait(BAR(B_FULL + sb), (bi / P.sb) & 1);
+                    if (P.dbg) wait_b += clock64() - tw;
                     tc_fence_after();
                     if (bi == 0) STAMP(4);
                     const Tap &tap = ph.taps[tp];
@@ -290,6 +295,10 @@ __global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_consta
             }
             tc_commit(BAR(ACC_FULL));
             STAMP(5);
+            if (P.dbg && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 4096) {
+                P.dbg[blockIdx.x * 16 + 8] = wait_a;
+                P.dbg[blockIdx.x * 16 + 9] = wait_b;
+            }
         }
         __syncwarp();
     } else if (warp == 5) {
@@ -453,7 +462,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     }
     {
         static long long *dbg = nullptr;
-        if (getenv("RDFC_UMMA_DBG") && !dbg) cudaMalloc(&dbg, 4096 * 8 * sizeof(long long));
+        if (getenv("RDFC_UMMA_DBG") && !dbg) cudaMalloc(&dbg, 4096 * 16 * sizeof(long long));
         P.dbg = getenv("RDFC_UMMA_DBG") ? dbg : nullptr;
         g_umma_dbg = dbg;
     }
@@ -552,5 +561,5 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
 // development aid (not in the public header): copies the per-CTA timestamps of the last instrumented launch
 extern "C" int rdfc_dev_umma_stamps(long long *host, int n_ctas) {
     if (!rdfc::g_umma_dbg) return -1;
-    return (int)cudaMemcpy(host, rdfc::g_umma_dbg, sizeof(long long) * 8 * n_ctas, cudaMemcpyDeviceToHost);
+    return (int)cudaMemcpy(host, rdfc::g_umma_dbg, sizeof(long long) * 16 * n_ctas, cudaMemcpyDeviceToHost);
 }

@@ -343,7 +343,7 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
             if (const char *e = getenv("RDFC_NLSPN_STAGES")) stages = atoi(e);
             while (stages > 1 && stages * stage_bytes + 64 > 200 * 1024) --stages;
             const size_t smem = stages * stage_bytes + 64;
-            const bool rows_ok = !getenv("RDFC_NLSPN_SIMPLE") && W % 4 == 0 && W <= 1024 && smem <= 200 * 1024 &&
+            const bool rows_ok = getenv("RDFC_NLSPN_ROWS") && W % 4 == 0 && W <= 1024 && smem <= 200 * 1024 &&
                                  ((uintptr_t)off_g % 16) == 0 && ((uintptr_t)aff_g % 16) == 0;
             if (rows_ok) {
                 int per_sm = (int)((226 * 1024) / (smem + 1024));

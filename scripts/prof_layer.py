@@ -47,15 +47,17 @@ def conv(B=8, Cin=64, Cout=64, H=228, W=304, k=3, stride=1, transposed=0, in_str
     if os.environ.get("RDFC_UMMA_DBG"):
         import numpy as np
         n = 1024
-        buf = (ctypes.c_longlong * (8 * n))()
+        buf = (ctypes.c_longlong * (16 * n))()
         C.lib.rdfc_dev_umma_stamps(buf, n)
-        a = np.frombuffer(buf, dtype=np.int64).reshape(n, 8).astype(np.float64)
+        full = np.frombuffer(buf, dtype=np.int64).reshape(n, 16).astype(np.float64)
+        a = full[:, :8]
         t0 = a[:, 0].min()
         rel = (a - a[:, :1]) / 1e3
         names = ["entry", "setup", "A0 issued", "A0 full", "B0 full", "last commit", "acc full", "epi done"]
         print("per-CTA timeline (us since CTA entry), median over", n, "CTAs:")
         for i, nm in enumerate(names):
             print(f"   {nm:12s} {np.median(rel[:, i]):8.2f}   p90 {np.percentile(rel[:, i], 90):8.2f}")
+        print(f"   MMA thread cycles waiting: A_FULL median {np.median(full[:, 8]):.0f}, B_FULL median {np.median(full[:, 9]):.0f}")
         print(f"   first CTA entry -> last CTA done: {(a[:, 7].max() - t0) / 1e3:.1f} us; CTA lifetimes median {np.median(rel[:, 7]):.2f}")
     print(f"conv B={B} {Cin}->{Cout} {H}x{W} k{k} s{stride} T{transposed}: {ms*1e3:.1f} us  {flops/ms/1e9:.1f} TFLOP/s "
           f"env={ {k_: v for k_, v in os.environ.items() if k_.startswith('RDFC_')} }")
