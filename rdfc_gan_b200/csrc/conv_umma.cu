@@ -1,24 +1,29 @@
 // Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), bf16 x bf16 -> fp32.
+// Persistent, warp-specialised, double-buffered in TMEM.
 //
 // One kernel covers every GEMM-shaped layer of the generator (encoder_decoder/common.py:29-61, the torchvision
 // BasicBlock convs, the decode heads rdf_generator.py:68-102 and the per-pixel EqualLinear of W-AdaIN
 // model_utils.py:72-75): 3x3 / 1x1, stride 1 / 2, and ConvTranspose2d(k3,s2,p1,op1) as four sub-pixel phases.
 //
-// GEMM view (per CTA):  D[128*NACC pixels, BN couts] += A[pixels, 32 cin] * B[couts, 32 cin]^T
-//   * the CTA owns a 16 x (8*NACC) pixel tile of one image; accumulator j (128 TMEM lanes x BN fp32 columns) holds
-//     the 16 x 8 sub-tile j, MMA row m = 8*r + c.
-//   * A: the input HALO of the tile (all pixels any tap can touch) is staged ONCE per 32-channel block by the four
-//     producer warps with 16-byte cp.async (zero-fill outside the image = the conv padding), in the UMMA
-//     no-swizzle K-major layout [cin/8][pixel][8]: a core matrix is 8 consecutive pixels of a row (128 contiguous
-//     bytes), SBO = the plane's row pitch, LBO = the cin-chunk pitch.  Every filter tap is then just a different
-//     start address into the same staged plane, so the input is read from L2 ~1.2x instead of 9x.
-//     Stride-2 layers stage the four input-parity planes; transposed layers run one launch with the four output
-//     phases in blockIdx.z, each a 1/2/2/4-tap convolution over the input grid.
-//   * B: filters are pre-packed on the host as [tap][cin/8][cout][8]; warp 5 streams one (tap, 32-cin) block per
-//     stage with cp.async.bulk (TMA 1-D) onto an mbarrier.
-//   * warp 4 / lane 0 issues tcgen05.mma (M=128, N=BN, K=16) and releases stages with tcgen05.commit.
-//   * epilogue (warps 0-3): tcgen05.ld 32 lanes x 16 columns, y = act(acc*scale + shift + residual), bf16, 32-byte
-//     vector stores into the NHWC channel slice (this is how every torch.cat of the reference disappears).
+// GEMM view of one tile:  D[128*NACC pixels, BN couts] += A[pixels, 32 cin] * B[couts, 32 cin]^T  over (cin block, tap)
+//   * a tile is a 16 x (8*NACC) pixel patch of one image; accumulator j (128 TMEM lanes x BN fp32 columns) holds the
+//     16 x 8 sub-patch j, MMA row m = 8*r + c.
+//   * CTAs are persistent (grid = min(#tiles, #SMs)) and walk tiles round-robin.  Four roles run decoupled through
+//     mbarrier rings that continue across tiles, so the loads of tile t+1 and the epilogue of tile t-1 overlap the
+//     MMAs of tile t:
+//       warps 0-3   A producers: stage the tile's input HALO (every pixel any tap can touch) once per 32-channel block
+//                   with 16-byte cp.async (zero-fill outside the image = the conv padding) in the UMMA no-swizzle
+//                   K-major layout [cin/8][pixel][8].  A core matrix is 8 consecutive pixels of a row (128 contiguous
+//                   bytes), SBO = the plane's row pitch, LBO = the cin-chunk pitch, and every filter tap is just a
+//                   different descriptor start address into the same staged plane (input leaves L2 ~1.2x, not 9x).
+//                   Stride-2 layers stage the four input-parity planes; a transposed conv enumerates its four
+//                   output phases as separate tiles, each a 1/2/2/4-tap conv over the input grid.
+//       warp 13     B loader: one pre-packed (tap, 32-cin, BN) filter block per stage, cp.async.bulk (TMA 1-D).
+//       warp 12     MMA issuer: lane 0 issues tcgen05.mma (M=128, N=BN, K=16), frees stages with tcgen05.commit.
+//       warps 4-11  epilogue: tcgen05.ld 32x32b.x16 -> y = act(acc*scale + shift + residual) -> bf16 NHWC channel
+//                   slice (this is how every torch.cat of the reference disappears) or, for the fused decode heads,
+//                   one fp32 plane per output column.  TMEM holds two accumulator sets (when 2*NACC*BN <= 512), so
+//                   the MMA warp fills set (t+1)&1 while the epilogue drains set t&1.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,8 +34,9 @@ namespace {
 constexpr int BK = 32;            // input channels per A stage (2 MMAs of K=16)
 constexpr int KCH = BK / 8;       // 16-byte cin chunks per stage
 constexpr int TH = 16;            // tile rows (= 8-row groups of one M=128 MMA)
-constexpr int NPROD = 128;        // producer / epilogue threads (warps 0-3)
-constexpr int NTHREADS = 256;     // + warp 4 (MMA) + warp 5 (B loader) + warps 6-7; warps 4-7 form the 2nd epilogue group
+constexpr int NPROD = 128;        // A producer threads (warps 0-3)
+constexpr int EPI_WARP0 = 4, NEPI_WARPS = 8, MMA_WARP = 12, BLOAD_WARP = 13;
+constexpr int NTHREADS = 14 * 32;
 constexpr int MAX_PLANES = 4, MAX_TAPS = 9;
 
 struct Plane {
@@ -48,7 +54,7 @@ struct Phase {                     // one sub-pixel phase of a transposed conv (
 struct Params {
     const __nv_bfloat16 *in;
     int in_stride, B, Hi, Wi;
-    int Ht, Wt, tiles_y, tiles_x;  // tile space
+    int Ht, Wt, tiles_y, tiles_x, n_tiles_n, nphases, ntiles;   // tile space
     const __nv_bfloat16 *w;
     int CoutP, cin_chunks, nkb;    // padded Cout, Cin/8, Cin/BK
     __nv_bfloat16 *out;
@@ -56,8 +62,7 @@ struct Params {
     const __nv_bfloat16 *res;
     int res_stride;
     const float *scale, *shift;
-    int act, nacc, bn, sa, sb, npix_pad, nplanes, tmem_cols;
-    long long *dbg;                // development: per-CTA %globaltimer stamps (8 per CTA) or NULL
+    int act, nacc, bn, sa, sb, npix_pad, nplanes, tmem_cols, nsets;
     int planar, ncols;             // planar != 0: fp32 output planes, one per output column (fused decode heads)
     float *plane[16];
     long long plane_bstride[16];
@@ -65,6 +70,20 @@ struct Params {
     Plane planes[MAX_PLANES];
     Phase phases[4];
 };
+
+struct Tile {
+    int b, ty0, tx0, n0, z;
+};
+__device__ __forceinline__ Tile decode_tile(const Params &P, int tile) {
+    Tile t;
+    const int nt = tile % P.n_tiles_n; tile /= P.n_tiles_n;      // Cout tile fastest: the A halo stays hot in L2
+    const int txi = tile % P.tiles_x; tile /= P.tiles_x;
+    const int tyi = tile % P.tiles_y; tile /= P.tiles_y;
+    t.z = tile % P.nphases; tile /= P.nphases;
+    t.b = tile;
+    t.ty0 = tyi * TH; t.tx0 = txi * 8 * P.nacc; t.n0 = nt * P.bn;
+    return t;
+}
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,10 +111,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (ok) return;
-        if (kBackoff) __nanosleep(256);      // long waits (accumulator ready): do not steal issue slots from the MMA warp
+        if (kBackoff) __nanosleep(128);      // long waits: do not steal issue slots from the MMA / producer warps
         if (clock64() - t0 > 8000000000ll) {
-            printf("rdfc conv_umma: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-                   threadIdx.x);
+            printf("rdfc conv_umma: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+                   bar, parity);
             __trap();
         }
     }
@@ -133,292 +152,285 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ long long gtime() {
-    long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-#define STAMP(i) do { if (P.dbg && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 4096) P.dbg[blockIdx.x * 16 + (i)] = gtime(); } while (0)
-
 // no-swizzle K-major shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
            (1ull << 46);
 }
 
-__global__ void __launch_bounds__(NTHREADS) conv_umma_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_stage_bytes = KCH * P.npix_pad * 16, b_stage_bytes = KCH * P.bn * 16;
     unsigned char *sA = smem;
     unsigned char *sB = sA + (size_t)P.sa * a_stage_bytes;
-    int *pix_off = reinterpret_cast<int *>(sB + (size_t)P.sb * b_stage_bytes);
-    float *s_scale = reinterpret_cast<float *>(pix_off + P.npix_pad);
-    float *s_shift = s_scale + P.bn;
-    uint64_t *bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(s_shift + P.bn) + 7) & ~uintptr_t(7));
-    // barrier map: [0,sa) a_full, [sa,2sa) a_empty, [2sa,2sa+sb) b_full, [2sa+sb,2sa+2sb) b_empty, then acc_full
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)P.sb * b_stage_bytes);
+    // barrier map: a_full[sa] a_empty[sa] b_full[sb] b_empty[sb] acc_full[2] acc_empty[2]
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    const int A_FULL = 0, A_EMPTY = P.sa, B_FULL = 2 * P.sa, B_EMPTY = 2 * P.sa + P.sb, ACC_FULL = 2 * P.sa + 2 * P.sb;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + ACC_FULL + 1);
-
-    // ---- tile decode
-    const Phase &ph = P.phases[blockIdx.z];
-    int t = blockIdx.x;
-    const int txi = t % P.tiles_x; t /= P.tiles_x;
-    const int tyi = t % P.tiles_y; t /= P.tiles_y;
-    const int b = t;
-    const int ty0 = tyi * TH, tx0 = txi * 8 * P.nacc;
-    const int n0 = blockIdx.y * P.bn;
+    const int A_FULL = 0, A_EMPTY = P.sa, B_FULL = 2 * P.sa, B_EMPTY = 2 * P.sa + P.sb, ACC_FULL = 2 * P.sa + 2 * P.sb,
+              ACC_EMPTY = ACC_FULL + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + ACC_EMPTY + 2);
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
-        STAMP(0);
         for (int i = 0; i < P.sa; ++i) { mbar_init(BAR(A_FULL + i), NPROD); mbar_init(BAR(A_EMPTY + i), 1); }
         for (int i = 0; i < P.sb; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
-        mbar_init(BAR(ACC_FULL), 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), 1); mbar_init(BAR(ACC_EMPTY + i), NEPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"((uint32_t)P.tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // gather table: element offset of every staged pixel (or -1 outside the image)
-    for (int e = threadIdx.x; e < P.npix_pad; e += NTHREADS) {
-        int off = -1;
-        for (int pl = 0; pl < P.nplanes; ++pl) {
-            const Plane &q = P.planes[pl];
-            const int rel = e - q.base;
-            if (rel >= 0 && rel < q.rows * q.cols) {
-                const int iy = q.ystep * (ty0 + rel / q.cols) + q.yoff, ix = q.xstep * (tx0 + rel % q.cols) + q.xoff;
-                if (iy >= 0 && iy < P.Hi && ix >= 0 && ix < P.Wi) off = ((b * P.Hi + iy) * P.Wi + ix);
-            }
-        }
-        pix_off[e] = off;
-    }
-    for (int e = threadIdx.x; e < P.bn; e += NTHREADS) {
-        const int co = n0 + e;
-        s_scale[e] = (P.scale && co < P.Cout) ? P.scale[co] : 1.f;
-        s_shift[e] = (P.shift && co < P.Cout) ? P.shift[co] : 0.f;
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (threadIdx.x == 0) STAMP(1);
+    const int set_cols = P.nacc * P.bn;
 
     if (warp < 4) {
-        // ================= A producers: stage the halo planes of each 32-channel block =================
-        // Four independent cp.async chains per loop trip: one producer warp per scheduler has nobody to hide the
-        // LDS -> address -> LDGSTS latency behind, so the ILP has to come from unrolling.
-        const int nelem = P.npix_pad * KCH;
-        const int in_stride = P.in_stride, npix_pad = P.npix_pad;
-        for (int i = 0; i < P.nkb; ++i) {
-            const int s = i % P.sa;
-            mbar_wait(BAR(A_EMPTY + s), ((i / P.sa) & 1) ^ 1);
-            const uint32_t dst0 = smem_u32(sA + (size_t)s * a_stage_bytes);
-            const __nv_bfloat16 *src0 = P.in + i * BK;
-            for (int e0 = threadIdx.x; e0 < nelem; e0 += 4 * NPROD) {
-                int off[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int e = e0 + u * NPROD;
-                    off[u] = e < nelem ? pix_off[e / KCH] : -2;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int e = e0 + u * NPROD, pixel = e / KCH, ch = e % KCH;
-                    if (off[u] != -2) {
-                        const __nv_bfloat16 *src = off[u] >= 0 ? src0 + (long long)off[u] * in_stride + ch * 8 : P.in;
-                        cp_async16(dst0 + (uint32_t)(ch * npix_pad + pixel) * 16u, src, off[u] >= 0 ? 16u : 0u);
+        // ================= A producers =================
+        // warp w stages plane rows w, w+4, ...; lanes walk the (pixel, 16-byte chunk) pairs of a row, so no index
+        // table and no division is needed.  Publication of k-block i is deferred until k-block i+1 is in flight.
+        const int in_stride = P.in_stride, npix_pad = P.npix_pad, Hi = P.Hi, Wi = P.Wi;
+        int ia = 0;                 // running k-block counter (ring position), continues across tiles
+        int pending = -1;           // stage whose cp.async group is committed but not yet published
+        for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+            const Tile t = decode_tile(P, tile);
+            const __nv_bfloat16 *img = P.in + (long long)t.b * Hi * Wi * in_stride;
+            for (int i = 0; i < P.nkb; ++i, ++ia) {
+                const int s = ia % P.sa;
+                mbar_wait(BAR(A_EMPTY + s), ((ia / P.sa) & 1) ^ 1);
+                const uint32_t dst0 = smem_u32(sA + (size_t)s * a_stage_bytes);
+                const __nv_bfloat16 *src0 = img + i * BK;
+                for (int pl = 0; pl < P.nplanes; ++pl) {
+                    const Plane &q = P.planes[pl];
+                    const int row_elems = q.cols * KCH;
+                    for (int r = warp; r < q.rows; r += 4) {
+                        const int iy = q.ystep * (t.ty0 + r) + q.yoff;
+                        const bool yok = iy >= 0 && iy < Hi;
+                        const __nv_bfloat16 *srow = src0 + (long long)iy * Wi * in_stride;
+                        const uint32_t drow = dst0 + (uint32_t)(q.base + r * q.cols) * 16u;
+                        for (int e = lane; e < row_elems; e += 32) {
+                            const int c = e >> 2, ch = e & 3;
+                            const int ix = q.xstep * (t.tx0 + c) + q.xoff;
+                            const bool ok = yok && ix >= 0 && ix < Wi;
+                            const __nv_bfloat16 *src = ok ? srow + (long long)ix * in_stride + ch * 8 : P.in;
+                            cp_async16(drow + (uint32_t)(ch * npix_pad + c) * 16u, src, ok ? 16u : 0u);
+                        }
                     }
                 }
-            }
-            cp_async_commit();
-            if (i == 0 && threadIdx.x == 0) STAMP(2);
-            if (P.sa == 1) {                  // single-stage ring: publish at once (nothing to overlap with)
-                cp_async_wait<0>();
-                fence_proxy_async();
-                mbar_arrive(BAR(A_FULL));
-            } else if (i >= 1) {              // publish stage i-1 while stage i is in flight
-                cp_async_wait<1>();
-                fence_proxy_async();
-                mbar_arrive(BAR(A_FULL + (i - 1) % P.sa));
+                cp_async_commit();
+                if (P.sa == 1) {                  // single-stage ring: publish at once (nothing to overlap with)
+                    cp_async_wait<0>();
+                    fence_proxy_async();
+                    mbar_arrive(BAR(A_FULL));
+                } else {
+                    if (pending >= 0) {           // publish the previous k-block while this one is in flight
+                        cp_async_wait<1>();
+                        fence_proxy_async();
+                        mbar_arrive(BAR(A_FULL + pending));
+                    }
+                    pending = s;
+                }
             }
         }
-        if (P.sa > 1) {
+        if (pending >= 0) {
             cp_async_wait<0>();
             fence_proxy_async();
-            mbar_arrive(BAR(A_FULL + (P.nkb - 1) % P.sa));
+            mbar_arrive(BAR(A_FULL + pending));
         }
-    } else if (warp == 4) {
+    } else if (warp == MMA_WARP) {
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | (8u << 24);
             const uint32_t a_lbo = (uint32_t)P.npix_pad * 16u, b_lbo = (uint32_t)P.bn * 16u;
             const int nacc = P.nacc, bn = P.bn;
-            int bi = 0;   // running B-stage counter
-            long long wait_a = 0, wait_b = 0;
-            for (int i = 0; i < P.nkb; ++i) {
-                const int s = i % P.sa;
-                long long tw = P.dbg ? clock64() : 0;
-                mbar_wait(BAR(A_FULL + s), (i / P.sa) & 1);
-                if (P.dbg) wait_a += clock64() - tw;
+            int ia = 0, bi = 0, it = 0;
+            for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
+                const Tile t = decode_tile(P, tile);
+                const Phase &ph = P.phases[t.z];
+                const int set = P.nsets == 2 ? (it & 1) : 0;
+                const int use = P.nsets == 2 ? (it >> 1) : it;          // how often this set has been used before
+                mbar_wait(BAR(ACC_EMPTY + set), (use & 1) ^ 1);         // epilogue has drained this accumulator set
                 tc_fence_after();
-                if (i == 0) STAMP(3);
-                const uint32_t a_base = smem_u32(sA + (size_t)s * a_stage_bytes);
-                for (int tp = 0; tp < ph.ntaps; ++tp, ++bi) {
-                    const int sb = bi % P.sb;
-                    tw = P.dbg ? clock64() : 0;
-                    mbar_wait(BAR(B_FULL + sb), (bi / P.sb) & 1);
-                    if (P.dbg) wait_b += clock64() - tw;
+                const uint32_t d_base = tmem_base + (uint32_t)(set * set_cols);
+                for (int i = 0; i < P.nkb; ++i, ++ia) {
+                    const int s = ia % P.sa;
+                    mbar_wait(BAR(A_FULL + s), (ia / P.sa) & 1);
                     tc_fence_after();
-                    if (bi == 0) STAMP(4);
-                    const Tap &tap = ph.taps[tp];
-                    const Plane &q = P.planes[tap.plane];
-                    const uint32_t b_base = smem_u32(sB + (size_t)sb * b_stage_bytes);
-                    const uint32_t a_tap = a_base + (uint32_t)(q.base + tap.sy * q.cols + tap.sx) * 16u;
-                    const uint32_t a_sbo = (uint32_t)q.cols * 16u;
+                    const uint32_t a_base = smem_u32(sA + (size_t)s * a_stage_bytes);
+                    for (int tp = 0; tp < ph.ntaps; ++tp, ++bi) {
+                        const int sb = bi % P.sb;
+                        mbar_wait(BAR(B_FULL + sb), (bi / P.sb) & 1);
+                        tc_fence_after();
+                        const Tap &tap = ph.taps[tp];
+                        const Plane &q = P.planes[tap.plane];
+                        const uint32_t b_base = smem_u32(sB + (size_t)sb * b_stage_bytes);
+                        const uint32_t a_tap = a_base + (uint32_t)(q.base + tap.sy * q.cols + tap.sx) * 16u;
+                        const uint32_t a_sbo = (uint32_t)q.cols * 16u;
 #pragma unroll
-                    for (int k2 = 0; k2 < BK / 16; ++k2) {
-                        const uint64_t db = make_desc(b_base + (uint32_t)k2 * 2u * b_lbo, b_lbo, 128u);
-                        for (int j = 0; j < nacc; ++j) {     // consecutive MMAs target different accumulators
-                            const uint64_t da = make_desc(a_tap + (uint32_t)j * 128u + (uint32_t)k2 * 2u * a_lbo, a_lbo, a_sbo);
-                            tc_mma(tmem_base + (uint32_t)(j * bn), da, db, idesc, (i | tp | k2) ? 1u : 0u);
+                        for (int k2 = 0; k2 < BK / 16; ++k2) {
+                            const uint64_t db = make_desc(b_base + (uint32_t)k2 * 2u * b_lbo, b_lbo, 128u);
+                            for (int j = 0; j < nacc; ++j) {     // consecutive MMAs target different accumulators
+                                const uint64_t da = make_desc(a_tap + (uint32_t)j * 128u + (uint32_t)k2 * 2u * a_lbo, a_lbo, a_sbo);
+                                tc_mma(d_base + (uint32_t)(j * bn), da, db, idesc, (i | tp | k2) ? 1u : 0u);
+                            }
                         }
+                        tc_commit(BAR(B_EMPTY + sb));
                     }
-                    tc_commit(BAR(B_EMPTY + sb));
+                    tc_commit(BAR(A_EMPTY + s));
                 }
-                tc_commit(BAR(A_EMPTY + s));
-            }
-            tc_commit(BAR(ACC_FULL));
-            STAMP(5);
-            if (P.dbg && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 4096) {
-                P.dbg[blockIdx.x * 16 + 8] = wait_a;
-                P.dbg[blockIdx.x * 16 + 9] = wait_b;
+                tc_commit(BAR(ACC_FULL + set));
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == BLOAD_WARP) {
         // ================= B loader (TMA 1-D bulk copies of pre-packed filter blocks) =================
         if (lane == 0) {
             int bi = 0;
             const uint32_t piece = (uint32_t)P.bn * 16u;
-            for (int i = 0; i < P.nkb; ++i)
-                for (int tp = 0; tp < ph.ntaps; ++tp, ++bi) {
-                    const int sb = bi % P.sb;
-                    mbar_wait(BAR(B_EMPTY + sb), ((bi / P.sb) & 1) ^ 1);
-                    mbar_expect_tx(BAR(B_FULL + sb), piece * KCH);
-                    const uint32_t dst = smem_u32(sB + (size_t)sb * b_stage_bytes);
-                    const int wt = ph.taps[tp].wtap;
+            for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+                const Tile t = decode_tile(P, tile);
+                const Phase &ph = P.phases[t.z];
+                for (int i = 0; i < P.nkb; ++i)
+                    for (int tp = 0; tp < ph.ntaps; ++tp, ++bi) {
+                        const int sb = bi % P.sb;
+                        mbar_wait(BAR(B_EMPTY + sb), ((bi / P.sb) & 1) ^ 1);
+                        mbar_expect_tx(BAR(B_FULL + sb), piece * KCH);
+                        const uint32_t dst = smem_u32(sB + (size_t)sb * b_stage_bytes);
+                        const int wt = ph.taps[tp].wtap;
 #pragma unroll
-                    for (int ch = 0; ch < KCH; ++ch) {
-                        const __nv_bfloat16 *src =
-                            P.w + (((long long)wt * P.cin_chunks + (i * KCH + ch)) * P.CoutP + n0) * 8;
-                        bulk_g2s(dst + (uint32_t)ch * piece, src, piece, BAR(B_FULL + sb));
+                        for (int ch = 0; ch < KCH; ++ch) {
+                            const __nv_bfloat16 *src =
+                                P.w + (((long long)wt * P.cin_chunks + (i * KCH + ch)) * P.CoutP + t.n0) * 8;
+                            bulk_g2s(dst + (uint32_t)ch * piece, src, piece, BAR(B_FULL + sb));
+                        }
                     }
-                }
+            }
         }
         __syncwarp();
-    }
-
-    // ================= epilogue: all 8 warps; warp w reads TMEM lanes 32*(w%4).., group w/4 takes every other
-    // accumulator.  y = act(acc*scale + shift + residual) -> bf16 NHWC slice, or fp32 planes (fused decode heads).
-    {
-        mbar_wait<true>(BAR(ACC_FULL), 0);
-        tc_fence_after();
-        if (threadIdx.x == 0) STAMP(6);
-        const int wq = warp & 3, grp = warp >> 2;
+    } else {
+        // ================= epilogue (warps 4..11): warp w reads TMEM lanes 32*(w%4).., group (w-4)/4 takes every
+        // other accumulator.  y = act(acc*scale + shift + residual) -> bf16 NHWC slice, or fp32 planes (heads).
+        const int wq = warp & 3, grp = (warp - EPI_WARP0) >> 2;
         const int r = 4 * wq + (lane >> 3), c = lane & 7;     // MMA row m = 32*wq + lane = 8*r + c
         const int bn = P.bn, Cout = P.Cout, out_stride = P.out_stride, res_stride = P.res_stride, act = P.act;
         const float slope = act == RDFC_ACT_RELU ? 0.f : (act == RDFC_ACT_LEAKY02 ? 0.2f : 1.f);
         const __nv_bfloat16 *res = P.res;
-        for (int j = grp; j < P.nacc; j += 2) {
-            const int yy = ty0 + r, xx = tx0 + 8 * j + c;
-            const int oy = P.oys * yy + ph.oyo, ox = P.oxs * xx + ph.oxo;
-            const bool ok = yy < P.Ht && xx < P.Wt && oy < P.Ho && ox < P.Wo;
-            const long long opix = ((long long)b * P.Ho + oy) * P.Wo + ox;
-            const uint32_t trow = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(j * bn);
-            for (int n = 0; n < bn; n += 16) {
-                uint32_t v[16];
-                tc_ld16(trow + (uint32_t)n, v);   // warp-collective
-                if (!ok || n0 + n >= Cout) continue;
-                float f[16];
+        const float *gscale = P.scale, *gshift = P.shift;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
+            const Tile t = decode_tile(P, tile);
+            const Phase &ph = P.phases[t.z];
+            const int set = P.nsets == 2 ? (it & 1) : 0;
+            const int use = P.nsets == 2 ? (it >> 1) : it;
+            mbar_wait<true>(BAR(ACC_FULL + set), use & 1);
+            tc_fence_after();
+            const int n0 = t.n0;
+            for (int j = grp; j < P.nacc; j += 2) {
+                const int yy = t.ty0 + r, xx = t.tx0 + 8 * j + c;
+                const int oy = P.oys * yy + ph.oyo, ox = P.oxs * xx + ph.oxo;
+                const bool ok = yy < P.Ht && xx < P.Wt && oy < P.Ho && ox < P.Wo;
+                const long long opix = ((long long)t.b * P.Ho + oy) * P.Wo + ox;
+                const uint32_t trow = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(set * set_cols + j * bn);
+                for (int n = 0; n < bn; n += 16) {
+                    uint32_t v[16];
+                    tc_ld16(trow + (uint32_t)n, v);   // warp-collective
+                    if (!ok || n0 + n >= Cout) continue;
+                    float f[16];
+                    const bool full = n0 + n + 16 <= Cout;
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const float4 sc = *reinterpret_cast<const float4 *>(s_scale + n + 4 * q4);
-                    const float4 sh = *reinterpret_cast<const float4 *>(s_shift + n + 4 * q4);
-                    f[4 * q4 + 0] = fmaf(__uint_as_float(v[4 * q4 + 0]), sc.x, sh.x);
-                    f[4 * q4 + 1] = fmaf(__uint_as_float(v[4 * q4 + 1]), sc.y, sh.y);
-                    f[4 * q4 + 2] = fmaf(__uint_as_float(v[4 * q4 + 2]), sc.z, sh.z);
-                    f[4 * q4 + 3] = fmaf(__uint_as_float(v[4 * q4 + 3]), sc.w, sh.w);
-                }
-                if (P.planar) {
-                    // fused decode heads: column q -> its own fp32 plane with its own activation
-                    const long long pp = (long long)oy * P.Wo + ox;
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (full) {                // (scale, shift) vectors are padded to a multiple of 16 by the host? no: guard
+                            if (gscale) sc = __ldg(reinterpret_cast<const float4 *>(gscale + n0 + n) + q4);
+                            if (gshift) sh = __ldg(reinterpret_cast<const float4 *>(gshift + n0 + n) + q4);
+                        } else {
+                            const int cb = n0 + n + 4 * q4;
+                            if (gscale) {
+                                sc.x = cb + 0 < Cout ? __ldg(gscale + cb + 0) : 1.f; sc.y = cb + 1 < Cout ? __ldg(gscale + cb + 1) : 1.f;
+                                sc.z = cb + 2 < Cout ? __ldg(gscale + cb + 2) : 1.f; sc.w = cb + 3 < Cout ? __ldg(gscale + cb + 3) : 1.f;
+                            }
+                            if (gshift) {
+                                sh.x = cb + 0 < Cout ? __ldg(gshift + cb + 0) : 0.f; sh.y = cb + 1 < Cout ? __ldg(gshift + cb + 1) : 0.f;
+                                sh.z = cb + 2 < Cout ? __ldg(gshift + cb + 2) : 0.f; sh.w = cb + 3 < Cout ? __ldg(gshift + cb + 3) : 0.f;
+                            }
+                        }
+                        f[4 * q4 + 0] = fmaf(__uint_as_float(v[4 * q4 + 0]), sc.x, sh.x);
+                        f[4 * q4 + 1] = fmaf(__uint_as_float(v[4 * q4 + 1]), sc.y, sh.y);
+                        f[4 * q4 + 2] = fmaf(__uint_as_float(v[4 * q4 + 2]), sc.z, sh.z);
+                        f[4 * q4 + 3] = fmaf(__uint_as_float(v[4 * q4 + 3]), sc.w, sh.w);
+                    }
+                    if (P.planar) {
+                        // fused decode heads: column q -> its own fp32 plane with its own activation
+                        const long long pp = (long long)oy * P.Wo + ox;
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        if (q < P.ncols) {
-                            const int a = P.act_col[q];
-                            float y = f[q];
-                            if (a == RDFC_ACT_TANH) y = tanhf(y);
-                            else if (a == RDFC_ACT_SIGMOID) y = 1.f / (1.f + expf(-y));
-                            P.plane[q][(long long)b * P.plane_bstride[q] + pp] = y;
+                        for (int q = 0; q < 16; ++q) {
+                            if (q < P.ncols) {
+                                const int a = P.act_col[q];
+                                float y = f[q];
+                                if (a == RDFC_ACT_TANH) y = tanhf(y);
+                                else if (a == RDFC_ACT_SIGMOID) y = 1.f / (1.f + expf(-y));
+                                P.plane[q][(long long)t.b * P.plane_bstride[q] + pp] = y;
+                            }
+                        }
+                        continue;
+                    }
+                    if (res) {
+                        const uint4 *rp = reinterpret_cast<const uint4 *>(res + opix * res_stride + n0 + n);
+                        const uint4 r0 = rp[0], r1 = rp[1];
+                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float2 p2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr[q]));
+                            f[2 * q] += p2.x;
+                            f[2 * q + 1] += p2.y;
                         }
                     }
-                    continue;
-                }
-                if (res) {
-                    const uint4 *rp = reinterpret_cast<const uint4 *>(res + opix * res_stride + n0 + n);
-                    const uint4 r0 = rp[0], r1 = rp[1];
-                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                    if (act <= RDFC_ACT_LEAKY02) {         // none / relu / leaky, branch-free: max(v, slope*v)
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float2 p2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr[q]));
-                        f[2 * q] += p2.x;
-                        f[2 * q + 1] += p2.y;
+                        for (int q = 0; q < 16; ++q) f[q] = fmaxf(f[q], slope * f[q]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) f[q] = act == RDFC_ACT_TANH ? tanhf(f[q]) : 1.f / (1.f + expf(-f[q]));
+                    }
+                    __nv_bfloat16 *op = P.out + opix * out_stride + n0 + n;
+                    if (full) {
+                        uint32_t o[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+                            o[q] = *reinterpret_cast<const uint32_t *>(&h2);
+                        }
+                        uint4 *o4 = reinterpret_cast<uint4 *>(op);
+                        o4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                        o4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                    } else {
+                        const int nvalid = Cout - n0 - n;
+#pragma unroll
+                        for (int q = 0; q < 16; ++q)
+                            if (q < nvalid) op[q] = __float2bfloat16_rn(f[q]);
                     }
                 }
-                if (act <= RDFC_ACT_LEAKY02) {         // none / relu / leaky in one branch-free form: max(v, slope*v)
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) f[q] = fmaxf(f[q], slope * f[q]);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) f[q] = act == RDFC_ACT_TANH ? tanhf(f[q]) : 1.f / (1.f + expf(-f[q]));
-                }
-                uint32_t o[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
-                    o[q] = *reinterpret_cast<const uint32_t *>(&h2);
-                }
-                __nv_bfloat16 *op = P.out + opix * out_stride + n0 + n;
-                if (n0 + n + 16 <= Cout) {
-                    uint4 *o4 = reinterpret_cast<uint4 *>(op);
-                    o4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                    o4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                } else {
-                    const int nvalid = Cout - n0 - n;
-#pragma unroll
-                    for (int q = 0; q < 16; ++q)
-                        if (q < nvalid) op[q] = __float2bfloat16_rn(f[q]);
-                }
             }
+            // this warp is done reading the accumulator set: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + set));
         }
-        tc_fence_before();
-        if (threadIdx.x == 0) STAMP(7);
     }
+    tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols)
                      : "memory");
     }
 }
-
-long long *g_umma_dbg = nullptr;
 
 int next_pow2_cols(int c) {
     int p = 32;
@@ -439,6 +451,8 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     RDFC_REQUIRE(!d->residual.ptr || (d->residual.dtype == RDFC_BF16 && d->residual.pix_stride % 8 == 0 &&
                                       ((uintptr_t)d->residual.ptr % 16) == 0),
                  "UMMA conv: residual must be an aligned bf16 NHWC view");
+    RDFC_REQUIRE((!d->scale || ((uintptr_t)d->scale % 16) == 0) && (!d->shift || ((uintptr_t)d->shift % 16) == 0),
+                 "UMMA conv: scale / shift vectors must be 16-byte aligned");
     const bool k3 = d->kh == 3 && d->kw == 3, k1 = d->kh == 1 && d->kw == 1;
     RDFC_REQUIRE(k3 || k1, "UMMA conv: 3x3 or 1x1 kernels only");
     RDFC_REQUIRE(d->stride == 1 || d->stride == 2, "UMMA conv: stride 1 or 2");
@@ -460,33 +474,40 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
             P.plane[q] = heads->out[q]; P.plane_bstride[q] = heads->out_bstride[q]; P.act_col[q] = heads->act[q];
         }
     }
-    {
-        static long long *dbg = nullptr;
-        if (getenv("RDFC_UMMA_DBG") && !dbg) cudaMalloc(&dbg, 4096 * 16 * sizeof(long long));
-        P.dbg = getenv("RDFC_UMMA_DBG") ? dbg : nullptr;
-        g_umma_dbg = dbg;
-    }
 
     // tile space: output grid for convs, input grid for the sub-pixel phases of a transposed conv
     P.Ht = d->transposed ? d->Hi : d->Ho;
     P.Wt = d->transposed ? d->Wi : d->Wo;
     P.oys = P.oxs = d->transposed ? 2 : 1;
-    // one tcgen05.mma (M=128,K=16) costs max(~76, N/2) cycles (measured, scripts/umma_rate.cu): use the widest N
-    int bn_max = 256;
+    P.nphases = d->transposed ? 4 : 1;
+    // Cout tile.  One tcgen05.mma (M=128, K=16) costs max(~76, N/2) cycles (measured, scripts/umma_rate.cu), so N
+    // should be >= 128; N = 128 rather than 256 leaves room for two accumulator sets of two accumulators in TMEM.
+    int bn_max = 128;
+    if (P.CoutP > 128 && P.CoutP % 128 != 0) bn_max = 256;               // e.g. 160: one tile beats 2 x 80
     if (const char *e = getenv("RDFC_UMMA_BN")) bn_max = atoi(e);        // development knob
     P.bn = P.CoutP < bn_max ? P.CoutP : bn_max;
     while (P.CoutP % P.bn) P.bn -= 16;   // largest multiple of 16 <= bn_max dividing the padded Cout
-    // accumulators per CTA: wide tiles amortise the filter stream; small problems need more CTAs
-    const long long pixels = (long long)P.B * P.Ht * P.Wt;
-    P.nacc = 4;
-    while (P.nacc * P.bn > 512) P.nacc /= 2;   // TMEM: 512 fp32 columns
-    while (P.nacc > 1 && (P.Wt <= 8 * (P.nacc / 2) || pixels / (128 * P.nacc) * (P.CoutP / P.bn) < 2 * sm_count())) P.nacc /= 2;
+    P.n_tiles_n = P.CoutP / P.bn;
+    // accumulators per tile: wide tiles amortise the filter stream (B bytes per MMA ~ 1/NACC); double-buffer TMEM
+    // whenever two sets of >= 2 accumulators fit; small problems need more tiles than SMs.
+    const long long pixels = (long long)P.B * P.Ht * P.Wt * P.nphases;
+    if (2 * 2 * P.bn <= 512) {            // N <= 128: two accumulator sets of 2..4 accumulators
+        P.nsets = 2;
+        P.nacc = 512 / (2 * P.bn) < 4 ? 512 / (2 * P.bn) : 4;
+    } else {                              // wide N (e.g. 160, 256): one set
+        P.nsets = 1;
+        P.nacc = 512 / P.bn < 4 ? 512 / P.bn : 4;
+    }
+    while (P.nacc > 1 && (P.Wt <= 8 * (P.nacc - 1) || pixels / (128 * P.nacc) * P.n_tiles_n < sm_count())) --P.nacc;
     if (d->stride == 2 && !d->transposed && k3 && P.nacc > 2) P.nacc = 2;   // four parity planes: keep the stage small
     if (const char *e = getenv("RDFC_UMMA_NACC")) P.nacc = atoi(e);      // development knob
+    if (const char *e = getenv("RDFC_UMMA_NSETS")) P.nsets = atoi(e);    // development knob
+    if (P.nsets * P.nacc * P.bn > 512) P.nsets = 1;
     const int TW = 8 * P.nacc;
     P.tiles_y = cdiv(P.Ht, TH); P.tiles_x = cdiv(P.Wt, TW);
+    P.ntiles = P.tiles_x * P.tiles_y * P.B * P.nphases * P.n_tiles_n;
 
-    int nphases = 1, base = 0;
+    int base = 0;
     auto add_plane = [&](int ystep, int yoff, int xstep, int xoff, int rows, int cols) {
         P.planes[P.nplanes] = Plane{ystep, yoff, xstep, xoff, rows, cols, base};
         base += rows * cols;
@@ -495,7 +516,6 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     if (d->transposed) {
         // oy = 2*iy - 1 + ky: even rows take ky = 1 (iy = y); odd rows take ky = 0 (iy = y + 1) and ky = 2 (iy = y)
         const int pl = add_plane(1, 0, 1, 0, TH + 1, TW + 1);
-        nphases = 4;
         for (int a = 0; a < 2; ++a)
             for (int bq = 0; bq < 2; ++bq) {
                 Phase &ph = P.phases[a * 2 + bq];
@@ -526,40 +546,31 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
                 ph.taps[ph.ntaps++] = Tap{pl[ky != 1][kx != 1], ky == 2 ? 1 : 0, kx == 2 ? 1 : 0, ky * 3 + kx};
     }
     P.npix_pad = (base + 7) / 8 * 8;
-    P.tmem_cols = next_pow2_cols(P.nacc * P.bn);
+    P.tmem_cols = next_pow2_cols(P.nsets * P.nacc * P.bn);
     RDFC_REQUIRE(P.tmem_cols <= 512, "UMMA conv: accumulators exceed TMEM");
 
     const int a_stage = KCH * P.npix_pad * 16, b_stage = KCH * P.bn * 16;
-    const int fixed = P.npix_pad * 4 + 2 * P.bn * 4 + 8 + (2 * 4 + 2 * 8 + 2) * 8 + 16 + 128;
-    const int budget = 200 * 1024;
-    // A ring first (>= 2 stages whenever there are >= 2 channel blocks: the producers publish stage i while filling
-    // stage i+1), then as many B stages as fit (2..4).
-    const int sa_want = P.nkb < 2 ? 1 : 2;
-    P.sb = 4;
+    const int fixed = (2 * 8 + 2 * 8 + 4) * 8 + 16 + 256;
+    const int budget = 220 * 1024;
+    // A ring first (>= 2 stages: the producers publish k-block i while k-block i+1 is in flight), then B stages (2..6)
+    P.sb = 6;
     if (const char *e = getenv("RDFC_UMMA_SB")) P.sb = atoi(e);          // development knob (<= 8)
-    while (P.sb > 2 && sa_want * a_stage + P.sb * b_stage + fixed > budget) --P.sb;
+    while (P.sb > 2 && 2 * a_stage + P.sb * b_stage + fixed > budget) --P.sb;
     P.sa = (budget - fixed - P.sb * b_stage) / a_stage;
     if (P.sa > 4) P.sa = 4;
     if (const char *e = getenv("RDFC_UMMA_SA")) P.sa = atoi(e) < P.sa ? atoi(e) : P.sa;
-    if (P.sa > P.nkb) P.sa = P.nkb < 1 ? 1 : P.nkb;
-    RDFC_REQUIRE(P.sa >= 1, "UMMA conv: tile does not fit shared memory");
+    RDFC_REQUIRE(P.sa >= 1 && P.sa <= 8 && P.sb >= 1 && P.sb <= 8, "UMMA conv: tile does not fit shared memory");
     const size_t smem = (size_t)P.sa * a_stage + (size_t)P.sb * b_stage + fixed;
     static bool attr_set = false;
     if (!attr_set) {
         RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    dim3 grid(P.tiles_x * P.tiles_y * P.B, P.CoutP / P.bn, nphases);
-    RDFC_REQUIRE(grid.y <= 65535, "UMMA conv: too many Cout tiles");
+    int grid = P.ntiles < sm_count() ? P.ntiles : sm_count();
+    if (const char *e = getenv("RDFC_UMMA_GRID")) grid = atoi(e) < P.ntiles ? atoi(e) : P.ntiles;   // development knob
     conv_umma_kernel<<<grid, NTHREADS, smem, st>>>(P);
     RDFC_CHECK_LAUNCH("conv_umma_kernel");
     return 0;
 }
 
 }  // namespace rdfc
-
-// development aid (not in the public header): copies the per-CTA timestamps of the last instrumented launch
-extern "C" int rdfc_dev_umma_stamps(long long *host, int n_ctas) {
-    if (!rdfc::g_umma_dbg) return -1;
-    return (int)cudaMemcpy(host, rdfc::g_umma_dbg, sizeof(long long) * 16 * n_ctas, cudaMemcpyDeviceToHost);
-}

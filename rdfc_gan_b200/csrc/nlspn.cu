@@ -203,26 +203,25 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) nlspn_prop_rows_kerne
     }
     __syncthreads();
     const uint32_t row_bytes = (uint32_t)W * 4u;
-    auto issue = [&](long long row, int s) {          // thread 0: 25 bulk copies of one row
+    // threads 0..24 each issue ONE plane's bulk copy (a single issuing thread serialises ~25 x 80 cycles per row)
+    auto issue = [&](long long row, int s) {
+        if (x >= 25) return;
         const int b = (int)(row / H), y = (int)(row % H);
         const uint32_t bar = smem_u32(bars + s);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(25u * row_bytes) : "memory");
-        const uint32_t dst = smem_u32(stage_base + (size_t)s * 25 * W);
-        const float *offp = offset + (long long)b * 18 * P + (long long)y * W;
-        const float *affp = aff + (long long)b * 9 * P + (long long)y * W;
-        int slot = 0;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            if (k == 4) continue;                     // the centre tap's offsets are identically zero
-            bulk_g2s(dst + (uint32_t)(slot++) * row_bytes, offp + (long long)(2 * k) * P, row_bytes, bar);
-            bulk_g2s(dst + (uint32_t)(slot++) * row_bytes, offp + (long long)(2 * k + 1) * P, row_bytes, bar);
+        if (x == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(25u * row_bytes) : "memory");
+        const uint32_t dst = smem_u32(stage_base + (size_t)s * 25 * W) + (uint32_t)x * row_bytes;
+        const float *src;
+        if (x < 16) {
+            const int j = x >> 1, k = j < 4 ? j : j + 1;       // slot 2j / 2j+1 <- offset channels 2k / 2k+1
+            src = offset + ((long long)b * 18 + 2 * k + (x & 1)) * P + (long long)y * W;
+        } else {
+            src = aff + ((long long)b * 9 + (x - 16)) * P + (long long)y * W;
         }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) bulk_g2s(dst + (uint32_t)(16 + k) * row_bytes, affp + (long long)k * P, row_bytes, bar);
+        bulk_g2s(dst, src, row_bytes, bar);
     };
-    if (x == 0)
-        for (int s = 0; s < stages; ++s)
-            if (r0 + s < r1) issue(r0 + s, s);
+    for (int s = 0; s < stages; ++s)
+        if (r0 + s < r1) issue(r0 + s, s);
 
     int it = 0;
     for (long long row = r0; row < r1; ++row, ++it) {
@@ -245,7 +244,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) nlspn_prop_rows_kerne
             if (inter) inter[o] = acc;
         }
         __syncthreads();                               // everyone is done reading stage s
-        if (x == 0 && row + stages < r1) issue(row + stages, s);
+        if (row + stages < r1) issue(row + stages, s);
     }
 }
 
@@ -339,7 +338,7 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
             const size_t stage_bytes = (size_t)25 * W * sizeof(float);
             const int nt = (W + 31) / 32 * 32;
             // many small CTAs per SM (1 stage each) hide the bulk-copy latency by interleaving; wide rows get 2 stages
-            int stages = nt <= 320 ? 1 : 2;
+            int stages = 2;
             if (const char *e = getenv("RDFC_NLSPN_STAGES")) stages = atoi(e);
             while (stages > 1 && stages * stage_bytes + 64 > 200 * 1024) --stages;
             const size_t smem = stages * stage_bytes + 64;
@@ -348,7 +347,7 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
             if (rows_ok) {
                 int per_sm = (int)((226 * 1024) / (smem + 1024));
                 if (per_sm * nt > 2048) per_sm = 2048 / nt;
-                if (nt <= 320 && per_sm > 4) per_sm = 4;       // register budget of the <320,4> instantiation
+                if (nt <= 320 && per_sm > 3) per_sm = 3;       // register budget of the <320,3> instantiation (64 regs)
                 if (per_sm < 1) per_sm = 1;
                 if (const char *e = getenv("RDFC_NLSPN_CTAS_PER_SM")) per_sm = atoi(e);
                 const long long total_rows = (long long)nb * H;
@@ -363,7 +362,7 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
         nlspn_prop_rows_kernel<CL, MT, MB><<<(int)nctas, nt, smem, st>>>(cur, off_g, aff_g, dst, it, nb, H, W, stages, rpc); \
     } while (0)
                 if (nt <= 320) {
-                    if (clamp) RDFC_ROWS(true, 320, 4); else RDFC_ROWS(false, 320, 4);
+                    if (clamp) RDFC_ROWS(true, 320, 3); else RDFC_ROWS(false, 320, 3);
                 } else {
                     if (clamp) RDFC_ROWS(true, 1024, 1); else RDFC_ROWS(false, 1024, 1);
                 }

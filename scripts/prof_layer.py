@@ -44,7 +44,7 @@ def conv(B=8, Cin=64, Cout=64, H=228, W=304, k=3, stride=1, transposed=0, in_str
     ms = time_it(lambda: C.check(C.lib.rdfc_conv_forward(ctypes.byref(d), s)))
     taps = k * k / (4 if transposed else 1)
     flops = 2.0 * B * Ho * Wo * Cin * Cout * taps
-    if os.environ.get("RDFC_UMMA_DBG"):
+    if os.environ.get("RDFC_UMMA_DBG") and hasattr(C.lib, "rdfc_dev_umma_stamps"):
         import numpy as np
         n = 1024
         buf = (ctypes.c_longlong * (16 * n))()
