@@ -200,6 +200,36 @@ __global__ void __launch_bounds__(256) conv_smallc_kernel(ConvGeo g) {
 // produces one pixel x 16 output channels per pass and writes them as one 32/64-byte NHWC vector.
 constexpr int ST_TX = 32, ST_TY = 8, ST_MAXC = 4;
 
+// 16 consecutive channels of one pixel: vector stores when the slice is 16-byte aligned, scalar tail otherwise
+__device__ __forceinline__ void store16(float *p, const float (&y)[16], int nvalid, bool vec_ok) {
+    if (vec_ok && nvalid >= 16) {
+        float4 *q = reinterpret_cast<float4 *>(p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < nvalid) p[j] = y[j];
+    }
+}
+__device__ __forceinline__ void store16(__nv_bfloat16 *p, const float (&y)[16], int nvalid, bool vec_ok) {
+    if (vec_ok && nvalid >= 16) {
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
+            o[i] = *reinterpret_cast<const uint32_t *>(&h2);
+        }
+        uint4 *q = reinterpret_cast<uint4 *>(p);
+        q[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        q[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < nvalid) p[j] = __float2bfloat16_rn(y[j]);
+    }
+}
+
 template <typename TOut>
 __global__ void __launch_bounds__(ST_TX *ST_TY) conv_stem_kernel(ConvGeo g) {
     extern __shared__ float st_smem[];
@@ -228,6 +258,7 @@ __global__ void __launch_bounds__(ST_TX *ST_TY) conv_stem_kernel(ConvGeo g) {
         for (int t = 0; t < 9; ++t) v[ci * 9 + t] = s_in[(ci * (ST_TY + 2) + threadIdx.y + t / 3) * (ST_TX + 2) + threadIdx.x + t % 3];
     const long long pix = ((long long)b * g.Ho + y) * g.Wo + x;
     TOut *op = (TOut *)g.out + pix * g.out_stride;
+    const bool vec_ok = ((uintptr_t)g.out % 16) == 0 && (g.out_stride * sizeof(TOut)) % 16 == 0;
     for (int c0 = 0; c0 < g.Cout; c0 += 16) {
         float acc[16];
 #pragma unroll
@@ -243,14 +274,14 @@ __global__ void __launch_bounds__(ST_TX *ST_TY) conv_stem_kernel(ConvGeo g) {
                 acc[4 * j4 + 3] = fmaf(v[q], w.w, acc[4 * j4 + 3]);
             }
         }
+        float y[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int co = c0 + j;
-            if (co < g.Cout) {
-                const float r = acc[j] * (g.scale ? __ldg(g.scale + co) : 1.f) + (g.shift ? __ldg(g.shift + co) : 0.f);
-                stf(op + co, apply_act(r, g.act));
-            }
+            const float r = co < g.Cout ? acc[j] * (g.scale ? __ldg(g.scale + co) : 1.f) + (g.shift ? __ldg(g.shift + co) : 0.f) : 0.f;
+            y[j] = apply_act(r, g.act);
         }
+        store16(op + c0, y, g.Cout - c0, vec_ok);
     }
 }
 

@@ -68,7 +68,14 @@ struct Params {
     long long plane_bstride[16];
     int act_col[16];
     Plane planes[MAX_PLANES];
-    Phase phases[4];
+    // per (phase, tap), precomputed on the host so the MMA / filter-loader threads only add:
+    //   tap_alo / tap_ahi : A-operand shared-memory descriptor of the tap's shifted view, without the stage base
+    //   tap_w             : element offset of the tap's filter block in the packed weights
+    int ntaps[4], oyo[4], oxo[4];
+    uint32_t tap_alo[4][MAX_TAPS], tap_ahi[4][MAX_TAPS];
+    long long tap_w[4][MAX_TAPS];
+    long long w_kb_stride;         // elements between consecutive 32-cin blocks of one tap
+    int b_contig;                  // the 4 cin chunks of a stage are contiguous in the packed weights (one Cout tile)
 };
 
 struct Tile {
@@ -98,19 +105,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug traps after ~4 s instead of hanging the GPU.
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 template <bool kBackoff = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;  // fast path: no clock read, no loop
     const long long t0 = clock64();
     for (;;) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) return;
+        if (mbar_try_wait(bar, parity)) return;
         if (kBackoff) __nanosleep(128);      // long waits: do not steal issue slots from the MMA / producer warps
         if (clock64() - t0 > 8000000000ll) {
             printf("rdfc conv_umma: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
@@ -142,6 +153,32 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
+}
+// descriptors passed as (lo, hi) words: advancing an operand is one 32-bit add on the start-address field
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// all MMAs of one (k-block, tap): BK/16 k-steps x NACC accumulators, fully unrolled
+template <int NACC>
+__device__ __forceinline__ void issue_tap(uint32_t d_base, uint32_t bn, uint32_t a_lo, uint32_t a_hi, uint32_t a_kstep,
+                                          uint32_t b_lo, uint32_t b_hi, uint32_t b_kstep, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+    for (int k2 = 0; k2 < BK / 16; ++k2)
+#pragma unroll
+        for (int j = 0; j < NACC; ++j)      // consecutive MMAs target different accumulators
+            tc_mma2(d_base + (uint32_t)j * bn, a_lo + (uint32_t)j * 8u + (uint32_t)k2 * a_kstep, a_hi,
+                    b_lo + (uint32_t)k2 * b_kstep, b_hi, idesc, k2 ? 1u : acc0);
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -196,14 +233,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         // warp w stages plane rows w, w+4, ...; lanes walk the (pixel, 16-byte chunk) pairs of a row, so no index
         // table and no division is needed.  Publication of k-block i is deferred until k-block i+1 is in flight.
         const int in_stride = P.in_stride, npix_pad = P.npix_pad, Hi = P.Hi, Wi = P.Wi;
-        int ia = 0;                 // running k-block counter (ring position), continues across tiles
+        int s = 0;                  // ring position, continues across tiles
+        uint32_t par = 1;           // parity to wait for on A_EMPTY[s]
         int pending = -1;           // stage whose cp.async group is committed but not yet published
         for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
             const Tile t = decode_tile(P, tile);
             const __nv_bfloat16 *img = P.in + (long long)t.b * Hi * Wi * in_stride;
-            for (int i = 0; i < P.nkb; ++i, ++ia) {
-                const int s = ia % P.sa;
-                mbar_wait(BAR(A_EMPTY + s), ((ia / P.sa) & 1) ^ 1);
+            for (int i = 0; i < P.nkb; ++i) {
+                mbar_wait(BAR(A_EMPTY + s), par);
                 const uint32_t dst0 = smem_u32(sA + (size_t)s * a_stage_bytes);
                 const __nv_bfloat16 *src0 = img + i * BK;
                 for (int pl = 0; pl < P.nplanes; ++pl) {
@@ -236,6 +273,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                     }
                     pending = s;
                 }
+                if (++s == P.sa) { s = 0; par ^= 1u; }
             }
         }
         if (pending >= 0) {
@@ -245,70 +283,81 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         }
     } else if (warp == MMA_WARP) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | (8u << 24);
-            const uint32_t a_lbo = (uint32_t)P.npix_pad * 16u, b_lbo = (uint32_t)P.bn * 16u;
-            const int nacc = P.nacc, bn = P.bn;
-            int ia = 0, bi = 0, it = 0;
-            for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
-                const Tile t = decode_tile(P, tile);
-                const Phase &ph = P.phases[t.z];
-                const int set = P.nsets == 2 ? (it & 1) : 0;
-                const int use = P.nsets == 2 ? (it >> 1) : it;          // how often this set has been used before
-                mbar_wait(BAR(ACC_EMPTY + set), (use & 1) ^ 1);         // epilogue has drained this accumulator set
-                tc_fence_after();
-                const uint32_t d_base = tmem_base + (uint32_t)(set * set_cols);
-                for (int i = 0; i < P.nkb; ++i, ++ia) {
-                    const int s = ia % P.sa;
-                    mbar_wait(BAR(A_FULL + s), (ia / P.sa) & 1);
+        // The whole warp walks the loop convergently (barrier waits, ring bookkeeping); one elected lane issues.  Per
+        // MMA the issue cost is one 32-bit add on a descriptor word: everything tap-dependent comes from P.tap_*.
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | (8u << 24);
+        const uint32_t a_kstep = 2u * (uint32_t)P.npix_pad, b_kstep = 2u * (uint32_t)P.bn;   // 16 channels, in 16-byte units
+        const uint32_t b_hi = (128u >> 4) | (1u << 14);                                     // SBO = 128 B, version bit 46
+        const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | ((uint32_t)P.bn << 16);   // LBO = bn * 16 B
+        const uint32_t a_lo0 = (smem_u32(sA) & 0x3FFFFu) >> 4;
+        const uint32_t a_stage16 = (uint32_t)a_stage_bytes >> 4, b_stage16 = (uint32_t)b_stage_bytes >> 4;
+        const uint32_t bn = (uint32_t)P.bn;
+        const int nacc = P.nacc, sa_n = P.sa, sb_n = P.sb, nkb = P.nkb;
+        int s = 0, sb = 0, it = 0;
+        uint32_t a_par = 0, b_par = 0;
+        for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
+            const Tile t = decode_tile(P, tile);
+            const int z = t.z, ntaps = P.ntaps[z];
+            const int set = P.nsets == 2 ? (it & 1) : 0;
+            const int use = P.nsets == 2 ? (it >> 1) : it;          // how often this set has been used before
+            mbar_wait(BAR(ACC_EMPTY + set), (use & 1) ^ 1);         // epilogue has drained this accumulator set
+            tc_fence_after();
+            const uint32_t d_base = tmem_base + (uint32_t)(set * set_cols);
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(BAR(A_FULL + s), a_par);
+                const uint32_t a_stage_lo = a_lo0 + (uint32_t)s * a_stage16;
+                for (int tp = 0; tp < ntaps; ++tp) {
+                    const uint32_t a_lo = P.tap_alo[z][tp] + a_stage_lo, a_hi = P.tap_ahi[z][tp];
+                    const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage16;
+                    mbar_wait(BAR(B_FULL + sb), b_par);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(sA + (size_t)s * a_stage_bytes);
-                    for (int tp = 0; tp < ph.ntaps; ++tp, ++bi) {
-                        const int sb = bi % P.sb;
-                        mbar_wait(BAR(B_FULL + sb), (bi / P.sb) & 1);
-                        tc_fence_after();
-                        const Tap &tap = ph.taps[tp];
-                        const Plane &q = P.planes[tap.plane];
-                        const uint32_t b_base = smem_u32(sB + (size_t)sb * b_stage_bytes);
-                        const uint32_t a_tap = a_base + (uint32_t)(q.base + tap.sy * q.cols + tap.sx) * 16u;
-                        const uint32_t a_sbo = (uint32_t)q.cols * 16u;
-#pragma unroll
-                        for (int k2 = 0; k2 < BK / 16; ++k2) {
-                            const uint64_t db = make_desc(b_base + (uint32_t)k2 * 2u * b_lbo, b_lbo, 128u);
-                            for (int j = 0; j < nacc; ++j) {     // consecutive MMAs target different accumulators
-                                const uint64_t da = make_desc(a_tap + (uint32_t)j * 128u + (uint32_t)k2 * 2u * a_lbo, a_lbo, a_sbo);
-                                tc_mma(d_base + (uint32_t)(j * bn), da, db, idesc, (i | tp | k2) ? 1u : 0u);
-                            }
+                    if (elect_one()) {
+                        const uint32_t acc0 = (i | tp) ? 1u : 0u;
+                        switch (nacc) {
+                            case 1: issue_tap<1>(d_base, bn, a_lo, a_hi, a_kstep, b_lo, b_hi, b_kstep, idesc, acc0); break;
+                            case 2: issue_tap<2>(d_base, bn, a_lo, a_hi, a_kstep, b_lo, b_hi, b_kstep, idesc, acc0); break;
+                            case 3: issue_tap<3>(d_base, bn, a_lo, a_hi, a_kstep, b_lo, b_hi, b_kstep, idesc, acc0); break;
+                            default: issue_tap<4>(d_base, bn, a_lo, a_hi, a_kstep, b_lo, b_hi, b_kstep, idesc, acc0); break;
                         }
                         tc_commit(BAR(B_EMPTY + sb));
+                        if (tp == ntaps - 1) {
+                            tc_commit(BAR(A_EMPTY + s));
+                            if (i == nkb - 1) tc_commit(BAR(ACC_FULL + set));
+                        }
                     }
-                    tc_commit(BAR(A_EMPTY + s));
+                    __syncwarp();
+                    if (++sb == sb_n) { sb = 0; b_par ^= 1u; }
                 }
-                tc_commit(BAR(ACC_FULL + set));
+                if (++s == sa_n) { s = 0; a_par ^= 1u; }
             }
         }
-        __syncwarp();
     } else if (warp == BLOAD_WARP) {
         // ================= B loader (TMA 1-D bulk copies of pre-packed filter blocks) =================
         if (lane == 0) {
-            int bi = 0;
             const uint32_t piece = (uint32_t)P.bn * 16u;
+            const long long chunk_stride = (long long)P.CoutP * 8;
+            const uint32_t sB0 = smem_u32(sB);
+            const int sb_n = P.sb, nkb = P.nkb;
+            int sb = 0;
+            uint32_t par = 1;
             for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
                 const Tile t = decode_tile(P, tile);
-                const Phase &ph = P.phases[t.z];
-                for (int i = 0; i < P.nkb; ++i)
-                    for (int tp = 0; tp < ph.ntaps; ++tp, ++bi) {
-                        const int sb = bi % P.sb;
-                        mbar_wait(BAR(B_EMPTY + sb), ((bi / P.sb) & 1) ^ 1);
+                const int z = t.z, ntaps = P.ntaps[z];
+                const __nv_bfloat16 *w_n0 = P.w + (long long)t.n0 * 8;
+                for (int i = 0; i < nkb; ++i, w_n0 += P.w_kb_stride)
+                    for (int tp = 0; tp < ntaps; ++tp) {
+                        const __nv_bfloat16 *src = w_n0 + P.tap_w[z][tp];
+                        const uint32_t dst = sB0 + (uint32_t)sb * (uint32_t)b_stage_bytes;
+                        mbar_wait(BAR(B_EMPTY + sb), par);
                         mbar_expect_tx(BAR(B_FULL + sb), piece * KCH);
-                        const uint32_t dst = smem_u32(sB + (size_t)sb * b_stage_bytes);
-                        const int wt = ph.taps[tp].wtap;
+                        if (P.b_contig) {
+                            bulk_g2s(dst, src, piece * KCH, BAR(B_FULL + sb));
+                        } else {
 #pragma unroll
-                        for (int ch = 0; ch < KCH; ++ch) {
-                            const __nv_bfloat16 *src =
-                                P.w + (((long long)wt * P.cin_chunks + (i * KCH + ch)) * P.CoutP + t.n0) * 8;
-                            bulk_g2s(dst + (uint32_t)ch * piece, src, piece, BAR(B_FULL + sb));
+                            for (int ch = 0; ch < KCH; ++ch)
+                                bulk_g2s(dst + (uint32_t)ch * piece, src + ch * chunk_stride, piece, BAR(B_FULL + sb));
                         }
+                        if (++sb == sb_n) { sb = 0; par ^= 1u; }
                     }
             }
         }
@@ -325,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         int it = 0;
         for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
             const Tile t = decode_tile(P, tile);
-            const Phase &ph = P.phases[t.z];
+            const int oyo = P.oyo[t.z], oxo = P.oxo[t.z];
             const int set = P.nsets == 2 ? (it & 1) : 0;
             const int use = P.nsets == 2 ? (it >> 1) : it;
             mbar_wait<true>(BAR(ACC_FULL + set), use & 1);
@@ -333,7 +382,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
             const int n0 = t.n0;
             for (int j = grp; j < P.nacc; j += 2) {
                 const int yy = t.ty0 + r, xx = t.tx0 + 8 * j + c;
-                const int oy = P.oys * yy + ph.oyo, ox = P.oxs * xx + ph.oxo;
+                const int oy = P.oys * yy + oyo, ox = P.oxs * xx + oxo;
                 const bool ok = yy < P.Ht && xx < P.Wt && oy < P.Ho && ox < P.Wo;
                 const long long opix = ((long long)t.b * P.Ho + oy) * P.Wo + ox;
                 const uint32_t trow = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(set * set_cols + j * bn);
@@ -507,6 +556,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     P.tiles_y = cdiv(P.Ht, TH); P.tiles_x = cdiv(P.Wt, TW);
     P.ntiles = P.tiles_x * P.tiles_y * P.B * P.nphases * P.n_tiles_n;
 
+    Phase phases[4] = {};
     int base = 0;
     auto add_plane = [&](int ystep, int yoff, int xstep, int xoff, int rows, int cols) {
         P.planes[P.nplanes] = Plane{ystep, yoff, xstep, xoff, rows, cols, base};
@@ -518,7 +568,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
         const int pl = add_plane(1, 0, 1, 0, TH + 1, TW + 1);
         for (int a = 0; a < 2; ++a)
             for (int bq = 0; bq < 2; ++bq) {
-                Phase &ph = P.phases[a * 2 + bq];
+                Phase &ph = phases[a * 2 + bq];
                 ph.oyo = a; ph.oxo = bq; ph.ntaps = 0;
                 for (int ky = 0; ky < 3; ++ky)
                     for (int kx = 0; kx < 3; ++kx) {
@@ -528,24 +578,40 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
             }
     } else if (d->stride == 1) {
         const int pl = add_plane(1, -d->pad, 1, -d->pad, TH + d->kh - 1, TW + d->kw - 1);
-        Phase &ph = P.phases[0];
+        Phase &ph = phases[0];
         for (int ky = 0; ky < d->kh; ++ky)
             for (int kx = 0; kx < d->kw; ++kx) ph.taps[ph.ntaps++] = Tap{pl, ky, kx, ky * d->kw + kx};
     } else if (k1) {
         const int pl = add_plane(2, 0, 2, 0, TH, TW);
-        P.phases[0].taps[P.phases[0].ntaps++] = Tap{pl, 0, 0, 0};
+        phases[0].taps[phases[0].ntaps++] = Tap{pl, 0, 0, 0};
     } else {
         // iy = 2*oy - 1 + ky: ky = 1 reads the even-row plane; ky = 0 / 2 read the odd-row plane (rows oy-1 / oy)
         int pl[2][2];
         for (int py = 0; py < 2; ++py)
             for (int px = 0; px < 2; ++px)
                 pl[py][px] = add_plane(2, py ? -1 : 0, 2, px ? -1 : 0, TH + py, TW + px);
-        Phase &ph = P.phases[0];
+        Phase &ph = phases[0];
         for (int ky = 0; ky < 3; ++ky)
             for (int kx = 0; kx < 3; ++kx)
                 ph.taps[ph.ntaps++] = Tap{pl[ky != 1][kx != 1], ky == 2 ? 1 : 0, kx == 2 ? 1 : 0, ky * 3 + kx};
     }
     P.npix_pad = (base + 7) / 8 * 8;
+    RDFC_REQUIRE(P.npix_pad < (1 << 14), "UMMA conv: staged halo too large for the descriptor LBO field");
+    P.w_kb_stride = (long long)KCH * P.CoutP * 8;
+    P.b_contig = P.n_tiles_n == 1;
+    for (int z = 0; z < P.nphases; ++z) {
+        const Phase &ph = phases[z];
+        P.ntaps[z] = ph.ntaps; P.oyo[z] = ph.oyo; P.oxo[z] = ph.oxo;
+        for (int tp = 0; tp < ph.ntaps; ++tp) {
+            const Tap &tap = ph.taps[tp];
+            const Plane &q = P.planes[tap.plane];
+            // no-swizzle K-major descriptor: start = tap's shifted view (16-byte units), LBO = cin-chunk pitch,
+            // SBO = plane row pitch (8 pixels of a row form one core matrix), bit 46 = descriptor version
+            P.tap_alo[z][tp] = (uint32_t)(q.base + tap.sy * q.cols + tap.sx) | ((uint32_t)P.npix_pad << 16);
+            P.tap_ahi[z][tp] = (uint32_t)q.cols | (1u << 14);
+            P.tap_w[z][tp] = (long long)tap.wtap * P.cin_chunks * P.CoutP * 8;
+        }
+    }
     P.tmem_cols = next_pow2_cols(P.nsets * P.nacc * P.bn);
     RDFC_REQUIRE(P.tmem_cols <= 512, "UMMA conv: accumulators exceed TMEM");
 

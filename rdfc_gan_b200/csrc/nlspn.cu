@@ -52,13 +52,13 @@ __global__ void __launch_bounds__(TX *TY) nlspn_affinity_kernel(const float *__r
                                                                 const float *__restrict__ aff_scale, int affinity,
                                                                 int conf_prop, float *__restrict__ offset,
                                                                 float *__restrict__ aff, int H, int W) {
-    __shared__ float s_w[24 * 72];
+    __shared__ __align__(16) float s_w[72 * 24];     // [(ci*9 + tap)][24 outputs]: one LDS.128 feeds 4 FMAs
     __shared__ float s_b[24];
     __shared__ float s_g[8][TY + 2][TX + 2];
     const int tid = threadIdx.y * TX + threadIdx.x;
     const int b = blockIdx.z, x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const long long P = (long long)H * W;
-    for (int e = tid; e < 24 * 72; e += TX * TY) s_w[e] = conv_w[e];
+    for (int e = tid; e < 24 * 72; e += TX * TY) s_w[(e % 72) * 24 + e / 72] = conv_w[e];
     if (tid < 24) s_b[tid] = conv_b[tid];
     for (int e = tid; e < 8 * (TY + 2) * (TX + 2); e += TX * TY) {
         const int c = e / ((TY + 2) * (TX + 2)), r = e % ((TY + 2) * (TX + 2));
@@ -78,8 +78,15 @@ __global__ void __launch_bounds__(TX *TY) nlspn_affinity_kernel(const float *__r
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
             const float g = s_g[ci][threadIdx.y + t / 3][threadIdx.x + t % 3];
+            const float4 *w4 = reinterpret_cast<const float4 *>(s_w + (ci * 9 + t) * 24);
 #pragma unroll
-            for (int c = 0; c < 24; ++c) o[c] = fmaf(s_w[c * 72 + ci * 9 + t], g, o[c]);
+            for (int c4 = 0; c4 < 6; ++c4) {
+                const float4 w = w4[c4];
+                o[4 * c4 + 0] = fmaf(w.x, g, o[4 * c4 + 0]);
+                o[4 * c4 + 1] = fmaf(w.y, g, o[4 * c4 + 1]);
+                o[4 * c4 + 2] = fmaf(w.z, g, o[4 * c4 + 2]);
+                o[4 * c4 + 3] = fmaf(w.w, g, o[4 * c4 + 3]);
+            }
         }
 
     const float scale = __ldg(aff_scale);

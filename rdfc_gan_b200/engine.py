@@ -282,9 +282,11 @@ class GeneratorEngine:
             pw = self._pack_nlspn(precision)
             plan.keep.append(pw)
             aff_mode, conf_prop, preserve, T = C.AFFINITY[pl.affinity], int(bool(pl.conf_prop)), int(bool(pl.preserve_input)), pl.prop_time
+            plan.names.append('nlspn_affinity')
             plan.steps.append(lambda s: C.check(C.lib.rdfc_nlspn_affinity_forward(
                 C.ptr(plan.guide), C.ptr(plan.conf), C.ptr(pw.weight), C.ptr(pw.shift), C.ptr(pw.scale), aff_mode, conf_prop,
                 C.ptr(plan.offset), C.ptr(plan.aff), B, H, W, s)))
+            plan.names.append(f'nlspn_propagate x{T}')
             plan.steps.append(lambda s: C.check(C.lib.rdfc_nlspn_propagate_forward(
                 C.ptr(plan.pred_init), C.ptr(plan.offset), C.ptr(plan.aff), C.ptr(plan.depth) if preserve else None, preserve,
                 C.ptr(plan.d2raw), C.ptr(plan.scratch), None, B, H, W, T, 0, s)))
@@ -292,6 +294,7 @@ class GeneratorEngine:
             d2src = plan.d2raw
         else:
             d2src = plan.pred_init
+        plan.names.append('fuse_depth')
         plan.steps.append(lambda s: C.check(C.lib.rdfc_fuse_depth_forward(
             C.ptr(plan.d1), C.ptr(plan.c1), C.ptr(d2src), C.ptr(plan.conf), C.ptr(plan.d2), C.ptr(plan.pred), n, s)))
         plan.n_launch += 1
@@ -332,6 +335,7 @@ class GeneratorEngine:
                 q += 1
         d.ncols = q
         plan.keep.append((d, pk))
+        plan.names.append(f'heads {name} {Ctot}->{q}')
         plan.steps.append(lambda s, d=d: C.check(C.lib.rdfc_heads_forward(ctypes.byref(d), s)))
         plan.n_launch += 1
 
@@ -348,6 +352,7 @@ class GeneratorEngine:
         def stats(v, Cc, unbiased, want_std):
             part, mean, rstd = f32(B, nchunk, Cc, 2), f32(B, Cc), f32(B, Cc)
             plan.keep += [part, mean, rstd]
+            plan.names.append(f'instnorm_stats {Cc}ch {Hh}x{Ww}')
             plan.steps.append(lambda s: C.check(C.lib.rdfc_instnorm_stats(
                 ctypes.byref(v), B, Hh, Ww, 1e-5, unbiased, want_std, C.ptr(part), C.ptr(mean), C.ptr(rstd), s)))
             plan.n_launch += 2
@@ -368,6 +373,7 @@ class GeneratorEngine:
                      xr, (gwbw, 0, 2 * Cx), 1, hin=hw, hout=hw)
                 vgw, vbw = C.view(gwbw, Cx, 0), C.view(gwbw, Cx, Cx)
             plan.keep += [vgb, vgw, vbw, gb]
+            plan.names.append(f'wadain_apply {Cx}ch {Hh}x{Ww}')
             plan.steps.append(lambda s: C.check(C.lib.rdfc_wadain_apply(
                 ctypes.byref(vx), ctypes.byref(vgb), ctypes.byref(vgw) if vgw is not None else None,
                 ctypes.byref(vbw) if vbw is not None else None, C.ptr(mean), C.ptr(rstd), ctypes.byref(vout), B, Hh, Ww, s)))
@@ -376,6 +382,7 @@ class GeneratorEngine:
             assert Cx == Cd, "AdaIN needs equal channel counts (model_utils.py:107)"
             cm, cs = stats(vx, Cx, 1, 1)
             sm, ss = stats(vd, Cd, 1, 1)
+            plan.names.append(f'adain_apply {Cx}ch {Hh}x{Ww}')
             plan.steps.append(lambda s: C.check(C.lib.rdfc_adain_apply(
                 ctypes.byref(vx), C.ptr(cm), C.ptr(cs), C.ptr(sm), C.ptr(ss), ctypes.byref(vout), B, Hh, Ww, s)))
             plan.n_launch += 1
@@ -385,6 +392,7 @@ class GeneratorEngine:
                 mean, rstd = stats(v, Cc, 0, 0)
                 vo = C.view(both, Cc, c0)
                 plan.keep.append(vo)
+                plan.names.append(f'norm_apply {Cc}ch {Hh}x{Ww}')
                 plan.steps.append(lambda s, v=v, mean=mean, rstd=rstd, vo=vo: C.check(C.lib.rdfc_norm_apply(
                     ctypes.byref(v), C.ptr(mean), C.ptr(rstd), ctypes.byref(vo), B, Hh, Ww, s)))
                 plan.n_launch += 1
