@@ -4,6 +4,7 @@
 namespace rdfc {
 int conv_simt_forward(const rdfc_conv_desc *d, cudaStream_t st);
 int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads);
+int conv_umma_read_dbg(long long *host, int n);
 }  // namespace rdfc
 
 using namespace rdfc;
@@ -41,3 +42,6 @@ extern "C" int rdfc_heads_forward(const rdfc_heads_desc *h, void *stream) {
     d.weight = h->weight; d.scale = nullptr; d.shift = h->shift;
     return conv_umma_forward(&d, (cudaStream_t)stream, h);
 }
+
+// development aid (not part of the public ABI): role timers of the last conv_umma launch under RDFC_UMMA_DBG=1
+extern "C" int rdfc_dev_umma_timers(long long *host, int n) { return conv_umma_read_dbg(host, n); }

@@ -34,10 +34,15 @@ namespace {
 constexpr int BK = 32;            // input channels per A stage (2 MMAs of K=16)
 constexpr int KCH = BK / 8;       // 16-byte cin chunks per stage
 constexpr int TH = 16;            // tile rows (= 8-row groups of one M=128 MMA)
-constexpr int NPROD = 128;        // A producer threads (warps 0-3)
-constexpr int EPI_WARP0 = 4, NEPI_WARPS = 8, MMA_WARP = 12, BLOAD_WARP = 13;
-constexpr int NTHREADS = 14 * 32;
+// 16 warps: the register file is split per scheduler (16K registers each), so 4 warps per scheduler leave 128
+// registers per thread; 18 warps (5 on two schedulers) would cap every thread at 96 and spill the epilogue.
+constexpr int NPROD_WARPS = 6, NPROD = NPROD_WARPS * 32;   // A producer threads (warps 0-5)
+constexpr int PIXPASS = NPROD / 4;                         // pixels staged per pass of the producer threads (48)
+constexpr int JMAX = 24;          // pixel slots per producer thread and k-block: a stage holds <= JMAX * PIXPASS pixels
+constexpr int MMA_WARP = 6, BLOAD_WARP = 7, EPI_WARP0 = 8, NEPI_WARPS = 8;
+constexpr int NTHREADS = 16 * 32;
 constexpr int MAX_PLANES = 4, MAX_TAPS = 9;
+constexpr int BAR_BYTES = (2 * 8 + 2 * 16 + 4) * 8 + 16;   // mbarriers for <= 8 A stages, <= 16 B stages, 2+2 accumulator sets; TMEM slot
 
 struct Plane {
     int ystep, yoff, xstep, xoff;  // input pixel = (ystep*(ty0+r) + yoff, xstep*(tx0+c) + xoff)
@@ -62,7 +67,7 @@ struct Params {
     const __nv_bfloat16 *res;
     int res_stride;
     const float *scale, *shift;
-    int act, nacc, bn, sa, sb, npix_pad, nplanes, tmem_cols, nsets;
+    int act, nacc, bn, sa, sb, npix, npix_pad, nplanes, tmem_cols, nsets;
     int planar, ncols;             // planar != 0: fp32 output planes, one per output column (fused decode heads)
     float *plane[16];
     long long plane_bstride[16];
@@ -74,7 +79,11 @@ struct Params {
     int ntaps[4], oyo[4], oxo[4];
     uint32_t tap_alo[4][MAX_TAPS], tap_ahi[4][MAX_TAPS];
     long long tap_w[4][MAX_TAPS];
+    int dbg_flags;                 // development aid (RDFC_UMMA_SKIP): 1 = no output stores, 2 = no TMEM loads
+    long long *dbg;                // development aid: per-CTA role timers (RDFC_UMMA_DBG=1), else nullptr
     long long w_kb_stride;         // elements between consecutive 32-cin blocks of one tap
+    int gtaps;                     // filter taps per B stage (3 for 3x3 convs: one wait / commit per filter row)
+    int vec32;                     // output (and residual) slices are 32-byte aligned: 256-bit stores / loads
     int b_contig;                  // the 4 cin chunks of a stage are contiguous in the packed weights (one Cout tile)
 };
 
@@ -180,6 +189,22 @@ __device__ __forceinline__ void issue_tap(uint32_t d_base, uint32_t bn, uint32_t
             tc_mma2(d_base + (uint32_t)j * bn, a_lo + (uint32_t)j * 8u + (uint32_t)k2 * a_kstep, a_hi,
                     b_lo + (uint32_t)k2 * b_kstep, b_hi, idesc, k2 ? 1u : acc0);
 }
+// issue only; the registers are valid after tc_wait_ld(v)
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+// the "+r" operands tie every later use of v to this wait (the compiler may not hoist them above it)
+__device__ __forceinline__ void tc_wait_ld(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -195,10 +220,37 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes,
            (1ull << 46);
 }
 
+// opaque register copy: stops ptxas from re-reading a kernel parameter from the constant bank inside hot loops (with a
+// ~200 KB shared-memory carve-out an LDC / local-memory access costs hundreds of cycles there)
+__device__ __forceinline__ int keep(int x) { asm volatile("" : "+r"(x)); return x; }
+__device__ __forceinline__ uint32_t keep(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
+__device__ __forceinline__ void st_global_v8(void *p, const uint32_t (&o)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                 "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void *p, uint32_t (&o)[8]) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
+                 : "l"(p));
+}
+
+// role timers (development aid): accumulate clock64() deltas only when P.dbg is set
+#ifdef RDFC_UMMA_TIMERS       // compile-time: the 64-bit accumulators cost registers in every role
+#define DBG_ON (P.dbg != nullptr)
+#else
+#define DBG_ON false
+#endif
+#define DBG_T0() const long long _t0 = DBG_ON ? clock64() : 0
+#define DBG_ACC(var) if (DBG_ON) var += clock64() - _t0
+
+// kGeneral = false: the hot variant (bf16 NHWC output, act in {none, ReLU, LeakyReLU}); true adds the planar decode-head
+// outputs and tanh / sigmoid, whose code would otherwise cost the hot epilogue registers.
+template <bool kGeneral>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a_stage_bytes = KCH * P.npix_pad * 16, b_stage_bytes = KCH * P.bn * 16;
+    const int a_stage_bytes = KCH * P.npix_pad * 16, b_tap_bytes = KCH * P.bn * 16, b_stage_bytes = P.gtaps * b_tap_bytes;
     unsigned char *sA = smem;
     unsigned char *sB = sA + (size_t)P.sa * a_stage_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)P.sb * b_stage_bytes);
@@ -208,6 +260,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     const int A_FULL = 0, A_EMPTY = P.sa, B_FULL = 2 * P.sa, B_EMPTY = 2 * P.sa + P.sb, ACC_FULL = 2 * P.sa + 2 * P.sb,
               ACC_EMPTY = ACC_FULL + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + ACC_EMPTY + 2);
+    // per-channel epilogue vectors, padded to CoutP with (1, 0): 16-byte aligned after the barrier block
+    float *s_scale = reinterpret_cast<float *>(sB + (size_t)P.sb * b_stage_bytes + BAR_BYTES);
+    float *s_shift = s_scale + P.CoutP;
+    uint2 *s_tap = reinterpret_cast<uint2 *>(s_shift + P.CoutP);      // [phase][tap] A-descriptor words (lo, hi)
+    if (threadIdx.x < 4 * MAX_TAPS)
+        s_tap[threadIdx.x] = make_uint2(P.tap_alo[threadIdx.x / MAX_TAPS][threadIdx.x % MAX_TAPS],
+                                        P.tap_ahi[threadIdx.x / MAX_TAPS][threadIdx.x % MAX_TAPS]);
+    for (int i = threadIdx.x; i < P.CoutP; i += NTHREADS) {
+        s_scale[i] = (P.scale && i < P.Cout) ? P.scale[i] : 1.f;
+        s_shift[i] = (P.shift && i < P.Cout) ? P.shift[i] : 0.f;
+    }
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
@@ -228,99 +291,141 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     const int set_cols = P.nacc * P.bn;
 
-    if (warp < 4) {
+    if (warp < NPROD_WARPS) {
         // ================= A producers =================
-        // warp w stages plane rows w, w+4, ...; lanes walk the (pixel, 16-byte chunk) pairs of a row, so no index
-        // table and no division is needed.  Publication of k-block i is deferred until k-block i+1 is in flight.
-        const int in_stride = P.in_stride, npix_pad = P.npix_pad, Hi = P.Hi, Wi = P.Wi;
+        // Thread t owns 16-byte chunk (t & 3) of pixel slots (t >> 2) + PIXPASS * j of every stage.  Which plane pixel a slot
+        // is never changes, so its plane-relative input coordinates are decoded once per kernel; per tile they become
+        // a byte offset into the image + a validity bit (outside the image = the conv zero padding); per k-block a
+        // slot costs one add and one cp.async.  Publication of k-block i is deferred until k-block i+LAG is in flight.
+        const int ch = threadIdx.x & 3, p0 = threadIdx.x >> 2;
+        const int nj = (P.npix + PIXPASS - 1) / PIXPASS;
+        uint32_t rel2[JMAX / 2];    // per slot 16 bits: (plane-relative input row + 1) | (column + 1) << 8 ; 0xffff = unused
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) {
+            const int p = j * PIXPASS + p0;
+            uint32_t v = 0xffffu;
+            if (j < nj && p < P.npix) {
+                int pl = 0;
+                while (pl + 1 < P.nplanes && p >= P.planes[pl + 1].base) ++pl;
+                const Plane &q = P.planes[pl];
+                const int r = (p - q.base) / q.cols, c = (p - q.base) % q.cols;
+                v = (uint32_t)(q.ystep * r + q.yoff + 1) | ((uint32_t)(q.xstep * c + q.xoff + 1) << 8);
+            }
+            if (j & 1) rel2[j >> 1] |= v << 16; else rel2[j >> 1] = v;
+        }
+        const int ystep = keep(P.planes[0].ystep), xstep = keep(P.planes[0].xstep);     // the same for every plane of a layer
+        const int Hi = keep(P.Hi), Wi = keep(P.Wi), in_stride = keep(P.in_stride), nkb = keep(P.nkb), sa_n = keep(P.sa);
+        const uint32_t dst_thread = smem_u32(sA) + (uint32_t)(ch * P.npix_pad + p0) * 16u;
+        const int lag = P.sa >= 3 ? 2 : 1;      // cp.async groups kept in flight before the oldest is published
         int s = 0;                  // ring position, continues across tiles
         uint32_t par = 1;           // parity to wait for on A_EMPTY[s]
-        int pending = -1;           // stage whose cp.async group is committed but not yet published
+        long long t_wait_empty = 0, t_issue = 0, t_wait_group = 0;
+        int issued = 0;             // k-blocks committed so far
+        int pub = 0;                // next stage to publish
         for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
             const Tile t = decode_tile(P, tile);
-            const __nv_bfloat16 *img = P.in + (long long)t.b * Hi * Wi * in_stride;
-            for (int i = 0; i < P.nkb; ++i) {
-                mbar_wait(BAR(A_EMPTY + s), par);
-                const uint32_t dst0 = smem_u32(sA + (size_t)s * a_stage_bytes);
-                const __nv_bfloat16 *src0 = img + i * BK;
-                for (int pl = 0; pl < P.nplanes; ++pl) {
-                    const Plane &q = P.planes[pl];
-                    const int row_elems = q.cols * KCH;
-                    for (int r = warp; r < q.rows; r += 4) {
-                        const int iy = q.ystep * (t.ty0 + r) + q.yoff;
-                        const bool yok = iy >= 0 && iy < Hi;
-                        const __nv_bfloat16 *srow = src0 + (long long)iy * Wi * in_stride;
-                        const uint32_t drow = dst0 + (uint32_t)(q.base + r * q.cols) * 16u;
-                        for (int e = lane; e < row_elems; e += 32) {
-                            const int c = e >> 2, ch = e & 3;
-                            const int ix = q.xstep * (t.tx0 + c) + q.xoff;
-                            const bool ok = yok && ix >= 0 && ix < Wi;
-                            const __nv_bfloat16 *src = ok ? srow + (long long)ix * in_stride + ch * 8 : P.in;
-                            cp_async16(drow + (uint32_t)(ch * npix_pad + c) * 16u, src, ok ? 16u : 0u);
-                        }
-                    }
-                }
+            const char *img = reinterpret_cast<const char *>(P.in + (long long)t.b * Hi * Wi * in_stride) + ch * 16;
+            const int y0 = ystep * t.ty0 - 1, x0 = xstep * t.tx0 - 1;
+            uint32_t off[JMAX];
+            uint32_t vmask = 0;
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) {
+                const uint32_t rj = (rel2[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+                const int iy = y0 + (int)(rj & 0xffu), ix = x0 + (int)(rj >> 8);
+                const bool ok = rj != 0xffffu && (unsigned)iy < (unsigned)Hi && (unsigned)ix < (unsigned)Wi;
+                off[j] = ok ? (uint32_t)((iy * Wi + ix) * in_stride) * 2u : 0u;
+                vmask |= ok ? (1u << j) : 0u;
+            }
+            for (int i = 0; i < nkb; ++i, img += BK * 2) {
+                { DBG_T0(); mbar_wait(BAR(A_EMPTY + s), par); DBG_ACC(t_wait_empty); }
+                const long long _ti = DBG_ON ? clock64() : 0;
+                const uint32_t dst = dst_thread + (uint32_t)s * (uint32_t)a_stage_bytes;
+#pragma unroll
+                for (int j = 0; j < JMAX; ++j)
+                    if (j < nj && ((rel2[j >> 1] >> (16 * (j & 1))) & 0xffffu) != 0xffffu)
+                        cp_async16(dst + (uint32_t)j * (uint32_t)(PIXPASS * 16), img + off[j], (vmask >> j) & 1u ? 16u : 0u);
                 cp_async_commit();
-                if (P.sa == 1) {                  // single-stage ring: publish at once (nothing to overlap with)
-                    cp_async_wait<0>();
+                if (DBG_ON) t_issue += clock64() - _ti;
+                ++issued;
+                if (issued > lag) {               // publish the oldest k-block in flight
+                    { DBG_T0(); if (lag == 2) cp_async_wait<2>(); else cp_async_wait<1>(); DBG_ACC(t_wait_group); }
                     fence_proxy_async();
-                    mbar_arrive(BAR(A_FULL));
-                } else {
-                    if (pending >= 0) {           // publish the previous k-block while this one is in flight
-                        cp_async_wait<1>();
-                        fence_proxy_async();
-                        mbar_arrive(BAR(A_FULL + pending));
-                    }
-                    pending = s;
+                    mbar_arrive(BAR(A_FULL + pub));
+                    if (++pub == sa_n) pub = 0;
                 }
-                if (++s == P.sa) { s = 0; par ^= 1u; }
+                if (++s == sa_n) { s = 0; par ^= 1u; }
             }
         }
-        if (pending >= 0) {
+        // drain: publish what is still in flight, oldest first
+        const int left = issued < lag ? issued : lag;
+        if (left == 2) {
+            cp_async_wait<1>();
+            fence_proxy_async();
+            mbar_arrive(BAR(A_FULL + pub));
+            if (++pub == P.sa) pub = 0;
+        }
+        if (left >= 1) {
             cp_async_wait<0>();
             fence_proxy_async();
-            mbar_arrive(BAR(A_FULL + pending));
+            mbar_arrive(BAR(A_FULL + pub));
+        }
+        if (DBG_ON && threadIdx.x == 0) {
+            P.dbg[blockIdx.x * 16 + 6] = t_wait_empty; P.dbg[blockIdx.x * 16 + 7] = t_issue; P.dbg[blockIdx.x * 16 + 8] = t_wait_group;
         }
     } else if (warp == MMA_WARP) {
         // ================= MMA issuer =================
         // The whole warp walks the loop convergently (barrier waits, ring bookkeeping); one elected lane issues.  Per
-        // MMA the issue cost is one 32-bit add on a descriptor word: everything tap-dependent comes from P.tap_*.
+        // MMA the issue cost is one 32-bit add on a descriptor word; the per-tap descriptor words come from the
+        // shared-memory table and are fetched before the wait on the filter stage.
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | (8u << 24);
-        const uint32_t a_kstep = 2u * (uint32_t)P.npix_pad, b_kstep = 2u * (uint32_t)P.bn;   // 16 channels, in 16-byte units
+        const uint32_t a_kstep = keep(2u * (uint32_t)P.npix_pad), b_kstep = keep(2u * (uint32_t)P.bn);   // 16 channels, 16-byte units
         const uint32_t b_hi = (128u >> 4) | (1u << 14);                                     // SBO = 128 B, version bit 46
-        const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | ((uint32_t)P.bn << 16);   // LBO = bn * 16 B
-        const uint32_t a_lo0 = (smem_u32(sA) & 0x3FFFFu) >> 4;
-        const uint32_t a_stage16 = (uint32_t)a_stage_bytes >> 4, b_stage16 = (uint32_t)b_stage_bytes >> 4;
-        const uint32_t bn = (uint32_t)P.bn;
-        const int nacc = P.nacc, sa_n = P.sa, sb_n = P.sb, nkb = P.nkb;
+        const uint32_t b_lo0 = keep(((smem_u32(sB) & 0x3FFFFu) >> 4) | ((uint32_t)P.bn << 16));   // LBO = bn * 16 B
+        const uint32_t a_lo0 = keep((smem_u32(sA) & 0x3FFFFu) >> 4);
+        const uint32_t a_stage16 = keep((uint32_t)a_stage_bytes >> 4), b_stage16 = keep((uint32_t)b_stage_bytes >> 4);
+        const uint32_t b_tap16 = keep((uint32_t)b_tap_bytes >> 4);
+        const uint32_t bn = keep((uint32_t)P.bn);
+        const int nacc = keep(P.nacc), sa_n = keep(P.sa), sb_n = keep(P.sb), nkb = keep(P.nkb), gtaps = keep(P.gtaps);
+        const int nsets = keep(P.nsets);
         int s = 0, sb = 0, it = 0;
         uint32_t a_par = 0, b_par = 0;
+        long long t_acc = 0, t_a = 0, t_b = 0;
+        const long long t_start = DBG_ON ? clock64() : 0;
         for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
             const Tile t = decode_tile(P, tile);
-            const int z = t.z, ntaps = P.ntaps[z];
-            const int set = P.nsets == 2 ? (it & 1) : 0;
-            const int use = P.nsets == 2 ? (it >> 1) : it;          // how often this set has been used before
-            mbar_wait(BAR(ACC_EMPTY + set), (use & 1) ^ 1);         // epilogue has drained this accumulator set
+            const int z = t.z, ngroups = P.ntaps[z] / gtaps;
+            const uint2 *ztap = s_tap + z * MAX_TAPS;
+            const int set = nsets == 2 ? (it & 1) : 0;
+            const int use = nsets == 2 ? (it >> 1) : it;          // how often this set has been used before
+            { DBG_T0(); mbar_wait(BAR(ACC_EMPTY + set), (use & 1) ^ 1); DBG_ACC(t_acc); }   // epilogue has drained this set
             tc_fence_after();
             const uint32_t d_base = tmem_base + (uint32_t)(set * set_cols);
             for (int i = 0; i < nkb; ++i) {
-                mbar_wait(BAR(A_FULL + s), a_par);
+                { DBG_T0(); mbar_wait(BAR(A_FULL + s), a_par); DBG_ACC(t_a); }
                 const uint32_t a_stage_lo = a_lo0 + (uint32_t)s * a_stage16;
-                for (int tp = 0; tp < ntaps; ++tp) {
-                    const uint32_t a_lo = P.tap_alo[z][tp] + a_stage_lo, a_hi = P.tap_ahi[z][tp];
+                for (int gi = 0; gi < ngroups; ++gi) {
+                    uint2 td[3];
+#pragma unroll
+                    for (int tg = 0; tg < 3; ++tg) td[tg] = ztap[gi * gtaps + (tg < gtaps ? tg : 0)];
                     const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage16;
-                    mbar_wait(BAR(B_FULL + sb), b_par);
+                    { DBG_T0(); mbar_wait(BAR(B_FULL + sb), b_par); DBG_ACC(t_b); }
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t acc0 = (i | tp) ? 1u : 0u;
-                        switch (nacc) {
-                            case 1: issue_tap<1>(d_base, bn, a_lo, a_hi, a_kstep, b_lo, b_hi, b_kstep, idesc, acc0); break;
-                            case 2: issue_tap<2>(d_base, bn, a_lo, a_hi, a_kstep, b_lo, b_hi, b_kstep, idesc, acc0); break;
-                            case 3: issue_tap<3>(d_base, bn, a_lo, a_hi, a_kstep, b_lo, b_hi, b_kstep, idesc, acc0); break;
-                            default: issue_tap<4>(d_base, bn, a_lo, a_hi, a_kstep, b_lo, b_hi, b_kstep, idesc, acc0); break;
+#pragma unroll
+                        for (int tg = 0; tg < 3; ++tg) {
+                            if (tg < gtaps) {
+                                const uint32_t acc0 = (i | gi | tg) ? 1u : 0u;
+                                const uint32_t a_lo = td[tg].x + a_stage_lo, a_hi = td[tg].y, bl = b_lo + (uint32_t)tg * b_tap16;
+                                switch (nacc) {
+                                    case 1: issue_tap<1>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0); break;
+                                    case 2: issue_tap<2>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0); break;
+                                    case 3: issue_tap<3>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0); break;
+                                    default: issue_tap<4>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0); break;
+                                }
+                            }
                         }
                         tc_commit(BAR(B_EMPTY + sb));
-                        if (tp == ntaps - 1) {
+                        if (gi == ngroups - 1) {
                             tc_commit(BAR(A_EMPTY + s));
                             if (i == nkb - 1) tc_commit(BAR(ACC_FULL + set));
                         }
@@ -331,92 +436,116 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                 if (++s == sa_n) { s = 0; a_par ^= 1u; }
             }
         }
+        if (DBG_ON && lane == 0) {
+            long long *o = P.dbg + blockIdx.x * 16;
+            o[0] = clock64() - t_start; o[1] = t_acc; o[2] = t_a; o[3] = t_b;
+        }
     } else if (warp == BLOAD_WARP) {
         // ================= B loader (TMA 1-D bulk copies of pre-packed filter blocks) =================
         if (lane == 0) {
-            const uint32_t piece = (uint32_t)P.bn * 16u;
+            const uint32_t piece = keep((uint32_t)P.bn * 16u);
             const long long chunk_stride = (long long)P.CoutP * 8;
             const uint32_t sB0 = smem_u32(sB);
-            const int sb_n = P.sb, nkb = P.nkb;
+            const int sb_n = keep(P.sb), nkb = keep(P.nkb), gtaps = keep(P.gtaps), b_contig = keep(P.b_contig);
             int sb = 0;
             uint32_t par = 1;
+            long long t_be = 0;
             for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
                 const Tile t = decode_tile(P, tile);
-                const int z = t.z, ntaps = P.ntaps[z];
+                const int z = t.z, ngroups = P.ntaps[z] / gtaps;
                 const __nv_bfloat16 *w_n0 = P.w + (long long)t.n0 * 8;
                 for (int i = 0; i < nkb; ++i, w_n0 += P.w_kb_stride)
-                    for (int tp = 0; tp < ntaps; ++tp) {
-                        const __nv_bfloat16 *src = w_n0 + P.tap_w[z][tp];
+                    for (int gi = 0; gi < ngroups; ++gi) {
                         const uint32_t dst = sB0 + (uint32_t)sb * (uint32_t)b_stage_bytes;
-                        mbar_wait(BAR(B_EMPTY + sb), par);
-                        mbar_expect_tx(BAR(B_FULL + sb), piece * KCH);
-                        if (P.b_contig) {
-                            bulk_g2s(dst, src, piece * KCH, BAR(B_FULL + sb));
-                        } else {
+                        { DBG_T0(); mbar_wait(BAR(B_EMPTY + sb), par); DBG_ACC(t_be); }
+                        mbar_expect_tx(BAR(B_FULL + sb), (uint32_t)b_stage_bytes);
+                        for (int tg = 0; tg < gtaps; ++tg) {
+                            const __nv_bfloat16 *src = w_n0 + P.tap_w[z][gi * gtaps + tg];
+                            const uint32_t d = dst + (uint32_t)tg * (uint32_t)b_tap_bytes;
+                            if (b_contig) {
+                                bulk_g2s(d, src, piece * KCH, BAR(B_FULL + sb));
+                            } else {
 #pragma unroll
-                            for (int ch = 0; ch < KCH; ++ch)
-                                bulk_g2s(dst + (uint32_t)ch * piece, src + ch * chunk_stride, piece, BAR(B_FULL + sb));
+                                for (int ch = 0; ch < KCH; ++ch)
+                                    bulk_g2s(d + (uint32_t)ch * piece, src + ch * chunk_stride, piece, BAR(B_FULL + sb));
+                            }
                         }
                         if (++sb == sb_n) { sb = 0; par ^= 1u; }
                     }
             }
+            if (DBG_ON) P.dbg[blockIdx.x * 16 + 5] = t_be;
         }
         __syncwarp();
     } else {
-        // ================= epilogue (warps 4..11): warp w reads TMEM lanes 32*(w%4).., group (w-4)/4 takes every
+        // ================= epilogue (warps 8..15): warp w reads TMEM lanes 32*(w%4).., group (w-8)/4 takes every
         // other accumulator.  y = act(acc*scale + shift + residual) -> bf16 NHWC slice, or fp32 planes (heads).
+        // 16 columns per step, software-pipelined: the tcgen05.ld and the residual load of step g+1 are in flight
+        // while step g is computed and stored; (scale, shift) come from shared memory (the L1 left beside a 200 KB
+        // carve-out is too small to keep them: every __ldg was an L2 round trip).
         const int wq = warp & 3, grp = (warp - EPI_WARP0) >> 2;
         const int r = 4 * wq + (lane >> 3), c = lane & 7;     // MMA row m = 32*wq + lane = 8*r + c
-        const int bn = P.bn, Cout = P.Cout, out_stride = P.out_stride, res_stride = P.res_stride, act = P.act;
+        const int bn = P.bn, Cout = P.Cout, out_stride = P.out_stride, res_stride = P.res_stride;
+        // bit 0 planar, bit 1 vec32, bits 2.. development skip flags: one register for the inner-loop switches
+        const int flags = (P.planar ? 1 : 0) | (P.vec32 ? 2 : 0) | (P.dbg_flags << 2);
+        const int act = P.act, nacc = P.nacc, nsets = P.nsets;
+        const int Ht = P.Ht, Wt = P.Wt, Ho = P.Ho, Wo = P.Wo, oys = P.oys, oxs = P.oxs;
+#define planar (kGeneral && (flags & 1))
+#define vec32 (flags & 2)
+#define skip (flags >> 2)
         const float slope = act == RDFC_ACT_RELU ? 0.f : (act == RDFC_ACT_LEAKY02 ? 0.2f : 1.f);
         const __nv_bfloat16 *res = P.res;
-        const float *gscale = P.scale, *gshift = P.shift;
+        __nv_bfloat16 *const outp = P.out;
+        const int G = bn >> 4;
         int it = 0;
+        long long t_accfull = 0, t_epi = 0;
         for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
             const Tile t = decode_tile(P, tile);
             const int oyo = P.oyo[t.z], oxo = P.oxo[t.z];
-            const int set = P.nsets == 2 ? (it & 1) : 0;
-            const int use = P.nsets == 2 ? (it >> 1) : it;
-            mbar_wait<true>(BAR(ACC_FULL + set), use & 1);
+            const int set = nsets == 2 ? (it & 1) : 0;
+            const int use = nsets == 2 ? (it >> 1) : it;
+            { DBG_T0(); mbar_wait<true>(BAR(ACC_FULL + set), use & 1); DBG_ACC(t_accfull); }
             tc_fence_after();
+            const long long _te = DBG_ON ? clock64() : 0;
             const int n0 = t.n0;
-            for (int j = grp; j < P.nacc; j += 2) {
+            for (int j = grp; j < nacc; j += 2) {
                 const int yy = t.ty0 + r, xx = t.tx0 + 8 * j + c;
-                const int oy = P.oys * yy + oyo, ox = P.oxs * xx + oxo;
-                const bool ok = yy < P.Ht && xx < P.Wt && oy < P.Ho && ox < P.Wo;
-                const long long opix = ((long long)t.b * P.Ho + oy) * P.Wo + ox;
+                const int oy = oys * yy + oyo, ox = oxs * xx + oxo;
+                const bool ok = yy < Ht && xx < Wt && oy < Ho && ox < Wo;
+                const long long opix = ok ? ((long long)t.b * Ho + oy) * Wo + ox : 0;
                 const uint32_t trow = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(set * set_cols + j * bn);
-                for (int n = 0; n < bn; n += 16) {
-                    uint32_t v[16];
-                    tc_ld16(trow + (uint32_t)n, v);   // warp-collective
-                    if (!ok || n0 + n >= Cout) continue;
+                const __nv_bfloat16 *rrow = res ? res + opix * res_stride + n0 : nullptr;
+                __nv_bfloat16 *orow = planar ? nullptr : outp + opix * out_stride + n0;
+                const long long pp = (long long)oy * Wo + ox;
+
+                auto load_res = [&](int g, uint4 &r0, uint4 &r1) {
+                    if (rrow && ok && n0 + 16 * g + 16 <= Cout) {
+                        if (vec32) {
+                            uint32_t rr[8];
+                            ld_global_v8(rrow + 16 * g, rr);
+                            r0 = make_uint4(rr[0], rr[1], rr[2], rr[3]); r1 = make_uint4(rr[4], rr[5], rr[6], rr[7]);
+                        } else {
+                            const uint4 *rp = reinterpret_cast<const uint4 *>(rrow + 16 * g);
+                            r0 = rp[0]; r1 = rp[1];
+                        }
+                    } else {
+                        r0 = r1 = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                };
+                auto process = [&](const uint32_t (&v)[16], const uint4 &r0, const uint4 &r1, int g) {
+                    const int n = 16 * g;
+                    if (!ok || n0 + n >= Cout) return;
                     float f[16];
-                    const bool full = n0 + n + 16 <= Cout;
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
-                        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (full) {                // (scale, shift) vectors are padded to a multiple of 16 by the host? no: guard
-                            if (gscale) sc = __ldg(reinterpret_cast<const float4 *>(gscale + n0 + n) + q4);
-                            if (gshift) sh = __ldg(reinterpret_cast<const float4 *>(gshift + n0 + n) + q4);
-                        } else {
-                            const int cb = n0 + n + 4 * q4;
-                            if (gscale) {
-                                sc.x = cb + 0 < Cout ? __ldg(gscale + cb + 0) : 1.f; sc.y = cb + 1 < Cout ? __ldg(gscale + cb + 1) : 1.f;
-                                sc.z = cb + 2 < Cout ? __ldg(gscale + cb + 2) : 1.f; sc.w = cb + 3 < Cout ? __ldg(gscale + cb + 3) : 1.f;
-                            }
-                            if (gshift) {
-                                sh.x = cb + 0 < Cout ? __ldg(gshift + cb + 0) : 0.f; sh.y = cb + 1 < Cout ? __ldg(gshift + cb + 1) : 0.f;
-                                sh.z = cb + 2 < Cout ? __ldg(gshift + cb + 2) : 0.f; sh.w = cb + 3 < Cout ? __ldg(gshift + cb + 3) : 0.f;
-                            }
-                        }
+                        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + n0 + n + 4 * q4);
+                        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + n0 + n + 4 * q4);
                         f[4 * q4 + 0] = fmaf(__uint_as_float(v[4 * q4 + 0]), sc.x, sh.x);
                         f[4 * q4 + 1] = fmaf(__uint_as_float(v[4 * q4 + 1]), sc.y, sh.y);
                         f[4 * q4 + 2] = fmaf(__uint_as_float(v[4 * q4 + 2]), sc.z, sh.z);
                         f[4 * q4 + 3] = fmaf(__uint_as_float(v[4 * q4 + 3]), sc.w, sh.w);
                     }
-                    if (P.planar) {
+                    if (planar) {
                         // fused decode heads: column q -> its own fp32 plane with its own activation
-                        const long long pp = (long long)oy * P.Wo + ox;
 #pragma unroll
                         for (int q = 0; q < 16; ++q) {
                             if (q < P.ncols) {
@@ -427,11 +556,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                                 P.plane[q][(long long)t.b * P.plane_bstride[q] + pp] = y;
                             }
                         }
-                        continue;
+                        return;
                     }
-                    if (res) {
-                        const uint4 *rp = reinterpret_cast<const uint4 *>(res + opix * res_stride + n0 + n);
-                        const uint4 r0 = rp[0], r1 = rp[1];
+                    const bool full = n0 + n + 16 <= Cout;
+                    if (res && full) {
                         const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
@@ -439,15 +567,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                             f[2 * q] += p2.x;
                             f[2 * q + 1] += p2.y;
                         }
+                    } else if (res) {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q)
+                            if (q < Cout - n0 - n) f[q] += __bfloat162float(rrow[n + q]);
                     }
-                    if (act <= RDFC_ACT_LEAKY02) {         // none / relu / leaky, branch-free: max(v, slope*v)
+                    if (!kGeneral || act <= RDFC_ACT_LEAKY02) {         // none / relu / leaky, branch-free: max(v, slope*v)
 #pragma unroll
                         for (int q = 0; q < 16; ++q) f[q] = fmaxf(f[q], slope * f[q]);
                     } else {
 #pragma unroll
                         for (int q = 0; q < 16; ++q) f[q] = act == RDFC_ACT_TANH ? tanhf(f[q]) : 1.f / (1.f + expf(-f[q]));
                     }
-                    __nv_bfloat16 *op = P.out + opix * out_stride + n0 + n;
+                    __nv_bfloat16 *op = orow + n;
+                    if (skip & 1) return;
                     if (full) {
                         uint32_t o[8];
 #pragma unroll
@@ -455,14 +588,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                             const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
                             o[q] = *reinterpret_cast<const uint32_t *>(&h2);
                         }
-                        uint4 *o4 = reinterpret_cast<uint4 *>(op);
-                        o4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                        o4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                        if (vec32) {
+                            st_global_v8(op, o);          // one full 32-byte sector per lane and instruction
+                        } else {
+                            uint4 *o4 = reinterpret_cast<uint4 *>(op);
+                            o4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                            o4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                        }
                     } else {
                         const int nvalid = Cout - n0 - n;
 #pragma unroll
                         for (int q = 0; q < 16; ++q)
                             if (q < nvalid) op[q] = __float2bfloat16_rn(f[q]);
+                    }
+                };
+
+                uint32_t va[16], vb[16];
+                uint4 ra0, ra1, rb0, rb1;
+                if (!(skip & 2))
+                tc_ld16_issue(trow, va);                 // warp-collective: never under a lane-dependent branch
+                load_res(0, ra0, ra1);
+                for (int g = 0; g < G; g += 2) {
+                    tc_wait_ld(va);
+                    if (g + 1 < G) { if (!(skip & 2)) tc_ld16_issue(trow + (uint32_t)(16 * (g + 1)), vb); load_res(g + 1, rb0, rb1); }
+                    process(va, ra0, ra1, g);
+                    if (g + 1 < G) {
+                        tc_wait_ld(vb);
+                        if (g + 2 < G) { if (!(skip & 2)) tc_ld16_issue(trow + (uint32_t)(16 * (g + 2)), va); load_res(g + 2, ra0, ra1); }
+                        process(vb, rb0, rb1, g + 1);
                     }
                 }
             }
@@ -470,7 +623,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + set));
+            if (DBG_ON) t_epi += clock64() - _te;
         }
+        if (DBG_ON && warp == EPI_WARP0 && lane == 0) { P.dbg[blockIdx.x * 16 + 9] = t_accfull; P.dbg[blockIdx.x * 16 + 10] = t_epi; }
+#undef planar
+#undef vec32
+#undef skip
     }
     tc_fence_before();
     __syncthreads();
@@ -480,6 +638,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                      : "memory");
     }
 }
+
+long long *g_dbg_buf = nullptr;
 
 int next_pow2_cols(int c) {
     int p = 32;
@@ -595,7 +755,13 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
             for (int kx = 0; kx < 3; ++kx)
                 ph.taps[ph.ntaps++] = Tap{pl[ky != 1][kx != 1], ky == 2 ? 1 : 0, kx == 2 ? 1 : 0, ky * 3 + kx};
     }
+    P.npix = base;
     P.npix_pad = (base + 7) / 8 * 8;
+    for (int pl = 0; pl < P.nplanes; ++pl)
+        RDFC_REQUIRE(P.planes[pl].ystep * (P.planes[pl].rows - 1) + 1 < 255 && P.planes[pl].xstep * (P.planes[pl].cols - 1) + 1 < 255,
+                     "UMMA conv: staged plane too large for the packed producer slot table");
+    RDFC_REQUIRE(P.npix <= JMAX * PIXPASS, "UMMA conv: staged halo (%d pixels) exceeds the producer slot table", P.npix);
+    RDFC_REQUIRE((long long)P.Hi * P.Wi * P.in_stride * 2 < (1ll << 32), "UMMA conv: image too large for 32-bit producer offsets");
     RDFC_REQUIRE(P.npix_pad < (1 << 14), "UMMA conv: staged halo too large for the descriptor LBO field");
     P.w_kb_stride = (long long)KCH * P.CoutP * 8;
     P.b_contig = P.n_tiles_n == 1;
@@ -615,27 +781,56 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     P.tmem_cols = next_pow2_cols(P.nsets * P.nacc * P.bn);
     RDFC_REQUIRE(P.tmem_cols <= 512, "UMMA conv: accumulators exceed TMEM");
 
-    const int a_stage = KCH * P.npix_pad * 16, b_stage = KCH * P.bn * 16;
-    const int fixed = (2 * 8 + 2 * 8 + 4) * 8 + 16 + 256;
+    // filter taps per B stage: one wait / commit per filter row of a 3x3 conv; the 1/2/2/4-tap phases of a transposed
+    // conv and 1x1 convs stream tap by tap
+    P.gtaps = (k3 && !d->transposed) ? 3 : 1;
+    if (const char *e = getenv("RDFC_UMMA_GTAPS")) P.gtaps = atoi(e);    // development knob (1 or 3)
+    P.vec32 = !heads && ((uintptr_t)d->out.ptr % 32) == 0 && d->out.pix_stride % 16 == 0 &&
+              (!d->residual.ptr || (((uintptr_t)d->residual.ptr % 32) == 0 && d->residual.pix_stride % 16 == 0));
+    const int a_stage = KCH * P.npix_pad * 16, b_stage = P.gtaps * KCH * P.bn * 16;
+    const int fixed = BAR_BYTES + 2 * P.CoutP * 4 + 4 * MAX_TAPS * 8 + 256;   // barriers, (scale, shift) and tap tables, slack
     const int budget = 220 * 1024;
     // A ring first (>= 2 stages: the producers publish k-block i while k-block i+1 is in flight), then B stages (2..6)
-    P.sb = 6;
-    if (const char *e = getenv("RDFC_UMMA_SB")) P.sb = atoi(e);          // development knob (<= 8)
+    // the filter stream is latency-bound: bytes in flight per SM = bandwidth x L2 latency (~2000 cycles), so keep
+    // >= 64 KB of filter stages in flight when the tile allows it
+    P.sb = (80 * 1024 + b_stage - 1) / b_stage;
+    if (P.sb < 3) P.sb = 3;
+    if (P.sb > 16) P.sb = 16;
+    if (const char *e = getenv("RDFC_UMMA_SB")) P.sb = atoi(e);          // development knob (<= 16)
+    while (P.sb > 3 && 3 * a_stage + P.sb * b_stage + fixed > budget) --P.sb;     // prefer >= 3 A stages (2 in flight)
     while (P.sb > 2 && 2 * a_stage + P.sb * b_stage + fixed > budget) --P.sb;
     P.sa = (budget - fixed - P.sb * b_stage) / a_stage;
     if (P.sa > 4) P.sa = 4;
     if (const char *e = getenv("RDFC_UMMA_SA")) P.sa = atoi(e) < P.sa ? atoi(e) : P.sa;
-    RDFC_REQUIRE(P.sa >= 1 && P.sa <= 8 && P.sb >= 1 && P.sb <= 8, "UMMA conv: tile does not fit shared memory");
+    RDFC_REQUIRE(P.sa >= 1 && P.sa <= 8 && P.sb >= 1 && P.sb <= 16, "UMMA conv: tile does not fit shared memory");
     const size_t smem = (size_t)P.sa * a_stage + (size_t)P.sb * b_stage + fixed;
     static bool attr_set = false;
     if (!attr_set) {
-        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
+    }
+    if (const char *e = getenv("RDFC_UMMA_SKIP")) P.dbg_flags = atoi(e);
+    static long long *dbg_buf = nullptr;
+    if (getenv("RDFC_UMMA_DBG")) {
+        if (!dbg_buf) RDFC_CUDA(cudaMalloc(&dbg_buf, 148 * 16 * sizeof(long long)));
+        RDFC_CUDA(cudaMemsetAsync(dbg_buf, 0, 148 * 16 * sizeof(long long), st));
+        P.dbg = dbg_buf;
+        g_dbg_buf = dbg_buf;
     }
     int grid = P.ntiles < sm_count() ? P.ntiles : sm_count();
     if (const char *e = getenv("RDFC_UMMA_GRID")) grid = atoi(e) < P.ntiles ? atoi(e) : P.ntiles;   // development knob
-    conv_umma_kernel<<<grid, NTHREADS, smem, st>>>(P);
+    if (P.planar || P.act > RDFC_ACT_LEAKY02) conv_umma_kernel<true><<<grid, NTHREADS, smem, st>>>(P);
+    else conv_umma_kernel<false><<<grid, NTHREADS, smem, st>>>(P);
     RDFC_CHECK_LAUNCH("conv_umma_kernel");
+    return 0;
+}
+
+// development aid: copies the role timers of the last RDFC_UMMA_DBG=1 launch (148 CTAs x 16 slots) to the host
+int conv_umma_read_dbg(long long *host, int n) {
+    if (!g_dbg_buf) return -1;
+    RDFC_CUDA(cudaDeviceSynchronize());
+    RDFC_CUDA(cudaMemcpy(host, g_dbg_buf, sizeof(long long) * (n < 148 * 16 ? n : 148 * 16), cudaMemcpyDeviceToHost));
     return 0;
 }
 

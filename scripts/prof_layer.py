@@ -44,21 +44,17 @@ def conv(B=8, Cin=64, Cout=64, H=228, W=304, k=3, stride=1, transposed=0, in_str
     ms = time_it(lambda: C.check(C.lib.rdfc_conv_forward(ctypes.byref(d), s)))
     taps = k * k / (4 if transposed else 1)
     flops = 2.0 * B * Ho * Wo * Cin * Cout * taps
-    if os.environ.get("RDFC_UMMA_DBG") and hasattr(C.lib, "rdfc_dev_umma_stamps"):
+    if os.environ.get("RDFC_UMMA_DBG") and hasattr(C.lib, "rdfc_dev_umma_timers"):
         import numpy as np
-        n = 1024
-        buf = (ctypes.c_longlong * (16 * n))()
-        C.lib.rdfc_dev_umma_stamps(buf, n)
-        full = np.frombuffer(buf, dtype=np.int64).reshape(n, 16).astype(np.float64)
-        a = full[:, :8]
-        t0 = a[:, 0].min()
-        rel = (a - a[:, :1]) / 1e3
-        names = ["entry", "setup", "A0 issued", "A0 full", "B0 full", "last commit", "acc full", "epi done"]
-        print("per-CTA timeline (us since CTA entry), median over", n, "CTAs:")
-        for i, nm in enumerate(names):
-            print(f"   {nm:12s} {np.median(rel[:, i]):8.2f}   p90 {np.percentile(rel[:, i], 90):8.2f}")
-        print(f"   MMA thread cycles waiting: A_FULL median {np.median(full[:, 8]):.0f}, B_FULL median {np.median(full[:, 9]):.0f}")
-        print(f"   first CTA entry -> last CTA done: {(a[:, 7].max() - t0) / 1e3:.1f} us; CTA lifetimes median {np.median(rel[:, 7]):.2f}")
+        buf = (ctypes.c_longlong * (148 * 16))()
+        C.lib.rdfc_dev_umma_timers(buf, 148 * 16)
+        a = np.frombuffer(buf, dtype=np.int64).reshape(148, 16).astype(np.float64)
+        a = a[a[:, 0] > 0]
+        names = {0: "MMA warp lifetime", 1: "MMA wait ACC_EMPTY", 2: "MMA wait A_FULL", 3: "MMA wait B_FULL", 5: "Bload wait B_EMPTY",
+                 6: "prod wait A_EMPTY", 7: "prod issue", 8: "prod wait_group", 9: "epi wait ACC_FULL", 10: "epi work"}
+        print(f"role timers, cycles, median over {len(a)} CTAs (thread 0 of each role):")
+        for i, nm in names.items():
+            print(f"   {nm:20s} {np.median(a[:, i]):10.0f}  ({100*np.median(a[:, i])/np.median(a[:, 0]):5.1f}% of MMA warp lifetime)")
     print(f"conv B={B} {Cin}->{Cout} {H}x{W} k{k} s{stride} T{transposed}: {ms*1e3:.1f} us  {flops/ms/1e9:.1f} TFLOP/s "
           f"env={ {k_: v for k_, v in os.environ.items() if k_.startswith('RDFC_')} }")
 
