@@ -260,7 +260,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "nlspn_prop_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    roofline = {"kernel": "nlspn_prop_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s",
+    roofline = {"kernel": "nlspn_prop_band_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": achieved / pk["hbm"], "traffic": traffic, "peak_source": pk["src"] + " (burst copy)",
                 "launch_us": launch_us, "launches_per_forward": launches,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL_ITER * P * min(group, B)}

@@ -164,6 +164,156 @@ __global__ void __launch_bounds__(TX *TY) nlspn_prop_kernel(const float *__restr
 
 
 // ------------------------------------------------------------------------------------------------------------------
+// Band kernel (the default): the thread-per-pixel kernel above is bound by the L1 tag stage (3.3 wavefronts per
+// gather request with 2-px offsets, 769 instructions per warp, DRAM only 41 % busy: profiles/).  Here a CTA owns a
+// contiguous run of image rows and first stages the feature rows its taps can reach (+- halo) in shared memory with
+// a zero border, so that
+//   * the 36 corner reads per pixel are LDS (bank-limited, no tag lookups) with NO bounds predicates: the DCN
+//     validity rule and per-corner zeroing (modulated_deform_im2col_cuda.cuh:25-54,180) fall out of clamping the
+//     sample position to [-1, H] x [-1, W] and reading zeros from the border;
+//   * the 25 streamed planes are read as 8-byte vectors, two pixels per thread, straight from HBM (no L1 allocation);
+//   * taps that leave the staged band (|offset| > halo) take the global-memory path of `bilinear` (rare).
+// Rows are dealt evenly over one wave of CTAs (a run may span two images).
+// Nine-tap gather from a staged band with the escape test hoisted out of the tap loop: the common case (no tap leaves
+// the band) is straight-line code with 36 independent LDS, so the loads of all taps overlap instead of serialising
+// behind a per-tap branch.  dy/dx/a: the pixel's 9 offsets and affinities; (y, x): the pixel.
+struct BandView {
+    const float *tile;      // [nrows][pitch], tile row 0 = image row ty0, tile column tc = image column tc - 1
+    const float *im;        // the image in global memory (fallback path)
+    int pitch, ty0, nrows, H, W;
+    float Hf, Wf;
+};
+template <typename FDy, typename FDx, typename FA>
+__device__ __forceinline__ float gather9(const BandView &v, FDy dyf, FDx dxf, FA af, int y, int x) {
+    // pass 1: does any tap leave the staged band?  (rows only: columns are staged over the full width)
+    float ymin = 1e30f, ymax = -1e30f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float cy = fminf(fmaxf((float)(y - 1 + k / 3) + dyf(k), -1.f), v.Hf);
+        ymin = fminf(ymin, cy);
+        ymax = fmaxf(ymax, cy);
+    }
+    const bool esc = ((int)floorf(ymin) < v.ty0) | ((int)floorf(ymax) + 1 >= v.ty0 + v.nrows);
+    float acc = 0.f;
+    if (!esc) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const float cy = fminf(fmaxf((float)(y - 1 + k / 3) + dyf(k), -1.f), v.Hf);
+            const float cx = fminf(fmaxf((float)(x - 1 + k % 3) + dxf(k), -1.f), v.Wf);
+            const float fy = floorf(cy), fx = floorf(cx);
+            const float ly = cy - fy, lx = cx - fx, hy = 1.f - ly, hx = 1.f - lx;
+            const float *q = v.tile + ((int)fy - v.ty0) * v.pitch + (int)fx + 1;
+            acc = fmaf(af(k), hy * hx * q[0] + hy * lx * q[1] + ly * hx * q[v.pitch] + ly * lx * q[v.pitch + 1], acc);
+        }
+    } else {                     // some tap left the staged band: global-memory path
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            acc = fmaf(af(k), bilinear(v.im, v.H, v.W, (float)(y - 1 + k / 3) + dyf(k), (float)(x - 1 + k % 3) + dxf(k)), acc);
+    }
+    return acc;
+}
+
+constexpr int BAND_THREADS = 256;
+
+__device__ __forceinline__ float2 ld_stream2(const float *p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+template <bool kClamp, int kPix, int kMinBlocks>
+__global__ void __launch_bounds__(BAND_THREADS, kMinBlocks) nlspn_prop_band_kernel(const float *__restrict__ in,
+                                                                          const float *__restrict__ offset,
+                                                                          const float *__restrict__ aff,
+                                                                          float *__restrict__ out, float *__restrict__ inter,
+                                                                          int B, int H, int W, int rows_per_cta, int halo, int prefetch) {
+    extern __shared__ float band_tile[];
+    const int pitch = W + 4;                         // tile column tc <-> image column tc - 1 (-1 .. W + 2)
+    const long long total = (long long)B * H, P = (long long)H * W;
+    long long row = (long long)blockIdx.x * rows_per_cta;
+    const long long row_end = row + rows_per_cta < total ? row + rows_per_cta : total;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Wp = W / kPix;
+    const float Hf = (float)H, Wf = (float)W;
+    while (row < row_end) {
+        const int b = (int)(row / H), y_lo = (int)(row - (long long)b * H);
+        const int nr = (int)((row_end - row) < (long long)(H - y_lo) ? (row_end - row) : (long long)(H - y_lo));   // rows of this image
+        const int ty0 = y_lo - halo - 1;             // image row of tile row 0
+        const int nrows = nr + 2 * halo + 3;
+        const float *im = in + (long long)b * P;
+        __syncthreads();                              // previous sub-band is done with the tile
+        for (int tr = warp; tr < nrows; tr += BAND_THREADS / 32) {
+            const int iy = ty0 + tr;
+            const bool yok = iy >= 0 && iy < H;
+            const float *src = im + (long long)iy * W - 1;
+            float *dst = band_tile + tr * pitch;
+            for (int tc = lane; tc < pitch; tc += 32) dst[tc] = (yok && tc >= 1 && tc <= W) ? __ldg(src + tc) : 0.f;
+        }
+        __syncthreads();
+        const BandView bv{band_tile, im, pitch, ty0, nrows, H, W, Hf, Wf};
+        const int nitems = nr * Wp;
+        for (int idx = threadIdx.x; idx < nitems; idx += BAND_THREADS) {
+            const int ry = idx / Wp, x = kPix * (idx - ry * Wp), y = y_lo + ry;
+            const long long pix = (long long)y * W + x;
+            const float *offp = offset + (long long)b * 18 * P + pix;
+            const float *affp = aff + (long long)b * 9 * P + pix;
+            const long long o = (long long)b * P + pix;
+            if (prefetch && idx + BAND_THREADS < nitems) {
+                // the thread's next item: start its 25 plane lines on their way from HBM to L2 while this one is gathered
+                const int idn = idx + BAND_THREADS, ryn = idn / Wp;
+                const long long dpix = (long long)(y_lo + ryn) * W + kPix * (idn - ryn * Wp) - pix;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(affp + (long long)k * P + dpix));
+                    if (k != 4) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(offp + (long long)(2 * k) * P + dpix));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(offp + (long long)(2 * k + 1) * P + dpix));
+                    }
+                }
+            }
+            if (kPix == 2) {
+                float2 a[9], dy[9], dx[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    a[k] = ld_stream2(affp + (long long)k * P);
+                    if (k == 4) {
+                        dy[k] = dx[k] = make_float2(0.f, 0.f);
+                    } else {
+                        dy[k] = ld_stream2(offp + (long long)(2 * k) * P);
+                        dx[k] = ld_stream2(offp + (long long)(2 * k + 1) * P);
+                    }
+                }
+                float acc0 = gather9(bv, [&](int k) { return dy[k].x; }, [&](int k) { return dx[k].x; }, [&](int k) { return a[k].x; }, y, x);
+                float acc1 = gather9(bv, [&](int k) { return dy[k].y; }, [&](int k) { return dx[k].y; }, [&](int k) { return a[k].y; }, y, x + 1);
+                if (kClamp) {
+                    acc0 = fminf(fmaxf(acc0, -1.f), 1.f);
+                    acc1 = fminf(fmaxf(acc1, -1.f), 1.f);
+                }
+                *reinterpret_cast<float2 *>(out + o) = make_float2(acc0, acc1);
+                if (inter) *reinterpret_cast<float2 *>(inter + o) = make_float2(acc0, acc1);
+            } else {
+                float a[9], dy[9], dx[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    a[k] = ld_stream(affp + (long long)k * P);
+                    if (k == 4) {
+                        dy[k] = dx[k] = 0.f;
+                    } else {
+                        dy[k] = ld_stream(offp + (long long)(2 * k) * P);
+                        dx[k] = ld_stream(offp + (long long)(2 * k + 1) * P);
+                    }
+                }
+                float acc = gather9(bv, [&](int k) { return dy[k]; }, [&](int k) { return dx[k]; }, [&](int k) { return a[k]; }, y, x);
+                if (kClamp) acc = fminf(fmaxf(acc, -1.f), 1.f);
+                out[o] = acc;
+                if (inter) inter[o] = acc;
+            }
+        }
+        row += nr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Row-streaming propagation kernel (the default when W % 4 == 0): persistent CTAs, one image row per trip, one
 // thread per pixel.  The 25 offset/affinity planes of a row are staged in shared memory by TMA 1-D bulk copies
 // (cp.async.bulk, W*4 bytes each) onto an mbarrier, `stages` rows ahead of the compute, so HBM requests stay in
@@ -252,6 +402,118 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) nlspn_prop_rows_kerne
         }
         __syncthreads();                               // everyone is done reading stage s
         if (row + stages < r1) issue(row + stages, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Ring kernel (the default when W % 4 == 0): the band kernel's shared-memory gathers + the row kernel's TMA stream,
+// warp-specialised so that neither waits for the other.  One persistent CTA per SM owns a contiguous run of rows:
+//   * producer warp: for every stage (G rows) 25 x G bulk copies (cp.async.bulk, one image row of one plane each)
+//     onto an mbarrier, S stages ahead, released by the consumer warps through an "empty" mbarrier;
+//   * consumer warps: stage the feature rows their taps can reach (+- halo, zero border) in shared memory once per
+//     sub-band, then per stage read the 25 streamed values of a pixel from shared memory (conflict-free) and gather
+//     the 36 corners with LDS; taps outside the staged band fall back to `bilinear` on global memory.
+// HBM requests therefore stay in flight during the gathers (the band kernel's load -> wait -> compute phases left DRAM
+// 47 % busy), and no thread holds the streamed values in registers.
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <bool kClamp>
+__global__ void __launch_bounds__(992, 1) nlspn_prop_ring_kernel(const float *__restrict__ in, const float *__restrict__ offset,
+                                                                 const float *__restrict__ aff, float *__restrict__ out,
+                                                                 float *__restrict__ inter, int B, int H, int W,
+                                                                 int rows_per_cta, int halo, int G, int S, int nr_max) {
+    extern __shared__ __align__(128) unsigned char ring_smem[];
+    const int pitch = W + 4;
+    float *ring = reinterpret_cast<float *>(ring_smem);                                  // [S][G][25][W]
+    float *tile = ring + (size_t)S * G * 25 * W;                                         // [nr_max + 2 halo + 3][pitch]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tile + (size_t)(nr_max + 2 * halo + 3) * pitch);   // full[S], empty[S]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncw = (blockDim.x >> 5) - 1;                                               // consumer warps; warp ncw produces
+    const long long total = (long long)B * H, P = (long long)H * W;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = r0 + rows_per_cta < total ? r0 + rows_per_cta : total;
+    if (r0 >= r1) return;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + S + s)), "r"(ncw));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t row_bytes = (uint32_t)W * 4u;
+    if (warp == ncw) {
+        // ---------------- producer
+        int i = 0;
+        for (long long row = r0; row < r1; row += G, ++i) {
+            const int s = i % S;
+            const int ng = (int)((r1 - row) < G ? (r1 - row) : G);
+            mbar_wait_parity(smem_u32(bars + S + s), (uint32_t)(((i / S) & 1) ^ 1));      // consumers released the slot
+            const uint32_t full = smem_u32(bars + s);
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(25u * row_bytes * (uint32_t)ng) : "memory");
+            __syncwarp();
+            for (int c = lane; c < 25 * ng; c += 32) {
+                const int g = c / 25, k = c - 25 * g;
+                const long long rg = row + g;
+                const int b = (int)(rg / H), y = (int)(rg - (long long)b * H);
+                const float *src;
+                if (k < 16) {
+                    const int j = k >> 1, kk = j < 4 ? j : j + 1;      // slot 2j / 2j+1 <- offset channels 2kk / 2kk+1
+                    src = offset + ((long long)b * 18 + 2 * kk + (k & 1)) * P + (long long)y * W;
+                } else {
+                    src = aff + ((long long)b * 9 + (k - 16)) * P + (long long)y * W;
+                }
+                bulk_g2s(smem_u32(ring + ((size_t)(s * G + g) * 25 + k) * W), src, row_bytes, full);
+            }
+        }
+        return;
+    }
+    // ---------------- consumers
+    const int nseg = (W + 31) >> 5;
+    const float Hf = (float)H, Wf = (float)W;
+    const int nthr_c = ncw * 32;
+    int i = 0;
+    long long row = r0;
+    while (row < r1) {
+        const int b = (int)(row / H), y_lo = (int)(row - (long long)b * H);
+        int nr = (int)((r1 - row) < (long long)(H - y_lo) ? (r1 - row) : (long long)(H - y_lo));
+        if (nr > nr_max) nr = nr_max;
+        const int ty0 = y_lo - halo - 1, nrows = nr + 2 * halo + 3;
+        const float *im = in + (long long)b * P;
+        asm volatile("bar.sync 1, %0;" ::"r"(nthr_c) : "memory");          // previous sub-band is done with the tile
+        for (int tr = warp; tr < nrows; tr += ncw) {
+            const int iy = ty0 + tr;
+            const bool yok = iy >= 0 && iy < H;
+            const float *src = im + (long long)iy * W - 1;
+            float *dst = tile + tr * pitch;
+            for (int tc = lane; tc < pitch; tc += 32) dst[tc] = (yok && tc >= 1 && tc <= W) ? __ldg(src + tc) : 0.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(nthr_c) : "memory");
+        const BandView bv{tile, im, pitch, ty0, nrows, H, W, Hf, Wf};
+        for (int rr = 0; rr < nr; rr += G, ++i) {
+            const int s = i % S;
+            mbar_wait_parity(smem_u32(bars + s), (uint32_t)((i / S) & 1));
+            for (int seg = warp; seg < G * nseg; seg += ncw) {
+                const int g = seg / nseg, x = (seg - g * nseg) * 32 + lane, y = y_lo + rr + g;
+                if (rr + g < nr && x < W) {
+                    const float *st = ring + (size_t)(s * G + g) * 25 * W + x;
+                    float acc = gather9(bv,
+                                        [&](int k) { return k == 4 ? 0.f : st[(2 * (k < 4 ? k : k - 1)) * W]; },
+                                        [&](int k) { return k == 4 ? 0.f : st[(2 * (k < 4 ? k : k - 1) + 1) * W]; },
+                                        [&](int k) { return st[(16 + k) * W]; }, y, x);
+                    if (kClamp) acc = fminf(fmaxf(acc, -1.f), 1.f);
+                    const long long o = (long long)b * P + (long long)y * W + x;
+                    out[o] = acc;
+                    if (inter) inter[o] = acc;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(smem_u32(bars + S + s));        // this warp is done reading the stage
+        }
+        row += nr;
     }
 }
 
@@ -349,6 +611,78 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
             if (const char *e = getenv("RDFC_NLSPN_STAGES")) stages = atoi(e);
             while (stages > 1 && stages * stage_bytes + 64 > 200 * 1024) --stages;
             const size_t smem = stages * stage_bytes + 64;
+            // ring kernel: TMA row stream + shared-memory band gathers, one persistent CTA per SM
+            {
+                int halo_r = 8;
+                if (const char *e = getenv("RDFC_NLSPN_HALO")) halo_r = atoi(e);
+                const int nseg = (W + 31) / 32;
+                int G = (H % 3 == 0 && nseg <= 10) ? 3 : ((H % 2 == 0 && nseg <= 15) ? 2 : 1);   // rows per stage ~ 30 warps of work
+                if (const char *e = getenv("RDFC_NLSPN_G")) G = atoi(e);
+                int ncw = G * nseg > 30 ? 30 : G * nseg;
+                if (const char *e = getenv("RDFC_NLSPN_NCW")) ncw = atoi(e);
+                const size_t stage_b = (size_t)G * 25 * W * 4;
+                int S = stage_b >= 48 * 1024 ? 2 : 3;
+                if (const char *e = getenv("RDFC_NLSPN_STAGES")) S = atoi(e);
+                const long long total_rows = (long long)nb * H;
+                long long nctas = sm_count();
+                if (const char *e = getenv("RDFC_NLSPN_RING_CTAS")) nctas = atoll(e);
+                long long rpc = (total_rows + nctas - 1) / nctas;
+                rpc = (rpc + G - 1) / G * G;
+                const long long left = 220 * 1024 - (long long)S * stage_b - 2 * S * 8 - 128;
+                long long nr_max = left / ((W + 4) * 4) - 2 * halo_r - 3;
+                if (nr_max > rpc) nr_max = rpc;
+                nr_max = nr_max / G * G;
+                const bool ring_ok = getenv("RDFC_NLSPN_RING") && !getenv("RDFC_NLSPN_SIMPLE") && !getenv("RDFC_NLSPN_ROWS") &&
+                                     W % 4 == 0 && H % G == 0 && nr_max >= G && nr_max >= 4 && ncw >= 1 && ncw <= 30 &&
+                                     ((uintptr_t)off_g % 16) == 0 && ((uintptr_t)aff_g % 16) == 0 && (P % 4) == 0;
+                if (ring_ok) {
+                    const size_t smem = (size_t)S * stage_b + (size_t)(nr_max + 2 * halo_r + 3) * (W + 4) * 4 + 2 * S * 8 + 128;
+                    const int grid_r = (int)((total_rows + rpc - 1) / rpc);
+                    if (clamp) {
+                        RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                        nlspn_prop_ring_kernel<true><<<grid_r, (ncw + 1) * 32, smem, st>>>(cur, off_g, aff_g, dst, it, nb, H, W, (int)rpc, halo_r, G, S, (int)nr_max);
+                    } else {
+                        RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                        nlspn_prop_ring_kernel<false><<<grid_r, (ncw + 1) * 32, smem, st>>>(cur, off_g, aff_g, dst, it, nb, H, W, (int)rpc, halo_r, G, S, (int)nr_max);
+                    }
+                    RDFC_CHECK_LAUNCH("nlspn_prop_ring_kernel");
+                    cur = dst;
+                    continue;
+                }
+            }
+            // band kernel: even W (8-byte plane vectors), tile must fit shared memory
+            int halo = 8;
+            if (const char *e = getenv("RDFC_NLSPN_HALO")) halo = atoi(e);
+            const long long total_rows_b = (long long)nb * H;
+            int band_pix = 2;                      // pixels per thread: 2 -> 3 CTAs / SM (measured best), 1 -> 5 CTAs / SM
+            if (W % 2 != 0) band_pix = 1;
+            if (const char *e = getenv("RDFC_NLSPN_PIX")) band_pix = atoi(e);
+            const int band_per_sm = band_pix == 2 ? 3 : 5;
+            int band_prefetch = 0;        // measured: L2 prefetch of the next item costs more LSU slots than it hides (1058 vs 957 us)
+            if (const char *e = getenv("RDFC_NLSPN_PREFETCH")) band_prefetch = atoi(e);
+            long long band_ctas = (long long)sm_count() * band_per_sm;
+            if (const char *e = getenv("RDFC_NLSPN_BAND_CTAS")) band_ctas = atoll(e);
+            if (band_ctas > total_rows_b) band_ctas = total_rows_b;
+            const int band_rpc = (int)((total_rows_b + band_ctas - 1) / band_ctas);
+            const size_t band_smem = (size_t)(band_rpc + 2 * halo + 3) * (W + 4) * sizeof(float);
+            const size_t band_smem_max = (size_t)(220 * 1024) / band_per_sm;
+            const bool band_ok = !getenv("RDFC_NLSPN_SIMPLE") && !getenv("RDFC_NLSPN_ROWS") && W % band_pix == 0 && band_smem <= band_smem_max &&
+                                 ((uintptr_t)off_g % 8) == 0 && ((uintptr_t)aff_g % 8) == 0 && ((uintptr_t)dst % 8) == 0 &&
+                                 (!it || ((uintptr_t)it % 8) == 0) && (P % 2) == 0;
+            if (band_ok) {
+                const int nctas = (int)((total_rows_b + band_rpc - 1) / band_rpc);
+#define RDFC_BAND(CL, PX, MB)                                                                                                  \
+    do {                                                                                                                       \
+        RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_band_kernel<CL, PX, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)); \
+        nlspn_prop_band_kernel<CL, PX, MB><<<nctas, BAND_THREADS, band_smem, st>>>(cur, off_g, aff_g, dst, it, nb, H, W, band_rpc, halo, band_prefetch); \
+    } while (0)
+                if (band_pix == 2) { if (clamp) RDFC_BAND(true, 2, 3); else RDFC_BAND(false, 2, 3); }
+                else { if (clamp) RDFC_BAND(true, 1, 5); else RDFC_BAND(false, 1, 5); }
+#undef RDFC_BAND
+                RDFC_CHECK_LAUNCH("nlspn_prop_band_kernel");
+                cur = dst;
+                continue;
+            }
             const bool rows_ok = getenv("RDFC_NLSPN_ROWS") && W % 4 == 0 && W <= 1024 && smem <= 200 * 1024 &&
                                  ((uintptr_t)off_g % 16) == 0 && ((uintptr_t)aff_g % 16) == 0;
             if (rows_ok) {
