@@ -151,6 +151,24 @@ typedef struct {
 
 int rdfc_heads_forward(const rdfc_heads_desc *d, void *stream);
 
+/* Fused input stems (rdf_generator.py:286-292: rgb_branch_en1, depth_branch_en1_rgb, depth_branch_en1_depth; each a
+ * conv_bn_relu 3x3 / stride 1 / pad 1 of encoder_decoder/common.py:29-43 over 3 / 3 / 1 input channels): ONE
+ * tensor-core launch.  The producer warps build the im2col rows k = ci*9 + ky*3 + kx (in0's channels first, then
+ * in1's nine taps, zero-padded to 64) straight from the fp32 NCHW inputs; the filter bank is a 1x1 UMMA weight with
+ * Cin = 64 whose columns [0, out.C) are written to `out` and [out.C, out.C + out2.C) to `out2` (bf16 NHWC slices). */
+typedef struct {
+    int B, H, W;
+    const float *in0;            /* fp32 NCHW (B, C0, H, W) */
+    int C0;                      /* 1..6 */
+    const float *in1;            /* fp32 NCHW (B, 1, H, W) or NULL */
+    rdfc_view out, out2;         /* bf16 NHWC; out2.ptr == NULL: single destination */
+    const void *weight;          /* bf16 [1][8][CoutP][8], CoutP = out.C + out2.C padded to 16 */
+    const float *scale, *shift;  /* per column (folded BatchNorm / bias) */
+    int act;                     /* rdfc_act: none / ReLU / LeakyReLU(0.2) */
+} rdfc_stem_desc;
+
+int rdfc_stem_forward(const rdfc_stem_desc *d, void *stream);
+
 /* per-(b,c) mean and 1/sqrt(var+eps) over the pixels of an NHWC view.  unbiased != 0 divides by (n-1) (AdaIN,
  * model_utils.py:98) and returns sqrt(var+eps) in `rstd` instead of its reciprocal when want_std != 0.
  * partial: workspace of B*nchunk*C*2 floats with nchunk = rdfc_instnorm_nchunk(H*W). mean/rstd: (B,C) fp32. */

@@ -39,6 +39,11 @@ class HeadsDesc(ctypes.Structure):
                 ("ncols", c_int), ("act", c_int * 16), ("out", c_void_p * 16), ("out_bstride", ctypes.c_longlong * 16)]
 
 
+class StemDesc(ctypes.Structure):
+    _fields_ = [("B", c_int), ("H", c_int), ("W", c_int), ("in0", c_void_p), ("C0", c_int), ("in1", c_void_p),
+                ("out", View), ("out2", View), ("weight", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("act", c_int)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -56,6 +61,7 @@ def _load():
     lib.rdfc_nlspn_propagate_forward.argtypes = [c_void_p] * 4 + [c_int] + [c_void_p] * 3 + [c_int] * 5 + [c_void_p]
     lib.rdfc_conv_forward.argtypes = [ctypes.POINTER(ConvDesc), c_void_p]
     lib.rdfc_heads_forward.argtypes = [ctypes.POINTER(HeadsDesc), c_void_p]
+    lib.rdfc_stem_forward.argtypes = [ctypes.POINTER(StemDesc), c_void_p]
     lib.rdfc_instnorm_stats.argtypes = [ctypes.POINTER(View), c_int, c_int, c_int, c_float, c_int, c_int, c_void_p,
                                         c_void_p, c_void_p, c_void_p]
     lib.rdfc_wadain_apply.argtypes = [ctypes.POINTER(View)] * 4 + [c_void_p, c_void_p, ctypes.POINTER(View), c_int,

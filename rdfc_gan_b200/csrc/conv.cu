@@ -3,7 +3,7 @@
 
 namespace rdfc {
 int conv_simt_forward(const rdfc_conv_desc *d, cudaStream_t st);
-int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads);
+int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads, const rdfc_stem_desc *stem);
 int conv_umma_read_dbg(long long *host, int n);
 }  // namespace rdfc
 
@@ -24,7 +24,7 @@ extern "C" int rdfc_conv_forward(const rdfc_conv_desc *d, void *stream) {
     RDFC_REQUIRE(d->in.nchw || d->in.pix_stride >= d->in.C, "conv: input pixel stride smaller than its channel count");
     RDFC_REQUIRE(d->out.nchw || d->out.pix_stride >= d->out.C, "conv: output pixel stride smaller than its channel count");
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->path == RDFC_PATH_UMMA_BF16) return conv_umma_forward(d, st, nullptr);
+    if (d->path == RDFC_PATH_UMMA_BF16) return conv_umma_forward(d, st, nullptr, nullptr);
     if (d->path == RDFC_PATH_SIMT_F32) return conv_simt_forward(d, st);
     return fail(RDFC_ERR_INVALID, "conv: unknown path %d", d->path);
 }
@@ -40,7 +40,25 @@ extern "C" int rdfc_heads_forward(const rdfc_heads_desc *h, void *stream) {
     d.in = h->in;
     d.out.ptr = h->out[0]; d.out.dtype = RDFC_F32; d.out.C = 16; d.out.pix_stride = 16;
     d.weight = h->weight; d.scale = nullptr; d.shift = h->shift;
-    return conv_umma_forward(&d, (cudaStream_t)stream, h);
+    return conv_umma_forward(&d, (cudaStream_t)stream, h, nullptr);
+}
+
+extern "C" int rdfc_stem_forward(const rdfc_stem_desc *m, void *stream) {
+    RDFC_REQUIRE(m != nullptr && m->in0 && m->out.ptr && m->weight, "stem: NULL argument");
+    RDFC_REQUIRE(m->B > 0 && m->H > 0 && m->W > 0, "stem: empty dimension");
+    RDFC_REQUIRE(m->C0 >= 1 && 9 * (m->C0 + (m->in1 ? 1 : 0)) <= 64, "stem: at most 7 input channels in total (64 im2col rows)");
+    RDFC_REQUIRE(m->act == RDFC_ACT_NONE || m->act == RDFC_ACT_RELU || m->act == RDFC_ACT_LEAKY02, "stem: unsupported activation");
+    RDFC_REQUIRE(m->out.dtype == RDFC_BF16 && !m->out.nchw && (!m->out2.ptr || (m->out2.dtype == RDFC_BF16 && !m->out2.nchw)),
+                 "stem: bf16 NHWC destinations only");
+    RDFC_REQUIRE(!m->out2.ptr || (m->out.C % 16 == 0 && m->out2.pix_stride % 8 == 0 && ((uintptr_t)m->out2.ptr % 16) == 0),
+                 "stem: the first destination must take a multiple of 16 columns; the second must be 16-byte aligned");
+    rdfc_conv_desc d{};
+    d.B = m->B; d.Hi = d.Ho = m->H; d.Wi = d.Wo = m->W;
+    d.kh = d.kw = 1; d.stride = 1; d.pad = 0; d.act = m->act; d.path = RDFC_PATH_UMMA_BF16;
+    d.in.ptr = (void *)m->in0; d.in.dtype = RDFC_F32; d.in.C = 64; d.in.pix_stride = 64;      // the virtual im2col matrix
+    d.out = m->out;
+    d.weight = m->weight; d.scale = m->scale; d.shift = m->shift;
+    return conv_umma_forward(&d, (cudaStream_t)stream, nullptr, m);
 }
 
 // development aid (not part of the public ABI): role timers of the last conv_umma launch under RDFC_UMMA_DBG=1

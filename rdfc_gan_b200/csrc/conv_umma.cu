@@ -24,6 +24,7 @@
 //                   slice (this is how every torch.cat of the reference disappears) or, for the fused decode heads,
 //                   one fp32 plane per output column.  TMEM holds two accumulator sets (when 2*NACC*BN <= 512), so
 //                   the MMA warp fills set (t+1)&1 while the epilogue drains set t&1.
+#include <limits.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -82,6 +83,11 @@ struct Params {
     int dbg_flags;                 // development aid (RDFC_UMMA_SKIP): 1 = no output stores, 2 = no TMEM loads
     long long *dbg;                // development aid: per-CTA role timers (RDFC_UMMA_DBG=1), else nullptr
     long long w_kb_stride;         // elements between consecutive 32-cin blocks of one tap
+    // fused input stems (rdfc_stem_forward): the producers build im2col rows from fp32 NCHW inputs instead of copying
+    const float *stem_in0, *stem_in1;
+    int stem_c0, stem_k;           // channels of in0; im2col rows in use (9 * channels), the rest of the 64 are zero
+    __nv_bfloat16 *out2;           // second destination for output columns >= split (NULL: none)
+    int out2_stride, split;
     int gtaps;                     // filter taps per B stage (3 for 3x3 convs: one wait / commit per filter row)
     int vec32;                     // output (and residual) slices are 32-byte aligned: 256-bit stores / loads
     int b_contig;                  // the 4 cin chunks of a stage are contiguous in the packed weights (one Cout tile)
@@ -291,7 +297,72 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     const int set_cols = P.nacc * P.bn;
 
-    if (warp < NPROD_WARPS) {
+    if (warp < NPROD_WARPS && P.stem_in0) {
+        // ================= A producers, stem mode =================
+        // The "input" of the 1x1 GEMM is the im2col matrix of the 3x3 stems, built on the fly: slot (pixel p, chunk ch)
+        // of k-block i holds rows k = 32 i + 8 ch .. + 8, row k = (channel k / 9, tap k % 9) of the fp32 NCHW inputs.
+        // A thread's chunk is fixed, so its 2 x 8 (channel plane, dy, dx) triples are decoded once.
+        const int ch = threadIdx.x & 3, p0 = threadIdx.x >> 2;
+        const int Hi = P.Hi, Wi = P.Wi, TWs = 8 * P.nacc, nj = (P.npix + PIXPASS - 1) / PIXPASS;
+        const long long HW = (long long)Hi * Wi;
+        int delta[2][8];            // element offset from the centre pixel within one image's planes; INT_MIN = zero row
+        int dyx[2][8];              // (dy + 1) | (dx + 1) << 2 | (from in1) << 4
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = 32 * i + 8 * ch + e;
+                if (k < P.stem_k) {
+                    const int ci = k / 9, tp = k - 9 * ci, dy = tp / 3 - 1, dx = tp % 3 - 1;
+                    const bool second = ci >= P.stem_c0;
+                    delta[i][e] = (second ? 0 : ci) * (int)HW + dy * Wi + dx;
+                    dyx[i][e] = (dy + 1) | ((dx + 1) << 2) | (second ? 16 : 0);
+                } else {
+                    delta[i][e] = INT_MIN;
+                    dyx[i][e] = 0;
+                }
+            }
+        const uint32_t dst_thread = smem_u32(sA) + (uint32_t)(ch * P.npix_pad + p0) * 16u;
+        int s = 0;
+        uint32_t par = 1;
+        for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+            const Tile t = decode_tile(P, tile);
+            const float *b0 = P.stem_in0 + (long long)t.b * P.stem_c0 * HW;
+            const float *b1 = P.stem_in1 ? P.stem_in1 + (long long)t.b * HW : b0;
+            for (int i = 0; i < P.nkb; ++i) {
+                mbar_wait(BAR(A_EMPTY + s), par);
+                const uint32_t dst = dst_thread + (uint32_t)s * (uint32_t)a_stage_bytes;
+                for (int j = 0; j < nj; ++j) {
+                    const int p = j * PIXPASS + p0;
+                    if (p >= P.npix) break;
+                    const int y = t.ty0 + p / TWs, x = t.tx0 + p % TWs;
+                    const bool inimg = y < Hi && x < Wi;
+                    // rows / columns a tap may not read: bit (dy + 1) of ybad, bit (dx + 1) of xbad
+                    const int ybad = (y == 0 ? 1 : 0) | (y == Hi - 1 ? 4 : 0), xbad = (x == 0 ? 1 : 0) | (x == Wi - 1 ? 4 : 0);
+                    const long long centre = (long long)y * Wi + x;
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int dl = i == 0 ? delta[0][e] : delta[1][e], q = i == 0 ? dyx[0][e] : dyx[1][e];
+                        const bool ok = inimg && dl != INT_MIN && !((ybad >> (q & 3)) & 1) && !((xbad >> ((q >> 2) & 3)) & 1);
+                        v[e] = ok ? __ldg(((q & 16) ? b1 : b0) + centre + dl) : 0.f;
+                    }
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                        w[e] = *reinterpret_cast<const uint32_t *>(&h2);
+                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)j * (uint32_t)(PIXPASS * 16)),
+                                 "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                                 : "memory");
+                }
+                fence_proxy_async();              // generic-proxy stores -> visible to the tensor core (async proxy)
+                mbar_arrive(BAR(A_FULL + s));
+                if (++s == P.sa) { s = 0; par ^= 1u; }
+            }
+        }
+    } else if (warp < NPROD_WARPS) {
         // ================= A producers =================
         // Thread t owns 16-byte chunk (t & 3) of pixel slots (t >> 2) + PIXPASS * j of every stage.  Which plane pixel a slot
         // is never changes, so its plane-relative input coordinates are decoded once per kernel; per tile they become
@@ -316,7 +387,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         const int ystep = keep(P.planes[0].ystep), xstep = keep(P.planes[0].xstep);     // the same for every plane of a layer
         const int Hi = keep(P.Hi), Wi = keep(P.Wi), in_stride = keep(P.in_stride), nkb = keep(P.nkb), sa_n = keep(P.sa);
         const uint32_t dst_thread = smem_u32(sA) + (uint32_t)(ch * P.npix_pad + p0) * 16u;
-        const int lag = P.sa >= 3 ? 2 : 1;      // cp.async groups kept in flight before the oldest is published
+        // cp.async groups kept in flight before the oldest is published.  Publishing k-block i-lag needs k-block i
+        // issued, i.e. the stage of k-block i-sa drained by the MMAs: lag <= sa - 2 keeps one published stage for the
+        // tensor core to work on meanwhile (lag = sa - 1 serialises MMA and staging).
+        const int lag = P.sa >= 4 ? 2 : (P.sa == 3 ? 1 : 0);
         int s = 0;                  // ring position, continues across tiles
         uint32_t par = 1;           // parity to wait for on A_EMPTY[s]
         long long t_wait_empty = 0, t_issue = 0, t_wait_group = 0;
@@ -348,7 +422,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                 if (DBG_ON) t_issue += clock64() - _ti;
                 ++issued;
                 if (issued > lag) {               // publish the oldest k-block in flight
-                    { DBG_T0(); if (lag == 2) cp_async_wait<2>(); else cp_async_wait<1>(); DBG_ACC(t_wait_group); }
+                    { DBG_T0(); if (lag == 2) cp_async_wait<2>(); else if (lag == 1) cp_async_wait<1>(); else cp_async_wait<0>(); DBG_ACC(t_wait_group); }
                     fence_proxy_async();
                     mbar_arrive(BAR(A_FULL + pub));
                     if (++pub == sa_n) pub = 0;
@@ -515,6 +589,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                 const uint32_t trow = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(set * set_cols + j * bn);
                 const __nv_bfloat16 *rrow = res ? res + opix * res_stride + n0 : nullptr;
                 __nv_bfloat16 *orow = planar ? nullptr : outp + opix * out_stride + n0;
+                __nv_bfloat16 *orow2 = P.out2 ? P.out2 + opix * P.out2_stride + n0 - P.split : nullptr;
                 const long long pp = (long long)oy * Wo + ox;
 
                 auto load_res = [&](int g, uint4 &r0, uint4 &r1) {
@@ -579,7 +654,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
 #pragma unroll
                         for (int q = 0; q < 16; ++q) f[q] = act == RDFC_ACT_TANH ? tanhf(f[q]) : 1.f / (1.f + expf(-f[q]));
                     }
-                    __nv_bfloat16 *op = orow + n;
+                    __nv_bfloat16 *op = (orow2 && n0 + n >= P.split ? orow2 : orow) + n;
                     if (skip & 1) return;
                     if (full) {
                         uint32_t o[8];
@@ -650,11 +725,11 @@ int next_pow2_cols(int c) {
 }  // namespace
 
 // Host-side planning: planes, taps, tile shape, stage counts.
-int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads) {
-    RDFC_REQUIRE(d->in.dtype == RDFC_BF16 && (heads || d->out.dtype == RDFC_BF16), "UMMA conv: bf16 in/out only");
+int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads, const rdfc_stem_desc *stem) {
+    RDFC_REQUIRE((stem || d->in.dtype == RDFC_BF16) && (heads || d->out.dtype == RDFC_BF16), "UMMA conv: bf16 in/out only");
     RDFC_REQUIRE(!d->in.nchw && !d->out.nchw && !d->in2.ptr, "UMMA conv: single NHWC source / NHWC output only");
     RDFC_REQUIRE(d->in.C % BK == 0, "UMMA conv: Cin (%d) must be a multiple of %d", d->in.C, BK);
-    RDFC_REQUIRE(d->in.pix_stride % 8 == 0 && ((uintptr_t)d->in.ptr % 16) == 0 && ((uintptr_t)d->weight % 16) == 0 &&
+    RDFC_REQUIRE((stem || (d->in.pix_stride % 8 == 0 && ((uintptr_t)d->in.ptr % 16) == 0)) && ((uintptr_t)d->weight % 16) == 0 &&
                      (heads || (d->out.pix_stride % 8 == 0 && ((uintptr_t)d->out.ptr % 16) == 0)),
                  "UMMA conv: views must be 16-byte aligned with pixel strides that are multiples of 8 elements");
     RDFC_REQUIRE(!d->residual.ptr || (d->residual.dtype == RDFC_BF16 && d->residual.pix_stride % 8 == 0 &&
@@ -677,6 +752,14 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     P.out = (__nv_bfloat16 *)d->out.ptr; P.out_stride = d->out.pix_stride; P.Ho = d->Ho; P.Wo = d->Wo;
     P.res = (const __nv_bfloat16 *)d->residual.ptr; P.res_stride = d->residual.pix_stride;
     P.scale = d->scale; P.shift = d->shift; P.act = d->act;
+    if (stem) {
+        P.stem_in0 = stem->in0; P.stem_in1 = stem->in1; P.stem_c0 = stem->C0;
+        P.stem_k = 9 * (stem->C0 + (stem->in1 ? 1 : 0));
+        if (stem->out2.ptr) {
+            P.out2 = (__nv_bfloat16 *)stem->out2.ptr; P.out2_stride = stem->out2.pix_stride; P.split = stem->out.C;
+            P.Cout = stem->out.C + stem->out2.C; P.CoutP = (P.Cout + 15) / 16 * 16;
+        }
+    }
     if (heads) {
         P.planar = 1; P.ncols = heads->ncols;
         for (int q = 0; q < 16; ++q) {
@@ -786,6 +869,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     P.gtaps = (k3 && !d->transposed) ? 3 : 1;
     if (const char *e = getenv("RDFC_UMMA_GTAPS")) P.gtaps = atoi(e);    // development knob (1 or 3)
     P.vec32 = !heads && ((uintptr_t)d->out.ptr % 32) == 0 && d->out.pix_stride % 16 == 0 &&
+              (!P.out2 || (((uintptr_t)P.out2 % 32) == 0 && P.out2_stride % 16 == 0 && P.split % 16 == 0)) &&
               (!d->residual.ptr || (((uintptr_t)d->residual.ptr % 32) == 0 && d->residual.pix_stride % 16 == 0));
     const int a_stage = KCH * P.npix_pad * 16, b_stage = P.gtaps * KCH * P.bn * 16;
     const int fixed = BAR_BYTES + 2 * P.CoutP * 4 + 4 * MAX_TAPS * 8 + 256;   // barriers, (scale, shift) and tap tables, slack
@@ -793,14 +877,19 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     // A ring first (>= 2 stages: the producers publish k-block i while k-block i+1 is in flight), then B stages (2..6)
     // the filter stream is latency-bound: bytes in flight per SM = bandwidth x L2 latency (~2000 cycles), so keep
     // >= 64 KB of filter stages in flight when the tile allows it
-    P.sb = (80 * 1024 + b_stage - 1) / b_stage;
-    if (P.sb < 3) P.sb = 3;
-    if (P.sb > 16) P.sb = 16;
+    // filter ring: enough stages to cover ~2500 cycles of L2 latency at the rate the tensor core drains them
+    {
+        const int mma_cycles = P.bn / 2 > 54 ? P.bn / 2 : 54;                 // measured: max(N/2, ~54) per M=128, K=16 MMA
+        const int stage_cycles = P.gtaps * P.nacc * (BK / 16) * mma_cycles;
+        P.sb = 2500 / stage_cycles + 2;
+        if (P.sb < 3) P.sb = 3;
+        if (P.sb > 16) P.sb = 16;
+    }
     if (const char *e = getenv("RDFC_UMMA_SB")) P.sb = atoi(e);          // development knob (<= 16)
     while (P.sb > 3 && 3 * a_stage + P.sb * b_stage + fixed > budget) --P.sb;     // prefer >= 3 A stages (2 in flight)
     while (P.sb > 2 && 2 * a_stage + P.sb * b_stage + fixed > budget) --P.sb;
     P.sa = (budget - fixed - P.sb * b_stage) / a_stage;
-    if (P.sa > 4) P.sa = 4;
+    if (P.sa > 6) P.sa = 6;
     if (const char *e = getenv("RDFC_UMMA_SA")) P.sa = atoi(e) < P.sa ? atoi(e) : P.sa;
     RDFC_REQUIRE(P.sa >= 1 && P.sa <= 8 && P.sb >= 1 && P.sb <= 16, "UMMA conv: tile does not fit shared memory");
     const size_t smem = (size_t)P.sa * a_stage + (size_t)P.sb * b_stage + fixed;

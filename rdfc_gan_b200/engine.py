@@ -195,11 +195,15 @@ class GeneratorEngine:
         # ---- stems (rdf_generator.py:286-292): NCHW fp32 in, NHWC slice out
         L = C.ACT_LEAKY02
         full = (H, W)
-        conv('rgb_branch_en1', [seq_src(g.rgb_branch_en1)], plan.stem_in, fe1['r'], 3, act=L, in_nchw=True, hin=full, hout=full)
-        conv('depth_branch_en1_rgb', [seq_src(g.depth_branch_en1_rgb)], plan.stem_in, (fe1['d'][0], fe1['d'][1], 48), 3,
-             act=L, in_nchw=True, hin=full, hout=full)
-        conv('depth_branch_en1_depth', [seq_src(g.depth_branch_en1_depth)], plan.depth,
-             (fe1['d'][0], fe1['d'][1] + 48, 16), 3, act=L, in_nchw=True, hin=full, hout=full)
+        if bf16 and 9 * (Cs + 1) <= 64:
+            # all three stems as ONE tensor-core launch: im2col rows built by the producer warps from the fp32 NCHW inputs
+            self._plan_stem(plan, B, H, W, Cs, fe1)
+        else:
+            conv('rgb_branch_en1', [seq_src(g.rgb_branch_en1)], plan.stem_in, fe1['r'], 3, act=L, in_nchw=True, hin=full, hout=full)
+            conv('depth_branch_en1_rgb', [seq_src(g.depth_branch_en1_rgb)], plan.stem_in, (fe1['d'][0], fe1['d'][1], 48), 3,
+                 act=L, in_nchw=True, hin=full, hout=full)
+            conv('depth_branch_en1_depth', [seq_src(g.depth_branch_en1_depth)], plan.depth,
+                 (fe1['d'][0], fe1['d'][1] + 48, 16), 3, act=L, in_nchw=True, hin=full, hout=full)
 
         # ---- encoders (rdf_generator.py:295-312)
         feat = {}
@@ -300,6 +304,37 @@ class GeneratorEngine:
         plan.n_launch += 1
         plan.outputs = (plan.d1, plan.c1, plan.d2, plan.conf, plan.pred)
         return plan
+
+    def _plan_stem(self, plan, B, H, W, Cs, fe1):
+        """rgb_branch_en1 | depth_branch_en1_rgb | depth_branch_en1_depth (rdf_generator.py:286-292) as one 64 -> 128
+        GEMM over im2col rows k = ci*9 + ky*3 + kx (stem input channels first, then the depth map's nine taps)."""
+        g = self.gen
+        K = 64
+
+        def padded(mod, k0):
+            def f():
+                w = mod[0].weight.detach().float()                     # (Cout, Cin, 3, 3)
+                out = w.new_zeros(w.shape[0], K, 1, 1)
+                out[:, k0:k0 + w.shape[1] * 9, 0, 0] = w.reshape(w.shape[0], -1)
+                return out
+            return f
+
+        def src(mod, k0):
+            bn = mod[1] if len(mod) > 1 and isinstance(mod[1], torch.nn.BatchNorm2d) else None
+            return (padded(mod, k0), bn, mod[0].bias)
+
+        srcs = [src(g.rgb_branch_en1, 0), src(g.depth_branch_en1_rgb, 0), src(g.depth_branch_en1_depth, 9 * Cs)]
+        pk = self._pack('stems', srcs, 'bf16', True)
+        d = C.StemDesc()
+        d.B, d.H, d.W = B, H, W
+        d.in0, d.C0, d.in1 = plan.stem_in.data_ptr(), Cs, plan.depth.data_ptr()
+        d.out = C.view(fe1['r'][0], fe1['r'][2], fe1['r'][1])
+        d.out2 = C.view(fe1['d'][0], fe1['d'][2], fe1['d'][1])
+        d.weight, d.scale, d.shift, d.act = pk.weight.data_ptr(), pk.scale.data_ptr(), pk.shift.data_ptr(), C.ACT_LEAKY02
+        plan.keep.append((d, pk))
+        plan.names.append(f'stems {Cs}+1 -> 64|64 ({H}, {W}) umma')
+        plan.steps.append(lambda s, d=d: C.check(C.lib.rdfc_stem_forward(ctypes.byref(d), s)))
+        plan.n_launch += 1
 
     def _plan_heads(self, plan, name, buf, B, H, W, cols):
         """One rdfc_heads_forward over the NHWC head buffer `buf`.  cols: dicts with the head's conv module, activation,
