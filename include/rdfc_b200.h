@@ -169,6 +169,25 @@ typedef struct {
 
 int rdfc_stem_forward(const rdfc_stem_desc *d, void *stream);
 
+/* W-AdaIN with the style projection fused (model_utils.py:53-90 without `weighting`): ONE tensor-core launch computes
+ * the per-pixel EqualLinear  [gamma | beta] = style[p, :] . W^T + bias  (a 1x1 convolution Cd -> 2C) and applies
+ *   out[p, c] = gamma[p, c] * (x[p, c] - mean[b, c]) * rstd[b, c] + beta[p, c]
+ * in its epilogue, so the (B,H,W,2C) gamma/beta tensor never exists.  The filter rows are packed in tiles of
+ * `rdfc_wadain_tile(C)` columns: tile t = gamma rows of channels [t*h, (t+1)*h) followed by their beta rows, h = tile/2;
+ * `bias` is permuted the same way.  mean / rstd: (B, C) fp32 from rdfc_instnorm_stats. */
+typedef struct {
+    int B, H, W;
+    rdfc_view style;             /* bf16 NHWC, Cd % 32 == 0 */
+    rdfc_view x;                 /* bf16 NHWC, C channels, C % 64 == 0 */
+    rdfc_view out;               /* bf16 NHWC, C channels */
+    const void *weight;          /* bf16 [1][Cd/8][2C][8], rows permuted as described */
+    const float *bias;           /* 2C floats, permuted */
+    const float *mean, *rstd;    /* (B, C) */
+} rdfc_wadain_conv_desc;
+
+int rdfc_wadain_tile(int C);
+int rdfc_wadain_conv_forward(const rdfc_wadain_conv_desc *d, void *stream);
+
 /* per-(b,c) mean and 1/sqrt(var+eps) over the pixels of an NHWC view.  unbiased != 0 divides by (n-1) (AdaIN,
  * model_utils.py:98) and returns sqrt(var+eps) in `rstd` instead of its reciprocal when want_std != 0.
  * partial: workspace of B*nchunk*C*2 floats with nchunk = rdfc_instnorm_nchunk(H*W). mean/rstd: (B,C) fp32. */

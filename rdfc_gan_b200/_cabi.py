@@ -44,6 +44,11 @@ class StemDesc(ctypes.Structure):
                 ("out", View), ("out2", View), ("weight", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("act", c_int)]
 
 
+class WadainConvDesc(ctypes.Structure):
+    _fields_ = [("B", c_int), ("H", c_int), ("W", c_int), ("style", View), ("x", View), ("out", View), ("weight", c_void_p),
+                ("bias", c_void_p), ("mean", c_void_p), ("rstd", c_void_p)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -62,6 +67,8 @@ def _load():
     lib.rdfc_conv_forward.argtypes = [ctypes.POINTER(ConvDesc), c_void_p]
     lib.rdfc_heads_forward.argtypes = [ctypes.POINTER(HeadsDesc), c_void_p]
     lib.rdfc_stem_forward.argtypes = [ctypes.POINTER(StemDesc), c_void_p]
+    lib.rdfc_wadain_conv_forward.argtypes = [ctypes.POINTER(WadainConvDesc), c_void_p]
+    lib.rdfc_wadain_tile.argtypes = [c_int]
     lib.rdfc_instnorm_stats.argtypes = [ctypes.POINTER(View), c_int, c_int, c_int, c_float, c_int, c_int, c_void_p,
                                         c_void_p, c_void_p, c_void_p]
     lib.rdfc_wadain_apply.argtypes = [ctypes.POINTER(View)] * 4 + [c_void_p, c_void_p, ctypes.POINTER(View), c_int,

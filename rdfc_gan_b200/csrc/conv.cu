@@ -3,7 +3,9 @@
 
 namespace rdfc {
 int conv_simt_forward(const rdfc_conv_desc *d, cudaStream_t st);
-int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads, const rdfc_stem_desc *stem);
+int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads, const rdfc_stem_desc *stem,
+                      const rdfc_wadain_conv_desc *wad);
+int wadain_tile(int C);
 int conv_umma_read_dbg(long long *host, int n);
 }  // namespace rdfc
 
@@ -24,7 +26,7 @@ extern "C" int rdfc_conv_forward(const rdfc_conv_desc *d, void *stream) {
     RDFC_REQUIRE(d->in.nchw || d->in.pix_stride >= d->in.C, "conv: input pixel stride smaller than its channel count");
     RDFC_REQUIRE(d->out.nchw || d->out.pix_stride >= d->out.C, "conv: output pixel stride smaller than its channel count");
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->path == RDFC_PATH_UMMA_BF16) return conv_umma_forward(d, st, nullptr, nullptr);
+    if (d->path == RDFC_PATH_UMMA_BF16) return conv_umma_forward(d, st, nullptr, nullptr, nullptr);
     if (d->path == RDFC_PATH_SIMT_F32) return conv_simt_forward(d, st);
     return fail(RDFC_ERR_INVALID, "conv: unknown path %d", d->path);
 }
@@ -40,7 +42,7 @@ extern "C" int rdfc_heads_forward(const rdfc_heads_desc *h, void *stream) {
     d.in = h->in;
     d.out.ptr = h->out[0]; d.out.dtype = RDFC_F32; d.out.C = 16; d.out.pix_stride = 16;
     d.weight = h->weight; d.scale = nullptr; d.shift = h->shift;
-    return conv_umma_forward(&d, (cudaStream_t)stream, h, nullptr);
+    return conv_umma_forward(&d, (cudaStream_t)stream, h, nullptr, nullptr);
 }
 
 extern "C" int rdfc_stem_forward(const rdfc_stem_desc *m, void *stream) {
@@ -58,7 +60,27 @@ extern "C" int rdfc_stem_forward(const rdfc_stem_desc *m, void *stream) {
     d.in.ptr = (void *)m->in0; d.in.dtype = RDFC_F32; d.in.C = 64; d.in.pix_stride = 64;      // the virtual im2col matrix
     d.out = m->out;
     d.weight = m->weight; d.scale = m->scale; d.shift = m->shift;
-    return conv_umma_forward(&d, (cudaStream_t)stream, nullptr, m);
+    return conv_umma_forward(&d, (cudaStream_t)stream, nullptr, m, nullptr);
+}
+
+extern "C" int rdfc_wadain_tile(int C) { return wadain_tile(C); }
+
+extern "C" int rdfc_wadain_conv_forward(const rdfc_wadain_conv_desc *w, void *stream) {
+    RDFC_REQUIRE(w != nullptr && w->style.ptr && w->x.ptr && w->out.ptr && w->weight && w->bias && w->mean && w->rstd,
+                 "wadain conv: NULL argument");
+    RDFC_REQUIRE(w->B > 0 && w->H > 0 && w->W > 0, "wadain conv: empty dimension");
+    RDFC_REQUIRE(w->x.C % 64 == 0 && w->out.C == w->x.C, "wadain conv: C (%d) must be a multiple of 64 and match the output", w->x.C);
+    RDFC_REQUIRE(w->x.dtype == RDFC_BF16 && w->out.dtype == RDFC_BF16 && w->style.dtype == RDFC_BF16 && !w->x.nchw && !w->out.nchw,
+                 "wadain conv: bf16 NHWC views only");
+    RDFC_REQUIRE(((uintptr_t)w->x.ptr % 32) == 0 && w->x.pix_stride % 16 == 0 && ((uintptr_t)w->out.ptr % 32) == 0 &&
+                     w->out.pix_stride % 16 == 0,
+                 "wadain conv: x / out slices must be 32-byte aligned");
+    rdfc_conv_desc d{};
+    d.B = w->B; d.Hi = d.Ho = w->H; d.Wi = d.Wo = w->W;
+    d.kh = d.kw = 1; d.stride = 1; d.pad = 0; d.act = RDFC_ACT_NONE; d.path = RDFC_PATH_UMMA_BF16;
+    d.in = w->style; d.out = w->out;
+    d.weight = w->weight; d.scale = nullptr; d.shift = w->bias;
+    return conv_umma_forward(&d, (cudaStream_t)stream, nullptr, nullptr, w);
 }
 
 // development aid (not part of the public ABI): role timers of the last conv_umma launch under RDFC_UMMA_DBG=1

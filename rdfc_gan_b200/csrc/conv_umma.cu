@@ -88,6 +88,10 @@ struct Params {
     int stem_c0, stem_k;           // channels of in0; im2col rows in use (9 * channels), the rest of the 64 are zero
     __nv_bfloat16 *out2;           // second destination for output columns >= split (NULL: none)
     int out2_stride, split;
+    // fused W-AdaIN epilogue (rdfc_wadain_conv_forward): tile columns = [gamma half | beta half]
+    const __nv_bfloat16 *wad_x;    // normalised tensor (NULL: not a W-AdaIN launch)
+    int wad_x_stride, wad_C;
+    const float *wad_mean, *wad_rstd;
     int gtaps;                     // filter taps per B stage (3 for 3x3 convs: one wait / commit per filter row)
     int vec32;                     // output (and residual) slices are 32-byte aligned: 256-bit stores / loads
     int b_contig;                  // the 4 cin chunks of a stage are contiguous in the packed weights (one Cout tile)
@@ -252,8 +256,11 @@ __device__ __forceinline__ void ld_global_v8(const void *p, uint32_t (&o)[8]) {
 
 // kGeneral = false: the hot variant (bf16 NHWC output, act in {none, ReLU, LeakyReLU}); true adds the planar decode-head
 // outputs and tanh / sigmoid, whose code would otherwise cost the hot epilogue registers.
-template <bool kGeneral>
+// and kMode = MODE_WADAIN (W-AdaIN epilogue over [gamma | beta] column tiles).
+enum { MODE_STD = 0, MODE_GENERAL = 1, MODE_WADAIN = 2 };
+template <int kMode>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_constant__ Params P) {
+    constexpr bool kGeneral = kMode == MODE_GENERAL;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_stage_bytes = KCH * P.npix_pad * 16, b_tap_bytes = KCH * P.bn * 16, b_stage_bytes = P.gtaps * b_tap_bytes;
@@ -270,6 +277,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     float *s_scale = reinterpret_cast<float *>(sB + (size_t)P.sb * b_stage_bytes + BAR_BYTES);
     float *s_shift = s_scale + P.CoutP;
     uint2 *s_tap = reinterpret_cast<uint2 *>(s_shift + P.CoutP);      // [phase][tap] A-descriptor words (lo, hi)
+    float *s_stat = reinterpret_cast<float *>(s_tap + 4 * MAX_TAPS);   // W-AdaIN: mean[C], rstd[C] of the current image
     if (threadIdx.x < 4 * MAX_TAPS)
         s_tap[threadIdx.x] = make_uint2(P.tap_alo[threadIdx.x / MAX_TAPS][threadIdx.x % MAX_TAPS],
                                         P.tap_ahi[threadIdx.x / MAX_TAPS][threadIdx.x % MAX_TAPS]);
@@ -570,7 +578,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         const __nv_bfloat16 *res = P.res;
         __nv_bfloat16 *const outp = P.out;
         const int G = bn >> 4;
-        int it = 0;
+        int it = 0, wad_b = -1;
         long long t_accfull = 0, t_epi = 0;
         for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
             const Tile t = decode_tile(P, tile);
@@ -580,6 +588,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
             { DBG_T0(); mbar_wait<true>(BAR(ACC_FULL + set), use & 1); DBG_ACC(t_accfull); }
             tc_fence_after();
             const long long _te = DBG_ON ? clock64() : 0;
+            if (kMode == MODE_WADAIN) {
+                // ---- W-AdaIN: out = (acc_g + bias_g) * (x - mean) * rstd + (acc_b + bias_b), 16 channels per step
+                const int C = P.wad_C, half = bn >> 1, c0 = (t.n0 / bn) * half;
+                if (t.b != wad_b) {                       // (mean, rstd) of this image -> shared memory
+                    asm volatile("bar.sync 2, %0;" ::"n"(NEPI_WARPS * 32) : "memory");
+                    for (int e = threadIdx.x - EPI_WARP0 * 32; e < C; e += NEPI_WARPS * 32) {
+                        s_stat[e] = P.wad_mean[(long long)t.b * C + e];
+                        s_stat[C + e] = P.wad_rstd[(long long)t.b * C + e];
+                    }
+                    asm volatile("bar.sync 2, %0;" ::"n"(NEPI_WARPS * 32) : "memory");
+                    wad_b = t.b;
+                }
+                for (int j = grp; j < nacc; j += 2) {
+                    const int yy = t.ty0 + r, xx = t.tx0 + 8 * j + c;
+                    const bool ok = yy < Ht && xx < Wt;
+                    const long long opix = ok ? ((long long)t.b * Ho + yy) * Wo + xx : 0;
+                    const uint32_t trow = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(set * set_cols + j * bn);
+                    const __nv_bfloat16 *xrow = P.wad_x + opix * P.wad_x_stride + c0;
+                    __nv_bfloat16 *orow = outp + opix * out_stride + c0;
+                    for (int g = 0; g < (half >> 4); ++g) {
+                        uint32_t vg[16], vb[16], xr[8];
+                        tc_ld16_issue(trow + (uint32_t)(16 * g), vg);
+                        tc_ld16_issue(trow + (uint32_t)(half + 16 * g), vb);
+                        if (ok) ld_global_v8(xrow + 16 * g, xr);
+                        tc_wait_ld(vg);
+                        tc_wait_ld(vb);
+                        if (!ok) continue;
+                        uint32_t o[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int ch = c0 + 16 * g + 2 * q, ng = t.n0 + 16 * g + 2 * q, nb = ng + half;
+                            const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&xr[q]));
+                            const float n0v = (xv.x - s_stat[ch]) * s_stat[C + ch], n1v = (xv.y - s_stat[ch + 1]) * s_stat[C + ch + 1];
+                            const float y0 = fmaf(__uint_as_float(vg[2 * q]) + s_shift[ng], n0v, __uint_as_float(vb[2 * q]) + s_shift[nb]);
+                            const float y1 = fmaf(__uint_as_float(vg[2 * q + 1]) + s_shift[ng + 1], n1v, __uint_as_float(vb[2 * q + 1]) + s_shift[nb + 1]);
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+                            o[q] = *reinterpret_cast<const uint32_t *>(&h2);
+                        }
+                        st_global_v8(orow + 16 * g, o);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + set));
+                continue;
+            }
             const int n0 = t.n0;
             for (int j = grp; j < nacc; j += 2) {
                 const int yy = t.ty0 + r, xx = t.tx0 + 8 * j + c;
@@ -725,7 +779,10 @@ int next_pow2_cols(int c) {
 }  // namespace
 
 // Host-side planning: planes, taps, tile shape, stage counts.
-int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads, const rdfc_stem_desc *stem) {
+int wadain_tile(int C) { return (2 * C) % 256 == 0 ? 256 : 128; }
+
+int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads, const rdfc_stem_desc *stem,
+                      const rdfc_wadain_conv_desc *wad) {
     RDFC_REQUIRE((stem || d->in.dtype == RDFC_BF16) && (heads || d->out.dtype == RDFC_BF16), "UMMA conv: bf16 in/out only");
     RDFC_REQUIRE(!d->in.nchw && !d->out.nchw && !d->in2.ptr, "UMMA conv: single NHWC source / NHWC output only");
     RDFC_REQUIRE(d->in.C % BK == 0, "UMMA conv: Cin (%d) must be a multiple of %d", d->in.C, BK);
@@ -752,6 +809,11 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     P.out = (__nv_bfloat16 *)d->out.ptr; P.out_stride = d->out.pix_stride; P.Ho = d->Ho; P.Wo = d->Wo;
     P.res = (const __nv_bfloat16 *)d->residual.ptr; P.res_stride = d->residual.pix_stride;
     P.scale = d->scale; P.shift = d->shift; P.act = d->act;
+    if (wad) {
+        P.wad_x = (const __nv_bfloat16 *)wad->x.ptr; P.wad_x_stride = wad->x.pix_stride; P.wad_C = wad->x.C;
+        P.wad_mean = wad->mean; P.wad_rstd = wad->rstd;
+        P.Cout = 2 * wad->x.C; P.CoutP = P.Cout;              // GEMM columns; the output view has C channels
+    }
     if (stem) {
         P.stem_in0 = stem->in0; P.stem_in1 = stem->in1; P.stem_c0 = stem->C0;
         P.stem_k = 9 * (stem->C0 + (stem->in1 ? 1 : 0));
@@ -776,6 +838,8 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     // should be >= 128; N = 128 rather than 256 leaves room for two accumulator sets of two accumulators in TMEM.
     int bn_max = 128;
     if (P.CoutP > 128 && P.CoutP % 128 != 0) bn_max = 256;               // e.g. 160: one tile beats 2 x 80
+    if (k1 && P.CoutP % 256 == 0) bn_max = 256;                          // 1x1: the A stage feeds one tap only, so widen N
+    if (wad) bn_max = wadain_tile(wad->x.C);
     if (const char *e = getenv("RDFC_UMMA_BN")) bn_max = atoi(e);        // development knob
     P.bn = P.CoutP < bn_max ? P.CoutP : bn_max;
     while (P.CoutP % P.bn) P.bn -= 16;   // largest multiple of 16 <= bn_max dividing the padded Cout
@@ -872,7 +936,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
               (!P.out2 || (((uintptr_t)P.out2 % 32) == 0 && P.out2_stride % 16 == 0 && P.split % 16 == 0)) &&
               (!d->residual.ptr || (((uintptr_t)d->residual.ptr % 32) == 0 && d->residual.pix_stride % 16 == 0));
     const int a_stage = KCH * P.npix_pad * 16, b_stage = P.gtaps * KCH * P.bn * 16;
-    const int fixed = BAR_BYTES + 2 * P.CoutP * 4 + 4 * MAX_TAPS * 8 + 256;   // barriers, (scale, shift) and tap tables, slack
+    const int fixed = BAR_BYTES + 2 * P.CoutP * 4 + 4 * MAX_TAPS * 8 + 2 * P.wad_C * 4 + 256;   // barriers, (scale, shift) and tap tables, slack
     const int budget = 220 * 1024;
     // A ring first (>= 2 stages: the producers publish k-block i while k-block i+1 is in flight), then B stages (2..6)
     // the filter stream is latency-bound: bytes in flight per SM = bandwidth x L2 latency (~2000 cycles), so keep
@@ -895,8 +959,9 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     const size_t smem = (size_t)P.sa * a_stage + (size_t)P.sb * b_stage + fixed;
     static bool attr_set = false;
     if (!attr_set) {
-        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE_STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE_GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE_WADAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     if (const char *e = getenv("RDFC_UMMA_SKIP")) P.dbg_flags = atoi(e);
@@ -909,8 +974,9 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     }
     int grid = P.ntiles < sm_count() ? P.ntiles : sm_count();
     if (const char *e = getenv("RDFC_UMMA_GRID")) grid = atoi(e) < P.ntiles ? atoi(e) : P.ntiles;   // development knob
-    if (P.planar || P.act > RDFC_ACT_LEAKY02) conv_umma_kernel<true><<<grid, NTHREADS, smem, st>>>(P);
-    else conv_umma_kernel<false><<<grid, NTHREADS, smem, st>>>(P);
+    if (wad) conv_umma_kernel<MODE_WADAIN><<<grid, NTHREADS, smem, st>>>(P);
+    else if (P.planar || P.act > RDFC_ACT_LEAKY02) conv_umma_kernel<MODE_GENERAL><<<grid, NTHREADS, smem, st>>>(P);
+    else conv_umma_kernel<MODE_STD><<<grid, NTHREADS, smem, st>>>(P);
     RDFC_CHECK_LAUNCH("conv_umma_kernel");
     return 0;
 }

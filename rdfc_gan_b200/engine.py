@@ -393,7 +393,26 @@ class GeneratorEngine:
             plan.n_launch += 2
             return mean, rstd
 
-        if isinstance(layer, AdaptiveInstanceNorm):
+        if isinstance(layer, AdaptiveInstanceNorm) and precision == 'bf16' and not layer.weighting and Cx % 64 == 0 and Cd % 32 == 0:
+            # style projection + W-AdaIN apply as ONE tensor-core launch: the (B,H,W,2C) gamma/beta tensor never exists
+            lin = layer.style.linear
+            tile = C.lib.rdfc_wadain_tile(Cx)
+            half = tile // 2
+            perm = torch.cat([torch.cat([torch.arange(t * half, (t + 1) * half), Cx + torch.arange(t * half, (t + 1) * half)])
+                              for t in range(2 * Cx // tile)])
+            w = lambda lin=lin, perm=perm: lin.effective_weight().detach()[perm.to(lin.bias.device)].reshape(2 * Cx, Cd, 1, 1)
+            bias = lambda lin=lin, perm=perm: lin.bias.detach()[perm.to(lin.bias.device)]
+            pk = self._pack(f'fuse{n}.style_wadain', [(w, None, bias)], 'bf16', True)
+            mean, rstd = stats(vx, Cx, 0, 0)
+            d = C.WadainConvDesc()
+            d.B, d.H, d.W = B, Hh, Ww
+            d.style, d.x, d.out = vd, vx, vout
+            d.weight, d.bias, d.mean, d.rstd = pk.weight.data_ptr(), pk.shift.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+            plan.keep.append((d, pk, mean, rstd))
+            plan.names.append(f'wadain_conv fuse{n} {Cd}->2x{Cx} {Hh}x{Ww}')
+            plan.steps.append(lambda s, d=d: C.check(C.lib.rdfc_wadain_conv_forward(ctypes.byref(d), s)))
+            plan.n_launch += 1
+        elif isinstance(layer, AdaptiveInstanceNorm):
             lin = layer.style.linear
             gb = new(B, Hh, Ww, 2 * Cx)
             w = lambda lin=lin: lin.effective_weight().detach().reshape(lin.out_features, lin.in_features, 1, 1)
