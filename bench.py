@@ -111,7 +111,7 @@ def cpu_baseline(n_images, reps):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    n = 2
+    n = 4
     t_all = []
     import torch
     from _synth import synth_inputs
@@ -272,9 +272,9 @@ def main():
     # ---------------- CPU baseline (rank 0, N = 1 only): bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, ts = cpu_baseline(2, 3)
+        v, cores, ts = cpu_baseline(8, 4)
         cpu = {"value": v, "unit": "maps/s", "cores": cores, "kind": "port",
-               "sample": f"2-image batch x 3 repetitions (best) of the same forward, fp32, torch CPU + C DCN oracle; {sum(ts):.1f} s"}
+               "sample": f"8-image batch x 4 repetitions (best) of the same forward (1/4 of the 32-image step), fp32, torch CPU + C DCN oracle; {sum(ts):.1f} s timed"}
 
     if rank == 0:
         print(json.dumps({
