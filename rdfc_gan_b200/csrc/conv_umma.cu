@@ -68,7 +68,7 @@ struct Params {
     const __nv_bfloat16 *res;
     int res_stride;
     const float *scale, *shift;
-    int act, nacc, bn, sa, sb, npix, npix_pad, nplanes, tmem_cols, nsets;
+    int act, nacc, nax, bn, sa, sb, npix, npix_pad, nplanes, tmem_cols, nsets;   // nacc accumulators = nax across x (nacc / nax) down
     int planar, ncols;             // planar != 0: fp32 output planes, one per output column (fused decode heads)
     float *plane[16];
     long long plane_bstride[16];
@@ -107,7 +107,7 @@ __device__ __forceinline__ Tile decode_tile(const Params &P, int tile) {
     const int tyi = tile % P.tiles_y; tile /= P.tiles_y;
     t.z = tile % P.nphases; tile /= P.nphases;
     t.b = tile;
-    t.ty0 = tyi * TH; t.tx0 = txi * 8 * P.nacc; t.n0 = nt * P.bn;
+    t.ty0 = tyi * TH * (P.nacc / P.nax); t.tx0 = txi * 8 * P.nax; t.n0 = nt * P.bn;
     return t;
 }
 
@@ -189,14 +189,21 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 // all MMAs of one (k-block, tap): BK/16 k-steps x NACC accumulators, fully unrolled
+// accumulator j = (jy, jx) covers the 16 x 8 pixel block at rows 16 jy, columns 8 jx of the tile: its A view starts
+// jy * 16 plane rows + jx * 8 pixels further (jx_step = 8, jy_step = 16 * plane pitch, in 16-byte units)
 template <int NACC>
 __device__ __forceinline__ void issue_tap(uint32_t d_base, uint32_t bn, uint32_t a_lo, uint32_t a_hi, uint32_t a_kstep,
-                                          uint32_t b_lo, uint32_t b_hi, uint32_t b_kstep, uint32_t idesc, uint32_t acc0) {
+                                          uint32_t b_lo, uint32_t b_hi, uint32_t b_kstep, uint32_t idesc, uint32_t acc0,
+                                          const uint32_t (&jy16)[4], const uint32_t (&jx8)[4]) {
+    const uint32_t pitch = a_hi & 0x3fffu;           // plane row pitch in 16-byte units (the descriptor's SBO)
+    uint32_t joff[NACC];
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) joff[j] = jy16[j] * pitch + jx8[j];
 #pragma unroll
     for (int k2 = 0; k2 < BK / 16; ++k2)
 #pragma unroll
         for (int j = 0; j < NACC; ++j)      // consecutive MMAs target different accumulators
-            tc_mma2(d_base + (uint32_t)j * bn, a_lo + (uint32_t)j * 8u + (uint32_t)k2 * a_kstep, a_hi,
+            tc_mma2(d_base + (uint32_t)j * bn, a_lo + joff[j] + (uint32_t)k2 * a_kstep, a_hi,
                     b_lo + (uint32_t)k2 * b_kstep, b_hi, idesc, k2 ? 1u : acc0);
 }
 // issue only; the registers are valid after tc_wait_ld(v)
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         // of k-block i holds rows k = 32 i + 8 ch .. + 8, row k = (channel k / 9, tap k % 9) of the fp32 NCHW inputs.
         // A thread's chunk is fixed, so its 2 x 8 (channel plane, dy, dx) triples are decoded once.
         const int ch = threadIdx.x & 3, p0 = threadIdx.x >> 2;
-        const int Hi = P.Hi, Wi = P.Wi, TWs = 8 * P.nacc, nj = (P.npix + PIXPASS - 1) / PIXPASS;
+        const int Hi = P.Hi, Wi = P.Wi, TWs = 8 * P.nax, nj = (P.npix + PIXPASS - 1) / PIXPASS;
         const long long HW = (long long)Hi * Wi;
         int delta[2][8];            // element offset from the centre pixel within one image's planes; INT_MIN = zero row
         int dyx[2][8];              // (dy + 1) | (dx + 1) << 2 | (from in1) << 4
@@ -467,8 +474,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         const uint32_t a_stage16 = keep((uint32_t)a_stage_bytes >> 4), b_stage16 = keep((uint32_t)b_stage_bytes >> 4);
         const uint32_t b_tap16 = keep((uint32_t)b_tap_bytes >> 4);
         const uint32_t bn = keep((uint32_t)P.bn);
-        const int nacc = keep(P.nacc), sa_n = keep(P.sa), sb_n = keep(P.sb), nkb = keep(P.nkb), gtaps = keep(P.gtaps);
+        const int nacc = keep(P.nacc), nax = keep(P.nax), sa_n = keep(P.sa), sb_n = keep(P.sb), nkb = keep(P.nkb), gtaps = keep(P.gtaps);
         const int nsets = keep(P.nsets);
+        uint32_t jy16[4], jx8[4];                  // accumulator j: 16 * (rows down) and 8 * (blocks across), decoded once
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { jy16[j] = keep(16u * (uint32_t)(j / nax)); jx8[j] = keep(8u * (uint32_t)(j % nax)); }
         int s = 0, sb = 0, it = 0;
         uint32_t a_par = 0, b_par = 0;
         long long t_acc = 0, t_a = 0, t_b = 0;
@@ -499,10 +509,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                                 const uint32_t acc0 = (i | gi | tg) ? 1u : 0u;
                                 const uint32_t a_lo = td[tg].x + a_stage_lo, a_hi = td[tg].y, bl = b_lo + (uint32_t)tg * b_tap16;
                                 switch (nacc) {
-                                    case 1: issue_tap<1>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0); break;
-                                    case 2: issue_tap<2>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0); break;
-                                    case 3: issue_tap<3>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0); break;
-                                    default: issue_tap<4>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0); break;
+                                    case 1: issue_tap<1>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8); break;
+                                    case 2: issue_tap<2>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8); break;
+                                    case 3: issue_tap<3>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8); break;
+                                    default: issue_tap<4>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8); break;
                                 }
                             }
                         }
@@ -569,7 +579,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         const int bn = P.bn, Cout = P.Cout, out_stride = P.out_stride, res_stride = P.res_stride;
         // bit 0 planar, bit 1 vec32, bits 2.. development skip flags: one register for the inner-loop switches
         const int flags = (P.planar ? 1 : 0) | (P.vec32 ? 2 : 0) | (P.dbg_flags << 2);
-        const int act = P.act, nacc = P.nacc, nsets = P.nsets;
+        const int act = P.act, nacc = P.nacc, nax = P.nax, nsets = P.nsets;
         const int Ht = P.Ht, Wt = P.Wt, Ho = P.Ho, Wo = P.Wo, oys = P.oys, oxs = P.oxs;
 #define planar (kGeneral && (flags & 1))
 #define vec32 (flags & 2)
@@ -601,7 +611,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                     wad_b = t.b;
                 }
                 for (int j = grp; j < nacc; j += 2) {
-                    const int yy = t.ty0 + r, xx = t.tx0 + 8 * j + c;
+                    const int yy = t.ty0 + 16 * (j / nax) + r, xx = t.tx0 + 8 * (j % nax) + c;
                     const bool ok = yy < Ht && xx < Wt;
                     const long long opix = ok ? ((long long)t.b * Ho + yy) * Wo + xx : 0;
                     const uint32_t trow = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(set * set_cols + j * bn);
@@ -636,7 +646,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
             }
             const int n0 = t.n0;
             for (int j = grp; j < nacc; j += 2) {
-                const int yy = t.ty0 + r, xx = t.tx0 + 8 * j + c;
+                const int yy = t.ty0 + 16 * (j / nax) + r, xx = t.tx0 + 8 * (j % nax) + c;
                 const int oy = oys * yy + oyo, ox = oxs * xx + oxo;
                 const bool ok = yy < Ht && xx < Wt && oy < Ho && ox < Wo;
                 const long long opix = ok ? ((long long)t.b * Ho + oy) * Wo + ox : 0;
@@ -838,6 +848,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     // should be >= 128; N = 128 rather than 256 leaves room for two accumulator sets of two accumulators in TMEM.
     int bn_max = 128;
     if (P.CoutP > 128 && P.CoutP % 128 != 0) bn_max = 256;               // e.g. 160: one tile beats 2 x 80
+    if (k3 && !d->transposed && P.CoutP % 256 == 0 && P.CoutP >= 512) bn_max = 256;   // measured: 512 -> 512 gains 10 %
     if (k1 && P.CoutP % 256 == 0) bn_max = 256;                          // 1x1: the A stage feeds one tap only, so widen N
     if (wad) bn_max = wadain_tile(wad->x.C);
     if (const char *e = getenv("RDFC_UMMA_BN")) bn_max = atoi(e);        // development knob
@@ -859,7 +870,20 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     if (const char *e = getenv("RDFC_UMMA_NACC")) P.nacc = atoi(e);      // development knob
     if (const char *e = getenv("RDFC_UMMA_NSETS")) P.nsets = atoi(e);    // development knob
     if (P.nsets * P.nacc * P.bn > 512) P.nsets = 1;
-    const int TW = 8 * P.nacc;
+    // arrange the accumulators nax across x nay down so that the padded tile grid wastes the fewest pixels
+    {
+        long long best = -1;
+        for (int nax = 1; nax <= P.nacc; ++nax) {
+            if (P.nacc % nax) continue;
+            const int nay = P.nacc / nax;
+            const long long area = (long long)cdiv(P.Ht, 16 * nay) * 16 * nay * cdiv(P.Wt, 8 * nax) * 8 * nax;
+            // measured (64 -> 64 at 228x304): the 2 x 2 arrangement beats 4 x 1 by 7 % at equal area, so it wins ties within 3 %
+            const long long score = area * 100 + (nax == nay ? 0 : area * 3);
+            if (best < 0 || score < best) { best = score; P.nax = nax; }
+        }
+        if (const char *e = getenv("RDFC_UMMA_NAX")) P.nax = atoi(e);    // development knob
+    }
+    const int TW = 8 * P.nax, TH = rdfc::TH * (P.nacc / P.nax);
     P.tiles_y = cdiv(P.Ht, TH); P.tiles_x = cdiv(P.Wt, TW);
     P.ntiles = P.tiles_x * P.tiles_y * P.B * P.nphases * P.n_tiles_n;
 
