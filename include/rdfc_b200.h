@@ -159,7 +159,7 @@ int rdfc_heads_forward(const rdfc_heads_desc *d, void *stream);
 typedef struct {
     int B, H, W;
     const float *in0;            /* fp32 NCHW (B, C0, H, W) */
-    int C0;                      /* 1..6 */
+    int C0;                      /* C0 + (in1 != NULL) <= 4 input planes */
     const float *in1;            /* fp32 NCHW (B, 1, H, W) or NULL */
     rdfc_view out, out2;         /* bf16 NHWC; out2.ptr == NULL: single destination */
     const void *weight;          /* bf16 [1][8][CoutP][8], CoutP = out.C + out2.C padded to 16 */

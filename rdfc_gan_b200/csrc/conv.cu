@@ -48,7 +48,7 @@ extern "C" int rdfc_heads_forward(const rdfc_heads_desc *h, void *stream) {
 extern "C" int rdfc_stem_forward(const rdfc_stem_desc *m, void *stream) {
     RDFC_REQUIRE(m != nullptr && m->in0 && m->out.ptr && m->weight, "stem: NULL argument");
     RDFC_REQUIRE(m->B > 0 && m->H > 0 && m->W > 0, "stem: empty dimension");
-    RDFC_REQUIRE(m->C0 >= 1 && 9 * (m->C0 + (m->in1 ? 1 : 0)) <= 64, "stem: at most 7 input channels in total (64 im2col rows)");
+    RDFC_REQUIRE(m->C0 >= 1 && m->C0 + (m->in1 ? 1 : 0) <= 4, "stem: at most 4 input planes in total");
     RDFC_REQUIRE(m->act == RDFC_ACT_NONE || m->act == RDFC_ACT_RELU || m->act == RDFC_ACT_LEAKY02, "stem: unsupported activation");
     RDFC_REQUIRE(m->out.dtype == RDFC_BF16 && !m->out.nchw && (!m->out2.ptr || (m->out2.dtype == RDFC_BF16 && !m->out2.nchw)),
                  "stem: bf16 NHWC destinations only");

@@ -315,26 +315,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     if (warp < NPROD_WARPS && P.stem_in0) {
         // ================= A producers, stem mode =================
         // The "input" of the 1x1 GEMM is the im2col matrix of the 3x3 stems, built on the fly: slot (pixel p, chunk ch)
-        // of k-block i holds rows k = 32 i + 8 ch .. + 8, row k = (channel k / 9, tap k % 9) of the fp32 NCHW inputs.
-        // A thread's chunk is fixed, so its 2 x 8 (channel plane, dy, dx) triples are decoded once.
+        // of k-block i holds rows k = 32 i + 8 ch .. + 8, row k = (channel k / 9, tap k % 9).  Per tile the producers
+        // first stage the fp32 input patch (all channels, tile + 1-pixel halo, zeros outside the image) in shared
+        // memory, so a row is one LDS at a per-thread constant offset: no bounds tests, no L2 round trip per slot.
         const int ch = threadIdx.x & 3, p0 = threadIdx.x >> 2;
-        const int Hi = P.Hi, Wi = P.Wi, TWs = 8 * P.nax, nj = (P.npix + PIXPASS - 1) / PIXPASS;
+        const int Hi = P.Hi, Wi = P.Wi, TWs = 8 * P.nax, THs = TH * (P.nacc / P.nax), nj = (P.npix + PIXPASS - 1) / PIXPASS;
+        const int PW = TWs + 2, PH = THs + 2, nch = P.stem_k / 9, plane_sz = PH * PW, tw_shift = 31 - __clz(TWs);
         const long long HW = (long long)Hi * Wi;
-        int delta[2][8];            // element offset from the centre pixel within one image's planes; INT_MIN = zero row
-        int dyx[2][8];              // (dy + 1) | (dx + 1) << 2 | (from in1) << 4
+        float *patch = s_stat + 2 * P.wad_C;                     // [nch][PH][PW] + one zero cell
+        const int zero_cell = nch * plane_sz;
+        int delta[2][8];            // patch offset of row k relative to the slot's centre cell (r + 1, c + 1) of plane 0
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int k = 32 * i + 8 * ch + e;
                 if (k < P.stem_k) {
-                    const int ci = k / 9, tp = k - 9 * ci, dy = tp / 3 - 1, dx = tp % 3 - 1;
-                    const bool second = ci >= P.stem_c0;
-                    delta[i][e] = (second ? 0 : ci) * (int)HW + dy * Wi + dx;
-                    dyx[i][e] = (dy + 1) | ((dx + 1) << 2) | (second ? 16 : 0);
+                    const int ci = k / 9, tp = k - 9 * ci;
+                    delta[i][e] = ci * plane_sz + (tp / 3 - 1) * PW + (tp % 3 - 1);
                 } else {
                     delta[i][e] = INT_MIN;
-                    dyx[i][e] = 0;
                 }
             }
         const uint32_t dst_thread = smem_u32(sA) + (uint32_t)(ch * P.npix_pad + p0) * 16u;
@@ -344,23 +344,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
             const Tile t = decode_tile(P, tile);
             const float *b0 = P.stem_in0 + (long long)t.b * P.stem_c0 * HW;
             const float *b1 = P.stem_in1 ? P.stem_in1 + (long long)t.b * HW : b0;
+            asm volatile("bar.sync 3, %0;" ::"n"(NPROD) : "memory");          // the previous tile's slots are built
+            // 4-byte cp.async per patch cell (zero-fill outside the image): every cell of the thread is in flight at
+            // once, so the fill costs one L2 round trip instead of one per loop trip
+            {
+                const uint32_t patch_s = smem_u32(patch);
+                int pr = threadIdx.x / PW, pc = threadIdx.x - pr * PW;       // flat cell index = pr * PW + pc, pr over nch * PH rows
+                const int dr = NPROD / PW, dc = NPROD - dr * PW;
+                for (int e = threadIdx.x; e < nch * plane_sz; e += NPROD) {
+                    const int ci = pr >= 3 * PH ? 3 : (pr >= 2 * PH ? 2 : (pr >= PH ? 1 : 0));    // nch <= 4 here (asserted on the host)
+                    const int iy = t.ty0 + (pr - ci * PH) - 1, ix = t.tx0 + pc - 1;
+                    const bool ok = iy >= 0 && iy < Hi && ix >= 0 && ix < Wi;
+                    const float *src = ok ? (ci < P.stem_c0 ? b0 + (long long)ci * HW : b1) + (long long)iy * Wi + ix : b0;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(patch_s + 4u * (uint32_t)e), "l"(src), "r"(ok ? 4u : 0u) : "memory");
+                    pr += dr; pc += dc;
+                    if (pc >= PW) { pc -= PW; ++pr; }
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+            }
+            if (threadIdx.x == 0) patch[zero_cell] = 0.f;
+            asm volatile("bar.sync 3, %0;" ::"n"(NPROD) : "memory");
             for (int i = 0; i < P.nkb; ++i) {
                 mbar_wait(BAR(A_EMPTY + s), par);
                 const uint32_t dst = dst_thread + (uint32_t)s * (uint32_t)a_stage_bytes;
                 for (int j = 0; j < nj; ++j) {
                     const int p = j * PIXPASS + p0;
                     if (p >= P.npix) break;
-                    const int y = t.ty0 + p / TWs, x = t.tx0 + p % TWs;
-                    const bool inimg = y < Hi && x < Wi;
-                    // rows / columns a tap may not read: bit (dy + 1) of ybad, bit (dx + 1) of xbad
-                    const int ybad = (y == 0 ? 1 : 0) | (y == Hi - 1 ? 4 : 0), xbad = (x == 0 ? 1 : 0) | (x == Wi - 1 ? 4 : 0);
-                    const long long centre = (long long)y * Wi + x;
+                    const int centre = ((p >> tw_shift) + 1) * PW + (p & (TWs - 1)) + 1;      // TWs is 8, 16 or 32
                     float v[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const int dl = i == 0 ? delta[0][e] : delta[1][e], q = i == 0 ? dyx[0][e] : dyx[1][e];
-                        const bool ok = inimg && dl != INT_MIN && !((ybad >> (q & 3)) & 1) && !((xbad >> ((q >> 2) & 3)) & 1);
-                        v[e] = ok ? __ldg(((q & 16) ? b1 : b0) + centre + dl) : 0.f;
+                        const int dl = i == 0 ? delta[0][e] : delta[1][e];
+                        v[e] = patch[dl == INT_MIN ? zero_cell : centre + dl];
                     }
                     uint32_t w[4];
 #pragma unroll
@@ -825,6 +840,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
         P.Cout = 2 * wad->x.C; P.CoutP = P.Cout;              // GEMM columns; the output view has C channels
     }
     if (stem) {
+        RDFC_REQUIRE(stem->C0 + (stem->in1 ? 1 : 0) <= 4, "stem: at most 4 input planes in total");
         P.stem_in0 = stem->in0; P.stem_in1 = stem->in1; P.stem_c0 = stem->C0;
         P.stem_k = 9 * (stem->C0 + (stem->in1 ? 1 : 0));
         if (stem->out2.ptr) {
@@ -960,7 +976,8 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
               (!P.out2 || (((uintptr_t)P.out2 % 32) == 0 && P.out2_stride % 16 == 0 && P.split % 16 == 0)) &&
               (!d->residual.ptr || (((uintptr_t)d->residual.ptr % 32) == 0 && d->residual.pix_stride % 16 == 0));
     const int a_stage = KCH * P.npix_pad * 16, b_stage = P.gtaps * KCH * P.bn * 16;
-    const int fixed = BAR_BYTES + 2 * P.CoutP * 4 + 4 * MAX_TAPS * 8 + 2 * P.wad_C * 4 + 256;   // barriers, (scale, shift) and tap tables, slack
+    const int stem_patch = stem ? ((P.stem_k / 9) * (TH + 2) * (TW + 2) + 4) * 4 : 0;      // fp32 input patch of a tile (stem mode)
+    const int fixed = BAR_BYTES + 2 * P.CoutP * 4 + 4 * MAX_TAPS * 8 + 2 * P.wad_C * 4 + stem_patch + 256;   // barriers, (scale, shift) and tap tables, slack
     const int budget = 220 * 1024;
     // A ring first (>= 2 stages: the producers publish k-block i while k-block i+1 is in flight), then B stages (2..6)
     // the filter stream is latency-bound: bytes in flight per SM = bandwidth x L2 latency (~2000 cycles), so keep

@@ -195,7 +195,7 @@ class GeneratorEngine:
         # ---- stems (rdf_generator.py:286-292): NCHW fp32 in, NHWC slice out
         L = C.ACT_LEAKY02
         full = (H, W)
-        if bf16 and 9 * (Cs + 1) <= 64:
+        if bf16 and Cs + 1 <= 4:
             # all three stems as ONE tensor-core launch: im2col rows built by the producer warps from the fp32 NCHW inputs
             self._plan_stem(plan, B, H, W, Cs, fe1)
         else:
