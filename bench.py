@@ -212,22 +212,26 @@ def main():
     rgb_h, normal_h, depth_h = rgb.pin_memory(), normal.pin_memory(), depth.pin_memory()
     pred_h = torch.empty(B, 1, H, W).pin_memory()
 
-    def e2e_step():
-        with torch.no_grad():
-            o = G(rgb_h.to(dev, non_blocking=True), depth_h.to(dev, non_blocking=True), normal_h.to(dev, non_blocking=True))
-        pred_h.copy_(o["pred_depth"], non_blocking=True)
-    for _ in range(3):
-        e2e_step()
+    def host_batches(n):
+        for _ in range(n):
+            yield rgb_h, depth_h, normal_h
+
+    def e2e_run(n):
+        # public API: G.stream() overlaps the H2D copy of batch i+1 and the D2H read of batch i-1 with the forward of i
+        for o in G.stream(host_batches(n), outputs=("pred_depth",)):
+            pred_h.copy_(o["pred_depth"])                 # host-side use of the result (pinned -> pinned)
+    e2e_run(3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     barrier()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = B * world * args.steps / float(te.item())
-    h2d = rgb_h.numel() * 4 + normal_h.numel() * 4 + depth_h.numel() * 4
+    # RDFGenerator's stems read `normal` and `depth` only (rdf_generator.py:286-292: `rgb` is unused), so those are the
+    # tensors stream() copies
+    h2d = normal_h.numel() * 4 + depth_h.numel() * 4
     d2h = pred_h.numel() * 4
 
     # ---------------- roofline: NLSPN propagation kernel alone (18 launches per image group)

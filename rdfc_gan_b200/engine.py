@@ -457,7 +457,7 @@ class GeneratorEngine:
         return (out, 0, Cx)
 
     # ------------------------------------------------------------------------------------------- run ------------
-    def forward(self, stem_in, depth):
+    def forward(self, stem_in, depth, clone=True):
         g = self.gen
         B, Cs, H, W = stem_in.shape
         if Cs != g.semantic_channels_in:
@@ -484,7 +484,60 @@ class GeneratorEngine:
             plan.stem_in.copy_(stem_in)
             plan.depth.copy_(depth)
             plan.run()
-            return tuple(t.clone() for t in plan.outputs)
+            return tuple(t.clone() for t in plan.outputs) if clone else plan.outputs
+
+    def forward_stream(self, batches, device, want=(0, 1, 2, 3, 4)):
+        """Pipelined inference over an iterable of HOST batches (stem_in, depth), pinned or not.  Yields, in order, a
+        tuple of pinned CPU tensors (the outputs selected by `want`, indices into (d1, c1, d2, c2, pred)).
+
+        Three streams keep the copy engines and the SMs busy at the same time: the H2D copy of batch i+1 and the D2H
+        copy of batch i-1 run while batch i is computed.  Inputs land in ping-pong staging buffers and are moved into
+        the plan's fixed input buffers by a device copy just before the graph replay; outputs are moved out of the plan
+        into ping-pong buffers right after it, so neither copy engine ever touches memory a running graph uses."""
+        cur = torch.cuda.current_stream(device)
+        h2d, d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        slots = [dict() for _ in range(2)]
+        pending = []                                       # (slot index, d2h event)
+        with torch.cuda.device(device), torch.no_grad():
+            for i, (stem_h, depth_h) in enumerate(batches):
+                sl = slots[i % 2]
+                if 'stem' not in sl or sl['stem'].shape != stem_h.shape:
+                    sl['stem'] = torch.empty(stem_h.shape, dtype=torch.float32, device=device)
+                    sl['depth'] = torch.empty(depth_h.shape, dtype=torch.float32, device=device)
+                    sl['consumed'] = torch.cuda.Event()
+                    sl['consumed'].record(cur)
+                    sl['out_d'] = sl['out_h'] = None
+                with torch.cuda.stream(h2d):
+                    h2d.wait_event(sl['consumed'])             # the device copy of batch i-2 out of this slot is done
+                    sl['stem'].copy_(stem_h, non_blocking=True)
+                    sl['depth'].copy_(depth_h, non_blocking=True)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(h2d)
+                # results of batch i-2 (same slot) must have left the slot's output buffers before we overwrite them
+                while pending and pending[0][0] == i % 2:
+                    _, ev, outs = pending.pop(0)
+                    ev.synchronize()
+                    yield outs
+                cur.wait_event(ev_in)
+                outs_dev = self.forward(sl['stem'], sl['depth'], clone=False)
+                sl['consumed'].record(cur)                     # forward() copied the staging buffers into the plan first
+                if sl['out_d'] is None:
+                    sl['out_d'] = [torch.empty_like(outs_dev[k]) for k in want]
+                    sl['out_h'] = [torch.empty(outs_dev[k].shape, dtype=outs_dev[k].dtype).pin_memory() for k in want]
+                for dst, k in zip(sl['out_d'], want):
+                    dst.copy_(outs_dev[k], non_blocking=True)
+                ev_out = torch.cuda.Event()
+                ev_out.record(cur)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(ev_out)
+                    for dst, src in zip(sl['out_h'], sl['out_d']):
+                        dst.copy_(src, non_blocking=True)
+                    ev_done = torch.cuda.Event()
+                    ev_done.record(d2h)
+                pending.append((i % 2, ev_done, tuple(sl['out_h'])))
+            for _, ev, outs in pending:
+                ev.synchronize()
+                yield outs
 
     @staticmethod
     def _capture(plan):

@@ -132,6 +132,21 @@ class RDFGenerator(_GeneratorBase):
         self.use_pretrained_global_guidance_module = False
         self.pretrained_on_imagenet = pretrained_on_imagenet
 
+    def stream(self, batches, outputs=('depth_map_1', 'confidence_map_1', 'depth_map_2', 'confidence_map_2', 'pred_depth')):
+        """Pipelined inference for a stream of HOST batches: ``batches`` yields ``(rgb, depth, normal)`` CPU tensors
+        (pinned memory makes the copies asynchronous); yields one dict of pinned CPU tensors per batch, in order, with
+        the keys in ``outputs``.  Host->device and device->host copies overlap the forward of the neighbouring batches
+        (engine.forward_stream); the arithmetic is exactly ``forward``'s.  A yielded dict is reused two batches later."""
+        names = ('depth_map_1', 'confidence_map_1', 'depth_map_2', 'confidence_map_2', 'pred_depth')
+        want = tuple(names.index(k) for k in outputs)
+        dev = next(self.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError("rdfc_gan_b200 generators run on CUDA (sm_100a) devices only; move the module first")
+        if self.training and torch.is_grad_enabled():
+            raise RuntimeError("stream() is an inference API: call .eval() and run under torch.no_grad()")
+        for res in self.engine().forward_stream(((normal, depth) for _, depth, normal in batches), dev, want):
+            yield dict(zip(outputs, res))
+
     def forward(self, rgb, depth, normal):
         """rdf_generator.py:280-414: both stems read ``normal`` (:286,289); ``rgb`` is unused by the reference too."""
         d1, c1, d2, c2, pred = self._run(normal, depth)

@@ -99,3 +99,28 @@ def test_dcvgan_signature_and_errors():
     R = R.cuda().train()
     with pytest.raises(RuntimeError, match="training"):
         R(torch.zeros(1, 3, 32, 32).cuda(), torch.zeros(1, 1, 32, 32).cuda(), torch.zeros(1, 3, 32, 32).cuda())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_stream_matches_forward(precision):
+    """G.stream() (pipelined H2D / forward / D2H over host batches) returns exactly forward()'s outputs, in order."""
+    from rdfc_gan_b200.generator import RDFGenerator
+    nl = dict(prop_kernel=3, prop_time=6, affinity="TGASS", affinity_gamma=0.5, conf_prop=True, preserve_input=False)
+    G = RDFGenerator(pretrained_on_imagenet=False, use_nlspn_refine=True, nlspn_configs=nl).eval()
+    G.load_state_dict(synth_state_dict(G, seed=5, recipe="scaled", nlspn_stress=True))
+    G = G.cuda().set_precision(precision)
+    batches = []
+    for seed in range(5):
+        rgb, normal, depth = synth_inputs(2, 48, 64, seed=seed)
+        batches.append((rgb.pin_memory(), depth.pin_memory(), normal.pin_memory()))
+    with torch.no_grad():
+        want = [{k: v.cpu().clone() for k, v in G(r.cuda(), d.cuda(), n.cuda()).items()} for r, d, n in batches]
+    got = []
+    for out in G.stream(iter(batches)):
+        got.append({k: v.clone() for k, v in out.items()})          # a yielded dict is reused two batches later
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for k in KEYS:
+            assert torch.equal(g[k], w[k]), k
+    only = list(G.stream(iter(batches[:1]), outputs=("pred_depth",)))
+    assert list(only[0]) == ["pred_depth"] and torch.equal(only[0]["pred_depth"], want[0]["pred_depth"])
