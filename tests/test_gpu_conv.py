@@ -178,3 +178,74 @@ def test_instnorm_and_wadain():
     # AdaIN statistics: unbiased variance, std returned
     C.check(C.lib.rdfc_instnorm_stats(ctypes.byref(vx), B, H, W, 1e-5, 1, 1, C.ptr(part), C.ptr(mean), C.ptr(rstd), C.stream_ptr()))
     assert (rstd.cpu().double() - torch.sqrt(xd.var((2, 3), unbiased=True) + 1e-5)).abs().max() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# rdfc_stem_forward: the three input stems of rdf_generator.py:286-292 as one tensor-core launch
+@pytest.mark.parametrize("B,H,W", [(1, 16, 24), (2, 37, 45), (1, 228, 304)])
+def test_fused_stems_match_three_convs(B, H, W):
+    from rdfc_gan_b200 import _cabi as C
+    g = torch.Generator().manual_seed(H * W + B)
+    normal, depth = torch.randn(B, 3, H, W, generator=g), torch.randn(B, 1, H, W, generator=g)
+    w_r, w_dr, w_dd = (0.3 * torch.randn(64, 3, 3, 3, generator=g), 0.3 * torch.randn(48, 3, 3, 3, generator=g),
+                       0.3 * torch.randn(16, 1, 3, 3, generator=g))
+    bias = 0.1 * torch.randn(128, generator=g)
+    # reference (conv_bn_relu with bn=False: conv + bias + LeakyReLU(0.2)), on bf16-rounded operands like the kernel
+    rb = lambda t: t.bfloat16().float()
+    ref_r = F.leaky_relu(F.conv2d(rb(normal), rb(w_r), bias[:64], padding=1), 0.2)
+    ref_d = F.leaky_relu(torch.cat([F.conv2d(rb(normal), rb(w_dr), bias[64:112], padding=1),
+                                    F.conv2d(rb(depth), rb(w_dd), bias[112:], padding=1)], 1), 0.2)
+    # im2col filter bank: rows k = ci*9 + tap for the 3 `normal` channels, then the depth map's nine taps
+    Wk = torch.zeros(128, 64)
+    Wk[:64, :27], Wk[64:112, :27], Wk[112:, 27:36] = w_r.reshape(64, 27), w_dr.reshape(48, 27), w_dd.reshape(16, 9)
+    packed = Wk.reshape(128, 1, 8, 8).permute(1, 2, 0, 3).contiguous().to(torch.bfloat16).cuda()
+    out_r = torch.full((B, H, W, 96 + 64), 7.0, dtype=torch.bfloat16, device="cuda")       # destination slices of wider
+    out_d = torch.full((B, H, W, 160 + 64), 7.0, dtype=torch.bfloat16, device="cuda")      # buffers, as in the engine
+    n_d, d_d = normal.cuda().contiguous(), depth.cuda().contiguous()
+    sc, sh = torch.ones(128, device="cuda"), bias.cuda()
+    d = C.StemDesc()
+    d.B, d.H, d.W = B, H, W
+    d.in0, d.C0, d.in1 = n_d.data_ptr(), 3, d_d.data_ptr()
+    d.out, d.out2 = C.view(out_r, 64, 96), C.view(out_d, 64, 160)
+    d.weight, d.scale, d.shift, d.act = packed.data_ptr(), sc.data_ptr(), sh.data_ptr(), C.ACT_LEAKY02
+    C.check(C.lib.rdfc_stem_forward(ctypes.byref(d), C.stream_ptr()))
+    torch.cuda.synchronize()
+    assert (out_r[..., :96].float() == 7.0).all() and (out_d[..., :160].float() == 7.0).all(), "wrote outside its slice"
+    got_r, got_d = out_r[..., 96:].float().permute(0, 3, 1, 2).cpu(), out_d[..., 160:].float().permute(0, 3, 1, 2).cpu()
+    for got, ref in ((got_r, ref_r), (got_d, ref_d)):
+        tol = 2e-2 * float(ref.abs().max())          # bf16 output rounding (2^-9 relative) + fp32 accumulation order
+        assert float((got - ref).abs().max()) <= tol
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# rdfc_wadain_conv_forward: EqualLinear style projection + W-AdaIN apply (model_utils.py:53-90, weighting=False)
+@pytest.mark.parametrize("B,H,W,C,Cd", [(2, 15, 19, 512, 512), (1, 29, 38, 768, 768), (2, 20, 28, 192, 192), (1, 9, 11, 64, 32)])
+def test_fused_wadain_conv(B, H, W, C, Cd):
+    from rdfc_gan_b200 import _cabi as C_
+    g = torch.Generator().manual_seed(C + Cd + H)
+    x, style = torch.randn(B, C, H, W, generator=g), torch.randn(B, Cd, H, W, generator=g)
+    Wl = torch.randn(2 * C, Cd, generator=g) * math.sqrt(2 / Cd)
+    bias = torch.cat([torch.ones(C), torch.zeros(C)]) + 0.1 * torch.randn(2 * C, generator=g)
+    rb = lambda t: t.bfloat16().float()
+    xb, sb = rb(x), rb(style)
+    gb = torch.einsum("bdhw,nd->bnhw", sb, rb(Wl)) + bias.view(1, -1, 1, 1)
+    mean = xb.mean((2, 3), keepdim=True)
+    rstd = 1.0 / torch.sqrt(xb.var((2, 3), unbiased=False, keepdim=True) + 1e-5)
+    ref = gb[:, :C] * (xb - mean) * rstd + gb[:, C:]
+    tile = C_.lib.rdfc_wadain_tile(C)
+    half = tile // 2
+    perm = torch.cat([torch.cat([torch.arange(t * half, (t + 1) * half), C + torch.arange(t * half, (t + 1) * half)])
+                      for t in range(2 * C // tile)])
+    packed = Wl[perm].reshape(2 * C, 1, Cd // 8, 8).permute(1, 2, 0, 3).contiguous().to(torch.bfloat16).cuda()
+    x_d = xb.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    s_d = sb.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    out = torch.empty(B, H, W, C, dtype=torch.bfloat16, device="cuda")
+    b_d, m_d, r_d = bias[perm].cuda(), mean.reshape(B, C).cuda().contiguous(), rstd.reshape(B, C).cuda().contiguous()
+    d = C_.WadainConvDesc()
+    d.B, d.H, d.W = B, H, W
+    d.style, d.x, d.out = C_.view(s_d), C_.view(x_d), C_.view(out)
+    d.weight, d.bias, d.mean, d.rstd = packed.data_ptr(), b_d.data_ptr(), m_d.data_ptr(), r_d.data_ptr()
+    C_.check(C_.lib.rdfc_wadain_conv_forward(ctypes.byref(d), C_.stream_ptr()))
+    torch.cuda.synchronize()
+    got = out.float().permute(0, 3, 1, 2).cpu()
+    assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
