@@ -133,16 +133,17 @@ typedef struct {
 
 int rdfc_conv_forward(const rdfc_conv_desc *d, void *stream);
 
-/* Fused decode heads (rdf_generator.py:372-398): ONE 3x3 / stride-1 / pad-1 tensor-core convolution over an NHWC
- * bf16 view whose <= 16 output columns are the *_dec0 heads that read it (block-sparse filter bank packed like any
- * UMMA weight with Cout = 16).  Column q gets bias shift[q], activation act[q] and is written as an fp32 plane:
+/* Fused decode heads (rdf_generator.py:372-398): the <= 16 *_dec0 output columns that read one NHWC bf16 view, each a
+ * 3x3 / stride-1 / pad-1 convolution with its own bias and activation, as ONE launch: a tensor-core 1x1 GEMM to
+ * 9 * ncols columns  Y[p, t * ncols + q] = W_q[:, tap t] . x[p, :]  followed (same kernel, through shared memory) by
+ * out_q[p] = act_q(bias_q + sum_t Y[p + d_t, t * ncols + q]).  Column q is written as an fp32 plane:
  * out[q][b * out_bstride[q] + y * W + x]  -- so depth / confidence maps and the NCHW guidance tensor the NLSPN
  * kernels read come straight out of the epilogue. */
 typedef struct {
     int B, H, W;
     rdfc_view in;                /* bf16 NHWC, C % 32 == 0 */
-    const void *weight;          /* bf16 [9][C/8][16][8] */
-    const float *shift;          /* device, 16 floats (bias per column; unused columns 0) */
+    const void *weight;          /* bf16 [1][C/8][NP][8], NP = 9 * ncols padded to 16, row t * ncols + q = tap t (= ky*3+kx) of column q */
+    const float *shift;          /* device, NP floats: bias of column q at index q (q < ncols), the rest unused */
     int ncols;                   /* 1..16 */
     int act[16];                 /* rdfc_act per column */
     float *out[16];              /* device plane base pointers */

@@ -38,9 +38,9 @@ extern "C" int rdfc_heads_forward(const rdfc_heads_desc *h, void *stream) {
     for (int q = 0; q < h->ncols; ++q) RDFC_REQUIRE(h->out[q] != nullptr, "heads: output plane %d is NULL", q);
     rdfc_conv_desc d{};
     d.B = h->B; d.Hi = d.Ho = h->H; d.Wi = d.Wo = h->W;
-    d.kh = d.kw = 3; d.stride = 1; d.pad = 1; d.act = RDFC_ACT_NONE; d.path = RDFC_PATH_UMMA_BF16;
+    d.kh = d.kw = 1; d.stride = 1; d.pad = 0; d.act = RDFC_ACT_NONE; d.path = RDFC_PATH_UMMA_BF16;    // the GEMM part: 1x1
     d.in = h->in;
-    d.out.ptr = h->out[0]; d.out.dtype = RDFC_F32; d.out.C = 16; d.out.pix_stride = 16;
+    d.out.ptr = h->out[0]; d.out.dtype = RDFC_F32; d.out.C = (9 * h->ncols + 15) / 16 * 16; d.out.pix_stride = d.out.C;
     d.weight = h->weight; d.scale = nullptr; d.shift = h->shift;
     return conv_umma_forward(&d, (cudaStream_t)stream, h, nullptr, nullptr);
 }

@@ -24,6 +24,7 @@
 //                   slice (this is how every torch.cat of the reference disappears) or, for the fused decode heads,
 //                   one fp32 plane per output column.  TMEM holds two accumulator sets (when 2*NACC*BN <= 512), so
 //                   the MMA warp fills set (t+1)&1 while the epilogue drains set t&1.
+#include <cuda.h>
 #include <limits.h>
 #include <stdlib.h>
 
@@ -58,6 +59,11 @@ struct Phase {                     // one sub-pixel phase of a transposed conv (
     int oyo, oxo;                  // output pixel = (oys*(ty0+r) + oyo, oxs*(tx0+c) + oxo)
 };
 struct Params {
+    // A operand through TMA (a_tma != 0): one 4-D tensor map (C, W, H, B) over the NHWC input view; box = 32 channels x
+    // plane columns x plane rows, SWIZZLE_64B, zero fill outside the image = the conv padding
+    alignas(64) CUtensorMap tmap_a;
+    int a_tma, px16, a_plane_bytes, a_tx_bytes;   // a_tx_bytes: bytes the TMA loads of one stage deliver (planes x rows x cols x 64)
+    int _pad_tma;   // px16: 16-byte units per staged pixel (4 with TMA: [pixel][64 B]; 1: [cin/8][pixel][16 B])
     const __nv_bfloat16 *in;
     int in_stride, B, Hi, Wi;
     int Ht, Wt, tiles_y, tiles_x, n_tiles_n, nphases, ntiles;   // tile space
@@ -70,6 +76,7 @@ struct Params {
     const float *scale, *shift;
     int act, nacc, nax, bn, sa, sb, npix, npix_pad, nplanes, tmem_cols, nsets;   // nacc accumulators = nax across x (nacc / nax) down
     int planar, ncols;             // planar != 0: fp32 output planes, one per output column (fused decode heads)
+    int tstep_y, tstep_x, torg;    // tile origin = index * step + torg (shift-add heads: overlapping 16x16 regions, step 14, origin -1)
     float *plane[16];
     long long plane_bstride[16];
     int act_col[16];
@@ -107,7 +114,7 @@ __device__ __forceinline__ Tile decode_tile(const Params &P, int tile) {
     const int tyi = tile % P.tiles_y; tile /= P.tiles_y;
     t.z = tile % P.nphases; tile /= P.nphases;
     t.b = tile;
-    t.ty0 = tyi * TH * (P.nacc / P.nax); t.tx0 = txi * 8 * P.nax; t.n0 = nt * P.bn;
+    t.ty0 = tyi * P.tstep_y + P.torg; t.tx0 = txi * P.tstep_x + P.torg; t.n0 = nt * P.bn;
     return t;
 }
 
@@ -263,15 +270,18 @@ __device__ __forceinline__ void ld_global_v8(const void *p, uint32_t (&o)[8]) {
 
 // kGeneral = false: the hot variant (bf16 NHWC output, act in {none, ReLU, LeakyReLU}); true adds the planar decode-head
 // outputs and tanh / sigmoid, whose code would otherwise cost the hot epilogue registers.
-// and kMode = MODE_WADAIN (W-AdaIN epilogue over [gamma | beta] column tiles).
-enum { MODE_STD = 0, MODE_GENERAL = 1, MODE_WADAIN = 2 };
+// kMode = MODE_WADAIN: W-AdaIN epilogue over [gamma | beta] column tiles.  kMode = MODE_HEADS: the decode heads as ONE
+// 1x1 GEMM to 9 * ncols columns (tap-major) over overlapping 16x16 pixel regions + a shift-add through shared memory.
+enum { MODE_STD = 0, MODE_GENERAL = 1, MODE_WADAIN = 2, MODE_HEADS = 3 };
 template <int kMode>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_constant__ Params P) {
     constexpr bool kGeneral = kMode == MODE_GENERAL;
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a_stage_bytes = KCH * P.npix_pad * 16, b_tap_bytes = KCH * P.bn * 16, b_stage_bytes = P.gtaps * b_tap_bytes;
-    unsigned char *sA = smem;
+    const int a_stage_bytes = P.a_tma ? P.nplanes * P.a_plane_bytes : KCH * P.npix_pad * 16;
+    const int b_tap_bytes = KCH * P.bn * 16, b_stage_bytes = P.gtaps * b_tap_bytes;
+    // stages start on a 1 KB boundary (the SWIZZLE_64B pattern the TMA writes repeats every 1 KB; the host adds the slack)
+    unsigned char *sA = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     unsigned char *sB = sA + (size_t)P.sa * a_stage_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)P.sb * b_stage_bytes);
     // barrier map: a_full[sa] a_empty[sa] b_full[sb] b_empty[sb] acc_full[2] acc_empty[2]
@@ -284,7 +294,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     float *s_scale = reinterpret_cast<float *>(sB + (size_t)P.sb * b_stage_bytes + BAR_BYTES);
     float *s_shift = s_scale + P.CoutP;
     uint2 *s_tap = reinterpret_cast<uint2 *>(s_shift + P.CoutP);      // [phase][tap] A-descriptor words (lo, hi)
-    float *s_stat = reinterpret_cast<float *>(s_tap + 4 * MAX_TAPS);   // W-AdaIN: mean[C], rstd[C] of the current image
+    float *s_stat = reinterpret_cast<float *>(s_tap + 4 * MAX_TAPS);   // W-AdaIN: mean[C], rstd[C] of the current image; stem: input patch;
+                                                                       // shift-add heads: Y[256 region pixels][bn + 1] fp32
     if (threadIdx.x < 4 * MAX_TAPS)
         s_tap[threadIdx.x] = make_uint2(P.tap_alo[threadIdx.x / MAX_TAPS][threadIdx.x % MAX_TAPS],
                                         P.tap_ahi[threadIdx.x / MAX_TAPS][threadIdx.x % MAX_TAPS]);
@@ -295,7 +306,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
-        for (int i = 0; i < P.sa; ++i) { mbar_init(BAR(A_FULL + i), NPROD); mbar_init(BAR(A_EMPTY + i), 1); }
+        for (int i = 0; i < P.sa; ++i) { mbar_init(BAR(A_FULL + i), P.a_tma ? 1 : NPROD); mbar_init(BAR(A_EMPTY + i), 1); }
         for (int i = 0; i < P.sb; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), 1); mbar_init(BAR(ACC_EMPTY + i), NEPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -312,7 +323,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     const int set_cols = P.nacc * P.bn;
 
-    if (warp < NPROD_WARPS && P.stem_in0) {
+    if (warp < NPROD_WARPS && P.a_tma) {
+        // ================= A producer, TMA mode: one elected thread =================
+        // Per k-block and plane ONE cp.async.bulk.tensor: box = 32 channels x plane columns x plane rows of the NHWC
+        // input, SWIZZLE_64B into [pixel][64 B]; coordinates outside the image are zero-filled (= the conv padding).
+        // cp.async staging tops out at ~6 B/cycle/SM (L1 miss tracking x L2 latency); the TMA engine does not.
+        if (threadIdx.x == 0) {
+            const int nkb = P.nkb, sa_n = P.sa, npl = P.nplanes;
+            const uint32_t sA0 = smem_u32(sA), plane_b = (uint32_t)P.a_plane_bytes;
+            int s = 0;
+            uint32_t par = 1;
+            for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+                const Tile t = decode_tile(P, tile);
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(BAR(A_EMPTY + s), par);
+                    const uint32_t full = BAR(A_FULL + s);
+                    mbar_expect_tx(full, (uint32_t)P.a_tx_bytes);
+                    for (int pl = 0; pl < npl; ++pl) {
+                        const Plane &q = P.planes[pl];
+                        asm volatile(
+                            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                                sA0 + (uint32_t)s * (uint32_t)a_stage_bytes + (uint32_t)pl * plane_b),
+                            "l"(&P.tmap_a), "r"(i * BK), "r"(q.xstep * t.tx0 + q.xoff), "r"(q.ystep * t.ty0 + q.yoff), "r"(t.b), "r"(full)
+                            : "memory");
+                    }
+                    if (++s == sa_n) { s = 0; par ^= 1u; }
+                }
+            }
+        }
+    } else if (warp < NPROD_WARPS && P.stem_in0) {
         // ================= A producers, stem mode =================
         // The "input" of the 1x1 GEMM is the im2col matrix of the 3x3 stems, built on the fly: slot (pixel p, chunk ch)
         // of k-block i holds rows k = 32 i + 8 ch .. + 8, row k = (channel k / 9, tap k % 9).  Per tile the producers
@@ -482,7 +521,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         // MMA the issue cost is one 32-bit add on a descriptor word; the per-tap descriptor words come from the
         // shared-memory table and are fetched before the wait on the filter stage.
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | (8u << 24);
-        const uint32_t a_kstep = keep(2u * (uint32_t)P.npix_pad), b_kstep = keep(2u * (uint32_t)P.bn);   // 16 channels, 16-byte units
+        // one k-step = 16 channels: two chunk planes further in the [cin/8][pixel][16 B] layout, 32 bytes in [pixel][64 B]
+        const uint32_t a_kstep = keep(P.a_tma ? 2u : 2u * (uint32_t)P.npix_pad), b_kstep = keep(2u * (uint32_t)P.bn);
         const uint32_t b_hi = (128u >> 4) | (1u << 14);                                     // SBO = 128 B, version bit 46
         const uint32_t b_lo0 = keep(((smem_u32(sB) & 0x3FFFFu) >> 4) | ((uint32_t)P.bn << 16));   // LBO = bn * 16 B
         const uint32_t a_lo0 = keep((smem_u32(sA) & 0x3FFFFu) >> 4);
@@ -493,7 +533,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         const int nsets = keep(P.nsets);
         uint32_t jy16[4], jx8[4];                  // accumulator j: 16 * (rows down) and 8 * (blocks across), decoded once
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { jy16[j] = keep(16u * (uint32_t)(j / nax)); jx8[j] = keep(8u * (uint32_t)(j % nax)); }
+        for (int j = 0; j < 4; ++j) { jy16[j] = keep(16u * (uint32_t)(j / nax)); jx8[j] = keep(8u * (uint32_t)P.px16 * (uint32_t)(j % nax)); }
         int s = 0, sb = 0, it = 0;
         uint32_t a_par = 0, b_par = 0;
         long long t_acc = 0, t_a = 0, t_b = 0;
@@ -593,7 +633,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         const int r = 4 * wq + (lane >> 3), c = lane & 7;     // MMA row m = 32*wq + lane = 8*r + c
         const int bn = P.bn, Cout = P.Cout, out_stride = P.out_stride, res_stride = P.res_stride;
         // bit 0 planar, bit 1 vec32, bits 2.. development skip flags: one register for the inner-loop switches
-        const int flags = (P.planar ? 1 : 0) | (P.vec32 ? 2 : 0) | (P.dbg_flags << 2);
+        const int flags = (P.planar == 1 ? 1 : 0) | (P.vec32 ? 2 : 0) | (P.dbg_flags << 2);
         const int act = P.act, nacc = P.nacc, nax = P.nax, nsets = P.nsets;
         const int Ht = P.Ht, Wt = P.Wt, Ho = P.Ho, Wo = P.Wo, oys = P.oys, oxs = P.oxs;
 #define planar (kGeneral && (flags & 1))
@@ -613,6 +653,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
             { DBG_T0(); mbar_wait<true>(BAR(ACC_FULL + set), use & 1); DBG_ACC(t_accfull); }
             tc_fence_after();
             const long long _te = DBG_ON ? clock64() : 0;
+            if (kMode == MODE_HEADS) {
+                // ---- decode heads (rdf_generator.py:372-398), shift-add form.  The GEMM gave Y[p, t * ncols + q] =
+                // W_t[q, :] . X[p, :] for the 16 x 16 pixel region; head q at pixel p is act(bias_q + sum_t Y[p + d_t, t, q]).
+                // Regions overlap by 2 pixels: a region produces its inner 14 x 14 outputs (zero padding = Y of the
+                // zero-filled pixels outside the image).
+                float *Ys = s_stat;
+                const int pitch = bn + 1, ncols = P.ncols;
+                const int prow = (4 * wq + (lane >> 3)) * 16 + 8 * grp + (lane & 7);        // nacc == 2, nax == 2: j = grp
+                const uint32_t trow = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(set * set_cols + grp * bn);
+                asm volatile("bar.sync 2, %0;" ::"n"(NEPI_WARPS * 32) : "memory");          // previous region's sums are done with Ys
+                for (int g = 0; g < G; ++g) {
+                    uint32_t v[16];
+                    tc_ld16(trow + (uint32_t)(16 * g), v);
+                    float *yp = Ys + prow * pitch + 16 * g;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) yp[q] = __uint_as_float(v[q]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + set));
+                asm volatile("bar.sync 2, %0;" ::"n"(NEPI_WARPS * 32) : "memory");
+                for (int item = threadIdx.x - EPI_WARP0 * 32; item < 196 * ncols; item += NEPI_WARPS * 32) {
+                    const int q = item / 196, pi = item - q * 196, iy = pi / 14, ix = pi - iy * 14;
+                    const int oy = t.ty0 + 1 + iy, ox = t.tx0 + 1 + ix;
+                    if (oy >= Ho || ox >= Wo) continue;
+                    const float *yq = Ys + (iy * 16 + ix) * pitch + q;
+                    float acc = s_shift[q];
+#pragma unroll
+                    for (int t9 = 0; t9 < 9; ++t9) acc += yq[((t9 / 3) * 16 + (t9 % 3)) * pitch + t9 * ncols];
+                    const int a = P.act_col[q];
+                    if (a == RDFC_ACT_TANH) acc = tanhf(acc);
+                    else if (a == RDFC_ACT_SIGMOID) acc = 1.f / (1.f + expf(-acc));
+                    P.plane[q][(long long)t.b * P.plane_bstride[q] + (long long)oy * Wo + ox] = acc;
+                }
+                continue;
+            }
             if (kMode == MODE_WADAIN) {
                 // ---- W-AdaIN: out = (acc_g + bias_g) * (x - mean) * rstd + (acc_b + bias_b), 16 channels per step
                 const int C = P.wad_C, half = bn >> 1, c0 = (t.n0 / bn) * half;
@@ -804,6 +880,24 @@ int next_pow2_cols(int c) {
 }  // namespace
 
 // Host-side planning: planes, taps, tile shape, stage counts.
+typedef CUresult (*TmapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: the library keeps linking only cudart
+static TmapEncodeFn tmap_encoder() {
+    static TmapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        cudaDriverEntryPointQueryResult q;
+        void *p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (TmapEncodeFn)p;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
 int wadain_tile(int C) { return (2 * C) % 256 == 0 ? 256 : 128; }
 
 int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads, const rdfc_stem_desc *stem,
@@ -849,7 +943,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
         }
     }
     if (heads) {
-        P.planar = 1; P.ncols = heads->ncols;
+        P.planar = 2; P.ncols = heads->ncols;
         for (int q = 0; q < 16; ++q) {
             P.plane[q] = heads->out[q]; P.plane_bstride[q] = heads->out_bstride[q]; P.act_col[q] = heads->act[q];
         }
@@ -884,6 +978,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     while (P.nacc > 1 && (P.Wt <= 8 * (P.nacc - 1) || pixels / (128 * P.nacc) * P.n_tiles_n < sm_count())) --P.nacc;
     if (d->stride == 2 && !d->transposed && k3 && P.nacc > 2) P.nacc = 2;   // four parity planes: keep the stage small
     if (const char *e = getenv("RDFC_UMMA_NACC")) P.nacc = atoi(e);      // development knob
+    if (heads) P.nacc = 2;                                               // 16 x 16 pixel regions (see MODE_HEADS)
     if (const char *e = getenv("RDFC_UMMA_NSETS")) P.nsets = atoi(e);    // development knob
     if (P.nsets * P.nacc * P.bn > 512) P.nsets = 1;
     // arrange the accumulators nax across x nay down so that the padded tile grid wastes the fewest pixels
@@ -898,11 +993,22 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
             if (best < 0 || score < best) { best = score; P.nax = nax; }
         }
         if (const char *e = getenv("RDFC_UMMA_NAX")) P.nax = atoi(e);    // development knob
+        if (heads) P.nax = 2;
     }
     const int TW = 8 * P.nax, TH = rdfc::TH * (P.nacc / P.nax);
-    P.tiles_y = cdiv(P.Ht, TH); P.tiles_x = cdiv(P.Wt, TW);
+    P.tstep_y = TH; P.tstep_x = TW; P.torg = 0;
+    if (heads) {                              // overlapping 16 x 16 regions, each producing its inner 14 x 14 outputs
+        RDFC_REQUIRE(P.nacc == 2 && P.nax == 2 && TH == 16 && TW == 16, "heads: internal tile shape");
+        P.tstep_y = P.tstep_x = 14; P.torg = -1;
+    }
+    P.tiles_y = cdiv(P.Ht, P.tstep_y); P.tiles_x = cdiv(P.Wt, P.tstep_x);
     P.ntiles = P.tiles_x * P.tiles_y * P.B * P.nphases * P.n_tiles_n;
 
+    // A operand through TMA tensor-map loads unless the producers have to build it (stem mode) or the driver entry
+    // point is missing; RDFC_UMMA_TMA=0 forces the cp.async producers (development knob)
+    P.a_tma = !stem && tmap_encoder() != nullptr;
+    if (const char *e = getenv("RDFC_UMMA_TMA")) P.a_tma = P.a_tma && atoi(e) != 0;
+    P.px16 = P.a_tma ? 4 : 1;
     Phase phases[4] = {};
     int base = 0;
     auto add_plane = [&](int ystep, int yoff, int xstep, int xoff, int rows, int cols) {
@@ -936,7 +1042,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
         int pl[2][2];
         for (int py = 0; py < 2; ++py)
             for (int px = 0; px < 2; ++px)
-                pl[py][px] = add_plane(2, py ? -1 : 0, 2, px ? -1 : 0, TH + py, TW + px);
+                pl[py][px] = add_plane(2, py ? -1 : 0, 2, px ? -1 : 0, TH + (P.a_tma ? 1 : py), TW + (P.a_tma ? 1 : px));   // one TMA box shape
         Phase &ph = phases[0];
         for (int ky = 0; ky < 3; ++ky)
             for (int kx = 0; kx < 3; ++kx)
@@ -944,12 +1050,30 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     }
     P.npix = base;
     P.npix_pad = (base + 7) / 8 * 8;
-    for (int pl = 0; pl < P.nplanes; ++pl)
-        RDFC_REQUIRE(P.planes[pl].ystep * (P.planes[pl].rows - 1) + 1 < 255 && P.planes[pl].xstep * (P.planes[pl].cols - 1) + 1 < 255,
-                     "UMMA conv: staged plane too large for the packed producer slot table");
-    RDFC_REQUIRE(P.npix <= JMAX * PIXPASS, "UMMA conv: staged halo (%d pixels) exceeds the producer slot table", P.npix);
-    RDFC_REQUIRE((long long)P.Hi * P.Wi * P.in_stride * 2 < (1ll << 32), "UMMA conv: image too large for 32-bit producer offsets");
-    RDFC_REQUIRE(P.npix_pad < (1 << 14), "UMMA conv: staged halo too large for the descriptor LBO field");
+    if (P.a_tma) {
+        // every plane of a layer has the same box; a plane occupies rows * cols * 64 B rounded up to the 1 KB swizzle period
+        const Plane &q0 = P.planes[0];
+        for (int pl = 1; pl < P.nplanes; ++pl)
+            RDFC_REQUIRE(P.planes[pl].rows == q0.rows && P.planes[pl].cols == q0.cols, "UMMA conv: TMA planes must share a box");
+        P.a_plane_bytes = (q0.rows * q0.cols * 64 + 1023) / 1024 * 1024;
+        P.a_tx_bytes = P.nplanes * q0.rows * q0.cols * 64;
+        const cuuint64_t gdim[4] = {(cuuint64_t)d->in.C, (cuuint64_t)P.Wi, (cuuint64_t)P.Hi, (cuuint64_t)P.B};
+        const cuuint64_t gstr[3] = {(cuuint64_t)P.in_stride * 2, (cuuint64_t)P.Wi * P.in_stride * 2, (cuuint64_t)P.Hi * P.Wi * P.in_stride * 2};
+        const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(q0.xstep * (q0.cols - 1) + 1), (cuuint32_t)(q0.ystep * (q0.rows - 1) + 1), 1};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)q0.xstep, (cuuint32_t)q0.ystep, 1};
+        RDFC_REQUIRE(box[1] <= 256 && box[2] <= 256, "UMMA conv: TMA box too large");
+        const CUresult r = tmap_encoder()(&P.tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)d->in.ptr, gdim, gstr, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RDFC_REQUIRE(r == CUDA_SUCCESS, "UMMA conv: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    } else {
+        for (int pl = 0; pl < P.nplanes; ++pl)
+            RDFC_REQUIRE(P.planes[pl].ystep * (P.planes[pl].rows - 1) + 1 < 255 && P.planes[pl].xstep * (P.planes[pl].cols - 1) + 1 < 255,
+                         "UMMA conv: staged plane too large for the packed producer slot table");
+        RDFC_REQUIRE(P.npix <= JMAX * PIXPASS, "UMMA conv: staged halo (%d pixels) exceeds the producer slot table", P.npix);
+        RDFC_REQUIRE((long long)P.Hi * P.Wi * P.in_stride * 2 < (1ll << 32), "UMMA conv: image too large for 32-bit producer offsets");
+        RDFC_REQUIRE(P.npix_pad < (1 << 14), "UMMA conv: staged halo too large for the descriptor LBO field");
+    }
     P.w_kb_stride = (long long)KCH * P.CoutP * 8;
     P.b_contig = P.n_tiles_n == 1;
     for (int z = 0; z < P.nphases; ++z) {
@@ -960,8 +1084,17 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
             const Plane &q = P.planes[tap.plane];
             // no-swizzle K-major descriptor: start = tap's shifted view (16-byte units), LBO = cin-chunk pitch,
             // SBO = plane row pitch (8 pixels of a row form one core matrix), bit 46 = descriptor version
-            P.tap_alo[z][tp] = (uint32_t)(q.base + tap.sy * q.cols + tap.sx) | ((uint32_t)P.npix_pad << 16);
-            P.tap_ahi[z][tp] = (uint32_t)q.cols | (1u << 14);
+            if (P.a_tma) {
+                // SWIZZLE_64B K-major ([pixel][64 B], written by TMA): start = plane + shifted pixel, SBO = plane row pitch,
+                // LBO unused (K = 16 < the swizzle width), layout type 4 in bits 61-63; the swizzle is a function of the
+                // absolute shared-memory address, so an arbitrary pixel shift of the start address stays consistent
+                // (scripts/tma_swz_test.cu)
+                P.tap_alo[z][tp] = (uint32_t)(tap.plane * (P.a_plane_bytes >> 4) + (tap.sy * q.cols + tap.sx) * 4) | (1u << 16);
+                P.tap_ahi[z][tp] = (uint32_t)(q.cols * 4) | (1u << 14) | (4u << 29);
+            } else {
+                P.tap_alo[z][tp] = (uint32_t)(q.base + tap.sy * q.cols + tap.sx) | ((uint32_t)P.npix_pad << 16);
+                P.tap_ahi[z][tp] = (uint32_t)q.cols | (1u << 14);
+            }
             P.tap_w[z][tp] = (long long)tap.wtap * P.cin_chunks * P.CoutP * 8;
         }
     }
@@ -975,10 +1108,12 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     P.vec32 = !heads && ((uintptr_t)d->out.ptr % 32) == 0 && d->out.pix_stride % 16 == 0 &&
               (!P.out2 || (((uintptr_t)P.out2 % 32) == 0 && P.out2_stride % 16 == 0 && P.split % 16 == 0)) &&
               (!d->residual.ptr || (((uintptr_t)d->residual.ptr % 32) == 0 && d->residual.pix_stride % 16 == 0));
-    const int a_stage = KCH * P.npix_pad * 16, b_stage = P.gtaps * KCH * P.bn * 16;
+    const int a_stage = P.a_tma ? P.nplanes * P.a_plane_bytes : (KCH * P.npix_pad * 16 + 1023) / 1024 * 1024;
+    const int b_stage = P.gtaps * KCH * P.bn * 16;
     const int stem_patch = stem ? ((P.stem_k / 9) * (TH + 2) * (TW + 2) + 4) * 4 : 0;      // fp32 input patch of a tile (stem mode)
-    const int fixed = BAR_BYTES + 2 * P.CoutP * 4 + 4 * MAX_TAPS * 8 + 2 * P.wad_C * 4 + stem_patch + 256;   // barriers, (scale, shift) and tap tables, slack
-    const int budget = 220 * 1024;
+    const int heads_y = heads ? 256 * (P.bn + 1) * 4 : 0;                                   // shift-add heads: Y of a region
+    const int fixed = BAR_BYTES + 2 * P.CoutP * 4 + 4 * MAX_TAPS * 8 + 2 * P.wad_C * 4 + stem_patch + heads_y + 256;   // barriers, (scale, shift) and tap tables, slack
+    const int budget = 219 * 1024;
     // A ring first (>= 2 stages: the producers publish k-block i while k-block i+1 is in flight), then B stages (2..6)
     // the filter stream is latency-bound: bytes in flight per SM = bandwidth x L2 latency (~2000 cycles), so keep
     // >= 64 KB of filter stages in flight when the tile allows it
@@ -997,12 +1132,13 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     if (P.sa > 6) P.sa = 6;
     if (const char *e = getenv("RDFC_UMMA_SA")) P.sa = atoi(e) < P.sa ? atoi(e) : P.sa;
     RDFC_REQUIRE(P.sa >= 1 && P.sa <= 8 && P.sb >= 1 && P.sb <= 16, "UMMA conv: tile does not fit shared memory");
-    const size_t smem = (size_t)P.sa * a_stage + (size_t)P.sb * b_stage + fixed;
+    const size_t smem = (size_t)P.sa * a_stage + (size_t)P.sb * b_stage + fixed + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE_STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE_GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE_WADAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE_HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     if (const char *e = getenv("RDFC_UMMA_SKIP")) P.dbg_flags = atoi(e);
@@ -1015,7 +1151,8 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     }
     int grid = P.ntiles < sm_count() ? P.ntiles : sm_count();
     if (const char *e = getenv("RDFC_UMMA_GRID")) grid = atoi(e) < P.ntiles ? atoi(e) : P.ntiles;   // development knob
-    if (wad) conv_umma_kernel<MODE_WADAIN><<<grid, NTHREADS, smem, st>>>(P);
+    if (heads) conv_umma_kernel<MODE_HEADS><<<grid, NTHREADS, smem, st>>>(P);
+    else if (wad) conv_umma_kernel<MODE_WADAIN><<<grid, NTHREADS, smem, st>>>(P);
     else if (P.planar || P.act > RDFC_ACT_LEAKY02) conv_umma_kernel<MODE_GENERAL><<<grid, NTHREADS, smem, st>>>(P);
     else conv_umma_kernel<MODE_STD><<<grid, NTHREADS, smem, st>>>(P);
     RDFC_CHECK_LAUNCH("conv_umma_kernel");

@@ -342,19 +342,24 @@ class GeneratorEngine:
         (tensor, element offset, batch stride)."""
         Ctot = buf.shape[3]
 
+        nc = sum(c['mod'].weight.shape[0] for c in cols)
+        NP = (9 * nc + 15) // 16 * 16
+
         def fused_weight():
-            w16 = torch.zeros(16, Ctot, 3, 3, device=buf.device)
+            """(NP, Ctot, 1, 1): row t * nc + q = tap t (= ky * 3 + kx) of output column q, mapped onto buffer channels."""
+            wq = torch.zeros(nc, Ctot, 3, 3, device=buf.device)
             q = 0
             for c in cols:
                 w = c['mod'].weight.detach().float()
                 for s0, n, d0 in c['segs']:
-                    w16[q:q + w.shape[0], d0:d0 + n] = w[:, s0:s0 + n]
+                    wq[q:q + w.shape[0], d0:d0 + n] = w[:, s0:s0 + n]
                 q += w.shape[0]
-            return w16
+            out = torch.zeros(NP, Ctot, 1, 1, device=buf.device)
+            out[:9 * nc, :, 0, 0] = wq.permute(2, 3, 0, 1).reshape(9 * nc, Ctot)
+            return out
 
         def fused_bias():
-            return torch.cat([c['mod'].bias.detach().float() for c in cols] +
-                             [torch.zeros(16 - sum(c['mod'].weight.shape[0] for c in cols), device=buf.device)])
+            return torch.cat([c['mod'].bias.detach().float() for c in cols] + [torch.zeros(NP - nc, device=buf.device)])
 
         pk = self._pack(name, [(fused_weight, None, fused_bias)], 'bf16', True)
         d = C.HeadsDesc()

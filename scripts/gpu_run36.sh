@@ -1,0 +1,8 @@
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests/test_gpu_conv.py -q -x -m gpu 2>&1 | tail -8
+timeout 900 python -m pytest tests/test_gpu_generator.py -q -x -m gpu 2>&1 | tail -5
+for cfg in "32 64 64 228 304 3 1 0" "32 128 128 114 152 3 1 0" "32 128 160 228 304 3 1 0" "32 256 256 57 76 3 1 0" "32 512 512 29 38 3 1 0" "32 64 128 228 304 3 2 0" "32 192 64 114 152 3 2 1" "32 192 384 114 152 1 1 0"; do
+  timeout 120 python scripts/prof_layer.py conv $cfg
+done
+RDFC_UMMA_TMA=0 timeout 120 python scripts/prof_layer.py conv 32 64 64 228 304 3 1 0
+timeout 300 python scripts/prof_plan.py 32 bf16 --json gpurun_out/plan_steps_b32_v12.json 2>&1 | tee gpurun_out/plan_steps_b32_v12.log | head -30

@@ -56,6 +56,23 @@ def main():
     print("families:")
     for k, t in sorted(fam.items(), key=lambda kv: -kv[1]):
         print(f"  {t/1e3:8.2f} ms  {100*t/total:5.1f}%  {k}")
+    if "--timers" in sys.argv:      # needs a -DRDFC_UMMA_TIMERS build and RDFC_UMMA_DBG=1
+        import ctypes
+        import numpy as np
+        pat = sys.argv[sys.argv.index("--timers") + 1]
+        names = {0: "MMA warp lifetime", 1: "MMA wait ACC_EMPTY", 2: "MMA wait A_FULL", 3: "MMA wait B_FULL", 5: "Bload wait B_EMPTY",
+                 6: "prod wait A_EMPTY", 7: "prod issue", 8: "prod wait_group", 9: "epi wait ACC_FULL", 10: "epi work"}
+        for f, n in zip(plan.steps, plan.names):
+            if pat in n:
+                f(s)
+                torch.cuda.synchronize()
+                buf = (ctypes.c_longlong * (148 * 16))()
+                C.lib.rdfc_dev_umma_timers(buf, 148 * 16)
+                a = np.frombuffer(buf, dtype=np.int64).reshape(148, 16).astype(np.float64)
+                a = a[a[:, 0] > 0]
+                print(f"role timers for step '{n}' (cycles, median over {len(a)} CTAs):")
+                for i, nm in names.items():
+                    print(f"   {nm:20s} {np.median(a[:, i]):10.0f}  ({100*np.median(a[:, i])/np.median(a[:, 0]):5.1f}%)")
     if out_json:
         json.dump({"B": B, "precision": prec, "total_us": total, "steps": [{"name": n, "us": t} for t, n in zip(med, plan.names)],
                    "families_us": fam}, open(out_json, "w"), indent=1)
