@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         const int act = P.act, nacc = P.nacc, nax = P.nax, nsets = P.nsets;
         const int Ht = P.Ht, Wt = P.Wt, Ho = P.Ho, Wo = P.Wo, oys = P.oys, oxs = P.oxs;
 #define planar (kGeneral && (flags & 1))
-#define vec32 (flags & 2)
+#define vec32 (kMode == MODE_STD || (flags & 2))      // MODE_STD: the host guarantees 32-byte aligned slices and Cout % 16 == 0
 #define skip (flags >> 2)
         const float slope = act == RDFC_ACT_RELU ? 0.f : (act == RDFC_ACT_LEAKY02 ? 0.2f : 1.f);
         const __nv_bfloat16 *res = P.res;
@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                 const long long pp = (long long)oy * Wo + ox;
 
                 auto load_res = [&](int g, uint4 &r0, uint4 &r1) {
-                    if (rrow && ok && n0 + 16 * g + 16 <= Cout) {
+                    if (rrow && ok && (kMode == MODE_STD || n0 + 16 * g + 16 <= Cout)) {
                         if (vec32) {
                             uint32_t rr[8];
                             ld_global_v8(rrow + 16 * g, rr);
@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                 };
                 auto process = [&](const uint32_t (&v)[16], const uint4 &r0, const uint4 &r1, int g) {
                     const int n = 16 * g;
-                    if (!ok || n0 + n >= Cout) return;
+                    if (!ok || (kMode != MODE_STD && n0 + n >= Cout)) return;
                     float f[16];
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                         }
                         return;
                     }
-                    const bool full = n0 + n + 16 <= Cout;
+                    const bool full = kMode == MODE_STD || n0 + n + 16 <= Cout;
                     if (res && full) {
                         const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
@@ -1153,7 +1153,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     if (const char *e = getenv("RDFC_UMMA_GRID")) grid = atoi(e) < P.ntiles ? atoi(e) : P.ntiles;   // development knob
     if (heads) conv_umma_kernel<MODE_HEADS><<<grid, NTHREADS, smem, st>>>(P);
     else if (wad) conv_umma_kernel<MODE_WADAIN><<<grid, NTHREADS, smem, st>>>(P);
-    else if (P.planar || P.act > RDFC_ACT_LEAKY02) conv_umma_kernel<MODE_GENERAL><<<grid, NTHREADS, smem, st>>>(P);
+    else if (P.planar || P.act > RDFC_ACT_LEAKY02 || !P.vec32 || P.Cout % 16 != 0) conv_umma_kernel<MODE_GENERAL><<<grid, NTHREADS, smem, st>>>(P);
     else conv_umma_kernel<MODE_STD><<<grid, NTHREADS, smem, st>>>(P);
     RDFC_CHECK_LAUNCH("conv_umma_kernel");
     return 0;
