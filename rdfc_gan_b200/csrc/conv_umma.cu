@@ -958,7 +958,12 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     // should be >= 128; N = 128 rather than 256 leaves room for two accumulator sets of two accumulators in TMEM.
     int bn_max = 128;
     if (P.CoutP > 128 && P.CoutP % 128 != 0) bn_max = 256;               // e.g. 160: one tile beats 2 x 80
-    if (k3 && !d->transposed && P.CoutP % 256 == 0 && P.CoutP >= 512) bn_max = 256;   // measured: 512 -> 512 gains 10 %
+    // measured (B = 32, profiles/): N = 256 wins for 256- and 512-wide 3x3 stride-1 convs (+10..13 %) and the 512 -> 256
+    // transposed conv (+29 %); stride-2 convs prefer N = 128 with two accumulator sets unless the output is tiny (en6)
+    if (k3 && P.CoutP % 256 == 0) {
+        if (d->stride == 1 || d->transposed) bn_max = 256;
+        else if ((long long)d->B * d->Ho * d->Wo < 128ll * sm_count()) bn_max = 256;
+    }
     if (k1 && P.CoutP % 256 == 0) bn_max = 256;                          // 1x1: the A stage feeds one tap only, so widen N
     if (wad) bn_max = wadain_tile(wad->x.C);
     if (const char *e = getenv("RDFC_UMMA_BN")) bn_max = atoi(e);        // development knob
