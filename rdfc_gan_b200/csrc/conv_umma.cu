@@ -6,24 +6,29 @@
 // model_utils.py:72-75): 3x3 / 1x1, stride 1 / 2, and ConvTranspose2d(k3,s2,p1,op1) as four sub-pixel phases.
 //
 // GEMM view of one tile:  D[128*NACC pixels, BN couts] += A[pixels, 32 cin] * B[couts, 32 cin]^T  over (cin block, tap)
-//   * a tile is a 16 x (8*NACC) pixel patch of one image; accumulator j (128 TMEM lanes x BN fp32 columns) holds the
-//     16 x 8 sub-patch j, MMA row m = 8*r + c.
-//   * CTAs are persistent (grid = min(#tiles, #SMs)) and walk tiles round-robin.  Four roles run decoupled through
-//     mbarrier rings that continue across tiles, so the loads of tile t+1 and the epilogue of tile t-1 overlap the
-//     MMAs of tile t:
-//       warps 0-3   A producers: stage the tile's input HALO (every pixel any tap can touch) once per 32-channel block
-//                   with 16-byte cp.async (zero-fill outside the image = the conv padding) in the UMMA no-swizzle
-//                   K-major layout [cin/8][pixel][8].  A core matrix is 8 consecutive pixels of a row (128 contiguous
-//                   bytes), SBO = the plane's row pitch, LBO = the cin-chunk pitch, and every filter tap is just a
-//                   different descriptor start address into the same staged plane (input leaves L2 ~1.2x, not 9x).
-//                   Stride-2 layers stage the four input-parity planes; a transposed conv enumerates its four
-//                   output phases as separate tiles, each a 1/2/2/4-tap conv over the input grid.
-//       warp 13     B loader: one pre-packed (tap, 32-cin, BN) filter block per stage, cp.async.bulk (TMA 1-D).
-//       warp 12     MMA issuer: lane 0 issues tcgen05.mma (M=128, N=BN, K=16), frees stages with tcgen05.commit.
-//       warps 4-11  epilogue: tcgen05.ld 32x32b.x16 -> y = act(acc*scale + shift + residual) -> bf16 NHWC channel
-//                   slice (this is how every torch.cat of the reference disappears) or, for the fused decode heads,
-//                   one fp32 plane per output column.  TMEM holds two accumulator sets (when 2*NACC*BN <= 512), so
-//                   the MMA warp fills set (t+1)&1 while the epilogue drains set t&1.
+//   * a tile is NACC accumulators of 16 x 8 output pixels (128 TMEM lanes x BN fp32 columns each, MMA row m = 8*r + c),
+//     arranged nax across x (NACC / nax) down so that the padded tile grid wastes the fewest pixels.
+//   * CTAs are persistent (grid = min(#tiles, #SMs)), 16 warps (4 per scheduler = 128 registers per thread), and walk
+//     tiles round-robin.  The roles run decoupled through mbarrier rings that continue across tiles, so the loads of
+//     tile t+1 and the epilogue of tile t-1 overlap the MMAs of tile t:
+//       warp 0      A loader (one thread): per 32-channel block and plane ONE cp.async.bulk.tensor.4d of the tile's
+//                   input HALO (every pixel any tap can touch) through a tensor map over the NHWC input: box = 32
+//                   channels x plane columns x plane rows, SWIZZLE_64B into [pixel][64 B], out-of-bounds zero fill =
+//                   the conv padding.  A core-matrix group is 8 consecutive pixels of a row, SBO = the plane's row
+//                   pitch, and every filter tap is just a different descriptor start address into the same staged
+//                   plane (input leaves L2 ~1.2x, not 9x).  Stride-2 layers load the four input-parity planes with
+//                   element stride 2; a transposed conv enumerates its four output phases as separate tiles, each a
+//                   1/2/2/4-tap conv over the input grid.
+//                   (warps 0-5 are cp.async producers of a no-swizzle [cin/8][pixel][16 B] layout when RDFC_UMMA_TMA=0,
+//                   and the im2col builders of the fused input stems.)
+//       warp 7      B loader: one pre-packed (filter row, 32-cin, BN) block per stage, cp.async.bulk (TMA 1-D).
+//       warp 6      MMA issuer: convergent loop, one elected lane issues tcgen05.mma (M=128, N=BN, K=16) and frees
+//                   stages with tcgen05.commit.
+//       warps 8-15  epilogue: tcgen05.ld 32x32b.x16 -> y = act(acc*scale + shift + residual) -> bf16 NHWC channel
+//                   slice (this is how every torch.cat of the reference disappears); mode 2 applies W-AdaIN, mode 3
+//                   turns the 9 * ncols head columns into fp32 planes by a shift-add through shared memory.  TMEM holds
+//                   two accumulator sets (when 2*NACC*BN <= 512), so the MMA warp fills set (t+1)&1 while the epilogue
+//                   drains set t&1.
 #include <cuda.h>
 #include <limits.h>
 #include <stdlib.h>
