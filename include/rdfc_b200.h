@@ -170,6 +170,11 @@ typedef struct {
 
 int rdfc_stem_forward(const rdfc_stem_desc *d, void *stream);
 
+/* Stem inputs with many channels (RDF-GAN's 40-channel guidance, rdf_gan_generator.py:235-245): fp32 NCHW in0 (B,C0,H,W)
+ * and optional in1 (B,1,H,W) -> one bf16 NHWC tensor (B,H,W,Cpad) = [in0 | in1 | zeros], which rdfc_conv_forward then reads
+ * on the tensor cores.  Cpad % 8 == 0, Cpad <= 128. */
+int rdfc_pack_stem_input(const float *in0, int C0, const float *in1, void *out_bf16, int Cpad, int B, int H, int W, void *stream);
+
 /* W-AdaIN with the style projection fused (model_utils.py:53-90 without `weighting`): ONE tensor-core launch computes
  * the per-pixel EqualLinear  [gamma | beta] = style[p, :] . W^T + bias  (a 1x1 convolution Cd -> 2C) and applies
  *   out[p, c] = gamma[p, c] * (x[p, c] - mean[b, c]) * rstd[b, c] + beta[p, c]

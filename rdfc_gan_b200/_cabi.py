@@ -67,6 +67,7 @@ def _load():
     lib.rdfc_conv_forward.argtypes = [ctypes.POINTER(ConvDesc), c_void_p]
     lib.rdfc_heads_forward.argtypes = [ctypes.POINTER(HeadsDesc), c_void_p]
     lib.rdfc_stem_forward.argtypes = [ctypes.POINTER(StemDesc), c_void_p]
+    lib.rdfc_pack_stem_input.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.rdfc_wadain_conv_forward.argtypes = [ctypes.POINTER(WadainConvDesc), c_void_p]
     lib.rdfc_wadain_tile.argtypes = [c_int]
     lib.rdfc_instnorm_stats.argtypes = [ctypes.POINTER(View), c_int, c_int, c_int, c_float, c_int, c_int, c_void_p,

@@ -221,6 +221,58 @@ extern "C" int rdfc_adain_apply(const rdfc_view *x, const float *cmean, const fl
     return affine_norm(x, cmean, cstd, smean, sstd, 1, out, B, H, W, stream);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// fp32 NCHW stem inputs -> one bf16 NHWC tensor [in0's C0 channels | in1's channel | zeros] for the tensor-core stems of
+// generators whose stem input has many channels (RDF-GAN: 40-channel guidance, rdf_gan_generator.py:235-245).
+// A block transposes 64 pixels x all channels through shared memory: coalesced plane reads, 16-byte NHWC writes.
+namespace rdfc {
+namespace {
+__global__ void __launch_bounds__(256) pack_stem_kernel(const float *__restrict__ in0, int C0, const float *__restrict__ in1,
+                                                        __nv_bfloat16 *__restrict__ out, int Cpad, long long HW, long long total) {
+    extern __shared__ float ps_tile[];               // [Cpad][65]
+    const long long p0 = (long long)blockIdx.x * 64;
+    const int nsrc = C0 + (in1 ? 1 : 0);
+    for (int e = threadIdx.x; e < Cpad * 64; e += 256) {
+        const int c = e >> 6, px = e & 63;
+        const long long p = p0 + px;
+        float v = 0.f;
+        if (c < nsrc && p < total) {
+            const long long b = p / HW, q = p - b * HW;
+            v = c < C0 ? __ldg(in0 + (b * C0 + c) * HW + q) : __ldg(in1 + b * HW + q);
+        }
+        ps_tile[c * 65 + px] = v;
+    }
+    __syncthreads();
+    const int nchunk = Cpad >> 3;
+    for (int e = threadIdx.x; e < 64 * nchunk; e += 256) {
+        const int px = e / nchunk, ch = e - px * nchunk;
+        const long long p = p0 + px;
+        if (p >= total) continue;
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(ps_tile[(ch * 8 + 2 * k) * 65 + px], ps_tile[(ch * 8 + 2 * k + 1) * 65 + px]);
+            w[k] = *reinterpret_cast<const uint32_t *>(&h2);
+        }
+        *reinterpret_cast<uint4 *>(out + p * Cpad + ch * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+}  // namespace
+}  // namespace rdfc
+
+extern "C" int rdfc_pack_stem_input(const float *in0, int C0, const float *in1, void *out_bf16, int Cpad, int B, int H, int W,
+                                    void *stream) {
+    RDFC_REQUIRE(in0 && out_bf16, "pack_stem_input: NULL argument");
+    RDFC_REQUIRE(C0 >= 1 && Cpad % 8 == 0 && Cpad >= C0 + (in1 ? 1 : 0) && Cpad <= 128, "pack_stem_input: bad channel counts (%d -> %d)", C0, Cpad);
+    RDFC_REQUIRE(B > 0 && H > 0 && W > 0 && ((uintptr_t)out_bf16 % 16) == 0, "pack_stem_input: bad shape / alignment");
+    const long long HW = (long long)H * W, total = HW * B;
+    const size_t smem = (size_t)Cpad * 65 * sizeof(float);
+    rdfc::pack_stem_kernel<<<(unsigned)((total + 63) / 64), 256, smem, (cudaStream_t)stream>>>(in0, C0, in1, (__nv_bfloat16 *)out_bf16, Cpad,
+                                                                                              HW, total);
+    RDFC_CHECK_LAUNCH("pack_stem_kernel");
+    return 0;
+}
+
 extern "C" int rdfc_norm_apply(const rdfc_view *x, const float *mean, const float *rstd, const rdfc_view *out, int B,
                                int H, int W, void *stream) {
     return affine_norm(x, mean, rstd, nullptr, nullptr, 0, out, B, H, W, stream);

@@ -198,6 +198,31 @@ class GeneratorEngine:
         if bf16 and Cs + 1 <= 4:
             # all three stems as ONE tensor-core launch: im2col rows built by the producer warps from the fp32 NCHW inputs
             self._plan_stem(plan, B, H, W, Cs, fe1)
+        elif bf16 and Cs + 1 <= 128:
+            # many-channel stem input (RDF-GAN's 40-channel guidance): pack [stem | depth | 0] to bf16 NHWC once, then the
+            # stems are two tensor-core 3x3 convs over it (block-sparse filters: the depth column only feeds the 1 -> 16 stem)
+            Cpad = (Cs + 1 + 31) // 32 * 32
+            xin = new(B, H, W, Cpad)
+            plan.names.append(f'pack_stem_input {Cs}+1 -> {Cpad}')
+            plan.steps.append(lambda s: C.check(C.lib.rdfc_pack_stem_input(C.ptr(plan.stem_in), Cs, C.ptr(plan.depth), C.ptr(xin),
+                                                                         Cpad, B, H, W, s)))
+            plan.n_launch += 1
+
+            def padded(mod, c0):
+                def f():
+                    w = mod[0].weight.detach().float()
+                    out = w.new_zeros(w.shape[0], Cpad, 3, 3)
+                    out[:, c0:c0 + w.shape[1]] = w
+                    return out
+                return f
+
+            def src(mod, c0):
+                bn = mod[1] if len(mod) > 1 and isinstance(mod[1], torch.nn.BatchNorm2d) else None
+                return (padded(mod, c0), bn, mod[0].bias)
+
+            conv('rgb_branch_en1', [src(g.rgb_branch_en1, 0)], (xin, 0, Cpad), fe1['r'], 3, act=L, hin=full, hout=full)
+            conv('depth_branch_en1', [src(g.depth_branch_en1_rgb, 0), src(g.depth_branch_en1_depth, Cs)], (xin, 0, Cpad), fe1['d'], 3,
+                 act=L, hin=full, hout=full)
         else:
             conv('rgb_branch_en1', [seq_src(g.rgb_branch_en1)], plan.stem_in, fe1['r'], 3, act=L, in_nchw=True, hin=full, hout=full)
             conv('depth_branch_en1_rgb', [seq_src(g.depth_branch_en1_rgb)], plan.stem_in, (fe1['d'][0], fe1['d'][1], 48), 3,
