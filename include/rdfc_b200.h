@@ -178,7 +178,7 @@ int rdfc_pack_stem_input(const float *in0, int C0, const float *in1, void *out_b
 /* W-AdaIN with the style projection fused (model_utils.py:53-90 without `weighting`): ONE tensor-core launch computes
  * the per-pixel EqualLinear  [gamma | beta] = style[p, :] . W^T + bias  (a 1x1 convolution Cd -> 2C) and applies
  *   out[p, c] = gamma[p, c] * (x[p, c] - mean[b, c]) * rstd[b, c] + beta[p, c]
- * in its epilogue, so the (B,H,W,2C) gamma/beta tensor never exists.  The filter rows are packed in tiles of
+ * (times the optional per-pixel weights of `weighting=True`) in its epilogue, so the (B,H,W,2C) gamma/beta tensor never exists.  The filter rows are packed in tiles of
  * `rdfc_wadain_tile(C)` columns: tile t = gamma rows of channels [t*h, (t+1)*h) followed by their beta rows, h = tile/2;
  * `bias` is permuted the same way.  mean / rstd: (B, C) fp32 from rdfc_instnorm_stats. */
 typedef struct {
@@ -189,6 +189,8 @@ typedef struct {
     const void *weight;          /* bf16 [1][Cd/8][2C][8], rows permuted as described */
     const float *bias;           /* 2C floats, permuted */
     const float *mean, *rstd;    /* (B, C) */
+    rdfc_view gwbw;              /* optional (ptr NULL: none): bf16 NHWC, 2C channels [gamma weight | beta weight] =
+                                  * gamma/beta_weight_layer(x) (model_utils.py:84-88): out = gw*gamma*IN(x) + bw*beta */
 } rdfc_wadain_conv_desc;
 
 int rdfc_wadain_tile(int C);

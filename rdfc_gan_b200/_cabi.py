@@ -46,7 +46,7 @@ class StemDesc(ctypes.Structure):
 
 class WadainConvDesc(ctypes.Structure):
     _fields_ = [("B", c_int), ("H", c_int), ("W", c_int), ("style", View), ("x", View), ("out", View), ("weight", c_void_p),
-                ("bias", c_void_p), ("mean", c_void_p), ("rstd", c_void_p)]
+                ("bias", c_void_p), ("mean", c_void_p), ("rstd", c_void_p), ("gwbw", View)]
 
 
 def _load():

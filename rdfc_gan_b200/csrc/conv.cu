@@ -75,6 +75,9 @@ extern "C" int rdfc_wadain_conv_forward(const rdfc_wadain_conv_desc *w, void *st
     RDFC_REQUIRE(((uintptr_t)w->x.ptr % 32) == 0 && w->x.pix_stride % 16 == 0 && ((uintptr_t)w->out.ptr % 32) == 0 &&
                      w->out.pix_stride % 16 == 0,
                  "wadain conv: x / out slices must be 32-byte aligned");
+    RDFC_REQUIRE(!w->gwbw.ptr || (w->gwbw.dtype == RDFC_BF16 && !w->gwbw.nchw && w->gwbw.C == 2 * w->x.C &&
+                                  ((uintptr_t)w->gwbw.ptr % 32) == 0 && w->gwbw.pix_stride % 16 == 0),
+                 "wadain conv: gwbw must be a 32-byte aligned bf16 NHWC view with 2C channels");
     rdfc_conv_desc d{};
     d.B = w->B; d.Hi = d.Ho = w->H; d.Wi = d.Wo = w->W;
     d.kh = d.kw = 1; d.stride = 1; d.pad = 0; d.act = RDFC_ACT_NONE; d.path = RDFC_PATH_UMMA_BF16;

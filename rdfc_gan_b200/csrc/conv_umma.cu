@@ -104,6 +104,8 @@ struct Params {
     const __nv_bfloat16 *wad_x;    // normalised tensor (NULL: not a W-AdaIN launch)
     int wad_x_stride, wad_C;
     const float *wad_mean, *wad_rstd;
+    const __nv_bfloat16 *wad_w;    // optional [gamma weight | beta weight] tensor (2C channels), `weighting=True`
+    int wad_w_stride;
     int gtaps;                     // filter taps per B stage (3 for 3x3 convs: one wait / commit per filter row)
     int vec32;                     // output (and residual) slices are 32-byte aligned: 256-bit stores / loads
     int b_contig;                  // the 4 cin chunks of a stage are contiguous in the packed weights (one Cout tile)
@@ -712,12 +714,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                     const long long opix = ok ? ((long long)t.b * Ho + yy) * Wo + xx : 0;
                     const uint32_t trow = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(set * set_cols + j * bn);
                     const __nv_bfloat16 *xrow = P.wad_x + opix * P.wad_x_stride + c0;
+                    const __nv_bfloat16 *wrow = P.wad_w ? P.wad_w + opix * P.wad_w_stride + c0 : nullptr;
                     __nv_bfloat16 *orow = outp + opix * out_stride + c0;
                     for (int g = 0; g < (half >> 4); ++g) {
-                        uint32_t vg[16], vb[16], xr[8];
+                        uint32_t vg[16], vb[16], xr[8], gw[8], bw[8];
                         tc_ld16_issue(trow + (uint32_t)(16 * g), vg);
                         tc_ld16_issue(trow + (uint32_t)(half + 16 * g), vb);
                         if (ok) ld_global_v8(xrow + 16 * g, xr);
+                        if (ok && wrow) { ld_global_v8(wrow + 16 * g, gw); ld_global_v8(wrow + C + 16 * g, bw); }
                         tc_wait_ld(vg);
                         tc_wait_ld(vb);
                         if (!ok) continue;
@@ -727,8 +731,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                             const int ch = c0 + 16 * g + 2 * q, ng = t.n0 + 16 * g + 2 * q, nb = ng + half;
                             const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&xr[q]));
                             const float n0v = (xv.x - s_stat[ch]) * s_stat[C + ch], n1v = (xv.y - s_stat[ch + 1]) * s_stat[C + ch + 1];
-                            const float y0 = fmaf(__uint_as_float(vg[2 * q]) + s_shift[ng], n0v, __uint_as_float(vb[2 * q]) + s_shift[nb]);
-                            const float y1 = fmaf(__uint_as_float(vg[2 * q + 1]) + s_shift[ng + 1], n1v, __uint_as_float(vb[2 * q + 1]) + s_shift[nb + 1]);
+                            float g0 = __uint_as_float(vg[2 * q]) + s_shift[ng], g1 = __uint_as_float(vg[2 * q + 1]) + s_shift[ng + 1];
+                            float b0 = __uint_as_float(vb[2 * q]) + s_shift[nb], b1 = __uint_as_float(vb[2 * q + 1]) + s_shift[nb + 1];
+                            if (wrow) {
+                                const float2 gwv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gw[q]));
+                                const float2 bwv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&bw[q]));
+                                g0 *= gwv.x; g1 *= gwv.y; b0 *= bwv.x; b1 *= bwv.y;
+                            }
+                            const float y0 = fmaf(g0, n0v, b0);
+                            const float y1 = fmaf(g1, n1v, b1);
                             const __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
                             o[q] = *reinterpret_cast<const uint32_t *>(&h2);
                         }
@@ -936,6 +947,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     if (wad) {
         P.wad_x = (const __nv_bfloat16 *)wad->x.ptr; P.wad_x_stride = wad->x.pix_stride; P.wad_C = wad->x.C;
         P.wad_mean = wad->mean; P.wad_rstd = wad->rstd;
+        P.wad_w = (const __nv_bfloat16 *)wad->gwbw.ptr; P.wad_w_stride = wad->gwbw.pix_stride;
         P.Cout = 2 * wad->x.C; P.CoutP = P.Cout;              // GEMM columns; the output view has C channels
     }
     if (stem) {

@@ -423,7 +423,7 @@ class GeneratorEngine:
             plan.n_launch += 2
             return mean, rstd
 
-        if isinstance(layer, AdaptiveInstanceNorm) and precision == 'bf16' and not layer.weighting and Cx % 64 == 0 and Cd % 32 == 0:
+        if isinstance(layer, AdaptiveInstanceNorm) and precision == 'bf16' and Cx % 64 == 0 and Cd % 32 == 0:
             # style projection + W-AdaIN apply as ONE tensor-core launch: the (B,H,W,2C) gamma/beta tensor never exists
             lin = layer.style.linear
             tile = C.lib.rdfc_wadain_tile(Cx)
@@ -437,6 +437,14 @@ class GeneratorEngine:
             d = C.WadainConvDesc()
             d.B, d.H, d.W = B, Hh, Ww
             d.style, d.x, d.out = vd, vx, vout
+            d.gwbw = C.view(None)
+            if layer.weighting:         # model_utils.py:84-88: per-pixel weights of gamma / beta, two 1x1 convs of x fused into one
+                gwbw = new(B, Hh, Ww, 2 * Cx)
+                conv(f'fuse{n}.weighting', [(layer.gamma_weight_layer.weight, None, layer.gamma_weight_layer.bias),
+                                            (layer.beta_weight_layer.weight, None, layer.beta_weight_layer.bias)],
+                     xr, (gwbw, 0, 2 * Cx), 1, hin=hw, hout=hw)
+                d.gwbw = C.view(gwbw)
+                plan.keep.append(gwbw)
             d.weight, d.bias, d.mean, d.rstd = pk.weight.data_ptr(), pk.shift.data_ptr(), mean.data_ptr(), rstd.data_ptr()
             plan.keep.append((d, pk, mean, rstd))
             plan.names.append(f'wadain_conv fuse{n} {Cd}->2x{Cx} {Hh}x{Ww}')

@@ -219,8 +219,9 @@ def test_fused_stems_match_three_convs(B, H, W):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # rdfc_wadain_conv_forward: EqualLinear style projection + W-AdaIN apply (model_utils.py:53-90, weighting=False)
+@pytest.mark.parametrize("weighting", [False, True])
 @pytest.mark.parametrize("B,H,W,C,Cd", [(2, 15, 19, 512, 512), (1, 29, 38, 768, 768), (2, 20, 28, 192, 192), (1, 9, 11, 64, 32)])
-def test_fused_wadain_conv(B, H, W, C, Cd):
+def test_fused_wadain_conv(B, H, W, C, Cd, weighting):
     from rdfc_gan_b200 import _cabi as C_
     g = torch.Generator().manual_seed(C + Cd + H)
     x, style = torch.randn(B, C, H, W, generator=g), torch.randn(B, Cd, H, W, generator=g)
@@ -232,6 +233,9 @@ def test_fused_wadain_conv(B, H, W, C, Cd):
     mean = xb.mean((2, 3), keepdim=True)
     rstd = 1.0 / torch.sqrt(xb.var((2, 3), unbiased=False, keepdim=True) + 1e-5)
     ref = gb[:, :C] * (xb - mean) * rstd + gb[:, C:]
+    gwbw = rb(1.0 + 0.5 * torch.randn(B, 2 * C, H, W, generator=g))        # gamma/beta_weight_layer(x), model_utils.py:84-88
+    if weighting:
+        ref = gwbw[:, :C] * gb[:, :C] * (xb - mean) * rstd + gwbw[:, C:] * gb[:, C:]
     tile = C_.lib.rdfc_wadain_tile(C)
     half = tile // 2
     perm = torch.cat([torch.cat([torch.arange(t * half, (t + 1) * half), C + torch.arange(t * half, (t + 1) * half)])
@@ -245,7 +249,26 @@ def test_fused_wadain_conv(B, H, W, C, Cd):
     d.B, d.H, d.W = B, H, W
     d.style, d.x, d.out = C_.view(s_d), C_.view(x_d), C_.view(out)
     d.weight, d.bias, d.mean, d.rstd = packed.data_ptr(), b_d.data_ptr(), m_d.data_ptr(), r_d.data_ptr()
+    w_d = gwbw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    d.gwbw = C_.view(w_d) if weighting else C_.view(None)
     C_.check(C_.lib.rdfc_wadain_conv_forward(ctypes.byref(d), C_.stream_ptr()))
     torch.cuda.synchronize()
     got = out.float().permute(0, 3, 1, 2).cpu()
     assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("B,H,W,C0,Cpad,with_in1", [(2, 13, 17, 40, 64, True), (1, 228, 304, 40, 64, True), (3, 9, 9, 5, 8, False)])
+def test_pack_stem_input(B, H, W, C0, Cpad, with_in1):
+    """rdfc_pack_stem_input: [in0 | in1 | zeros] as bf16 NHWC, bit-exact against torch's round-to-nearest-even cast."""
+    from rdfc_gan_b200 import _cabi as C
+    g = torch.Generator().manual_seed(C0 + H)
+    in0 = torch.randn(B, C0, H, W, generator=g).cuda()
+    in1 = torch.randn(B, 1, H, W, generator=g).cuda() if with_in1 else None
+    out = torch.full((B, H, W, Cpad), 7.0, dtype=torch.bfloat16, device="cuda")
+    C.check(C.lib.rdfc_pack_stem_input(C.ptr(in0), C0, C.ptr(in1) if with_in1 else None, C.ptr(out), Cpad, B, H, W, C.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = torch.zeros(B, H, W, Cpad, device="cuda")
+    ref[..., :C0] = in0.permute(0, 2, 3, 1)
+    if with_in1:
+        ref[..., C0] = in1[:, 0]
+    assert torch.equal(out, ref.to(torch.bfloat16))
