@@ -49,7 +49,7 @@ constexpr int JMAX = 24;          // pixel slots per producer thread and k-block
 constexpr int MMA_WARP = 6, BLOAD_WARP = 7, EPI_WARP0 = 8, NEPI_WARPS = 8;
 constexpr int NTHREADS = 16 * 32;
 constexpr int MAX_PLANES = 4, MAX_TAPS = 9;
-constexpr int BAR_BYTES = (2 * 8 + 2 * 16 + 4) * 8 + 16;   // mbarriers for <= 8 A stages, <= 16 B stages, 2+2 accumulator sets; TMEM slot
+constexpr int BAR_BYTES = (3 * 8 + 3 * 16 + 4) * 8 + 16;   // mbarriers for <= 8 A stages, <= 16 B stages, 2+2 accumulator sets; TMEM slot
 
 struct Plane {
     int ystep, yoff, xstep, xoff;  // input pixel = (ystep*(ty0+r) + yoff, xstep*(tx0+c) + xoff)
@@ -67,6 +67,8 @@ struct Params {
     // A operand through TMA (a_tma != 0): one 4-D tensor map (C, W, H, B) over the NHWC input view; box = 32 channels x
     // plane columns x plane rows, SWIZZLE_64B, zero fill outside the image = the conv padding
     alignas(64) CUtensorMap tmap_a;
+    int pair;                      // cta_group::2: two CTAs (a cluster) work on two pixel tiles with ONE stream of M = 256 MMAs; each
+                                   // holds its own A stages and HALF of every filter stage (per-SM shared-memory reads per MMA: 4 KB + N*16 B)
     int a_tma, px16, a_plane_bytes, a_tx_bytes;   // a_tx_bytes: bytes the TMA loads of one stage deliver (planes x rows x cols x 64)
     int _pad_tma;   // px16: 16-byte units per staged pixel (4 with TMA: [pixel][64 B]; 1: [cin/8][pixel][16 B])
     const __nv_bfloat16 *in;
@@ -114,11 +116,22 @@ struct Params {
 struct Tile {
     int b, ty0, tx0, n0, z;
 };
-__device__ __forceinline__ Tile decode_tile(const Params &P, int tile) {
+// rank: the CTA's rank in its pair (0 without pairs).  In pair mode `tile` counts pairs of spatial tiles of one (image, phase,
+// Cout tile): the two CTAs take linear positions 2 * pp + rank of the image's tile grid; a position past its end is a dummy
+// tile (all coordinates out of bounds: the TMA zero-fills, the epilogue stores nothing).
+template <bool kPair>
+__device__ __forceinline__ Tile decode_tile(const Params &P, int tile, int rank) {
     Tile t;
     const int nt = tile % P.n_tiles_n; tile /= P.n_tiles_n;      // Cout tile fastest: the A halo stays hot in L2
-    const int txi = tile % P.tiles_x; tile /= P.tiles_x;
-    const int tyi = tile % P.tiles_y; tile /= P.tiles_y;
+    int txi, tyi;
+    if constexpr (kPair) {
+        const int per = (P.tiles_x * P.tiles_y + 1) >> 1;
+        const int l = 2 * (tile % per) + rank; tile /= per;
+        tyi = l / P.tiles_x; txi = l - tyi * P.tiles_x;
+    } else {
+        txi = tile % P.tiles_x; tile /= P.tiles_x;
+        tyi = tile % P.tiles_y; tile /= P.tiles_y;
+    }
     t.z = tile % P.nphases; tile /= P.nphases;
     t.b = tile;
     t.ty0 = tyi * P.tstep_y + P.torg; t.tx0 = txi * P.tstep_x + P.torg; t.n0 = nt * P.bn;
@@ -197,6 +210,35 @@ __device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma2_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once all prior MMAs are complete
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(saddr), "r"(rank));
+    return raddr;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -205,7 +247,7 @@ __device__ __forceinline__ bool elect_one() {
 // all MMAs of one (k-block, tap): BK/16 k-steps x NACC accumulators, fully unrolled
 // accumulator j = (jy, jx) covers the 16 x 8 pixel block at rows 16 jy, columns 8 jx of the tile: its A view starts
 // jy * 16 plane rows + jx * 8 pixels further (jx_step = 8, jy_step = 16 * plane pitch, in 16-byte units)
-template <int NACC>
+template <int NACC, bool kPair>
 __device__ __forceinline__ void issue_tap(uint32_t d_base, uint32_t bn, uint32_t a_lo, uint32_t a_hi, uint32_t a_kstep,
                                           uint32_t b_lo, uint32_t b_hi, uint32_t b_kstep, uint32_t idesc, uint32_t acc0,
                                           const uint32_t (&jy16)[4], const uint32_t (&jx8)[4]) {
@@ -217,8 +259,12 @@ __device__ __forceinline__ void issue_tap(uint32_t d_base, uint32_t bn, uint32_t
     for (int k2 = 0; k2 < BK / 16; ++k2)
 #pragma unroll
         for (int j = 0; j < NACC; ++j)      // consecutive MMAs target different accumulators
-            tc_mma2(d_base + (uint32_t)j * bn, a_lo + joff[j] + (uint32_t)k2 * a_kstep, a_hi,
-                    b_lo + (uint32_t)k2 * b_kstep, b_hi, idesc, k2 ? 1u : acc0);
+            if constexpr (kPair)
+                tc_mma2_pair(d_base + (uint32_t)j * bn, a_lo + joff[j] + (uint32_t)k2 * a_kstep, a_hi, b_lo + (uint32_t)k2 * b_kstep, b_hi,
+                             idesc, k2 ? 1u : acc0);
+            else
+                tc_mma2(d_base + (uint32_t)j * bn, a_lo + joff[j] + (uint32_t)k2 * a_kstep, a_hi, b_lo + (uint32_t)k2 * b_kstep, b_hi,
+                        idesc, k2 ? 1u : acc0);
 }
 // issue only; the registers are valid after tc_wait_ld(v)
 __device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
@@ -280,13 +326,20 @@ __device__ __forceinline__ void ld_global_v8(const void *p, uint32_t (&o)[8]) {
 // kMode = MODE_WADAIN: W-AdaIN epilogue over [gamma | beta] column tiles.  kMode = MODE_HEADS: the decode heads as ONE
 // 1x1 GEMM to 9 * ncols columns (tap-major) over overlapping 16x16 pixel regions + a shift-add through shared memory.
 enum { MODE_STD = 0, MODE_GENERAL = 1, MODE_WADAIN = 2, MODE_HEADS = 3 };
-template <int kMode>
+// kPair: the cta_group::2 instantiation (its instructions make ptxas require an even cluster size, so the single-CTA
+// kernels are separate instantiations).
+template <int kMode, bool kPair>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_constant__ Params P) {
     constexpr bool kGeneral = kMode == MODE_GENERAL;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_stage_bytes = P.a_tma ? P.nplanes * P.a_plane_bytes : KCH * P.npix_pad * 16;
-    const int b_tap_bytes = KCH * P.bn * 16, b_stage_bytes = P.gtaps * b_tap_bytes;
+    const int bn_cta = kPair ? P.bn >> 1 : P.bn;                 // filter rows this CTA stages (half with cta_group::2)
+    const int b_tap_bytes = KCH * bn_cta * 16, b_stage_bytes = P.gtaps * b_tap_bytes;
+    uint32_t rank_u = 0;
+    if constexpr (kPair) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank_u));
+    const int rank = kPair ? (int)rank_u : 0;
+    const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     // stages start on a 1 KB boundary (the SWIZZLE_64B pattern the TMA writes repeats every 1 KB; the host adds the slack)
     unsigned char *sA = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     unsigned char *sB = sA + (size_t)P.sa * a_stage_bytes;
@@ -294,9 +347,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     // barrier map: a_full[sa] a_empty[sa] b_full[sb] b_empty[sb] acc_full[2] acc_empty[2]
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    // pair mode adds peer_a_full[sa] peer_b_full[sb] (leader only: the peer CTA forwards its own full signals there)
     const int A_FULL = 0, A_EMPTY = P.sa, B_FULL = 2 * P.sa, B_EMPTY = 2 * P.sa + P.sb, ACC_FULL = 2 * P.sa + 2 * P.sb,
-              ACC_EMPTY = ACC_FULL + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + ACC_EMPTY + 2);
+              ACC_EMPTY = ACC_FULL + 2, PEER_A = ACC_EMPTY + 2, PEER_B = PEER_A + P.sa;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + PEER_B + P.sb);
     // per-channel epilogue vectors, padded to CoutP with (1, 0): 16-byte aligned after the barrier block
     float *s_scale = reinterpret_cast<float *>(sB + (size_t)P.sb * b_stage_bytes + BAR_BYTES);
     float *s_shift = s_scale + P.CoutP;
@@ -315,17 +369,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.sa; ++i) { mbar_init(BAR(A_FULL + i), P.a_tma ? 1 : NPROD); mbar_init(BAR(A_EMPTY + i), 1); }
         for (int i = 0; i < P.sb; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), 1); mbar_init(BAR(ACC_EMPTY + i), NEPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), 1); mbar_init(BAR(ACC_EMPTY + i), kPair ? 2 * NEPI_WARPS : NEPI_WARPS); }
+        if constexpr (kPair) {
+            for (int i = 0; i < P.sa; ++i) mbar_init(BAR(PEER_A + i), 1);
+            for (int i = 0; i < P.sb; ++i) mbar_init(BAR(PEER_B + i), 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)P.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)P.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)P.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();          // both CTAs' barriers exist before any remote arrive / multicast commit
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int set_cols = P.nacc * P.bn;
@@ -340,8 +406,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
             const uint32_t sA0 = smem_u32(sA), plane_b = (uint32_t)P.a_plane_bytes;
             int s = 0;
             uint32_t par = 1;
-            for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-                const Tile t = decode_tile(P, tile);
+            for (int tile = tile0; tile < P.ntiles; tile += tile_step) {
+                const Tile t = decode_tile<kPair>(P, tile, rank);
                 for (int i = 0; i < nkb; ++i) {
                     mbar_wait(BAR(A_EMPTY + s), par);
                     const uint32_t full = BAR(A_FULL + s);
@@ -386,8 +452,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         const uint32_t dst_thread = smem_u32(sA) + (uint32_t)(ch * P.npix_pad + p0) * 16u;
         int s = 0;
         uint32_t par = 1;
-        for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-            const Tile t = decode_tile(P, tile);
+        for (int tile = tile0; tile < P.ntiles; tile += tile_step) {
+            const Tile t = decode_tile<kPair>(P, tile, rank);
             const float *b0 = P.stem_in0 + (long long)t.b * P.stem_c0 * HW;
             const float *b1 = P.stem_in1 ? P.stem_in1 + (long long)t.b * HW : b0;
             asm volatile("bar.sync 3, %0;" ::"n"(NPROD) : "memory");          // the previous tile's slots are built
@@ -472,8 +538,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         long long t_wait_empty = 0, t_issue = 0, t_wait_group = 0;
         int issued = 0;             // k-blocks committed so far
         int pub = 0;                // next stage to publish
-        for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-            const Tile t = decode_tile(P, tile);
+        for (int tile = tile0; tile < P.ntiles; tile += tile_step) {
+            const Tile t = decode_tile<kPair>(P, tile, rank);
             const char *img = reinterpret_cast<const char *>(P.in + (long long)t.b * Hi * Wi * in_stride) + ch * 16;
             const int y0 = ystep * t.ty0 - 1, x0 = xstep * t.tx0 - 1;
             uint32_t off[JMAX];
@@ -527,11 +593,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         // The whole warp walks the loop convergently (barrier waits, ring bookkeeping); one elected lane issues.  Per
         // MMA the issue cost is one 32-bit add on a descriptor word; the per-tap descriptor words come from the
         // shared-memory table and are fetched before the wait on the filter stage.
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | (8u << 24);
+        // instruction descriptor: bf16 x bf16 -> fp32, N = bn, M = 128 (one CTA) or 256 (cta_group::2: 128 rows per CTA)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((kPair ? 16u : 8u) << 24);
         // one k-step = 16 channels: two chunk planes further in the [cin/8][pixel][16 B] layout, 32 bytes in [pixel][64 B]
-        const uint32_t a_kstep = keep(P.a_tma ? 2u : 2u * (uint32_t)P.npix_pad), b_kstep = keep(2u * (uint32_t)P.bn);
+        const uint32_t a_kstep = keep(P.a_tma ? 2u : 2u * (uint32_t)P.npix_pad), b_kstep = keep(2u * (uint32_t)bn_cta);
         const uint32_t b_hi = (128u >> 4) | (1u << 14);                                     // SBO = 128 B, version bit 46
-        const uint32_t b_lo0 = keep(((smem_u32(sB) & 0x3FFFFu) >> 4) | ((uint32_t)P.bn << 16));   // LBO = bn * 16 B
+        const uint32_t b_lo0 = keep(((smem_u32(sB) & 0x3FFFFu) >> 4) | ((uint32_t)bn_cta << 16));   // LBO = staged rows * 16 B
         const uint32_t a_lo0 = keep((smem_u32(sA) & 0x3FFFFu) >> 4);
         const uint32_t a_stage16 = keep((uint32_t)a_stage_bytes >> 4), b_stage16 = keep((uint32_t)b_stage_bytes >> 4);
         const uint32_t b_tap16 = keep((uint32_t)b_tap_bytes >> 4);
@@ -545,8 +612,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         uint32_t a_par = 0, b_par = 0;
         long long t_acc = 0, t_a = 0, t_b = 0;
         const long long t_start = DBG_ON ? clock64() : 0;
-        for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
-            const Tile t = decode_tile(P, tile);
+        constexpr bool pair = kPair;
+        if (pair && rank != 0) {
+            // peer CTA of a pair: no MMAs to issue.  Forward "my stage is full" to the leader, in consumption order (a TMA / bulk
+            // copy of the peer cannot complete on the leader's mbarrier directly: measured, it never arrives).
+            for (int tile = tile0; tile < P.ntiles; tile += tile_step) {
+                const Tile t = decode_tile<kPair>(P, tile, rank);
+                const int ngroups = P.ntaps[t.z] / gtaps;
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(BAR(A_FULL + s), a_par);
+                    if (lane == 0) mbar_arrive_remote(BAR(PEER_A + s), 0);
+                    for (int gi = 0; gi < ngroups; ++gi) {
+                        mbar_wait(BAR(B_FULL + sb), b_par);
+                        if (lane == 0) mbar_arrive_remote(BAR(PEER_B + sb), 0);
+                        if (++sb == sb_n) { sb = 0; b_par ^= 1u; }
+                    }
+                    if (++s == sa_n) { s = 0; a_par ^= 1u; }
+                }
+            }
+        } else
+        for (int tile = tile0; tile < P.ntiles; tile += tile_step, ++it) {
+            const Tile t = decode_tile<kPair>(P, tile, rank);
             const int z = t.z, ngroups = P.ntaps[z] / gtaps;
             const uint2 *ztap = s_tap + z * MAX_TAPS;
             const int set = nsets == 2 ? (it & 1) : 0;
@@ -555,14 +641,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
             tc_fence_after();
             const uint32_t d_base = tmem_base + (uint32_t)(set * set_cols);
             for (int i = 0; i < nkb; ++i) {
-                { DBG_T0(); mbar_wait(BAR(A_FULL + s), a_par); DBG_ACC(t_a); }
+                { DBG_T0(); mbar_wait(BAR(A_FULL + s), a_par); if (pair) mbar_wait(BAR(PEER_A + s), a_par); DBG_ACC(t_a); }
                 const uint32_t a_stage_lo = a_lo0 + (uint32_t)s * a_stage16;
                 for (int gi = 0; gi < ngroups; ++gi) {
                     uint2 td[3];
 #pragma unroll
                     for (int tg = 0; tg < 3; ++tg) td[tg] = ztap[gi * gtaps + (tg < gtaps ? tg : 0)];
                     const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage16;
-                    { DBG_T0(); mbar_wait(BAR(B_FULL + sb), b_par); DBG_ACC(t_b); }
+                    { DBG_T0(); mbar_wait(BAR(B_FULL + sb), b_par); if (pair) mbar_wait(BAR(PEER_B + sb), b_par); DBG_ACC(t_b); }
                     tc_fence_after();
                     if (elect_one()) {
 #pragma unroll
@@ -571,17 +657,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                                 const uint32_t acc0 = (i | gi | tg) ? 1u : 0u;
                                 const uint32_t a_lo = td[tg].x + a_stage_lo, a_hi = td[tg].y, bl = b_lo + (uint32_t)tg * b_tap16;
                                 switch (nacc) {
-                                    case 1: issue_tap<1>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8); break;
-                                    case 2: issue_tap<2>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8); break;
-                                    case 3: issue_tap<3>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8); break;
-                                    default: issue_tap<4>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8); break;
+                                    case 1:
+                                        issue_tap<1, kPair>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8);
+                                        break;
+                                    case 2:
+                                        issue_tap<2, kPair>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8);
+                                        break;
+                                    case 3:
+                                        issue_tap<3, kPair>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8);
+                                        break;
+                                    default:
+                                        issue_tap<4, kPair>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8);
+                                        break;
                                 }
                             }
                         }
-                        tc_commit(BAR(B_EMPTY + sb));
-                        if (gi == ngroups - 1) {
-                            tc_commit(BAR(A_EMPTY + s));
-                            if (i == nkb - 1) tc_commit(BAR(ACC_FULL + set));
+                        if constexpr (kPair) {        // the same barriers in both CTAs of the pair
+                            tc_commit_pair(BAR(B_EMPTY + sb));
+                            if (gi == ngroups - 1) {
+                                tc_commit_pair(BAR(A_EMPTY + s));
+                                if (i == nkb - 1) tc_commit_pair(BAR(ACC_FULL + set));
+                            }
+                        } else {
+                            tc_commit(BAR(B_EMPTY + sb));
+                            if (gi == ngroups - 1) {
+                                tc_commit(BAR(A_EMPTY + s));
+                                if (i == nkb - 1) tc_commit(BAR(ACC_FULL + set));
+                            }
                         }
                     }
                     __syncwarp();
@@ -597,31 +699,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     } else if (warp == BLOAD_WARP) {
         // ================= B loader (TMA 1-D bulk copies of pre-packed filter blocks) =================
         if (lane == 0) {
-            const uint32_t piece = keep((uint32_t)P.bn * 16u);
+            const uint32_t piece = keep((uint32_t)bn_cta * 16u);          // one cin chunk of this CTA's filter rows
             const long long chunk_stride = (long long)P.CoutP * 8;
             const uint32_t sB0 = smem_u32(sB);
             const int sb_n = keep(P.sb), nkb = keep(P.nkb), gtaps = keep(P.gtaps), b_contig = keep(P.b_contig);
             int sb = 0;
             uint32_t par = 1;
             long long t_be = 0;
-            for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-                const Tile t = decode_tile(P, tile);
+            for (int tile = tile0; tile < P.ntiles; tile += tile_step) {
+                const Tile t = decode_tile<kPair>(P, tile, rank);
                 const int z = t.z, ngroups = P.ntaps[z] / gtaps;
-                const __nv_bfloat16 *w_n0 = P.w + (long long)t.n0 * 8;
+                const __nv_bfloat16 *w_n0 = P.w + (long long)(t.n0 + rank * bn_cta) * 8;    // pair: rank r stages rows [r * bn / 2, ..)
                 for (int i = 0; i < nkb; ++i, w_n0 += P.w_kb_stride)
                     for (int gi = 0; gi < ngroups; ++gi) {
                         const uint32_t dst = sB0 + (uint32_t)sb * (uint32_t)b_stage_bytes;
                         { DBG_T0(); mbar_wait(BAR(B_EMPTY + sb), par); DBG_ACC(t_be); }
-                        mbar_expect_tx(BAR(B_FULL + sb), (uint32_t)b_stage_bytes);
+                        const uint32_t full = BAR(B_FULL + sb);
+                        mbar_expect_tx(full, (uint32_t)b_stage_bytes);
                         for (int tg = 0; tg < gtaps; ++tg) {
                             const __nv_bfloat16 *src = w_n0 + P.tap_w[z][gi * gtaps + tg];
                             const uint32_t d = dst + (uint32_t)tg * (uint32_t)b_tap_bytes;
                             if (b_contig) {
-                                bulk_g2s(d, src, piece * KCH, BAR(B_FULL + sb));
+                                bulk_g2s(d, src, piece * KCH, full);
                             } else {
 #pragma unroll
                                 for (int ch = 0; ch < KCH; ++ch)
-                                    bulk_g2s(d + (uint32_t)ch * piece, src + ch * chunk_stride, piece, BAR(B_FULL + sb));
+                                    bulk_g2s(d + (uint32_t)ch * piece, src + ch * chunk_stride, piece, full);
                             }
                         }
                         if (++sb == sb_n) { sb = 0; par ^= 1u; }
@@ -652,8 +755,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         const int G = bn >> 4;
         int it = 0, wad_b = -1;
         long long t_accfull = 0, t_epi = 0;
-        for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
-            const Tile t = decode_tile(P, tile);
+        for (int tile = tile0; tile < P.ntiles; tile += tile_step, ++it) {
+            const Tile t = decode_tile<kPair>(P, tile, rank);
             const int oyo = P.oyo[t.z], oxo = P.oxo[t.z];
             const int set = nsets == 2 ? (it & 1) : 0;
             const int use = nsets == 2 ? (it >> 1) : it;
@@ -679,7 +782,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + set));
+                if (lane == 0) { if (kPair && rank != 0) mbar_arrive_remote(BAR(ACC_EMPTY + set), 0); else mbar_arrive(BAR(ACC_EMPTY + set)); }
                 asm volatile("bar.sync 2, %0;" ::"n"(NEPI_WARPS * 32) : "memory");
                 for (int item = threadIdx.x - EPI_WARP0 * 32; item < 196 * ncols; item += NEPI_WARPS * 32) {
                     const int q = item / 196, pi = item - q * 196, iy = pi / 14, ix = pi - iy * 14;
@@ -748,7 +851,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + set));
+                if (lane == 0) { if (kPair && rank != 0) mbar_arrive_remote(BAR(ACC_EMPTY + set), 0); else mbar_arrive(BAR(ACC_EMPTY + set)); }
                 continue;
             }
             const int n0 = t.n0;
@@ -868,7 +971,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
             // this warp is done reading the accumulator set: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + set));
+            if (lane == 0) { if (kPair && rank != 0) mbar_arrive_remote(BAR(ACC_EMPTY + set), 0); else mbar_arrive(BAR(ACC_EMPTY + set)); }
             if (DBG_ON) t_epi += clock64() - _te;
         }
         if (DBG_ON && warp == EPI_WARP0 && lane == 0) { P.dbg[blockIdx.x * 16 + 9] = t_accfull; P.dbg[blockIdx.x * 16 + 10] = t_epi; }
@@ -877,11 +980,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
 #undef skip
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();          // the peer's shared memory / barriers stay valid until both CTAs are done
+    else __syncthreads();
     if (warp == MMA_WARP) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols)
-                     : "memory");
+        if constexpr (kPair)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
     }
 }
 
@@ -1024,13 +1130,20 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
         P.tstep_y = P.tstep_x = 14; P.torg = -1;
     }
     P.tiles_y = cdiv(P.Ht, P.tstep_y); P.tiles_x = cdiv(P.Wt, P.tstep_x);
-    P.ntiles = P.tiles_x * P.tiles_y * P.B * P.nphases * P.n_tiles_n;
 
     // A operand through TMA tensor-map loads unless the producers have to build it (stem mode) or the driver entry
     // point is missing; RDFC_UMMA_TMA=0 forces the cp.async producers (development knob)
     P.a_tma = !stem && tmap_encoder() != nullptr;
     if (const char *e = getenv("RDFC_UMMA_TMA")) P.a_tma = P.a_tma && atoi(e) != 0;
     P.px16 = P.a_tma ? 4 : 1;
+    // CTA pairs (tcgen05 cta_group::2, RDFC_UMMA_PAIR=1): each CTA stages half of every filter block and one stream of M = 256
+    // MMAs issued by the leader covers both CTAs' pixel tiles.  Correct (tests/test_gpu_conv.py runs it) but OFF by default:
+    // measured on B200 it is slower than two independent CTAs at the N <= 128 it was meant for (128 -> 128 @114x152: 108 cycles
+    // per M=256 N=128 MMA and 221 us, against 88 cycles per M=128 MMA and 166 us), and 1x1 / transposed convs lose 2x to the
+    // extra barrier hops (a peer's TMA cannot complete on the leader's mbarrier, so its "full" signals are forwarded).
+    P.pair = 0;
+    if (const char *e = getenv("RDFC_UMMA_PAIR")) P.pair = P.a_tma && P.bn % 32 == 0 && atoi(e) != 0;
+    P.ntiles = (P.pair ? (P.tiles_x * P.tiles_y + 1) / 2 : P.tiles_x * P.tiles_y) * P.B * P.nphases * P.n_tiles_n;   // pair mode: pairs of tiles
     Phase phases[4] = {};
     int base = 0;
     auto add_plane = [&](int ystep, int yoff, int xstep, int xoff, int rows, int cols) {
@@ -1097,7 +1210,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
         RDFC_REQUIRE(P.npix_pad < (1 << 14), "UMMA conv: staged halo too large for the descriptor LBO field");
     }
     P.w_kb_stride = (long long)KCH * P.CoutP * 8;
-    P.b_contig = P.n_tiles_n == 1;
+    P.b_contig = P.n_tiles_n == 1 && !P.pair;
     for (int z = 0; z < P.nphases; ++z) {
         const Phase &ph = phases[z];
         P.ntaps[z] = ph.ntaps; P.oyo[z] = ph.oyo; P.oxo[z] = ph.oxo;
@@ -1131,7 +1244,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
               (!P.out2 || (((uintptr_t)P.out2 % 32) == 0 && P.out2_stride % 16 == 0 && P.split % 16 == 0)) &&
               (!d->residual.ptr || (((uintptr_t)d->residual.ptr % 32) == 0 && d->residual.pix_stride % 16 == 0));
     const int a_stage = P.a_tma ? P.nplanes * P.a_plane_bytes : (KCH * P.npix_pad * 16 + 1023) / 1024 * 1024;
-    const int b_stage = P.gtaps * KCH * P.bn * 16;
+    const int b_stage = P.gtaps * KCH * (P.pair ? P.bn / 2 : P.bn) * 16;
     const int stem_patch = stem ? ((P.stem_k / 9) * (TH + 2) * (TW + 2) + 4) * 4 : 0;      // fp32 input patch of a tile (stem mode)
     const int heads_y = heads ? 256 * (P.bn + 1) * 4 : 0;                                   // shift-add heads: Y of a region
     const int fixed = BAR_BYTES + 2 * P.CoutP * 4 + 4 * MAX_TAPS * 8 + 2 * P.wad_C * 4 + stem_patch + heads_y + 256;   // barriers, (scale, shift) and tap tables, slack
@@ -1157,10 +1270,11 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     const size_t smem = (size_t)P.sa * a_stage + (size_t)P.sb * b_stage + fixed + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE_STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE_GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE_WADAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE_HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define RDFC_SMEM_ATTR(M)                                                                                                      \
+    RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));       \
+    RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+        RDFC_SMEM_ATTR(MODE_STD); RDFC_SMEM_ATTR(MODE_GENERAL); RDFC_SMEM_ATTR(MODE_WADAIN); RDFC_SMEM_ATTR(MODE_HEADS);
+#undef RDFC_SMEM_ATTR
         attr_set = true;
     }
     if (const char *e = getenv("RDFC_UMMA_SKIP")) P.dbg_flags = atoi(e);
@@ -1173,10 +1287,29 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     }
     int grid = P.ntiles < sm_count() ? P.ntiles : sm_count();
     if (const char *e = getenv("RDFC_UMMA_GRID")) grid = atoi(e) < P.ntiles ? atoi(e) : P.ntiles;   // development knob
-    if (heads) conv_umma_kernel<MODE_HEADS><<<grid, NTHREADS, smem, st>>>(P);
-    else if (wad) conv_umma_kernel<MODE_WADAIN><<<grid, NTHREADS, smem, st>>>(P);
-    else if (P.planar || P.act > RDFC_ACT_LEAKY02 || !P.vec32 || P.Cout % 16 != 0) conv_umma_kernel<MODE_GENERAL><<<grid, NTHREADS, smem, st>>>(P);
-    else conv_umma_kernel<MODE_STD><<<grid, NTHREADS, smem, st>>>(P);
+    const int mode = heads ? MODE_HEADS : wad ? MODE_WADAIN
+                     : (P.planar || P.act > RDFC_ACT_LEAKY02 || !P.vec32 || P.Cout % 16 != 0) ? MODE_GENERAL : MODE_STD;
+    void (*kern)(Params) = nullptr;
+    switch (mode) {
+        case MODE_HEADS: kern = P.pair ? conv_umma_kernel<MODE_HEADS, true> : conv_umma_kernel<MODE_HEADS, false>; break;
+        case MODE_WADAIN: kern = P.pair ? conv_umma_kernel<MODE_WADAIN, true> : conv_umma_kernel<MODE_WADAIN, false>; break;
+        case MODE_GENERAL: kern = P.pair ? conv_umma_kernel<MODE_GENERAL, true> : conv_umma_kernel<MODE_GENERAL, false>; break;
+        default: kern = P.pair ? conv_umma_kernel<MODE_STD, true> : conv_umma_kernel<MODE_STD, false>; break;
+    }
+    if (P.pair) {
+        // one cluster of two CTAs per tile pair (P.ntiles counts pairs; grid = 2 x min(pairs, #SMs / 2))
+        int pairs = P.ntiles < sm_count() / 2 ? P.ntiles : sm_count() / 2;
+        if (const char *e = getenv("RDFC_UMMA_GRID")) pairs = atoi(e) / 2 < pairs ? (atoi(e) / 2 > 0 ? atoi(e) / 2 : 1) : pairs;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        RDFC_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+    } else {
+        kern<<<grid, NTHREADS, smem, st>>>(P);
+    }
     RDFC_CHECK_LAUNCH("conv_umma_kernel");
     return 0;
 }

@@ -272,3 +272,23 @@ def test_pack_stem_input(B, H, W, C0, Cpad, with_in1):
     if with_in1:
         ref[..., C0] = in1[:, 0]
     assert torch.equal(out, ref.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 40, 40, 3, 1, False), (1, 128, 128, 57, 76, 3, 1, False), (2, 64, 128, 40, 40, 3, 2, False),
+                                   (1, 64, 64, 20, 20, 3, 2, True), (2, 96, 192, 33, 21, 1, 1, False)])
+def test_cta_pair_mode_matches(shape, monkeypatch):
+    """RDFC_UMMA_PAIR=1 (tcgen05 cta_group::2: two CTAs, one M=256 MMA stream, half the filter staged per CTA) gives the
+    same result as the default single-CTA kernel, bit for bit, and both match the torch reference."""
+    B, Cin, Cout, H, W, k, stride, transposed = shape
+    g = torch.Generator().manual_seed(sum(shape[:6]))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(*((Cin, Cout, k, k) if transposed else (Cout, Cin, k, k)), generator=g) / math.sqrt(Cin * k * k)
+    scale, shift = 1 + 0.1 * torch.randn(Cout, generator=g), 0.1 * torch.randn(Cout, generator=g)
+    kw = dict(stride=stride, pad=(1 if transposed else k // 2), act=1, transposed=transposed, bf16=True)
+    monkeypatch.setenv("RDFC_UMMA_PAIR", "0")
+    single = _run_conv(x, w, scale, shift, **kw)
+    monkeypatch.setenv("RDFC_UMMA_PAIR", "1")
+    pair = _run_conv(x, w, scale, shift, **kw)
+    assert torch.equal(single, pair)
+    ref = _ref_conv(x, w, scale, shift, **kw)
+    assert float((pair - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
