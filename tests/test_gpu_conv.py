@@ -292,3 +292,21 @@ def test_cta_pair_mode_matches(shape, monkeypatch):
     assert torch.equal(single, pair)
     ref = _ref_conv(x, w, scale, shift, **kw)
     assert float((pair - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 40, 40, 3, 1, False), (2, 64, 128, 40, 40, 3, 2, False), (1, 64, 64, 20, 20, 3, 2, True),
+                                   (2, 96, 192, 33, 21, 1, 2, False)])
+def test_cp_async_producer_fallback_matches(shape, monkeypatch):
+    """RDFC_UMMA_TMA=0 (six producer warps staging the halo with 16-byte cp.async into the no-swizzle layout; the path the
+    fused stems also use) gives the same result as the default TMA tensor-map path, bit for bit."""
+    B, Cin, Cout, H, W, k, stride, transposed = shape
+    g = torch.Generator().manual_seed(sum(shape[:6]) + 1)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(*((Cin, Cout, k, k) if transposed else (Cout, Cin, k, k)), generator=g) / math.sqrt(Cin * k * k)
+    scale, shift = 1 + 0.1 * torch.randn(Cout, generator=g), 0.1 * torch.randn(Cout, generator=g)
+    kw = dict(stride=stride, pad=(1 if transposed else k // 2), act=2, transposed=transposed, bf16=True)
+    monkeypatch.setenv("RDFC_UMMA_TMA", "1")
+    tma = _run_conv(x, w, scale, shift, **kw)
+    monkeypatch.setenv("RDFC_UMMA_TMA", "0")
+    cpasync = _run_conv(x, w, scale, shift, **kw)
+    assert torch.equal(tma, cpasync)
