@@ -20,6 +20,10 @@ def main():
     shutil.copytree(os.path.join(REF, "deformconv", "src"), src)
     for f in ("nlspn_model.py", "modulated_deform_conv_func.py"):
         shutil.copy(os.path.join(REF, f), os.path.join(OUT, f))
+    # the whole (unmodified) rdf_generator package, python files only, for the full-generator timing
+    gen = os.path.join(OUT, "rdf_generator")
+    shutil.rmtree(gen, ignore_errors=True)
+    shutil.copytree(os.path.dirname(REF), gen, ignore=shutil.ignore_patterns("src", "*.cu", "*.cuh", "*.cpp", "*.h", "__pycache__", "*.sh"))
     os.remove(os.path.join(src, "cuda", "deform_psroi_pooling_cuda.cu"))
     for f in ("modulated_deform_conv_cuda.cu", "deform_conv_cuda.cu"):
         p = os.path.join(src, "cuda", f)

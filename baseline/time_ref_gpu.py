@@ -71,5 +71,49 @@ def main():
               f"speed-up {t_ref / t_ours:6.1f}x | max-abs diff {diff:.2e}{note}")
 
 
+def full_generator():
+    """The reference's unmodified RDFGenerator (PyTorch / cuDNN convs + its own DCN extension) against this repo's, same
+    synthetic state dict and inputs: parity at B = 1 (fp32 mode here), throughput at B = 32."""
+    import bench
+    from _synth import synth_inputs, synth_state_dict
+    from rdfc_gan_b200.generator import RDFGenerator
+    sys.path.insert(0, REFD)
+    # rdf_generator.py imports ESANet (never used by RDFGenerator.forward); its own imports need the rest of the repo, so a
+    # stub module stands in for it -- the generator files themselves stay unmodified
+    for name in ("rdf_generator.segmentator", "rdf_generator.segmentator.esa_net"):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+    stub = types.ModuleType("rdf_generator.segmentator.esa_net.esa_net_one_modality")
+    stub.ESANetOneModality = type("ESANetOneModality", (), {})
+    sys.modules[stub.__name__] = stub
+    from rdf_generator.rdf_generator import RDFGenerator as RefG
+    nl = bench.NLSPN_CFG
+    ours = RDFGenerator(pretrained_on_imagenet=False, use_nlspn_refine=True, nlspn_configs=nl).eval()
+    sd = synth_state_dict(ours, seed=0, recipe="init", nlspn_stress=True)
+    ours.load_state_dict(sd)
+    theirs = RefG(pretrained_on_imagenet=False, use_nlspn_refine=True, nlspn_configs=nl).eval()
+    theirs.load_state_dict(sd)
+    ours, theirs = ours.cuda(), theirs.cuda()
+    for B in (1, 32):
+        rgb, normal, depth = (t.cuda() for t in synth_inputs(B, 228, 304, seed=0))
+        with torch.no_grad():
+            torch.backends.cudnn.allow_tf32 = False          # parity check against true-fp32 cuDNN convs ...
+            ot = theirs(rgb, depth, normal)
+            o32 = ours.set_precision("fp32")(rgb, depth, normal)
+            diff32 = max(float((o32[k] - ot[k]).abs().max()) for k in ot)
+            torch.backends.cudnn.allow_tf32 = True           # ... timing with torch's default (TF32 convs allowed)
+            ot = theirs(rgb, depth, normal)
+            diff_tf32 = max(float((o32[k] - ot[k]).abs().max()) for k in ot)
+            t_ref = timeit(lambda: theirs(rgb, depth, normal), reps=5)
+            o16 = ours.set_precision("bf16")(rgb, depth, normal)
+            diff16 = max(float((o16[k] - ot[k]).abs().max()) for k in ot)
+            t_ours = timeit(lambda: ours(rgb, depth, normal), reps=5)
+        print(f"RDFGenerator forward B={B} 228x304: reference (PyTorch/cuDNN fp32 + its DCN extension) {t_ref:8.2f} ms = {B / t_ref * 1e3:7.1f} maps/s | "
+              f"this repo bf16 {t_ours:7.2f} ms = {B / t_ours * 1e3:7.1f} maps/s | speed-up {t_ref / t_ours:5.1f}x | "
+              f"max-abs diff vs reference: fp32 mode {diff32:.2e} (reference with TF32 convs, torch's default: {diff_tf32:.2e}), bf16 mode {diff16:.2e}" + ("" if B == 1 else "  (B > 1: reference quirk 5)"))
+
+
 if __name__ == "__main__":
     main()
+    full_generator()
