@@ -47,27 +47,28 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe): one streaming
+    `nvidia-smi -lms 50` process, so that even a 0.2 s timed region yields several samples."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_evt = index, [], threading.Event()
+        self.index, self.rows, self.proc = index, [], None
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self.stop_evt.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if line.strip():
+                    self.rows.append([c.strip() for c in line.strip().split(",")])
+        except Exception:
+            pass
 
     def summary(self):
-        self.stop_evt.set()
+        if self.proc is not None:
+            self.proc.terminate()
         self.join(timeout=6)
         sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
@@ -193,6 +194,9 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    time.sleep(0.15)                         # let nvidia-smi start streaming; the GPU keeps running warm-up work meanwhile
+    for _ in range(2):
+        plan.run()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in evs:
         flush.zero_()
