@@ -26,6 +26,9 @@ def _deps_mtime():
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     hdr_m = _deps_mtime()
+    stamp = os.path.join(OBJ, ".flags")          # objects built with other flags (RDFC_NVCC_FLAGS) are stale
+    if not os.path.exists(stamp) or open(stamp).read() != " ".join(FLAGS):
+        force = True
     jobs = []
     for s in SOURCES:
         src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
@@ -40,6 +43,8 @@ def build(force=False, verbose=False):
             sys.stderr.write(f"== {s}\n{r.stdout}{r.stderr}")
         if r.returncode:
             raise RuntimeError(f"nvcc failed on {s}")
+    with open(stamp, "w") as f:
+        f.write(" ".join(FLAGS))
     objs = [os.path.join(OBJ, s[:-3] + ".o") for s in SOURCES]
     if jobs or not os.path.exists(LIB):
         subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart_static", "-ldl", "-lrt", "-lpthread"])

@@ -47,6 +47,7 @@ constexpr int NPROD_WARPS = 6, NPROD = NPROD_WARPS * 32;   // A producer threads
 constexpr int PIXPASS = NPROD / 4;                         // pixels staged per pass of the producer threads (48)
 constexpr int JMAX = 24;          // pixel slots per producer thread and k-block: a stage holds <= JMAX * PIXPASS pixels
 constexpr int MMA_WARP = 6, BLOAD_WARP = 7, EPI_WARP0 = 8, NEPI_WARPS = 8;
+constexpr int MMA2_WARP = 5;       // second MMA issuer (TMA mode only, where warps 1-5 have no staging work); another scheduler than MMA_WARP
 constexpr int NTHREADS = 16 * 32;
 constexpr int MAX_PLANES = 4, MAX_TAPS = 9;
 constexpr int BAR_BYTES = (3 * 8 + 3 * 16 + 4) * 8 + 16;   // mbarriers for <= 8 A stages, <= 16 B stages, 2+2 accumulator sets; TMEM slot
@@ -67,6 +68,7 @@ struct Params {
     // A operand through TMA (a_tma != 0): one 4-D tensor map (C, W, H, B) over the NHWC input view; box = 32 channels x
     // plane columns x plane rows, SWIZZLE_64B, zero fill outside the image = the conv padding
     alignas(64) CUtensorMap tmap_a;
+    int dual;                      // two MMA issuer warps (MMA_WARP and MMA2_WARP), each owning a subset of the accumulators
     int pair;                      // cta_group::2: two CTAs (a cluster) work on two pixel tiles with ONE stream of M = 256 MMAs; each
                                    // holds its own A stages and HALF of every filter stage (per-SM shared-memory reads per MMA: 4 KB + N*16 B)
     int a_tma, px16, a_plane_bytes, a_tx_bytes;   // a_tx_bytes: bytes the TMA loads of one stage deliver (planes x rows x cols x 64)
@@ -299,8 +301,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes,
 
 // opaque register copy: stops ptxas from re-reading a kernel parameter from the constant bank inside hot loops (with a
 // ~200 KB shared-memory carve-out an LDC / local-memory access costs hundreds of cycles there)
-__device__ __forceinline__ int keep(int x) { asm volatile("" : "+r"(x)); return x; }
-__device__ __forceinline__ uint32_t keep(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
+// An empty asm() does not do it: it vanishes in the PTX and ptxas re-materialises the ld.param as LDC at every use.  Adding
+// a zero ptxas cannot prove to be zero (%smid >> 31, read once per thread) makes the value a computed one that stays in a
+// register.
+__device__ __forceinline__ uint32_t opaque_zero() { uint32_t s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s >> 31; }
+__device__ __forceinline__ int keep_(int x, uint32_t kz) { return x + (int)kz; }
+__device__ __forceinline__ uint32_t keep_(uint32_t x, uint32_t kz) { return x + kz; }
+#define keep(x) keep_((x), kz)
 __device__ __forceinline__ void st_global_v8(void *p, const uint32_t (&o)[8]) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
                  "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
@@ -333,6 +340,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     constexpr bool kGeneral = kMode == MODE_GENERAL;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_kernel0 = DBG_ON ? clock64() : 0;
+    if (DBG_ON && threadIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.dbg[blockIdx.x * 16 + 15] = (long long)gt; }
     const int a_stage_bytes = P.a_tma ? P.nplanes * P.a_plane_bytes : KCH * P.npix_pad * 16;
     const int bn_cta = kPair ? P.bn >> 1 : P.bn;                 // filter rows this CTA stages (half with cta_group::2)
     const int b_tap_bytes = KCH * bn_cta * 16, b_stage_bytes = P.gtaps * b_tap_bytes;
@@ -348,7 +357,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     // pair mode adds peer_a_full[sa] peer_b_full[sb] (leader only: the peer CTA forwards its own full signals there)
-    const int A_FULL = 0, A_EMPTY = P.sa, B_FULL = 2 * P.sa, B_EMPTY = 2 * P.sa + P.sb, ACC_FULL = 2 * P.sa + 2 * P.sb,
+    const uint32_t kz = opaque_zero();
+    const int sa_k = keep(P.sa), sb_k = keep(P.sb);
+    const int A_FULL = 0, A_EMPTY = sa_k, B_FULL = 2 * sa_k, B_EMPTY = B_FULL + sb_k, ACC_FULL = B_EMPTY + sb_k,
               ACC_EMPTY = ACC_FULL + 2, PEER_A = ACC_EMPTY + 2, PEER_B = PEER_A + P.sa;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + PEER_B + P.sb);
     // per-channel epilogue vectors, padded to CoutP with (1, 0): 16-byte aligned after the barrier block
@@ -367,9 +378,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
-        for (int i = 0; i < P.sa; ++i) { mbar_init(BAR(A_FULL + i), P.a_tma ? 1 : NPROD); mbar_init(BAR(A_EMPTY + i), 1); }
-        for (int i = 0; i < P.sb; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), 1); mbar_init(BAR(ACC_EMPTY + i), kPair ? 2 * NEPI_WARPS : NEPI_WARPS); }
+        const int nissue = P.dual ? 2 : 1;           // every issuer commits on the "empty" / "accumulator full" barriers
+        for (int i = 0; i < P.sa; ++i) { mbar_init(BAR(A_FULL + i), P.a_tma ? 1 : NPROD); mbar_init(BAR(A_EMPTY + i), nissue); }
+        for (int i = 0; i < P.sb; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), nissue); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), nissue); mbar_init(BAR(ACC_EMPTY + i), kPair ? 2 * NEPI_WARPS : NEPI_WARPS); }
         if constexpr (kPair) {
             for (int i = 0; i < P.sa; ++i) mbar_init(BAR(PEER_A + i), 1);
             for (int i = 0; i < P.sb; ++i) mbar_init(BAR(PEER_B + i), 1);
@@ -396,7 +408,137 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     const int set_cols = P.nacc * P.bn;
 
-    if (warp < NPROD_WARPS && P.a_tma) {
+    const bool mma_role = warp == MMA_WARP || (warp == MMA2_WARP && P.dual);
+    if (mma_role) {
+        // ================= MMA issuer =================
+        // Measured (RDFC_UMMA_SKIP=4, every MMA issued with N = 16): the loop costs ~80 cycles per MMA in the issuing warp
+        // whatever N is -- R2UR moves of the descriptor words and the UTCHMMA issue itself -- so one issuer caps every
+        // layer with N <= 128.  With P.dual two warps on different schedulers issue disjoint halves of the accumulators of a
+        // tile (MMAs into different TMEM columns are independent); both commit on the same barriers (count 2).
+        // The whole warp walks the loop convergently (barrier waits, ring bookkeeping); one elected lane issues.  Per
+        // MMA the issue cost is one 32-bit add on a descriptor word; the per-tap descriptor words come from the
+        // shared-memory table and are fetched before the wait on the filter stage.
+        // instruction descriptor: bf16 x bf16 -> fp32, N = bn, M = 128 (one CTA) or 256 (cta_group::2: 128 rows per CTA)
+#ifdef RDFC_UMMA_TIMERS
+        // RDFC_UMMA_SKIP & 4: issue every MMA with N = 16 (wrong results): is the loop bound by issue or by the tensor pipe?
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(((P.dbg_flags & 4) ? 16 : P.bn) >> 3) << 17) | ((kPair ? 16u : 8u) << 24);
+#else
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((kPair ? 16u : 8u) << 24);
+#endif
+        // one k-step = 16 channels: two chunk planes further in the [cin/8][pixel][16 B] layout, 32 bytes in [pixel][64 B]
+        const uint32_t a_kstep = keep(P.a_tma ? 2u : 2u * (uint32_t)P.npix_pad), b_kstep = keep(2u * (uint32_t)bn_cta);
+        const uint32_t b_hi = (128u >> 4) | (1u << 14);                                     // SBO = 128 B, version bit 46
+        const uint32_t b_lo0 = keep(((smem_u32(sB) & 0x3FFFFu) >> 4) | ((uint32_t)bn_cta << 16));   // LBO = staged rows * 16 B
+        const uint32_t a_lo0 = keep((smem_u32(sA) & 0x3FFFFu) >> 4);
+        const uint32_t a_stage16 = keep((uint32_t)a_stage_bytes >> 4), b_stage16 = keep((uint32_t)b_stage_bytes >> 4);
+        const uint32_t b_tap16 = keep((uint32_t)b_tap_bytes >> 4);
+        const uint32_t bn = keep((uint32_t)P.bn);
+        const int nax = keep(P.nax), sa_n = keep(P.sa), sb_n = keep(P.sb), nkb = keep(P.nkb), gtaps = keep(P.gtaps);
+        const int nsets = keep(P.nsets), gt3 = keep(P.gtaps < 3 ? P.gtaps : 3);
+        // this issuer's accumulators: [jb, jb + nacc) of the tile's P.nacc
+        const int jb = keep(warp == MMA_WARP ? 0 : (P.nacc + 1) / 2);
+        const int nacc = keep(P.dual ? (warp == MMA_WARP ? (P.nacc + 1) / 2 : P.nacc / 2) : P.nacc);
+        uint32_t jy16[4], jx8[4];                  // accumulator j: 16 * (rows down) and 8 * (blocks across), decoded once
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { jy16[j] = keep(16u * (uint32_t)((j + jb) / nax)); jx8[j] = keep(8u * (uint32_t)P.px16 * (uint32_t)((j + jb) % nax)); }
+        int s = 0, sb = 0, it = 0;
+        uint32_t a_par = 0, b_par = 0;
+        long long t_acc = 0, t_a = 0, t_b = 0, t_mma = 0, t_commit = 0;
+        const long long t_start = DBG_ON ? clock64() : 0;
+        constexpr bool pair = kPair;
+        if (pair && rank != 0) {
+            // peer CTA of a pair: no MMAs to issue.  Forward "my stage is full" to the leader, in consumption order (a TMA / bulk
+            // copy of the peer cannot complete on the leader's mbarrier directly: measured, it never arrives).
+            for (int tile = tile0; tile < P.ntiles; tile += tile_step) {
+                const Tile t = decode_tile<kPair>(P, tile, rank);
+                const int ngroups = P.ntaps[t.z] / gtaps;
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(BAR(A_FULL + s), a_par);
+                    if (lane == 0) mbar_arrive_remote(BAR(PEER_A + s), 0);
+                    for (int gi = 0; gi < ngroups; ++gi) {
+                        mbar_wait(BAR(B_FULL + sb), b_par);
+                        if (lane == 0) mbar_arrive_remote(BAR(PEER_B + sb), 0);
+                        if (++sb == sb_n) { sb = 0; b_par ^= 1u; }
+                    }
+                    if (++s == sa_n) { s = 0; a_par ^= 1u; }
+                }
+            }
+        } else
+        for (int tile = tile0; tile < P.ntiles; tile += tile_step, ++it) {
+            const Tile t = decode_tile<kPair>(P, tile, rank);
+            const int z = t.z, ngroups = P.ntaps[z] / gtaps;
+            const uint2 *ztap = s_tap + z * MAX_TAPS;
+            const int set = nsets == 2 ? (it & 1) : 0;
+            const int use = nsets == 2 ? (it >> 1) : it;          // how often this set has been used before
+            { DBG_T0(); mbar_wait(BAR(ACC_EMPTY + set), (use & 1) ^ 1); DBG_ACC(t_acc); }   // epilogue has drained this set
+            tc_fence_after();
+            const uint32_t d_base = tmem_base + (uint32_t)(set * set_cols) + (uint32_t)jb * bn;
+            for (int i = 0; i < nkb; ++i) {
+                { DBG_T0(); mbar_wait(BAR(A_FULL + s), a_par); if (pair) mbar_wait(BAR(PEER_A + s), a_par); DBG_ACC(t_a); }
+                const uint32_t a_stage_lo = a_lo0 + (uint32_t)s * a_stage16;
+                for (int gi = 0; gi < ngroups; ++gi) {
+                    const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage16;
+                    { DBG_T0(); mbar_wait(BAR(B_FULL + sb), b_par); if (pair) mbar_wait(BAR(PEER_B + sb), b_par); DBG_ACC(t_b); }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const long long _tm0 = DBG_ON ? clock64() : 0;
+                        for (int r3 = 0; r3 < gtaps; r3 += 3) {        // a stage holds 1, 2, 3 or 9 taps: up to three at a time
+                        uint2 td[3];
+#pragma unroll
+                        for (int tg = 0; tg < 3; ++tg) td[tg] = ztap[gi * gtaps + r3 + (tg < gt3 ? tg : 0)];
+#pragma unroll
+                        for (int tg = 0; tg < 3; ++tg) {
+                            if (tg < gt3) {
+                                const uint32_t acc0 = (i | gi | r3 | tg) ? 1u : 0u;
+                                const uint32_t a_lo = td[tg].x + a_stage_lo, a_hi = td[tg].y, bl = b_lo + (uint32_t)(r3 + tg) * b_tap16;
+                                switch (nacc) {
+                                    case 1:
+                                        issue_tap<1, kPair>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8);
+                                        break;
+                                    case 2:
+                                        issue_tap<2, kPair>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8);
+                                        break;
+                                    case 3:
+                                        issue_tap<3, kPair>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8);
+                                        break;
+                                    default:
+                                        issue_tap<4, kPair>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8);
+                                        break;
+                                }
+                            }
+                        }
+                        }
+                        const long long _tm1 = DBG_ON ? clock64() : 0;
+                        if constexpr (kPair) {        // the same barriers in both CTAs of the pair
+                            tc_commit_pair(BAR(B_EMPTY + sb));
+                            if (gi == ngroups - 1) {
+                                tc_commit_pair(BAR(A_EMPTY + s));
+                                if (i == nkb - 1) tc_commit_pair(BAR(ACC_FULL + set));
+                            }
+                        } else {
+                            tc_commit(BAR(B_EMPTY + sb));
+                            if (gi == ngroups - 1) {
+                                tc_commit(BAR(A_EMPTY + s));
+                                if (i == nkb - 1) tc_commit(BAR(ACC_FULL + set));
+                            }
+                        }
+                        if (DBG_ON) { const long long _tm2 = clock64(); t_mma += _tm1 - _tm0; t_commit += _tm2 - _tm1; }
+                    }
+                    __syncwarp();
+                    if (++sb == sb_n) { sb = 0; b_par ^= 1u; }
+                }
+                if (++s == sa_n) { s = 0; a_par ^= 1u; }
+            }
+        }
+        if (DBG_ON && lane == 0 && warp == MMA_WARP) {
+            long long *o = P.dbg + blockIdx.x * 16;
+            o[0] = clock64() - t_start; o[1] = t_acc; o[2] = t_a; o[3] = t_b;
+        }
+        if (DBG_ON && warp == MMA_WARP) {            // the elected lane's own counters (it is not necessarily lane 0)
+            const long long m = t_mma, c = t_commit;
+            if (m | c) { P.dbg[blockIdx.x * 16 + 11] = m; P.dbg[blockIdx.x * 16 + 12] = c; }
+        }
+    } else if (warp < NPROD_WARPS && P.a_tma) {
         // ================= A producer, TMA mode: one elected thread =================
         // Per k-block and plane ONE cp.async.bulk.tensor: box = 32 channels x plane columns x plane rows of the NHWC
         // input, SWIZZLE_64B into [pixel][64 B]; coordinates outside the image are zero-filled (= the conv padding).
@@ -411,6 +553,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                 for (int i = 0; i < nkb; ++i) {
                     mbar_wait(BAR(A_EMPTY + s), par);
                     const uint32_t full = BAR(A_FULL + s);
+#ifdef RDFC_UMMA_TIMERS
+                    // RDFC_UMMA_SKIP & 8: stage nothing (wrong results): what do the TMA writes cost the tensor pipe?
+                    if (P.dbg_flags & 8) { mbar_arrive(full); if (++s == sa_n) { s = 0; par ^= 1u; } continue; }
+#endif
                     mbar_expect_tx(full, (uint32_t)P.a_tx_bytes);
                     for (int pl = 0; pl < npl; ++pl) {
                         const Plane &q = P.planes[pl];
@@ -588,114 +734,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         if (DBG_ON && threadIdx.x == 0) {
             P.dbg[blockIdx.x * 16 + 6] = t_wait_empty; P.dbg[blockIdx.x * 16 + 7] = t_issue; P.dbg[blockIdx.x * 16 + 8] = t_wait_group;
         }
-    } else if (warp == MMA_WARP) {
-        // ================= MMA issuer =================
-        // The whole warp walks the loop convergently (barrier waits, ring bookkeeping); one elected lane issues.  Per
-        // MMA the issue cost is one 32-bit add on a descriptor word; the per-tap descriptor words come from the
-        // shared-memory table and are fetched before the wait on the filter stage.
-        // instruction descriptor: bf16 x bf16 -> fp32, N = bn, M = 128 (one CTA) or 256 (cta_group::2: 128 rows per CTA)
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((kPair ? 16u : 8u) << 24);
-        // one k-step = 16 channels: two chunk planes further in the [cin/8][pixel][16 B] layout, 32 bytes in [pixel][64 B]
-        const uint32_t a_kstep = keep(P.a_tma ? 2u : 2u * (uint32_t)P.npix_pad), b_kstep = keep(2u * (uint32_t)bn_cta);
-        const uint32_t b_hi = (128u >> 4) | (1u << 14);                                     // SBO = 128 B, version bit 46
-        const uint32_t b_lo0 = keep(((smem_u32(sB) & 0x3FFFFu) >> 4) | ((uint32_t)bn_cta << 16));   // LBO = staged rows * 16 B
-        const uint32_t a_lo0 = keep((smem_u32(sA) & 0x3FFFFu) >> 4);
-        const uint32_t a_stage16 = keep((uint32_t)a_stage_bytes >> 4), b_stage16 = keep((uint32_t)b_stage_bytes >> 4);
-        const uint32_t b_tap16 = keep((uint32_t)b_tap_bytes >> 4);
-        const uint32_t bn = keep((uint32_t)P.bn);
-        const int nacc = keep(P.nacc), nax = keep(P.nax), sa_n = keep(P.sa), sb_n = keep(P.sb), nkb = keep(P.nkb), gtaps = keep(P.gtaps);
-        const int nsets = keep(P.nsets);
-        uint32_t jy16[4], jx8[4];                  // accumulator j: 16 * (rows down) and 8 * (blocks across), decoded once
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { jy16[j] = keep(16u * (uint32_t)(j / nax)); jx8[j] = keep(8u * (uint32_t)P.px16 * (uint32_t)(j % nax)); }
-        int s = 0, sb = 0, it = 0;
-        uint32_t a_par = 0, b_par = 0;
-        long long t_acc = 0, t_a = 0, t_b = 0;
-        const long long t_start = DBG_ON ? clock64() : 0;
-        constexpr bool pair = kPair;
-        if (pair && rank != 0) {
-            // peer CTA of a pair: no MMAs to issue.  Forward "my stage is full" to the leader, in consumption order (a TMA / bulk
-            // copy of the peer cannot complete on the leader's mbarrier directly: measured, it never arrives).
-            for (int tile = tile0; tile < P.ntiles; tile += tile_step) {
-                const Tile t = decode_tile<kPair>(P, tile, rank);
-                const int ngroups = P.ntaps[t.z] / gtaps;
-                for (int i = 0; i < nkb; ++i) {
-                    mbar_wait(BAR(A_FULL + s), a_par);
-                    if (lane == 0) mbar_arrive_remote(BAR(PEER_A + s), 0);
-                    for (int gi = 0; gi < ngroups; ++gi) {
-                        mbar_wait(BAR(B_FULL + sb), b_par);
-                        if (lane == 0) mbar_arrive_remote(BAR(PEER_B + sb), 0);
-                        if (++sb == sb_n) { sb = 0; b_par ^= 1u; }
-                    }
-                    if (++s == sa_n) { s = 0; a_par ^= 1u; }
-                }
-            }
-        } else
-        for (int tile = tile0; tile < P.ntiles; tile += tile_step, ++it) {
-            const Tile t = decode_tile<kPair>(P, tile, rank);
-            const int z = t.z, ngroups = P.ntaps[z] / gtaps;
-            const uint2 *ztap = s_tap + z * MAX_TAPS;
-            const int set = nsets == 2 ? (it & 1) : 0;
-            const int use = nsets == 2 ? (it >> 1) : it;          // how often this set has been used before
-            { DBG_T0(); mbar_wait(BAR(ACC_EMPTY + set), (use & 1) ^ 1); DBG_ACC(t_acc); }   // epilogue has drained this set
-            tc_fence_after();
-            const uint32_t d_base = tmem_base + (uint32_t)(set * set_cols);
-            for (int i = 0; i < nkb; ++i) {
-                { DBG_T0(); mbar_wait(BAR(A_FULL + s), a_par); if (pair) mbar_wait(BAR(PEER_A + s), a_par); DBG_ACC(t_a); }
-                const uint32_t a_stage_lo = a_lo0 + (uint32_t)s * a_stage16;
-                for (int gi = 0; gi < ngroups; ++gi) {
-                    uint2 td[3];
-#pragma unroll
-                    for (int tg = 0; tg < 3; ++tg) td[tg] = ztap[gi * gtaps + (tg < gtaps ? tg : 0)];
-                    const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage16;
-                    { DBG_T0(); mbar_wait(BAR(B_FULL + sb), b_par); if (pair) mbar_wait(BAR(PEER_B + sb), b_par); DBG_ACC(t_b); }
-                    tc_fence_after();
-                    if (elect_one()) {
-#pragma unroll
-                        for (int tg = 0; tg < 3; ++tg) {
-                            if (tg < gtaps) {
-                                const uint32_t acc0 = (i | gi | tg) ? 1u : 0u;
-                                const uint32_t a_lo = td[tg].x + a_stage_lo, a_hi = td[tg].y, bl = b_lo + (uint32_t)tg * b_tap16;
-                                switch (nacc) {
-                                    case 1:
-                                        issue_tap<1, kPair>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8);
-                                        break;
-                                    case 2:
-                                        issue_tap<2, kPair>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8);
-                                        break;
-                                    case 3:
-                                        issue_tap<3, kPair>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8);
-                                        break;
-                                    default:
-                                        issue_tap<4, kPair>(d_base, bn, a_lo, a_hi, a_kstep, bl, b_hi, b_kstep, idesc, acc0, jy16, jx8);
-                                        break;
-                                }
-                            }
-                        }
-                        if constexpr (kPair) {        // the same barriers in both CTAs of the pair
-                            tc_commit_pair(BAR(B_EMPTY + sb));
-                            if (gi == ngroups - 1) {
-                                tc_commit_pair(BAR(A_EMPTY + s));
-                                if (i == nkb - 1) tc_commit_pair(BAR(ACC_FULL + set));
-                            }
-                        } else {
-                            tc_commit(BAR(B_EMPTY + sb));
-                            if (gi == ngroups - 1) {
-                                tc_commit(BAR(A_EMPTY + s));
-                                if (i == nkb - 1) tc_commit(BAR(ACC_FULL + set));
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (++sb == sb_n) { sb = 0; b_par ^= 1u; }
-                }
-                if (++s == sa_n) { s = 0; a_par ^= 1u; }
-            }
-        }
-        if (DBG_ON && lane == 0) {
-            long long *o = P.dbg + blockIdx.x * 16;
-            o[0] = clock64() - t_start; o[1] = t_acc; o[2] = t_a; o[3] = t_b;
-        }
     } else if (warp == BLOAD_WARP) {
         // ================= B loader (TMA 1-D bulk copies of pre-packed filter blocks) =================
         if (lane == 0) {
@@ -715,6 +753,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                         const uint32_t dst = sB0 + (uint32_t)sb * (uint32_t)b_stage_bytes;
                         { DBG_T0(); mbar_wait(BAR(B_EMPTY + sb), par); DBG_ACC(t_be); }
                         const uint32_t full = BAR(B_FULL + sb);
+#ifdef RDFC_UMMA_TIMERS
+                        if (P.dbg_flags & 16) { mbar_arrive(full); if (++sb == sb_n) { sb = 0; par ^= 1u; } continue; }   // no filter loads
+#endif
                         mbar_expect_tx(full, (uint32_t)b_stage_bytes);
                         for (int tg = 0; tg < gtaps; ++tg) {
                             const __nv_bfloat16 *src = w_n0 + P.tap_w[z][gi * gtaps + tg];
@@ -982,6 +1023,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     tc_fence_before();
     if constexpr (kPair) cluster_sync_all();          // the peer's shared memory / barriers stay valid until both CTAs are done
     else __syncthreads();
+    if (DBG_ON && threadIdx.x == 0) {
+        P.dbg[blockIdx.x * 16 + 13] = clock64() - t_kernel0;
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        P.dbg[blockIdx.x * 16 + 14] = (long long)gt;
+    }
     if (warp == MMA_WARP) {
         tc_fence_after();
         if constexpr (kPair)
@@ -1102,6 +1148,10 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     } else {                              // wide N (e.g. 160, 256): one set
         P.nsets = 1;
         P.nacc = 512 / P.bn < 4 ? 512 / P.bn : 4;
+        // measured (B = 32): a 256-wide 3x3 stride-1 conv with ONE N tile (en4, 57x76) is 12-22 % faster with one accumulator
+        // and two TMEM sets (9 rounds of 128-pixel tiles instead of 5 rounds of 256, and the epilogue overlaps); with two N
+        // tiles (en5: 512 wide, 29x38) the filter stream of one-accumulator tiles (64 B/clk/SM) saturates L2: -17 %
+        if (k3 && d->stride == 1 && !d->transposed && P.n_tiles_n == 1 && 2 * P.bn <= 512) { P.nacc = 1; P.nsets = 2; }
     }
     while (P.nacc > 1 && (P.Wt <= 8 * (P.nacc - 1) || pixels / (128 * P.nacc) * P.n_tiles_n < sm_count())) --P.nacc;
     if (d->stride == 2 && !d->transposed && k3 && P.nacc > 2) P.nacc = 2;   // four parity planes: keep the stage small
@@ -1143,6 +1193,8 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     // extra barrier hops (a peer's TMA cannot complete on the leader's mbarrier, so its "full" signals are forwarded).
     P.pair = 0;
     if (const char *e = getenv("RDFC_UMMA_PAIR")) P.pair = P.a_tma && P.bn % 32 == 0 && atoi(e) != 0;
+    P.dual = P.a_tma && !P.pair && P.nacc >= 2;
+    if (const char *e = getenv("RDFC_UMMA_DUAL")) P.dual = P.dual && atoi(e) != 0;      // development knob
     P.ntiles = (P.pair ? (P.tiles_x * P.tiles_y + 1) / 2 : P.tiles_x * P.tiles_y) * P.B * P.nphases * P.n_tiles_n;   // pair mode: pairs of tiles
     Phase phases[4] = {};
     int base = 0;
@@ -1239,16 +1291,20 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     // filter taps per B stage: one wait / commit per filter row of a 3x3 conv; the 1/2/2/4-tap phases of a transposed
     // conv and 1x1 convs stream tap by tap
     P.gtaps = (k3 && !d->transposed) ? 3 : 1;
-    if (const char *e = getenv("RDFC_UMMA_GTAPS")) P.gtaps = atoi(e);    // development knob (1 or 3)
     P.vec32 = !heads && ((uintptr_t)d->out.ptr % 32) == 0 && d->out.pix_stride % 16 == 0 &&
               (!P.out2 || (((uintptr_t)P.out2 % 32) == 0 && P.out2_stride % 16 == 0 && P.split % 16 == 0)) &&
               (!d->residual.ptr || (((uintptr_t)d->residual.ptr % 32) == 0 && d->residual.pix_stride % 16 == 0));
     const int a_stage = P.a_tma ? P.nplanes * P.a_plane_bytes : (KCH * P.npix_pad * 16 + 1023) / 1024 * 1024;
-    const int b_stage = P.gtaps * KCH * (P.pair ? P.bn / 2 : P.bn) * 16;
     const int stem_patch = stem ? ((P.stem_k / 9) * (TH + 2) * (TW + 2) + 4) * 4 : 0;      // fp32 input patch of a tile (stem mode)
     const int heads_y = heads ? 256 * (P.bn + 1) * 4 : 0;                                   // shift-add heads: Y of a region
     const int fixed = BAR_BYTES + 2 * P.CoutP * 4 + 4 * MAX_TAPS * 8 + 2 * P.wad_C * 4 + stem_patch + heads_y + 256;   // barriers, (scale, shift) and tap tables, slack
     const int budget = 219 * 1024;
+    // The issuing warp pays ~1000 cycles per filter stage (barrier wait, commits, ring bookkeeping) that the tensor pipe does
+    // not overlap (role timers: issue is blocking at the pipe's rate), so a 3x3 conv stages all nine taps of a k-block at once
+    // when two such stages and two A stages fit.
+    if (k3 && !d->transposed && !stem && 2 * a_stage + 2 * 9 * KCH * (P.pair ? P.bn / 2 : P.bn) * 16 + fixed <= budget) P.gtaps = 9;
+    if (const char *e = getenv("RDFC_UMMA_GTAPS")) P.gtaps = atoi(e);    // development knob (1, 3 or 9)
+    const int b_stage = P.gtaps * KCH * (P.pair ? P.bn / 2 : P.bn) * 16;
     // A ring first (>= 2 stages: the producers publish k-block i while k-block i+1 is in flight), then B stages (2..6)
     // the filter stream is latency-bound: bytes in flight per SM = bandwidth x L2 latency (~2000 cycles), so keep
     // >= 64 KB of filter stages in flight when the tile allows it
@@ -1257,7 +1313,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
         const int mma_cycles = P.bn / 2 > 54 ? P.bn / 2 : 54;                 // measured: max(N/2, ~54) per M=128, K=16 MMA
         const int stage_cycles = P.gtaps * P.nacc * (BK / 16) * mma_cycles;
         P.sb = 2500 / stage_cycles + 2;
-        if (P.sb < 3) P.sb = 3;
+        if (P.sb < 3) P.sb = P.gtaps == 9 ? 2 : 3;
         if (P.sb > 16) P.sb = 16;
     }
     if (const char *e = getenv("RDFC_UMMA_SB")) P.sb = atoi(e);          // development knob (<= 16)

@@ -15,6 +15,7 @@ HBM layout (per image, C channels innermost; bf16 in 'bf16' mode, fp32 in 'fp32'
 NLSPN tensors stay fp32 NCHW as in the reference (guide (B,8,H,W), offset (B,18,H,W), aff (B,9,H,W)).
 """
 import ctypes
+import os
 import math
 
 import torch
@@ -50,11 +51,53 @@ class Plan:
         self.keep = []           # ctypes structs / tensors that must outlive the plan
         self.graph = None
         self.n_launch = 0
+        # Two lanes: the RGB and the depth branch are independent between their fusion points (rdf_generator.py:295-368), so
+        # the captured graph runs them on two streams.  Every conv is a persistent kernel of <= 148 CTAs; while the last
+        # round of one launch leaves SMs idle (29x38 layers: 2.2 rounds of tiles) the other lane's CTAs take them.
+        self.marks = []          # (step index, lane): steps from that index on run on `lane` (0 = main, 1 = side)
+        self.sync = {}           # step index -> ['fork' | 'join', ...] applied before that step
+
+    def lane(self, lane):
+        self.marks.append((len(self.steps), lane))
+
+    def fork(self):
+        self.sync.setdefault(len(self.steps), []).append('fork')
+
+    def join(self):
+        self.sync.setdefault(len(self.steps), []).append('join')
+        self.lane(0)
+
+    def lanes(self):
+        out, cur, marks = [], 0, sorted(self.marks, key=lambda m: m[0])
+        mi = 0
+        for i in range(len(self.steps)):
+            while mi < len(marks) and marks[mi][0] <= i:
+                cur = marks[mi][1]
+                mi += 1
+            out.append(cur)
+        return out
 
     def run_eager(self):
+        """All steps in list order on the current stream (list order respects every dependency)."""
         s = C.stream_ptr()
         for f in self.steps:
             f(s)
+
+    def run_lanes(self, side):
+        """Lane-1 steps on `side`, the rest on the current stream, with the recorded fork / join edges (used under capture)."""
+        main = torch.cuda.current_stream()
+        lanes = self.lanes()
+        for i, f in enumerate(self.steps):
+            for op in self.sync.get(i, ()):
+                if op == 'fork':
+                    side.wait_stream(main)
+                else:
+                    main.wait_stream(side)
+            f((side if lanes[i] else main).cuda_stream)
+        for op in self.sync.get(len(self.steps), ()):
+            if op == 'join':
+                main.wait_stream(side)
+        main.wait_stream(side)
 
     def run(self):
         if self.graph is not None:
@@ -162,7 +205,7 @@ class GeneratorEngine:
         fe1 = {'r': (head['r'], 96, 64), 'd': (head['d'], 160 if has_gd else 96, 64)}
         cat = {x: {l: new(B, Hs[l], Ws[l], dchan[l] + chan[l]) for l in (2, 3, 4, 5)} for x in 'rd'}
         fe6 = {x: new(B, Hs[6], Ws[6], 512) for x in 'rd'}
-        tmp = {l: [new(B, Hs[l], Ws[l], chan[l]) for _ in range(4)] for l in (2, 3, 4, 5)}   # t1, ya, yb, downsample
+        tmp = {x: {l: [new(B, Hs[l], Ws[l], chan[l]) for _ in range(4)] for l in (2, 3, 4, 5)} for x in 'rd'}   # t1, ya, yb, downsample
 
         def conv(name, sources, inp, out, k, stride=1, pad=None, act=C.ACT_NONE, transposed=False, residual=None,
                  in2=None, hin=None, hout=None, out_nchw=False, in_nchw=False):
@@ -232,12 +275,14 @@ class GeneratorEngine:
 
         # ---- encoders (rdf_generator.py:295-312)
         feat = {}
+        plan.fork()
         for x, ed in (('r', g.rgb_branch_encoder_decoder), ('d', g.depth_branch_encoder_decoder)):
+            plan.lane(0 if x == 'r' else 1)
             cur, hw_cur = fe1[x], full
             for l in (2, 3, 4, 5):
                 layer = getattr(ed, f'en{l}')
                 hw = (Hs[l], Ws[l])
-                t1, ya, yb, ds = tmp[l]
+                t1, ya, yb, ds = tmp[x][l]
                 for bi, blk in enumerate(layer):
                     last = bi == len(layer) - 1
                     dst = (cat[x][l], dchan[l], chan[l]) if last else ((ya if bi % 2 == 0 else yb), 0, chan[l])
@@ -257,21 +302,29 @@ class GeneratorEngine:
                 feat[(x, l)] = cur
             conv(f'{x}.en6', [seq_src(ed.en6)], cur, (fe6[x], 0, 512), 3, stride=2, act=L, hin=hw_cur, hout=(Hs[6], Ws[6]))
 
+        plan.join()
         # ---- decoders with RGB<-depth fusion (rdf_generator.py:315-368)
         xr, xd = (fe6['r'], 0, 512), (fe6['d'], 0, 512)
         lvl_in = 6
         for n, l in enumerate((5, 4, 3, 2), start=1):
             hw_in, hw_out = (Hs[lvl_in], Ws[lvl_in]), (Hs[l], Ws[l])      # ConvT output cropped to the skip's size
+            plan.fork()                  # the depth branch's ConvT only reads xd: it runs beside the fusion + RGB ConvT
             fz = self._plan_fuse(plan, conv, new, f32, getattr(g, f'fuse_layer{n}'), n, xr, xd, B, hw_in, precision)
             conv(f'r.de{l}', [seq_src(getattr(g.rgb_branch_encoder_decoder, f'de{l}'))], fz, (cat['r'][l], 0, dchan[l]), 3,
                  stride=2, pad=1, act=L, transposed=True, hin=hw_in, hout=hw_out)
+            plan.lane(1)
             conv(f'd.de{l}', [seq_src(getattr(g.depth_branch_encoder_decoder, f'de{l}'))], xd, (cat['d'][l], 0, dchan[l]), 3,
                  stride=2, pad=1, act=L, transposed=True, hin=hw_in, hout=hw_out)
+            plan.join()
             xr, xd = (cat['r'][l], 0, dchan[l] + chan[l]), (cat['d'][l], 0, dchan[l] + chan[l])
             lvl_in = l
 
         # ---- decode heads (rdf_generator.py:372-398); the *_dec1 convs that share an input run as ONE conv
+        # the RGB branch's heads (lane 1) run beside the depth branch's heads and the NLSPN refinement (lane 0)
+        plan.fork()
+        plan.lane(1)
         conv('r.dec1', [seq_src(g.rgb_pred_dec1), seq_src(g.rgb_conf_dec1)], xr, (head['r'], 0, 96), 3, act=L, hin=full, hout=full)
+        plan.lane(0)
         d_srcs = [seq_src(g.id_dec1), seq_src(g.cf_dec1)] + ([seq_src(g.gd_dec1)] if has_gd else [])
         conv('d.dec1', d_srcs, xd, (head['d'], 0, 160 if has_gd else 96), 3, act=L, hin=full, hout=full)
         plan.d1, plan.c1, plan.pred_init, plan.conf = f32(B, 1, H, W), f32(B, 1, H, W), f32(B, 1, H, W), f32(B, 1, H, W)
@@ -280,9 +333,11 @@ class GeneratorEngine:
         P_ = H * W
         if bf16:
             # all *_dec0 heads of a branch as ONE tensor-core conv over the whole head buffer (block-sparse filters)
+            plan.lane(1)
             self._plan_heads(plan, 'r.dec0', head['r'], B, H, W, [
                 dict(mod=g.rgb_pred_dec0[0], act=C.ACT_TANH, segs=[(0, 64, 0), (64, 64, 96)], out=[(plan.d1, 0, P_)]),
                 dict(mod=g.rgb_conf_dec0[0], act=C.ACT_SIGMOID, segs=[(0, 32, 64), (32, 64, 96)], out=[(plan.c1, 0, P_)])])
+            plan.lane(0)
             fe = 160 if has_gd else 96
             cols = [dict(mod=g.id_dec0[0], act=C.ACT_TANH, segs=[(0, 64, 0), (64, 64, fe)], out=[(plan.pred_init, 0, P_)]),
                     dict(mod=g.cf_dec0[0], act=C.ACT_SIGMOID, segs=[(0, 32, 64), (32, 64, fe)], out=[(plan.conf, 0, P_)])]
@@ -291,10 +346,12 @@ class GeneratorEngine:
                                  out=[(plan.guide, k * P_, 8 * P_) for k in range(8)]))
             self._plan_heads(plan, 'd.dec0', head['d'], B, H, W, cols)
         else:
+            plan.lane(1)
             conv('rgb_pred_dec0', [seq_src(g.rgb_pred_dec0)], (head['r'], 0, 64), plan.d1, 3, act=C.ACT_TANH, in2=fe1['r'],
                  out_nchw=True, hin=full, hout=full)
             conv('rgb_conf_dec0', [(g.rgb_conf_dec0[0].weight, None, g.rgb_conf_dec0[0].bias)], (head['r'], 64, 96), plan.c1, 3,
                  act=C.ACT_SIGMOID, out_nchw=True, hin=full, hout=full)
+            plan.lane(0)
             conv('id_dec0', [seq_src(g.id_dec0)], (head['d'], 0, 64), plan.pred_init, 3, act=C.ACT_TANH, in2=fe1['d'],
                  out_nchw=True, hin=full, hout=full)
             conv('cf_dec0', [(g.cf_dec0[0].weight, None, g.cf_dec0[0].bias)], (head['d'], 64, 32), plan.conf, 3,
@@ -323,6 +380,7 @@ class GeneratorEngine:
             d2src = plan.d2raw
         else:
             d2src = plan.pred_init
+        plan.join()
         plan.names.append('fuse_depth')
         plan.steps.append(lambda s: C.check(C.lib.rdfc_fuse_depth_forward(
             C.ptr(plan.d1), C.ptr(plan.c1), C.ptr(d2src), C.ptr(plan.conf), C.ptr(plan.d2), C.ptr(plan.pred), n, s)))
@@ -587,6 +645,11 @@ class GeneratorEngine:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
+        lane1 = torch.cuda.Stream()
         with torch.cuda.graph(graph):
-            plan.run_eager()
+            if os.environ.get('RDFC_LANES', '1') == '0':      # development knob: one stream
+                plan.run_eager()
+            else:
+                plan.run_lanes(lane1)
         plan.graph = graph
+        plan.keep.append(lane1)

@@ -59,18 +59,21 @@ def main():
     if "--timers" in sys.argv:      # needs a -DRDFC_UMMA_TIMERS build and RDFC_UMMA_DBG=1
         import ctypes
         import numpy as np
-        pat = sys.argv[sys.argv.index("--timers") + 1]
+        pats = sys.argv[sys.argv.index("--timers") + 1].split(",")
         names = {0: "MMA warp lifetime", 1: "MMA wait ACC_EMPTY", 2: "MMA wait A_FULL", 3: "MMA wait B_FULL", 5: "Bload wait B_EMPTY",
-                 6: "prod wait A_EMPTY", 7: "prod issue", 8: "prod wait_group", 9: "epi wait ACC_FULL", 10: "epi work"}
+                 6: "prod wait A_EMPTY", 7: "prod issue", 8: "prod wait_group", 9: "epi wait ACC_FULL", 10: "epi work",
+                 11: "MMA issue (elected)", 12: "MMA commits", 13: "CTA lifetime"}
         for f, n in zip(plan.steps, plan.names):
-            if pat in n:
+            if any(pat in n for pat in pats):
                 f(s)
                 torch.cuda.synchronize()
                 buf = (ctypes.c_longlong * (148 * 16))()
                 C.lib.rdfc_dev_umma_timers(buf, 148 * 16)
                 a = np.frombuffer(buf, dtype=np.int64).reshape(148, 16).astype(np.float64)
                 a = a[a[:, 0] > 0]
-                print(f"role timers for step '{n}' (cycles, median over {len(a)} CTAs):")
+                print(f"role timers for step '{n}' (cycles, median over {len(a)} CTAs; CTA lifetime max {a[:, 13].max():.0f}, "
+                      f"last CTA end - first CTA end {(a[:, 14].max() - a[:, 14].min()) / 1e3:.1f} us, "
+                      f"first start -> last end {(a[:, 14].max() - a[:, 15].min()) / 1e3:.1f} us):")
                 for i, nm in names.items():
                     print(f"   {nm:20s} {np.median(a[:, i]):10.0f}  ({100*np.median(a[:, i])/np.median(a[:, 0]):5.1f}%)")
     if out_json:
