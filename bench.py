@@ -245,11 +245,18 @@ def main():
     n_groups = (B + group - 1) // group
     s = C.stream_ptr()
 
-    def prop():
+    def prop_eager():
         C.check(C.lib.rdfc_nlspn_propagate_forward(C.ptr(plan.pred_init), C.ptr(plan.offset), C.ptr(plan.aff), None, 0,
-                                                   C.ptr(plan.d2raw), C.ptr(plan.scratch), None, B, H, W, T, 0, s))
+                                                   C.ptr(plan.d2raw), C.ptr(plan.scratch), None, B, H, W, T, 0, C.stream_ptr()))
     for _ in range(3):
-        prop()
+        prop_eager()
+    torch.cuda.synchronize()
+    # the T launches as the product issues them: nodes of a CUDA graph (no host launch gaps between the iterations)
+    prop_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(prop_graph):
+        prop_eager()
+    prop = prop_graph.replay
+    prop()
     torch.cuda.synchronize()
     reps = 10
     pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]

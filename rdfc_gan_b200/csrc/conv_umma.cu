@@ -596,32 +596,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                 }
             }
         const uint32_t dst_thread = smem_u32(sA) + (uint32_t)(ch * P.npix_pad + p0) * 16u;
-        int s = 0;
-        uint32_t par = 1;
-        for (int tile = tile0; tile < P.ntiles; tile += tile_step) {
+        // The patch is double-buffered: the 4-byte cp.asyncs of tile n+1 (zero-fill outside the image; every cell of a thread
+        // in flight at once) are issued before tile n's slots are built, so the L2 round trip of the fill -- ~2000 cycles,
+        // as long as building a whole tile -- is off the critical path.
+        const int patch_stride = nch * plane_sz + 4;               // floats per buffer: cells, the zero cell, padding
+        auto fill_patch = [&](int tile, int buf) {
             const Tile t = decode_tile<kPair>(P, tile, rank);
             const float *b0 = P.stem_in0 + (long long)t.b * P.stem_c0 * HW;
             const float *b1 = P.stem_in1 ? P.stem_in1 + (long long)t.b * HW : b0;
-            asm volatile("bar.sync 3, %0;" ::"n"(NPROD) : "memory");          // the previous tile's slots are built
-            // 4-byte cp.async per patch cell (zero-fill outside the image): every cell of the thread is in flight at
-            // once, so the fill costs one L2 round trip instead of one per loop trip
-            {
-                const uint32_t patch_s = smem_u32(patch);
-                int pr = threadIdx.x / PW, pc = threadIdx.x - pr * PW;       // flat cell index = pr * PW + pc, pr over nch * PH rows
-                const int dr = NPROD / PW, dc = NPROD - dr * PW;
-                for (int e = threadIdx.x; e < nch * plane_sz; e += NPROD) {
-                    const int ci = pr >= 3 * PH ? 3 : (pr >= 2 * PH ? 2 : (pr >= PH ? 1 : 0));    // nch <= 4 here (asserted on the host)
-                    const int iy = t.ty0 + (pr - ci * PH) - 1, ix = t.tx0 + pc - 1;
-                    const bool ok = iy >= 0 && iy < Hi && ix >= 0 && ix < Wi;
-                    const float *src = ok ? (ci < P.stem_c0 ? b0 + (long long)ci * HW : b1) + (long long)iy * Wi + ix : b0;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(patch_s + 4u * (uint32_t)e), "l"(src), "r"(ok ? 4u : 0u) : "memory");
-                    pr += dr; pc += dc;
-                    if (pc >= PW) { pc -= PW; ++pr; }
-                }
-                asm volatile("cp.async.wait_all;" ::: "memory");
+            const uint32_t patch_s = smem_u32(patch + buf * patch_stride);
+            int pr = threadIdx.x / PW, pc = threadIdx.x - pr * PW;       // flat cell index = pr * PW + pc, pr over nch * PH rows
+            const int dr = NPROD / PW, dc = NPROD - dr * PW;
+            for (int e = threadIdx.x; e < nch * plane_sz; e += NPROD) {
+                const int ci = pr >= 3 * PH ? 3 : (pr >= 2 * PH ? 2 : (pr >= PH ? 1 : 0));    // nch <= 4 here (asserted on the host)
+                const int iy = t.ty0 + (pr - ci * PH) - 1, ix = t.tx0 + pc - 1;
+                const bool ok = iy >= 0 && iy < Hi && ix >= 0 && ix < Wi;
+                const float *src = ok ? (ci < P.stem_c0 ? b0 + (long long)ci * HW : b1) + (long long)iy * Wi + ix : b0;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(patch_s + 4u * (uint32_t)e), "l"(src), "r"(ok ? 4u : 0u) : "memory");
+                pr += dr; pc += dc;
+                if (pc >= PW) { pc -= PW; ++pr; }
             }
-            if (threadIdx.x == 0) patch[zero_cell] = 0.f;
-            asm volatile("bar.sync 3, %0;" ::"n"(NPROD) : "memory");
+        };
+        if (tile0 < P.ntiles) fill_patch(tile0, 0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (threadIdx.x == 0) patch[zero_cell] = patch[patch_stride + zero_cell] = 0.f;      // never touched by the fills
+        int s = 0, it = 0;
+        uint32_t par = 1;
+        for (int tile = tile0; tile < P.ntiles; tile += tile_step, ++it) {
+            asm volatile("bar.sync 3, %0;" ::"n"(NPROD) : "memory");          // the previous tile's slots are built: its buffer is free
+            if (tile + tile_step < P.ntiles) fill_patch(tile + tile_step, (it + 1) & 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");               // this tile's patch has landed (my cells) ...
+            asm volatile("bar.sync 3, %0;" ::"n"(NPROD) : "memory");          // ... and everyone else's
+            const float *pb = patch + (it & 1) * patch_stride;
             for (int i = 0; i < P.nkb; ++i) {
                 mbar_wait(BAR(A_EMPTY + s), par);
                 const uint32_t dst = dst_thread + (uint32_t)s * (uint32_t)a_stage_bytes;
@@ -633,7 +640,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const int dl = i == 0 ? delta[0][e] : delta[1][e];
-                        v[e] = patch[dl == INT_MIN ? zero_cell : centre + dl];
+                        v[e] = pb[dl == INT_MIN ? zero_cell : centre + dl];
                     }
                     uint32_t w[4];
 #pragma unroll
@@ -1295,7 +1302,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
               (!P.out2 || (((uintptr_t)P.out2 % 32) == 0 && P.out2_stride % 16 == 0 && P.split % 16 == 0)) &&
               (!d->residual.ptr || (((uintptr_t)d->residual.ptr % 32) == 0 && d->residual.pix_stride % 16 == 0));
     const int a_stage = P.a_tma ? P.nplanes * P.a_plane_bytes : (KCH * P.npix_pad * 16 + 1023) / 1024 * 1024;
-    const int stem_patch = stem ? ((P.stem_k / 9) * (TH + 2) * (TW + 2) + 4) * 4 : 0;      // fp32 input patch of a tile (stem mode)
+    const int stem_patch = stem ? 2 * ((P.stem_k / 9) * (TH + 2) * (TW + 2) + 4) * 4 : 0;  // two fp32 input patches of a tile (stem mode)
     const int heads_y = heads ? 256 * (P.bn + 1) * 4 : 0;                                   // shift-add heads: Y of a region
     const int fixed = BAR_BYTES + 2 * P.CoutP * 4 + 4 * MAX_TAPS * 8 + 2 * P.wad_C * 4 + stem_patch + heads_y + 256;   // barriers, (scale, shift) and tap tables, slack
     const int budget = 219 * 1024;

@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(BAND_THREADS, kMinBlocks) nlspn_prop_band_kern
                                                                           const float *__restrict__ offset,
                                                                           const float *__restrict__ aff,
                                                                           float *__restrict__ out, float *__restrict__ inter,
-                                                                          int B, int H, int W, int rows_per_cta, int halo, int prefetch) {
+                                                                          int B, int H, int W, int rows_per_cta, int halo, int prefetch,
+                                                                          int pre) {
     extern __shared__ float band_tile[];
     const int pitch = W + 4;                         // tile column tc <-> image column tc - 1 (-1 .. W + 2)
     const long long total = (long long)B * H, P = (long long)H * W;
@@ -235,6 +236,33 @@ __global__ void __launch_bounds__(BAND_THREADS, kMinBlocks) nlspn_prop_band_kern
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Wp = W / kPix;
     const float Hf = (float)H, Wf = (float)W;
+    // Programmatic dependent launch: the next iteration's grid may take SM slots as this grid's CTAs retire (its CTAs then
+    // sit in griddepcontrol.wait until this grid has completed and flushed), which removes the launch gap and the CTA
+    // ramp-up between the 18 launches.  Nothing of the previous iteration is read before the wait; the offsets /
+    // affinities do not depend on it, so the lines of the thread's first `pre` items are sent on their way to L2 first.
+    if (pre && row < row_end) {
+        const int b = (int)(row / H), y_lo = (int)(row - (long long)b * H);
+        const int nr = (int)((row_end - row) < (long long)(H - y_lo) ? (row_end - row) : (long long)(H - y_lo));
+        for (int i = 0; i < pre; ++i) {
+            const int idx = threadIdx.x + i * BAND_THREADS;
+            if (idx < nr * Wp && (lane & 15) == 0) {         // one prefetch per 128-byte line (16 lanes x 8 bytes)
+                const int ry = idx / Wp, x = kPix * (idx - ry * Wp);
+                const long long pix = (long long)(y_lo + ry) * W + x;
+                const float *offp = offset + (long long)b * 18 * P + pix;
+                const float *affp = aff + (long long)b * 9 * P + pix;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(affp + (long long)k * P));
+                    if (k != 4) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(offp + (long long)(2 * k) * P));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(offp + (long long)(2 * k + 1) * P));
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     while (row < row_end) {
         const int b = (int)(row / H), y_lo = (int)(row - (long long)b * H);
         const int nr = (int)((row_end - row) < (long long)(H - y_lo) ? (row_end - row) : (long long)(H - y_lo));   // rows of this image
@@ -660,6 +688,10 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
             const int band_per_sm = band_pix == 2 ? 3 : 5;
             int band_prefetch = 0;        // measured: L2 prefetch of the next item costs more LSU slots than it hides (1058 vs 957 us)
             if (const char *e = getenv("RDFC_NLSPN_PREFETCH")) band_prefetch = atoi(e);
+            int band_pdl = 1;             // programmatic dependent launch between the iterations (see the kernel)
+            if (const char *e = getenv("RDFC_NLSPN_PDL")) band_pdl = atoi(e) != 0;
+            int band_pre = 0;             // items per thread whose offset / affinity lines are prefetched to L2 before the wait
+            if (const char *e = getenv("RDFC_NLSPN_PRE")) band_pre = atoi(e);
             long long band_ctas = (long long)sm_count() * band_per_sm;
             if (const char *e = getenv("RDFC_NLSPN_BAND_CTAS")) band_ctas = atoll(e);
             if (band_ctas > total_rows_b) band_ctas = total_rows_b;
@@ -674,7 +706,15 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
 #define RDFC_BAND(CL, PX, MB)                                                                                                  \
     do {                                                                                                                       \
         RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_band_kernel<CL, PX, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)); \
-        nlspn_prop_band_kernel<CL, PX, MB><<<nctas, BAND_THREADS, band_smem, st>>>(cur, off_g, aff_g, dst, it, nb, H, W, band_rpc, halo, band_prefetch); \
+        cudaLaunchConfig_t cfg = {};                                                                                       \
+        cfg.gridDim = dim3(nctas); cfg.blockDim = dim3(BAND_THREADS); cfg.dynamicSmemBytes = band_smem; cfg.stream = st;       \
+        cudaLaunchAttribute attr[1];                                                                                           \
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                       \
+        attr[0].val.programmaticStreamSerializationAllowed = band_pdl;                                                         \
+        cfg.attrs = attr; cfg.numAttrs = 1;                                                                                    \
+        RDFC_CUDA(cudaLaunchKernelEx(&cfg, nlspn_prop_band_kernel<CL, PX, MB>, (const float *)cur, (const float *)off_g,       \
+                                     (const float *)aff_g, (float *)dst, (float *)it, (int)nb, H, W, band_rpc, halo, band_prefetch, \
+                                     band_pre));                                                                               \
     } while (0)
                 if (band_pix == 2) { if (clamp) RDFC_BAND(true, 2, 3); else RDFC_BAND(false, 2, 3); }
                 else { if (clamp) RDFC_BAND(true, 1, 5); else RDFC_BAND(false, 1, 5); }
