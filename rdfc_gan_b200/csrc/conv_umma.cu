@@ -340,6 +340,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     constexpr bool kGeneral = kMode == MODE_GENERAL;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Programmatic dependent launch (host: cudaLaunchAttributeProgrammaticStreamSerialization): the next kernel of the stream
+    // may take this CTA's SM as soon as it exits and run its own setup / filter loads; every role that touches activations
+    // (A producers, epilogue) executes griddepcontrol.wait first, i.e. waits for the preceding grid to complete and flush.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const long long t_kernel0 = DBG_ON ? clock64() : 0;
     if (DBG_ON && threadIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.dbg[blockIdx.x * 16 + 15] = (long long)gt; }
     const int a_stage_bytes = P.a_tma ? P.nplanes * P.a_plane_bytes : KCH * P.npix_pad * 16;
@@ -544,6 +548,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         // input, SWIZZLE_64B into [pixel][64 B]; coordinates outside the image are zero-filled (= the conv padding).
         // cp.async staging tops out at ~6 B/cycle/SM (L1 miss tracking x L2 latency); the TMA engine does not.
         if (threadIdx.x == 0) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
             const int nkb = P.nkb, sa_n = P.sa, npl = P.nplanes;
             const uint32_t sA0 = smem_u32(sA), plane_b = (uint32_t)P.a_plane_bytes;
             int s = 0;
@@ -576,6 +581,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         // of k-block i holds rows k = 32 i + 8 ch .. + 8, row k = (channel k / 9, tap k % 9).  Per tile the producers
         // first stage the fp32 input patch (all channels, tile + 1-pixel halo, zeros outside the image) in shared
         // memory, so a row is one LDS at a per-thread constant offset: no bounds tests, no L2 round trip per slot.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         const int ch = threadIdx.x & 3, p0 = threadIdx.x >> 2;
         const int Hi = P.Hi, Wi = P.Wi, TWs = 8 * P.nax, THs = TH * (P.nacc / P.nax), nj = (P.npix + PIXPASS - 1) / PIXPASS;
         const int PW = TWs + 2, PH = THs + 2, nch = P.stem_k / 9, plane_sz = PH * PW, tw_shift = 31 - __clz(TWs);
@@ -663,6 +669,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         // is never changes, so its plane-relative input coordinates are decoded once per kernel; per tile they become
         // a byte offset into the image + a validity bit (outside the image = the conv zero padding); per k-block a
         // slot costs one add and one cp.async.  Publication of k-block i is deferred until k-block i+LAG is in flight.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         const int ch = threadIdx.x & 3, p0 = threadIdx.x >> 2;
         const int nj = (P.npix + PIXPASS - 1) / PIXPASS;
         uint32_t rel2[JMAX / 2];    // per slot 16 bits: (plane-relative input row + 1) | (column + 1) << 8 ; 0xffff = unused
@@ -787,6 +794,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         // 16 columns per step, software-pipelined: the tcgen05.ld and the residual load of step g+1 are in flight
         // while step g is computed and stored; (scale, shift) come from shared memory (the L1 left beside a 200 KB
         // carve-out is too small to keep them: every __ldg was an L2 round trip).
+        asm volatile("griddepcontrol.wait;" ::: "memory");       // before the first residual / statistics read and the first store
         const int wq = warp & 3, grp = (warp - EPI_WARP0) >> 2;
         const int r = 4 * wq + (lane >> 3), c = lane & 7;     // MMA row m = 32*wq + lane = 8*r + c
         const int bn = P.bn, Cout = P.Cout, out_stride = P.out_stride, res_stride = P.res_stride;
@@ -1371,7 +1379,17 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
         cfg.attrs = attr; cfg.numAttrs = 1;
         RDFC_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
     } else {
-        kern<<<grid, NTHREADS, smem, st>>>(P);
+        // measured with the two-lane graph: early launch of the next conv takes SMs the other lane's CTAs would have used, and the
+        // step does not get faster (10.61 / 10.63 ms with, 10.58 / 10.47 ms without), so it is off by default
+        static int pdl = -1;
+        if (pdl < 0) { const char *e = getenv("RDFC_UMMA_PDL"); pdl = e ? atoi(e) != 0 : 0; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = pdl;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        RDFC_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
     }
     RDFC_CHECK_LAUNCH("conv_umma_kernel");
     return 0;
