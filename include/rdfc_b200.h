@@ -96,6 +96,18 @@ int rdfc_nlspn_propagate_forward(const float *feat_init, const float *offset, co
                                  const float *feat_fix, int preserve_input, float *out, float *scratch,
                                  float *inter, int B, int H, int W, int prop_time, int clamp_out, void *stream);
 
+/* Backward of rdfc_nlspn_propagate_forward (training; replaces the reference's 18 ModulatedDeformConvFunction.backward calls,
+ * modulated_deform_conv_cuda.cu:124-280 with weight = 1, bias = 0, as nlspn_model.py:140-175 issues them).
+ * grad_out (B,1,H,W) = dL/d out; grad_inter NULL or (prop_time,B,1,H,W) = dL/d list_feat[t]; feat_init, offset, aff, feat_fix,
+ * preserve_input as in the forward; inter = the forward's `inter` buffer (required when prop_time > 1).
+ * Writes grad_feat_init (B,1,H,W), grad_offset (B,18,H,W), grad_aff (B,9,H,W) (overwritten, not accumulated).
+ * scratch: (prop_time + 1) * B*H*W floats.  The input-gradient scatter uses fp32 atomics (as the reference's col2im does), so
+ * the last bits depend on the execution order. */
+int rdfc_nlspn_propagate_backward(const float *grad_out, const float *grad_inter, const float *feat_init,
+                                  const float *inter, const float *offset, const float *aff, const float *feat_fix,
+                                  int preserve_input, float *grad_feat_init, float *grad_offset, float *grad_aff,
+                                  float *scratch, int B, int H, int W, int prop_time, void *stream);
+
 /* pred = softmax([c1,c2]) . [d1, clamp(d2)] ; d2_clamped receives clamp(d2,-1,1) (may alias d2). n = B*H*W. */
 int rdfc_fuse_depth_forward(const float *d1, const float *c1, const float *d2, const float *c2, float *d2_clamped,
                             float *pred, size_t n, void *stream);

@@ -86,3 +86,36 @@ def nlspn_forward(feat_init, guidance, confidence, feat_fix, conv_w, conv_b, aff
                                                  1, 1, 64)                             # :140-144
         inter.append(feat)
     return feat, offset, aff, inter
+
+
+def nlspn_propagate_backward(grad_out, feat_init, offset, aff, feat_fix=None, preserve_input=False, prop_time=18,
+                             grad_inter=None):
+    """Reverse-mode of the propagation loop of nlspn_model.py:157-173 exactly as autograd runs it: per iteration one
+    DCN.modulated_deform_conv_backward (modulated_deform_conv_cuda.cu:124-280) with weight = ones(1,1,3,3), bias = 0,
+    stride 1, pad 1; the blend feat = (1 - m) * feat + m * fix (:169) passes (1 - m) * grad to the previous iteration.
+    Returns (grad_feat_init, grad_offset, grad_aff), float64 accumulation of the per-iteration fp32 results.
+    Test infrastructure only."""
+    from . import dcn as odcn
+    f32 = np.float32
+    feat_init, offset, aff = (np.ascontiguousarray(t, f32) for t in (feat_init, offset, aff))
+    w, b = np.ones((1, 1, 3, 3), f32), np.zeros((1,), f32)
+    m = (np.asarray(feat_fix) > 0).astype(f32) if preserve_input else None
+    xs, x = [], feat_init                    # x'_{t-1}: the (blended) input of iteration t
+    for _ in range(prop_time):
+        if preserve_input:
+            x = (1.0 - m) * x + m * np.asarray(feat_fix, f32)
+        xs.append(np.ascontiguousarray(x, f32))
+        x = odcn.modulated_deform_conv_forward(xs[-1], w, b, offset, aff, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1)
+    g = np.array(grad_out, np.float64)
+    g_off, g_aff = np.zeros(offset.shape, np.float64), np.zeros(aff.shape, np.float64)
+    for t in range(prop_time, 0, -1):
+        if grad_inter is not None:
+            g = g + np.asarray(grad_inter[t - 1], np.float64)
+        gi, go, gm, _, _ = odcn.modulated_deform_conv_backward(xs[t - 1], w, b, offset, aff, g.astype(f32), 3, 3, 1, 1, 1, 1, 1, 1,
+                                                               1, 1)
+        g_off += go
+        g_aff += gm
+        g = gi.astype(np.float64)
+        if preserve_input:
+            g = (1.0 - m) * g
+    return g.astype(f32), g_off.astype(f32), g_aff.astype(f32)

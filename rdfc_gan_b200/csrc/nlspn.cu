@@ -762,6 +762,163 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Backward of the propagation (training).  One iteration is y = A x' with
+//   (A x')[p] = sum_k aff_k[p] * bilinear(x', p + tap_k + offset_k[p]),   x' = preserve_input ? blend(x, fix) : x,
+// the reference's 18 ModulatedDeformConvFunction calls with w = 1, b = 0 (nlspn_model.py:140-175).  Its backward
+// (modulated_deform_conv_cuda.cu:124-280, kernels modulated_deform_im2col_cuda.cuh:197-328) is split in two phases:
+//   1. g_{t-1} = A^T g_t for t = T..1: the col2im scatter (cuh:197-254); it needs no feature values, only offsets / affinities.
+//   2. ONE pass over the pixels that accumulates, over all T iterations, grad_aff_k += g_t * bilinear(x'_{t-1}) and
+//      grad_offset_k += g_t * aff_k * d bilinear / d(y, x) (col2im_coord, cuh:257-328) in registers and writes the 27 planes once,
+//      instead of 18 read-modify-write rounds over them.
+struct BwdPos { int yl, xl; float ly, lx; bool valid; };
+__device__ __forceinline__ BwdPos bwd_pos(float y, float x, int H, int W) {
+    BwdPos q;
+    q.valid = y > -1.f && x > -1.f && y < (float)H && x < (float)W;      // cuh:180 / :228
+    const float yf = floorf(y), xf = floorf(x);
+    q.yl = (int)yf; q.xl = (int)xf; q.ly = y - yf; q.lx = x - xf;
+    return q;
+}
+
+// g (raw) -> finalised in place: iterations below the last one add the gradient that arrived through list_feat and apply
+// the (1 - mask_fix) factor of the blend (nlspn_model.py:169); then scattered into gprev (zero-initialised).
+__global__ void __launch_bounds__(256) nlspn_bwd_scatter_kernel(float *__restrict__ g, const float *__restrict__ ginter,
+                                                                const float *__restrict__ fix, const float *__restrict__ offset,
+                                                                const float *__restrict__ aff, float *__restrict__ gprev,
+                                                                int finalize, int H, int W) {
+    const long long P = (long long)H * W;
+    const int b = blockIdx.y;
+    const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (pix >= P) return;
+    const long long o = (long long)b * P + pix;
+    float gv = g[o];
+    if (finalize) {
+        if (fix && __ldg(fix + o) > 0.f) gv = 0.f;
+        if (ginter) gv += __ldg(ginter + o);
+        g[o] = gv;
+    }
+    if (gv == 0.f) return;
+    const int y = (int)(pix / W), x = (int)(pix - (long long)y * W);
+    const float *offp = offset + (long long)b * 18 * P + pix;
+    const float *affp = aff + (long long)b * 9 * P + pix;
+    float *gim = gprev + (long long)b * P;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float sy = (float)(y - 1 + k / 3) + __ldg(offp + (long long)(2 * k) * P);
+        const float sx = (float)(x - 1 + k % 3) + __ldg(offp + (long long)(2 * k + 1) * P);
+        const BwdPos q = bwd_pos(sy, sx, H, W);
+        if (!q.valid) continue;
+        const float top = gv * __ldg(affp + (long long)k * P);
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int yy = q.yl + a, xx = q.xl + c;
+                if (yy >= 0 && yy <= H - 1 && xx >= 0 && xx <= W - 1)
+                    atomicAdd(gim + (long long)yy * W + xx, (a ? q.ly : 1.f - q.ly) * (c ? q.lx : 1.f - q.lx) * top);
+            }
+    }
+}
+
+// feats: x_0 = feat_init, x_t = inter[t-1]; G: finalised g_1..g_T at G + t * B * P.
+template <bool kPreserve>
+__global__ void __launch_bounds__(256) nlspn_bwd_coord_kernel(const float *__restrict__ feat_init, const float *__restrict__ inter,
+                                                              const float *__restrict__ fix, const float *__restrict__ G,
+                                                              const float *__restrict__ offset, const float *__restrict__ aff,
+                                                              float *__restrict__ goff, float *__restrict__ gaff,
+                                                              int B, int H, int W, int T) {
+    const long long P = (long long)H * W, BP = (long long)B * P;
+    const int b = blockIdx.y;
+    const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (pix >= P) return;
+    const long long o = (long long)b * P + pix;
+    const int y = (int)(pix / W), x = (int)(pix - (long long)y * W);
+    const float *offp = offset + (long long)b * 18 * P + pix;
+    const float *affp = aff + (long long)b * 9 * P + pix;
+    const float *fx = kPreserve ? fix + (long long)b * P : nullptr;
+#pragma unroll 1
+    for (int k = 0; k < 9; ++k) {
+        const float sy = (float)(y - 1 + k / 3) + __ldg(offp + (long long)(2 * k) * P);
+        const float sx = (float)(x - 1 + k % 3) + __ldg(offp + (long long)(2 * k + 1) * P);
+        const float m = __ldg(affp + (long long)k * P);
+        float a_m = 0.f, a_y = 0.f, a_x = 0.f;
+        // cuh:84-125 / :295-322: outside (-1, H) x (-1, W) every derivative is zero
+        if (!(sy <= -1.f || sy >= (float)H || sx <= -1.f || sx >= (float)W)) {
+            const BwdPos q = bwd_pos(sy, sx, H, W);
+            const int yh = q.yl + 1, xh = q.xl + 1;
+            const bool ok1 = q.yl >= 0 && q.xl >= 0, ok2 = q.yl >= 0 && xh <= W - 1, ok3 = yh <= H - 1 && q.xl >= 0,
+                       ok4 = yh <= H - 1 && xh <= W - 1;
+            const long long i1 = (long long)q.yl * W + q.xl, i2 = i1 + 1, i3 = i1 + W, i4 = i3 + 1;
+            const float hy = 1.f - q.ly, hx = 1.f - q.lx;
+            for (int t = 1; t <= T; ++t) {
+                const float gv = __ldg(G + (long long)t * BP + o);
+                if (gv == 0.f) continue;
+                const float *im = (t == 1 ? feat_init : inter + (long long)(t - 2) * BP) + (long long)b * P;
+                float v1 = ok1 ? __ldg(im + i1) : 0.f, v2 = ok2 ? __ldg(im + i2) : 0.f, v3 = ok3 ? __ldg(im + i3) : 0.f,
+                      v4 = ok4 ? __ldg(im + i4) : 0.f;
+                if (kPreserve) {        // x' = fix where fix > 0 (nlspn_model.py:159-160,169)
+                    const float f1 = ok1 ? __ldg(fx + i1) : 0.f, f2 = ok2 ? __ldg(fx + i2) : 0.f, f3 = ok3 ? __ldg(fx + i3) : 0.f,
+                                f4 = ok4 ? __ldg(fx + i4) : 0.f;
+                    v1 = f1 > 0.f ? f1 : v1; v2 = f2 > 0.f ? f2 : v2; v3 = f3 > 0.f ? f3 : v3; v4 = f4 > 0.f ? f4 : v4;
+                }
+                const float val = hy * hx * v1 + hy * q.lx * v2 + q.ly * hx * v3 + q.ly * q.lx * v4;
+                a_m += gv * val;
+                a_y += gv * (hx * (v3 - v1) + q.lx * (v4 - v2));
+                a_x += gv * (hy * (v2 - v1) + q.ly * (v4 - v3));
+            }
+        }
+        gaff[(long long)b * 9 * P + (long long)k * P + pix] = a_m;
+        goff[(long long)b * 18 * P + (long long)(2 * k) * P + pix] = a_y * m;
+        goff[(long long)b * 18 * P + (long long)(2 * k + 1) * P + pix] = a_x * m;
+    }
+}
+
+__global__ void nlspn_bwd_final_kernel(const float *__restrict__ g0, const float *__restrict__ fix, float *__restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (fix && __ldg(fix + i) > 0.f) ? 0.f : g0[i];
+}
+
+extern "C" int rdfc_nlspn_propagate_backward(const float *grad_out, const float *grad_inter, const float *feat_init,
+                                             const float *inter, const float *offset, const float *aff, const float *feat_fix,
+                                             int preserve_input, float *grad_feat_init, float *grad_offset, float *grad_aff,
+                                             float *scratch, int B, int H, int W, int prop_time, void *stream) {
+    RDFC_REQUIRE(grad_out && feat_init && offset && aff && grad_feat_init && grad_offset && grad_aff && scratch, "NULL pointer argument");
+    RDFC_REQUIRE(!preserve_input || feat_fix, "preserve_input requires feat_fix (nlspn_model.py:157-158)");
+    RDFC_REQUIRE(B > 0 && H > 0 && W > 0 && prop_time >= 0 && B <= 65535, "bad shape (%d,%d,%d) x %d", B, H, W, prop_time);
+    RDFC_REQUIRE(prop_time <= 1 || inter, "the backward needs the forward's intermediate results (inter)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long P = (long long)H * W, BP = (long long)B * P;
+    const int T = prop_time;
+    const float *fix = preserve_input ? feat_fix : nullptr;
+    if (T == 0) {
+        RDFC_CUDA(cudaMemcpyAsync(grad_feat_init, grad_out, sizeof(float) * BP, cudaMemcpyDeviceToDevice, st));
+        RDFC_CUDA(cudaMemsetAsync(grad_offset, 0, sizeof(float) * 18 * BP, st));
+        RDFC_CUDA(cudaMemsetAsync(grad_aff, 0, sizeof(float) * 9 * BP, st));
+        return 0;
+    }
+    // scratch = G[0..T]: G[T] = grad_out (the caller's grad_inter[T-1], if any, is added by the first scatter), the rest zero
+    float *G = scratch;
+    RDFC_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * T * BP, st));
+    RDFC_CUDA(cudaMemcpyAsync(G + (long long)T * BP, grad_out, sizeof(float) * BP, cudaMemcpyDeviceToDevice, st));
+    dim3 grid((unsigned)cdiv(P, 256), (unsigned)B);
+    for (int t = T; t >= 1; --t) {
+        const float *gi = grad_inter ? grad_inter + (long long)(t - 1) * BP : nullptr;
+        // the last iteration's output is not blended: only list_feat's gradient is added there
+        nlspn_bwd_scatter_kernel<<<grid, 256, 0, st>>>(G + (long long)t * BP, gi, t < T ? fix : nullptr, offset, aff,
+                                                       G + (long long)(t - 1) * BP, (t < T || gi) ? 1 : 0, H, W);
+        RDFC_CHECK_LAUNCH("nlspn_bwd_scatter_kernel");
+    }
+    const int nblk = (int)min((long long)cdiv(BP, 256), (long long)sm_count() * 8);
+    nlspn_bwd_final_kernel<<<nblk, 256, 0, st>>>(G, fix, grad_feat_init, BP);
+    RDFC_CHECK_LAUNCH("nlspn_bwd_final_kernel");
+    if (fix)
+        nlspn_bwd_coord_kernel<true><<<grid, 256, 0, st>>>(feat_init, inter, fix, G, offset, aff, grad_offset, grad_aff, B, H, W, T);
+    else
+        nlspn_bwd_coord_kernel<false><<<grid, 256, 0, st>>>(feat_init, inter, fix, G, offset, aff, grad_offset, grad_aff, B, H, W, T);
+    RDFC_CHECK_LAUNCH("nlspn_bwd_coord_kernel");
+    return 0;
+}
+
 extern "C" int rdfc_fuse_depth_forward(const float *d1, const float *c1, const float *d2, const float *c2,
                                        float *d2_clamped, float *pred, size_t n, void *stream) {
     RDFC_REQUIRE(d1 && c1 && d2 && c2 && pred, "NULL pointer argument");

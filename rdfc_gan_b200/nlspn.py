@@ -13,6 +13,48 @@ from . import _cabi as C
 from .dcn.functions import ModulatedDeformConvFunction
 
 
+class _PropagateFused(torch.autograd.Function):
+    """The T propagation iterations as one differentiable op: forward = rdfc_nlspn_propagate_forward (keeping every
+    iteration's result), backward = rdfc_nlspn_propagate_backward (the transposed gather as a scatter per iteration, then ONE
+    pass for grad_offset / grad_aff).  Replaces the reference's prop_time ModulatedDeformConvFunction calls and their
+    backwards (nlspn_model.py:140-175); feat_fix gets no gradient path worth keeping (the reference detaches the mask only,
+    the m * fix term's gradient is returned as well)."""
+
+    @staticmethod
+    def forward(ctx, feat_init, offset, aff, feat_fix, prop_time, preserve_input):
+        B, _, H, W = feat_init.shape
+        feat_init, offset, aff = feat_init.contiguous(), offset.contiguous(), aff.contiguous()
+        fix = feat_fix.contiguous() if (preserve_input and feat_fix is not None) else None
+        out = torch.empty_like(feat_init)
+        scratch = torch.empty_like(feat_init)
+        inter = torch.empty((max(prop_time, 1),) + tuple(feat_init.shape), dtype=torch.float32, device=feat_init.device)
+        with torch.cuda.device(feat_init.device):
+            C.check(C.lib.rdfc_nlspn_propagate_forward(
+                C.ptr(feat_init), C.ptr(offset), C.ptr(aff), C.ptr(fix), int(bool(preserve_input)), C.ptr(out),
+                C.ptr(scratch), C.ptr(inter), B, H, W, prop_time, 0, C.stream_ptr(feat_init.device)))
+        ctx.save_for_backward(feat_init, offset, aff, fix if fix is not None else feat_init.new_empty(0), inter)
+        ctx.cfg = (prop_time, bool(preserve_input), fix is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        feat_init, offset, aff, fix, inter = ctx.saved_tensors
+        prop_time, preserve, has_fix = ctx.cfg
+        B, _, H, W = feat_init.shape
+        grad_out = grad_out.contiguous()
+        g_feat, g_off, g_aff = torch.empty_like(feat_init), torch.empty_like(offset), torch.empty_like(aff)
+        scratch = torch.empty((prop_time + 1,) + tuple(feat_init.shape), dtype=torch.float32, device=feat_init.device)
+        with torch.cuda.device(feat_init.device):
+            C.check(C.lib.rdfc_nlspn_propagate_backward(
+                C.ptr(grad_out), None, C.ptr(feat_init), C.ptr(inter), C.ptr(offset), C.ptr(aff),
+                C.ptr(fix) if has_fix else None, int(preserve), C.ptr(g_feat), C.ptr(g_off), C.ptr(g_aff), C.ptr(scratch),
+                B, H, W, prop_time, C.stream_ptr(feat_init.device)))
+        g_fix = None
+        if has_fix and ctx.needs_input_grad[3]:
+            raise NotImplementedError("gradient w.r.t. feat_fix (the sparse input depth) is not provided by the fused NLSPN backward")
+        return g_feat, g_off, g_aff, g_fix, None, None
+
+
 class NLPSN(nn.Module):
     def __init__(self, channels_g, channels_f, k_g, k_f, prop_time=1, affinity=None, affinity_gamma=0.5,
                  conf_prop=True, preserve_input=False):
@@ -61,6 +103,7 @@ class NLPSN(nn.Module):
         self.deformable_groups = 1
         self.im2col_step = 64
         self.return_intermediates = True
+        self.fused_backward = True          # False: always differentiate through the reference's composition
 
     # ---- fused inference path --------------------------------------------------------------------------------
     def _fused_ok(self, *tensors):
@@ -70,6 +113,15 @@ class NLPSN(nn.Module):
                                         any(p.requires_grad for p in self.conv_offset_aff.parameters())):
             return False
         return all(t is None or t.dtype == torch.float32 for t in tensors)
+
+    def _fused_train_ok(self, feat_init, offset, aff, feat_fix):
+        """Gradients are needed: the fused forward + backward pair covers k_f = 3, fp32, no list_feat consumer and no
+        gradient into feat_fix; everything else takes the reference's composition below."""
+        if self.k_f != 3 or self.return_intermediates or not self.fused_backward:
+            return False
+        if self.preserve_input and feat_fix is not None and feat_fix.requires_grad:
+            return False
+        return all(t is None or t.dtype == torch.float32 for t in (feat_init, offset, aff, feat_fix))
 
     def _get_offset_affinity_fused(self, guidance, confidence):
         B, _, H, W = guidance.shape
@@ -170,6 +222,12 @@ class NLPSN(nn.Module):
             feat_result, list_feat = self._propagate_fused(feat_init, offset.contiguous(), aff.contiguous(), feat_fix,
                                                            self.return_intermediates)
             return feat_result, list_feat, offset, aff, self.aff_scale_const.data
+        if self._fused_train_ok(feat_init, offset, aff, feat_fix):
+            # training: the propagation as ONE differentiable op with a fused backward (list_feat is not returned, as
+            # NLSPNRefineModule drops it anyway, nlspn_model.py:193-197)
+            feat_result = _PropagateFused.apply(feat_init, offset, aff, feat_fix if self.preserve_input else None,
+                                                self.prop_time, self.preserve_input)
+            return feat_result, [], offset, aff, self.aff_scale_const.data
         if self.preserve_input:
             mask_fix = torch.sum(feat_fix > 0.0, dim=1, keepdim=True).detach()
             mask_fix = (mask_fix > 0.0).type_as(feat_fix)

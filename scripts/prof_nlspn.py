@@ -49,5 +49,42 @@ def main():
           f"{116.0*B*H*W*T/ms/1e6:.0f} GB/s algorithmic")
 
 
+
+
+def train_timing(B=8):
+    """fused forward + backward of the propagation against the reference's composition (prop_time DCN Function calls):
+        python scripts/prof_nlspn.py --train [B]"""
+    from rdfc_gan_b200.nlspn import NLSPNRefineModule
+    from _synth import nlspn_stress_inputs
+    H, W = bench.H, bench.W
+    x = nlspn_stress_inputs(B, H, W, 1)
+    t = {k: torch.from_numpy(v).cuda() for k, v in x.items()}
+    gout = torch.randn(B, 1, H, W, device="cuda")
+    for fused in (True, False):
+        mod = NLSPNRefineModule(prop_kernel=3, prop_time=18, affinity="TGASS", affinity_gamma=0.5, conf_prop=True).cuda().train()
+        mod.prop_layer.conv_offset_aff.weight.data.copy_(t["conv_w"])
+        mod.prop_layer.conv_offset_aff.bias.data.copy_(t["conv_b"])
+        mod.prop_layer.fused_backward = fused
+        ts = []
+        for rep in range(5):
+            g = t["guidance"].clone().requires_grad_(True)
+            p = t["pred_init"].clone().requires_grad_(True)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            y, _ = mod(p, g, t["confidence"], t["feat_fix"])
+            y.backward(gout)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        print(f"NLSPN forward+backward B={B} 228x304 x18, {'fused propagate fwd/bwd' if fused else 'composition (18 DCN Function calls)'}: "
+              f"{statistics.median(ts[1:]):.2f} ms")
+
+
+if __name__ == "__main__" and "--train" in sys.argv:
+    sys.argv.remove("--train")
+    train_timing(int(sys.argv[1]) if len(sys.argv) > 1 else 8)
+    sys.exit(0)
+
 if __name__ == "__main__":
     main()

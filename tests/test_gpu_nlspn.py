@@ -97,3 +97,74 @@ def test_full_size_properties():
     assert (prop(const)[:, :, 60:-60, 60:-60] - 0.37).abs().max() <= 2e-5
     a, b = torch.randn(B, 1, H, W, device="cuda", generator=g), torch.randn(B, 1, H, W, device="cuda", generator=g)
     assert (prop(2 * a - 3 * b) - (2 * prop(a) - 3 * prop(b))).abs().max() <= 1e-4
+
+
+def _prop_inputs(B, H, W, seed, preserve):
+    """offsets / affinities of the stress generator's own affinity stage + a random upstream gradient"""
+    from oracle import nlspn as onl
+    x = nlspn_stress_inputs(B, H, W, seed)
+    off, aff = onl.get_offset_affinity(x["guidance"], x["confidence"], x["conv_w"], x["conv_b"], np.array([4.0], np.float32))[:2]
+    rng = np.random.default_rng(seed + 100)
+    gout = rng.standard_normal((B, 1, H, W)).astype(np.float32)
+    return x, np.ascontiguousarray(off, np.float32), np.ascontiguousarray(aff, np.float32), gout
+
+
+@pytest.mark.parametrize("preserve", [False, True])
+def test_fused_backward_vs_oracle(preserve):
+    """rdfc_nlspn_propagate_backward (through the autograd Function) against the CPU restatement of the reference's
+    reverse loop (oracle.nlspn.nlspn_propagate_backward: one DCN backward per iteration)."""
+    from oracle import nlspn as onl
+    from rdfc_gan_b200.nlspn import _PropagateFused
+    B, H, W, T = 2, 19, 27, 5
+    x, off, aff, gout = _prop_inputs(B, H, W, 11, preserve)
+    ref = onl.nlspn_propagate_backward(gout, x["pred_init"], off, aff, x["feat_fix"], preserve, T)
+    f = torch.from_numpy(x["pred_init"]).cuda().requires_grad_(True)
+    o = torch.from_numpy(off).cuda().requires_grad_(True)
+    a = torch.from_numpy(aff).cuda().requires_grad_(True)
+    fix = torch.from_numpy(x["feat_fix"]).cuda()
+    y = _PropagateFused.apply(f, o, a, fix if preserve else None, T, preserve)
+    y.backward(torch.from_numpy(gout).cuda())
+    for got, want, name in ((f.grad, ref[0], "feat_init"), (o.grad, ref[1], "offset"), (a.grad, ref[2], "aff")):
+        want = torch.from_numpy(want)
+        err = (got.cpu() - want).abs().max().item()
+        assert err <= 1e-4 * max(1.0, want.abs().max().item()), (name, err, want.abs().max().item())
+
+
+@pytest.mark.parametrize("name", ["tgass18", "as12_preserve"])
+def test_fused_backward_matches_composition(name):
+    """Training through NLSPNRefineModule: the fused forward/backward pair gives the gradients of the reference's composition
+    (prop_time DCN Function calls) for the guidance, the initial depth and conv_offset_aff."""
+    cfg = NLSPN_CASES[name]
+    B, H, W = NLSPN_SHAPE
+    x = nlspn_stress_inputs(B, H, W, cfg["seed"])
+    t = {k: torch.from_numpy(v).cuda() for k, v in x.items()}
+    gout = torch.randn(B, 1, H, W, generator=torch.Generator().manual_seed(3)).cuda()
+    grads = {}
+    for fused in (True, False):
+        mod = _module(cfg, x).train()
+        mod.prop_layer.fused_backward = fused
+        g = t["guidance"].clone().requires_grad_(True)
+        p = t["pred_init"].clone().requires_grad_(True)
+        y, _ = mod(p, g, t["confidence"], t["feat_fix"])
+        y.backward(gout)
+        grads[fused] = (y.detach(), g.grad, p.grad, mod.prop_layer.conv_offset_aff.weight.grad, mod.prop_layer.conv_offset_aff.bias.grad)
+    for a, b, nm in zip(grads[True], grads[False], ("y", "d guidance", "d pred_init", "d conv w", "d conv b")):
+        scale = max(1.0, b.abs().max().item())
+        assert (a - b).abs().max().item() <= 2e-4 * scale, (nm, (a - b).abs().max().item(), scale)
+
+
+def test_fused_backward_full_size_linearity():
+    """At the bench size the oracle is too slow: the backward is linear in grad_out, and <A x, g> = <x, A^T g>."""
+    from rdfc_gan_b200.nlspn import _PropagateFused
+    B, H, W, T = 4, 228, 304, 18
+    x, off, aff, _ = _prop_inputs(B, 32, 40, 21, False)
+    rep = lambda v: torch.from_numpy(v).cuda().repeat(2, 1, 8, 8)[:B, :, :H, :W].contiguous()
+    o, a = rep(off), rep(aff)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    f = torch.randn(B, 1, H, W, device="cuda", generator=gen, dtype=torch.float64).float().requires_grad_(True)
+    g1 = torch.randn(B, 1, H, W, device="cuda", generator=gen)
+    y = _PropagateFused.apply(f, o, a, None, T, False)
+    (gf,) = torch.autograd.grad(y, f, g1)
+    lhs = (y.double() * g1.double()).sum().item()          # <A f, g>
+    rhs = (f.detach().double() * gf.double()).sum().item()  # <f, A^T g>
+    assert abs(lhs - rhs) <= 1e-3 * max(1.0, abs(lhs)), (lhs, rhs)
