@@ -89,3 +89,31 @@ def test_generator_oracle_matches_reference(name, golden_dir):
         if v.shape != g.shape:
             v = v[:, :, ::4, ::4]
         assert np.abs(v - g).max() <= 2e-5, k
+
+
+def test_oracle_nlspn_backward_matches_finite_differences():
+    """oracle.nlspn.nlspn_propagate_backward (the reference's reverse loop on the C DCN oracle) against central finite
+    differences of the oracle forward: pins the checker the GPU backward is compared with."""
+    from oracle import dcn as odcn
+    from oracle import nlspn as onl
+    from _synth import nlspn_stress_inputs
+    B, H, W, T = 1, 9, 11, 3
+    x = nlspn_stress_inputs(B, H, W, 3)
+    off, aff = onl.get_offset_affinity(x["guidance"], x["confidence"], x["conv_w"], x["conv_b"], np.array([4.0], np.float32))[:2]
+    off, aff = np.ascontiguousarray(off, np.float32), np.ascontiguousarray(aff, np.float32)
+    gout = np.random.default_rng(0).standard_normal((B, 1, H, W)).astype(np.float32)
+    for preserve in (False, True):
+        gf, go, ga = onl.nlspn_propagate_backward(gout, x["pred_init"], off, aff, x["feat_fix"], preserve, T)
+
+        def loss(f, o, a):
+            return float((odcn.nlspn_propagate(f, o, a, x["feat_fix"], preserve, 3, T).astype(np.float64) * gout).sum())
+        for name, arr, grad, idxs in (("feat", x["pred_init"], gf, [(0, 0, 4, 5), (0, 0, 2, 9)]),
+                                      ("aff", aff, ga, [(0, 3, 4, 5), (0, 7, 2, 9)])):
+            for idx in idxs:
+                e = 1e-2
+                hi, lo = arr.copy(), arr.copy()
+                hi[idx] += e
+                lo[idx] -= e
+                args = {"feat": lambda v: (v, off, aff), "aff": lambda v: (x["pred_init"], off, v)}[name]
+                fd = (loss(*args(hi)) - loss(*args(lo))) / (2 * e)        # the op is linear in feat and in aff
+                assert abs(fd - float(grad[idx])) <= 2e-3 * max(1.0, abs(fd)), (preserve, name, idx, fd, float(grad[idx]))
