@@ -230,6 +230,16 @@ int rdfc_adain_apply(const rdfc_view *x, const float *cmean, const float *cstd, 
 int rdfc_norm_apply(const rdfc_view *x, const float *mean, const float *rstd, const rdfc_view *out, int B, int H,
                     int W, void *stream);
 
+/* ------------------------------------------------------------------ evaluation glue --------------------------- */
+/* The sums behind RDFGANMetric (lib/metrics/rdf_gan_metric.py:59-151: RMSE, MAE, iRMSE, iMAE, REL, D^1..D^3), with the
+ * de-normalisation x * std + mean of Eval.inference (lib/evaluator/evaluator.py:27-29) fused in.  pred, gt: B images of n fp32
+ * pixels; evaluate_mask: NULL or B*n bytes (non-zero = evaluate).  A pixel counts when gt > t_valid (and its mask byte is set).
+ * sums (B,9) doubles: count, sum d^2, sum |d|, sum dinv^2, sum |dinv|, sum |d|/(gt+1e-8), #(ratio < 1.25), #(< 1.25^2),
+ * #(< 1.25^3); partial: scratch of B * rdfc_depth_metric_nchunk(n) * 9 doubles.  Deterministic (no atomics). */
+int rdfc_depth_metric_nchunk(long long n);
+int rdfc_depth_metric_sums(const float *pred, const float *gt, const unsigned char *evaluate_mask, float std, float mean,
+                           float t_valid, double *sums, double *partial, int B, long long n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

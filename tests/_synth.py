@@ -151,3 +151,20 @@ DCN_CASES = {
     "v1_plain": dict(B=2, Cin=4, Cout=6, H=7, W=8, k=3, s=1, p=1, d=1, g=1, dg=1, mask=False, off_std=2.0),
     "wide": dict(B=1, Cin=16, Cout=140, H=6, W=37, k=3, s=1, p=1, d=1, g=1, dg=2, mask=True, off_std=1.0),
 }
+
+
+def metric_inputs(seed, n_img, H, W, with_mask=False):
+    """Ground-truth depth with holes (gt <= t_valid), predictions with a few non-positive pixels (pred <= t_valid: inverse
+    metrics zero them) and ratios on both sides of the 1.25^k thresholds; optional evaluate masks."""
+    rng = np.random.default_rng(1000 + seed)
+    res = []
+    for _ in range(n_img):
+        gt = rng.uniform(0.5, 10.0, (H, W)).astype(np.float32)
+        gt[rng.random((H, W)) < 0.2] = 0.0                              # holes
+        pd = (gt * rng.lognormal(0.0, 0.25, (H, W))).astype(np.float32) + rng.normal(0, 0.05, (H, W)).astype(np.float32)
+        pd[rng.random((H, W)) < 0.01] = -0.1                            # invalid predictions
+        r = {"gt": gt, "pd": pd.astype(np.float32)}
+        if with_mask:
+            r["evaluate_mask"] = rng.random((H, W)) < 0.7
+        res.append(r)
+    return res

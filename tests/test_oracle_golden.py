@@ -117,3 +117,19 @@ def test_oracle_nlspn_backward_matches_finite_differences():
                 args = {"feat": lambda v: (v, off, aff), "aff": lambda v: (x["pred_init"], off, v)}[name]
                 fd = (loss(*args(hi)) - loss(*args(lo))) / (2 * e)        # the op is linear in feat and in aff
                 assert abs(fd - float(grad[idx])) <= 2e-3 * max(1.0, abs(fd)), (preserve, name, idx, fd, float(grad[idx]))
+
+
+def test_oracle_metrics_vs_reference_golden(golden_dir):
+    """oracle.metrics against the outputs of the reference's own RDFGANMetric (tests/golden/make_metric_golden.py)."""
+    import json
+    from oracle import metrics as om
+    from _synth import metric_inputs
+    gold = json.load(open(f"{golden_dir}/metric_golden.json"))
+    for seed, g in gold.items():
+        n_img, H, W, with_mask = g["cfg"]
+        res = metric_inputs(int(seed), n_img, H, W, with_mask)
+        got = om.evaluate_all(res)
+        for k, v in g["evaluate_all"].items():
+            assert abs(float(got[k]) - v) <= 2e-6 * max(1.0, abs(v)), (seed, k, float(got[k]), v)
+        b = om.evaluate_batch(np.stack([r["gt"] for r in res]), np.stack([r["pd"] for r in res]))
+        assert np.allclose(b[0], np.array(g["evaluate_batch"], np.float32), rtol=2e-5, atol=1e-6), (seed, b, g["evaluate_batch"])
