@@ -16,6 +16,8 @@ KEYS = [
     "smsp__sass_inst_executed_op_utcmma.sum", "smsp__sass_inst_executed_op_tmem_ldt.sum",
     "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "l1tex__m_xbar2l1tex_read_bytes.sum",
     "smsp__inst_executed_op_ldgsts.sum",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__cycles_elapsed.max.per_second",
 ]
 
 
