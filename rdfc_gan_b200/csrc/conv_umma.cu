@@ -750,7 +750,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         }
     } else if (warp == BLOAD_WARP) {
         // ================= B loader (TMA 1-D bulk copies of pre-packed filter blocks) =================
-        if (lane == 0) {
+        // The warp walks the ring convergently; lane 0 posts the byte count, then every lane issues its share of the stage's
+        // copies (a 9-tap stage of a filter view that is not contiguous over the k-block is 36 copies of ~1 KB: issued by one
+        // thread they took as long as the MMAs of the stage, which starved the issuer in cta_group::2 mode).
+        {
             const uint32_t piece = keep((uint32_t)bn_cta * 16u);          // one cin chunk of this CTA's filter rows
             const long long chunk_stride = (long long)P.CoutP * 8;
             const uint32_t sB0 = smem_u32(sB);
@@ -768,24 +771,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                         { DBG_T0(); mbar_wait(BAR(B_EMPTY + sb), par); DBG_ACC(t_be); }
                         const uint32_t full = BAR(B_FULL + sb);
 #ifdef RDFC_UMMA_TIMERS
-                        if (P.dbg_flags & 16) { mbar_arrive(full); if (++sb == sb_n) { sb = 0; par ^= 1u; } continue; }   // no filter loads
+                        if (P.dbg_flags & 16) { if (lane == 0) mbar_arrive(full); if (++sb == sb_n) { sb = 0; par ^= 1u; } continue; }   // no filter loads
 #endif
-                        mbar_expect_tx(full, (uint32_t)b_stage_bytes);
-                        for (int tg = 0; tg < gtaps; ++tg) {
-                            const __nv_bfloat16 *src = w_n0 + P.tap_w[z][gi * gtaps + tg];
-                            const uint32_t d = dst + (uint32_t)tg * (uint32_t)b_tap_bytes;
-                            if (b_contig) {
-                                bulk_g2s(d, src, piece * KCH, full);
-                            } else {
-#pragma unroll
-                                for (int ch = 0; ch < KCH; ++ch)
-                                    bulk_g2s(d + (uint32_t)ch * piece, src + ch * chunk_stride, piece, full);
+                        if (lane == 0) mbar_expect_tx(full, (uint32_t)b_stage_bytes);
+                        __syncwarp();
+                        if (b_contig) {
+                            for (int tg = lane; tg < gtaps; tg += 32)
+                                bulk_g2s(dst + (uint32_t)tg * (uint32_t)b_tap_bytes, w_n0 + P.tap_w[z][gi * gtaps + tg], piece * KCH, full);
+                        } else {
+                            for (int q = lane; q < gtaps * KCH; q += 32) {
+                                const int tg = q / KCH, ch = q - tg * KCH;
+                                bulk_g2s(dst + (uint32_t)tg * (uint32_t)b_tap_bytes + (uint32_t)ch * piece,
+                                         w_n0 + P.tap_w[z][gi * gtaps + tg] + ch * chunk_stride, piece, full);
                             }
                         }
                         if (++sb == sb_n) { sb = 0; par ^= 1u; }
                     }
             }
-            if (DBG_ON) P.dbg[blockIdx.x * 16 + 5] = t_be;
+            if (DBG_ON && lane == 0) P.dbg[blockIdx.x * 16 + 5] = t_be;
         }
         __syncwarp();
     } else {

@@ -70,6 +70,8 @@ def main():
                 buf = (ctypes.c_longlong * (148 * 16))()
                 C.lib.rdfc_dev_umma_timers(buf, 148 * 16)
                 a = np.frombuffer(buf, dtype=np.int64).reshape(148, 16).astype(np.float64)
+                if os.environ.get("RDFC_UMMA_PAIR") == "1":
+                    a = a[::2]                      # pair mode: the leader CTAs (even cluster ranks) issue the MMAs
                 a = a[a[:, 0] > 0]
                 print(f"role timers for step '{n}' (cycles, median over {len(a)} CTAs; CTA lifetime max {a[:, 13].max():.0f}, "
                       f"last CTA end - first CTA end {(a[:, 14].max() - a[:, 14].min()) / 1e3:.1f} us, "
