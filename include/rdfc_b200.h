@@ -96,6 +96,16 @@ int rdfc_nlspn_propagate_forward(const float *feat_init, const float *offset, co
                                  const float *feat_fix, int preserve_input, float *out, float *scratch,
                                  float *inter, int B, int H, int W, int prop_time, int clamp_out, void *stream);
 
+/* Backward of rdfc_nlspn_affinity_forward up to the conv output (training): grad_offset (B,18,H,W), grad_aff (B,9,H,W) ->
+ * grad_conv (B,24,H,W) = dL/d conv_offset_aff(guidance) (the caller back-propagates the 8 -> 24 channel conv itself),
+ * grad_confidence (B,1,H,W, overwritten; required when conf_prop) through the 1x1 DCN gathers of nlspn_model.py:96-119 (their
+ * offsets are detached in the reference), grad_aff_scale (1 float, overwritten; NULL to skip) for TGASS's learnable scale
+ * (nlspn_model.py:86-87).  offset = the forward's output.  fp32 atomics in the confidence scatter and the scale reduction. */
+int rdfc_nlspn_affinity_backward(const float *guidance, const float *confidence, const float *conv_w, const float *conv_b,
+                                 const float *aff_scale, int affinity, int conf_prop, const float *offset,
+                                 const float *grad_offset, const float *grad_aff, float *grad_conv, float *grad_confidence,
+                                 float *grad_aff_scale, int B, int H, int W, void *stream);
+
 /* Backward of rdfc_nlspn_propagate_forward (training; replaces the reference's 18 ModulatedDeformConvFunction.backward calls,
  * modulated_deform_conv_cuda.cu:124-280 with weight = 1, bias = 0, as nlspn_model.py:140-175 issues them).
  * grad_out (B,1,H,W) = dL/d out; grad_inter NULL or (prop_time,B,1,H,W) = dL/d list_feat[t]; feat_init, offset, aff, feat_fix,

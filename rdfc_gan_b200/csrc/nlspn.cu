@@ -763,6 +763,131 @@ extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Backward of the offset / affinity stage up to the conv output (training): given dL/d offset (B,18,H,W) and dL/d aff (B,9,H,W)
+// it produces dL/d conv_offset_aff(guidance) (B,24,H,W), scatters dL/d confidence (the 1x1 DCN gathers of nlspn_model.py:96-119,
+// offsets detached there) and accumulates dL/d aff_scale_const (TGASS).  The raw affinity channels are recomputed (8 of the 24
+// conv outputs); the offsets are read back from the forward's output.  The conv's own backward (8 <-> 24 channels, 0.24 GFLOP per
+// image) is left to the caller.
+__global__ void __launch_bounds__(TX *TY) nlspn_affinity_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ confidence,
+                                                                    const float *__restrict__ conv_w, const float *__restrict__ conv_b,
+                                                                    const float *__restrict__ aff_scale, int affinity, int conf_prop,
+                                                                    const float *__restrict__ offset, const float *__restrict__ g_offset,
+                                                                    const float *__restrict__ g_aff, float *__restrict__ g_conv,
+                                                                    float *__restrict__ g_conf, float *__restrict__ g_scale, int H, int W) {
+    __shared__ __align__(16) float s_w[72 * 8];      // the 8 affinity channels: [(ci*9 + tap)][8]
+    __shared__ float s_b[8];
+    __shared__ float s_g[8][TY + 2][TX + 2];
+    __shared__ float s_red[TX * TY / 32];
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    const int b = blockIdx.z, x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const long long P = (long long)H * W;
+    for (int e = tid; e < 8 * 72; e += TX * TY) s_w[(e % 72) * 8 + e / 72] = conv_w[16 * 72 + e];
+    if (tid < 8) s_b[tid] = conv_b[16 + tid];
+    for (int e = tid; e < 8 * (TY + 2) * (TX + 2); e += TX * TY) {
+        const int c = e / ((TY + 2) * (TX + 2)), r = e % ((TY + 2) * (TX + 2));
+        const int yy = y0 + r / (TX + 2) - 1, xx = x0 + r % (TX + 2) - 1;
+        s_g[c][r / (TX + 2)][r % (TX + 2)] =
+            (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(guidance + ((long long)b * 8 + c) * P + (long long)yy * W + xx) : 0.f;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const bool live = x < W && y < H;
+    float gs = 0.f;                                  // this pixel's contribution to dL/d aff_scale_const
+    if (live) {
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = s_b[j];
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float g = s_g[ci][threadIdx.y + t / 3][threadIdx.x + t % 3];
+                const float4 *w4 = reinterpret_cast<const float4 *>(s_w + (ci * 9 + t) * 8);
+                const float4 w0 = w4[0], w1 = w4[1];
+                r[0] = fmaf(w0.x, g, r[0]); r[1] = fmaf(w0.y, g, r[1]); r[2] = fmaf(w0.z, g, r[2]); r[3] = fmaf(w0.w, g, r[3]);
+                r[4] = fmaf(w1.x, g, r[4]); r[5] = fmaf(w1.y, g, r[5]); r[6] = fmaf(w1.z, g, r[6]); r[7] = fmaf(w1.w, g, r[7]);
+            }
+        const long long pix = (long long)y * W + x;
+        const float *offp = offset + (long long)b * 18 * P + pix;
+        const float *gop = g_offset + (long long)b * 18 * P + pix;
+        const float *gap = g_aff + (long long)b * 9 * P + pix;
+        float *gc = g_conv + (long long)b * 24 * P + pix;
+        const float scale = __ldg(aff_scale);
+        const float den = affinity == RDFC_AFF_TGASS ? scale + 1e-8f : scale;
+        const float *conf = conf_prop ? confidence + (long long)b * P : nullptr;
+        float t[8], v[8], c[8], u[8], dy[8], dx[8];
+        float abs_sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = j < 4 ? j : j + 1;
+            dy[j] = __ldg(offp + (long long)(2 * k) * P);
+            dx[j] = __ldg(offp + (long long)(2 * k + 1) * P);
+            t[j] = (affinity == RDFC_AFF_TC || affinity == RDFC_AFF_TGASS) ? tanhf(r[j]) : r[j];
+            v[j] = (affinity == RDFC_AFF_TC || affinity == RDFC_AFF_TGASS) ? t[j] / den : r[j];
+            c[j] = conf_prop ? bilinear(conf, H, W, (float)y + dy[j], (float)x + dx[j]) : 1.f;
+            u[j] = v[j] * c[j];
+            abs_sum += fabsf(u[j]);
+        }
+        abs_sum += 1e-4f;
+        bool clamped = false;
+        if ((affinity == RDFC_AFF_ASS || affinity == RDFC_AFF_TGASS) && abs_sum < 1.f) { abs_sum = 1.f; clamped = true; }
+        const float g_ref = __ldg(gap + 4 * P);           // aff_ref = 1 - sum(aff)  (nlspn_model.py:132-136)
+        float ga[8], dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = j < 4 ? j : j + 1;
+            ga[j] = __ldg(gap + (long long)k * P) - g_ref;
+            dot += ga[j] * u[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float gu = ga[j];
+            if (affinity != RDFC_AFF_TC) {                // aff = u / S, S = sum|u| + 1e-4 (clamped from below: constant)
+                const float sgn = u[j] > 0.f ? 1.f : (u[j] < 0.f ? -1.f : 0.f);
+                gu = ga[j] / abs_sum - (clamped ? 0.f : dot / (abs_sum * abs_sum) * sgn);
+            }
+            const float gv = gu * c[j];
+            if (conf_prop) {                              // dL/d confidence: transposed bilinear gather at (y + dy, x + dx)
+                const float gcj = gu * v[j], sy = (float)y + dy[j], sx = (float)x + dx[j];
+                if (gcj != 0.f && sy > -1.f && sx > -1.f && sy < (float)H && sx < (float)W) {
+                    const float fy = floorf(sy), fx = floorf(sx);
+                    const int yl = (int)fy, xl = (int)fx;
+                    const float ly = sy - fy, lx = sx - fx;
+                    float *gim = g_conf + (long long)b * P;
+#pragma unroll
+                    for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc) {
+                            const int yy = yl + aa, xx = xl + cc;
+                            if (yy >= 0 && yy <= H - 1 && xx >= 0 && xx <= W - 1)
+                                atomicAdd(gim + (long long)yy * W + xx, (aa ? ly : 1.f - ly) * (cc ? lx : 1.f - lx) * gcj);
+                        }
+                }
+            }
+            float gr = gv;
+            if (affinity == RDFC_AFF_TC || affinity == RDFC_AFF_TGASS) {
+                gr = gv * (1.f - t[j] * t[j]) / den;
+                gs -= gv * t[j] / (den * den);
+            }
+            gc[(long long)(16 + j) * P] = gr;
+            const int k = j < 4 ? j : j + 1;
+            gc[(long long)(2 * j) * P] = __ldg(gop + (long long)(2 * k) * P);          // conv channel 2j / 2j+1 = (dy, dx) of neighbour j
+            gc[(long long)(2 * j + 1) * P] = __ldg(gop + (long long)(2 * k + 1) * P);
+        }
+    }
+    if (g_scale) {                                    // block reduction, one atomic per CTA
+        for (int o = 16; o > 0; o >>= 1) gs += __shfl_down_sync(0xffffffffu, gs, o);
+        if ((tid & 31) == 0) s_red[tid >> 5] = gs;
+        __syncthreads();
+        if (tid == 0) {
+            float tot = 0.f;
+            for (int w = 0; w < TX * TY / 32; ++w) tot += s_red[w];
+            if (tot != 0.f) atomicAdd(g_scale, tot);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Backward of the propagation (training).  One iteration is y = A x' with
 //   (A x')[p] = sum_k aff_k[p] * bilinear(x', p + tap_k + offset_k[p]),   x' = preserve_input ? blend(x, fix) : x,
 // the reference's 18 ModulatedDeformConvFunction calls with w = 1, b = 0 (nlspn_model.py:140-175).  Its backward
@@ -876,6 +1001,24 @@ __global__ void __launch_bounds__(256) nlspn_bwd_coord_kernel(const float *__res
 __global__ void nlspn_bwd_final_kernel(const float *__restrict__ g0, const float *__restrict__ fix, float *__restrict__ out, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = (fix && __ldg(fix + i) > 0.f) ? 0.f : g0[i];
+}
+
+extern "C" int rdfc_nlspn_affinity_backward(const float *guidance, const float *confidence, const float *conv_w, const float *conv_b,
+                                            const float *aff_scale, int affinity, int conf_prop, const float *offset,
+                                            const float *grad_offset, const float *grad_aff, float *grad_conv, float *grad_confidence,
+                                            float *grad_aff_scale, int B, int H, int W, void *stream) {
+    RDFC_REQUIRE(guidance && conv_w && conv_b && aff_scale && offset && grad_offset && grad_aff && grad_conv, "NULL pointer argument");
+    RDFC_REQUIRE(!conf_prop || (confidence && grad_confidence), "conf_prop requires confidence and grad_confidence");
+    RDFC_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "bad shape (%d,%d,%d)", B, H, W);
+    RDFC_REQUIRE(affinity >= RDFC_AFF_AS && affinity <= RDFC_AFF_TGASS, "unknown affinity mode %d", affinity);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (conf_prop) RDFC_CUDA(cudaMemsetAsync(grad_confidence, 0, sizeof(float) * (size_t)B * H * W, st));
+    if (grad_aff_scale) RDFC_CUDA(cudaMemsetAsync(grad_aff_scale, 0, sizeof(float), st));
+    dim3 grid(cdiv(W, TX), cdiv(H, TY), B), block(TX, TY);
+    nlspn_affinity_bwd_kernel<<<grid, block, 0, st>>>(guidance, confidence, conv_w, conv_b, aff_scale, affinity, conf_prop, offset,
+                                                      grad_offset, grad_aff, grad_conv, grad_confidence, grad_aff_scale, H, W);
+    RDFC_CHECK_LAUNCH("nlspn_affinity_bwd_kernel");
+    return 0;
 }
 
 extern "C" int rdfc_nlspn_propagate_backward(const float *grad_out, const float *grad_inter, const float *feat_init,

@@ -55,6 +55,48 @@ class _PropagateFused(torch.autograd.Function):
         return g_feat, g_off, g_aff, g_fix, None, None
 
 
+class _AffinityFused(torch.autograd.Function):
+    """Offsets + affinities (nlspn_model.py:68-138) as one differentiable op: forward = rdfc_nlspn_affinity_forward, backward =
+    rdfc_nlspn_affinity_backward (tanh / scale, confidence product with its transposed 1x1 DCN gathers, abs-sum normalisation,
+    aff_ref) followed by the backward of the 8 -> 24 channel conv_offset_aff, which is left to cuDNN (0.24 GFLOP per image)."""
+
+    @staticmethod
+    def forward(ctx, guidance, confidence, weight, bias, aff_scale, affinity, conf_prop):
+        B, _, H, W = guidance.shape
+        guidance, weight, bias = guidance.contiguous(), weight.contiguous(), bias.contiguous()
+        conf = confidence.contiguous() if (conf_prop and confidence is not None) else None
+        offset = torch.empty((B, 18, H, W), dtype=torch.float32, device=guidance.device)
+        aff = torch.empty((B, 9, H, W), dtype=torch.float32, device=guidance.device)
+        scale = aff_scale.detach().contiguous()
+        with torch.cuda.device(guidance.device):
+            C.check(C.lib.rdfc_nlspn_affinity_forward(
+                C.ptr(guidance), C.ptr(conf), C.ptr(weight), C.ptr(bias), C.ptr(scale), C.AFFINITY[affinity], int(bool(conf_prop)),
+                C.ptr(offset), C.ptr(aff), B, H, W, C.stream_ptr(guidance.device)))
+        ctx.save_for_backward(guidance, conf if conf is not None else guidance.new_empty(0), weight, bias, scale, offset)
+        ctx.cfg = (affinity, bool(conf_prop), conf is not None)
+        return offset, aff
+
+    @staticmethod
+    def backward(ctx, g_offset, g_aff):
+        guidance, conf, weight, bias, scale, offset = ctx.saved_tensors
+        affinity, conf_prop, has_conf = ctx.cfg
+        B, _, H, W = guidance.shape
+        g_conv = torch.empty((B, 24, H, W), dtype=torch.float32, device=guidance.device)
+        g_conf = torch.empty((B, 1, H, W), dtype=torch.float32, device=guidance.device) if has_conf else None
+        g_scale = torch.empty((1,), dtype=torch.float32, device=guidance.device) if affinity == 'TGASS' else None
+        with torch.cuda.device(guidance.device):
+            C.check(C.lib.rdfc_nlspn_affinity_backward(
+                C.ptr(guidance), C.ptr(conf) if has_conf else None, C.ptr(weight), C.ptr(bias), C.ptr(scale), C.AFFINITY[affinity],
+                int(conf_prop and has_conf), C.ptr(offset), C.ptr(g_offset.contiguous()), C.ptr(g_aff.contiguous()), C.ptr(g_conv),
+                C.ptr(g_conf), C.ptr(g_scale), B, H, W, C.stream_ptr(guidance.device)))
+        need = ctx.needs_input_grad
+        g_guid = torch.nn.grad.conv2d_input(guidance.shape, weight, g_conv, padding=1) if need[0] else None
+        g_w = torch.nn.grad.conv2d_weight(guidance, weight.shape, g_conv, padding=1) if need[2] else None
+        g_b = g_conv.sum((0, 2, 3)) if need[3] else None
+        return (g_guid, g_conf if (has_conf and need[1]) else None, g_w, g_b,
+                g_scale if (g_scale is not None and need[4]) else None, None, None)
+
+
 class NLPSN(nn.Module):
     def __init__(self, channels_g, channels_f, k_g, k_f, prop_time=1, affinity=None, affinity_gamma=0.5,
                  conf_prop=True, preserve_input=False):
@@ -157,6 +199,11 @@ class NLPSN(nn.Module):
         C.require_cuda(guidance, confidence)
         if self._fused_ok(guidance, confidence):
             return self._get_offset_affinity_fused(guidance, confidence if self.conf_prop else None)
+        if (self.fused_backward and self.k_f == 3 and self.k_g == 3 and guidance.dtype == torch.float32 and
+                (confidence is None or confidence.dtype == torch.float32)):
+            # training: one differentiable op (see _AffinityFused)
+            return _AffinityFused.apply(guidance, confidence if self.conf_prop else None, self.conv_offset_aff.weight,
+                                        self.conv_offset_aff.bias, self.aff_scale_const, self.affinity, self.conf_prop)
         B, _, H, W = guidance.shape
         offset_aff = self.conv_offset_aff(guidance)
         o1, o2, aff = torch.chunk(offset_aff, 3, dim=1)

@@ -130,7 +130,7 @@ def test_fused_backward_vs_oracle(preserve):
         assert err <= 1e-4 * max(1.0, want.abs().max().item()), (name, err, want.abs().max().item())
 
 
-@pytest.mark.parametrize("name", ["tgass18", "as12_preserve"])
+@pytest.mark.parametrize("name", ["tgass18", "as12_preserve", "tc12_noconf", "ass18"])
 def test_fused_backward_matches_composition(name):
     """Training through NLSPNRefineModule: the fused forward/backward pair gives the gradients of the reference's composition
     (prop_time DCN Function calls) for the guidance, the initial depth and conv_offset_aff."""
@@ -145,10 +145,15 @@ def test_fused_backward_matches_composition(name):
         mod.prop_layer.fused_backward = fused
         g = t["guidance"].clone().requires_grad_(True)
         p = t["pred_init"].clone().requires_grad_(True)
-        y, _ = mod(p, g, t["confidence"], t["feat_fix"])
+        cf = t["confidence"].clone().requires_grad_(True)
+        y, _ = mod(p, g, cf, t["feat_fix"])
         y.backward(gout)
-        grads[fused] = (y.detach(), g.grad, p.grad, mod.prop_layer.conv_offset_aff.weight.grad, mod.prop_layer.conv_offset_aff.bias.grad)
-    for a, b, nm in zip(grads[True], grads[False], ("y", "d guidance", "d pred_init", "d conv w", "d conv b")):
+        grads[fused] = (y.detach(), g.grad, p.grad, mod.prop_layer.conv_offset_aff.weight.grad, mod.prop_layer.conv_offset_aff.bias.grad,
+                        mod.prop_layer.aff_scale_const.grad, cf.grad if cfg["conf_prop"] else None)
+    assert grads[True][5] is not None or cfg["affinity"] != "TGASS"
+    for a, b, nm in zip(grads[True], grads[False], ("y", "d guidance", "d pred_init", "d conv w", "d conv b", "d aff_scale", "d confidence")):
+        if a is None and b is None:
+            continue
         scale = max(1.0, b.abs().max().item())
         assert (a - b).abs().max().item() <= 2e-4 * scale, (nm, (a - b).abs().max().item(), scale)
 
