@@ -75,7 +75,9 @@ def main():
                 a = a[a[:, 0] > 0]
                 print(f"role timers for step '{n}' (cycles, median over {len(a)} CTAs; CTA lifetime max {a[:, 13].max():.0f}, "
                       f"last CTA end - first CTA end {(a[:, 14].max() - a[:, 14].min()) / 1e3:.1f} us, "
-                      f"first start -> last end {(a[:, 14].max() - a[:, 15].min()) / 1e3:.1f} us):")
+                      f"first start -> last end {(a[:, 14].max() - a[:, 15].min()) / 1e3:.1f} us, "
+                      f"last start - first start {(a[:, 15].max() - a[:, 15].min()) / 1e3:.1f} us, "
+                      f"CTA lifetime min {a[:, 13].min():.0f}):")
                 for i, nm in names.items():
                     print(f"   {nm:20s} {np.median(a[:, i]):10.0f}  ({100*np.median(a[:, i])/np.median(a[:, 0]):5.1f}%)")
     if out_json:
