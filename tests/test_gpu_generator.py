@@ -124,3 +124,29 @@ def test_stream_matches_forward(precision):
             assert torch.equal(g[k], w[k]), k
     only = list(G.stream(iter(batches[:1]), outputs=("pred_depth",)))
     assert list(only[0]) == ["pred_depth"] and torch.equal(only[0]["pred_depth"], want[0]["pred_depth"])
+
+
+def test_sunrgbd_shape_480x640_oracle_and_bf16():
+    """BASELINE.json config 5 (SUN RGB-D shape 480x640, NLSPN 18 iterations): fp32 mode against the CPU oracle on one image,
+    the bf16 tensor-core plan against the fp32 plan on a batch of three (tiles that straddle nothing at 228x304 do here:
+    480 = 30 x 16 rows, 640 = 80 x 8 columns, 60x80 / 30x40 / 15x20 at the deeper levels)."""
+    from oracle import generator as ogen
+    from rdfc_gan_b200.generator import RDFGenerator
+    kw = GEN_CASES["rdfc_full_init"][0]
+    G = RDFGenerator(pretrained_on_imagenet=False, **kw).eval()
+    sd = synth_state_dict(G, seed=77, recipe="init", nlspn_stress=True)
+    G.load_state_dict(sd)
+    rgb, stem, depth = synth_inputs(3, 480, 640, seed=77)
+    G = G.cuda().set_precision("fp32")
+    with torch.no_grad():
+        out32 = G(rgb.cuda(), depth.cuda(), stem.cuda())
+    ref = ogen.generator_forward({k: v.cpu() for k, v in G.state_dict().items()}, stem[:1], depth[:1], use_nlspn_refine=True,
+                                 nlspn_configs=kw["nlspn_configs"])
+    for k in KEYS:
+        assert (out32[k][:1].cpu() - ref[k]).abs().max() <= FP32_TOL, k
+    G.set_precision("bf16")
+    with torch.no_grad():
+        out16 = G(rgb.cuda(), depth.cuda(), stem.cuda())
+    for k in KEYS:
+        d = (out16[k].float() - out32[k]).cpu().numpy()
+        assert np.sqrt(np.mean(d ** 2)) <= 2e-3 and np.abs(d).max() <= 2e-2, (k, np.sqrt(np.mean(d ** 2)), np.abs(d).max())
