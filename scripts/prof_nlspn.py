@@ -24,6 +24,9 @@ def main():
         G(rgb.to(dev), depth.to(dev), normal.to(dev))
     plan = next(iter(G.engine()._plans.values()))
     T, H, W = 18, bench.H, bench.W
+    if os.environ.get("OFFSCALE"):          # how does the band halo behave with larger offsets?
+        plan.offset.mul_(float(os.environ["OFFSCALE"]))
+        print("offset std now", float(plan.offset.std()))
 
     def prop():
         C.check(C.lib.rdfc_nlspn_propagate_forward(C.ptr(plan.pred_init), C.ptr(plan.offset), C.ptr(plan.aff), None, 0,

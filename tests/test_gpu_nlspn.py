@@ -173,3 +173,26 @@ def test_fused_backward_full_size_linearity():
     lhs = (y.double() * g1.double()).sum().item()          # <A f, g>
     rhs = (f.detach().double() * gf.double()).sum().item()  # <f, A^T g>
     assert abs(lhs - rhs) <= 1e-3 * max(1.0, abs(lhs)), (lhs, rhs)
+
+
+@pytest.mark.parametrize("halo", [None, "0", "2", "12"])
+def test_large_offsets_leave_the_staged_band(halo, monkeypatch):
+    """Offsets far larger than the band kernel's halo (sigma = 7 px, some beyond the image): taps that leave the staged band
+    take the global-memory path; every halo setting (RDFC_NLSPN_HALO) must give the oracle's numbers."""
+    from oracle import dcn as odcn
+    from rdfc_gan_b200 import _cabi as C
+    if halo is not None:
+        monkeypatch.setenv("RDFC_NLSPN_HALO", halo)
+    B, H, W, T = 3, 70, 92, 4
+    rng = np.random.default_rng(17)
+    off = (7.0 * rng.standard_normal((B, 18, H, W))).astype(np.float32)
+    off[:, 8:10] = 0
+    aff = rng.uniform(-1, 1, (B, 9, H, W)).astype(np.float32)
+    aff /= np.abs(aff).sum(1, keepdims=True)
+    f = rng.standard_normal((B, 1, H, W)).astype(np.float32)
+    ref = odcn.nlspn_propagate(f, off, aff, None, False, 3, T)
+    tf, to, ta = (torch.from_numpy(v).cuda() for v in (f, off, aff))
+    out, scratch = torch.empty_like(tf), torch.empty_like(tf)
+    C.check(C.lib.rdfc_nlspn_propagate_forward(C.ptr(tf), C.ptr(to), C.ptr(ta), None, 0, C.ptr(out), C.ptr(scratch), None,
+                                               B, H, W, T, 0, C.stream_ptr()))
+    assert np.abs(out.cpu().numpy() - ref).max() <= TOL
