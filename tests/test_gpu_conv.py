@@ -310,3 +310,36 @@ def test_cp_async_producer_fallback_matches(shape, monkeypatch):
     monkeypatch.setenv("RDFC_UMMA_TMA", "0")
     cpasync = _run_conv(x, w, scale, shift, **kw)
     assert torch.equal(tma, cpasync)
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 36, 52, 1), (2, 64, 128, 37, 50, 2), (1, 128, 256, 30, 44, 2), (2, 256, 256, 19, 26, 1)])
+def test_conv_input_grad_on_the_forward_kernel(case):
+    """rdfc_gan_b200.conv_grad: dgrad of the generator's 3x3 convs as stride-1 / transposed convs on the tensor-core kernel,
+    against torch.nn.grad.conv2d_input on the same bf16-rounded operands."""
+    from rdfc_gan_b200.conv_grad import conv2d_input_grad
+    B, Cin, Cout, H, W, stride = case
+    gen = torch.Generator().manual_seed(sum(case))
+    w = (torch.randn(Cout, Cin, 3, 3, generator=gen) / math.sqrt(Cout * 9)).bfloat16().float()
+    Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    go = torch.randn(B, Cout, Ho, Wo, generator=gen).bfloat16().float()
+    ref = torch.nn.grad.conv2d_input((B, Cin, H, W), w.double(), go.double(), stride=stride, padding=1).float()
+    got = conv2d_input_grad(go.permute(0, 2, 3, 1).bfloat16().contiguous().cuda(), w.cuda(), stride, (H, W))
+    got = got.float().permute(0, 3, 1, 2).cpu()
+    assert tuple(got.shape) == (B, Cin, H, W)
+    err = (got - ref).abs().max().item()
+    assert err <= 1.5e-2 * max(1.0, ref.abs().max().item()), (case, err)        # one bf16 rounding of the output
+
+
+def test_conv_transpose_input_grad_on_the_forward_kernel():
+    from rdfc_gan_b200.conv_grad import conv_transpose2d_input_grad
+    B, Cin, Cout, H, W = 2, 192, 64, 19, 26
+    gen = torch.Generator().manual_seed(4)
+    w = (torch.randn(Cin, Cout, 3, 3, generator=gen) / math.sqrt(Cout * 9)).bfloat16().float()
+    x = torch.zeros(B, Cin, H, W, dtype=torch.double, requires_grad=True)
+    y = F.conv_transpose2d(x, w.double(), None, stride=2, padding=1, output_padding=1)
+    go = torch.randn(y.shape, generator=gen).bfloat16().float()
+    (ref,) = torch.autograd.grad(y, x, go.double())
+    got = conv_transpose2d_input_grad(go.permute(0, 2, 3, 1).bfloat16().contiguous().cuda(), w.cuda())
+    got = got.float().permute(0, 3, 1, 2).cpu()
+    assert tuple(got.shape) == (B, Cin, H, W)
+    assert (got - ref.float()).abs().max().item() <= 1.5e-2 * max(1.0, ref.abs().max().item())
