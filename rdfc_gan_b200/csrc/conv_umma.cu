@@ -21,9 +21,12 @@
 //                   1/2/2/4-tap conv over the input grid.
 //                   (warps 0-5 are cp.async producers of a no-swizzle [cin/8][pixel][16 B] layout when RDFC_UMMA_TMA=0,
 //                   and the im2col builders of the fused input stems.)
-//       warp 7      B loader: one pre-packed (filter row, 32-cin, BN) block per stage, cp.async.bulk (TMA 1-D).
+//       warp 7      B loader: one stage = the pre-packed (32-cin, BN) filter blocks of all nine taps of a k-block (3x3 convs
+//                   with N <= 128; one filter row = 3 taps when two such stages do not fit), cp.async.bulk (TMA 1-D) issued
+//                   by all lanes.
 //       warp 6      MMA issuer: convergent loop, one elected lane issues tcgen05.mma (M=128, N=BN, K=16) and frees
-//                   stages with tcgen05.commit.
+//                   stages with tcgen05.commit.  In TMA mode warp 5 is a second issuer for tiles of >= 2 accumulators
+//                   (each issuer owns half of them; both commit on the same barriers).
 //       warps 8-15  epilogue: tcgen05.ld 32x32b.x16 -> y = act(acc*scale + shift + residual) -> bf16 NHWC channel
 //                   slice (this is how every torch.cat of the reference disappears); mode 2 applies W-AdaIN, mode 3
 //                   turns the 9 * ncols head columns into fp32 planes by a shift-add through shared memory.  TMEM holds
