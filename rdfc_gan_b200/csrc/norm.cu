@@ -86,13 +86,23 @@ __global__ void __launch_bounds__(256) in_final_kernel(const float *__restrict__
     const int b = blockIdx.x;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float mean = 0.f, m2 = 0.f, n = 0.f;
-        for (int k = 0; k < nchunk; ++k) {
-            const float *p = partial + (((long long)b * nchunk + k) * C + c) * 2;
-            const float nb = (float)min(CHUNK_PIX, npix - k * CHUNK_PIX);
-            const float delta = p[0] - mean, nn = n + nb;
-            mean += delta * nb / nn;
-            m2 += p[1] + delta * delta * n * nb / nn;
-            n = nn;
+        // the combination is a serial chain, the loads are not: fetch eight chunks' partials at once (one L2 round trip per
+        // eight chunks instead of one per chunk), then combine them in chunk order as before
+        for (int k0 = 0; k0 < nchunk; k0 += 8) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (k0 + u < nchunk) v[u] = __ldg(reinterpret_cast<const float2 *>(partial + (((long long)b * nchunk + k0 + u) * C + c) * 2));
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (k0 + u < nchunk) {
+                    const int k = k0 + u;
+                    const float nb = (float)min(CHUNK_PIX, npix - k * CHUNK_PIX);
+                    const float delta = v[u].x - mean, nn = n + nb;
+                    mean += delta * nb / nn;
+                    m2 += v[u].y + delta * delta * n * nb / nn;
+                    n = nn;
+                }
         }
         const float var = m2 / (unbiased ? (n - 1.f) : n) + eps;
         mean_o[(long long)b * C + c] = mean;
