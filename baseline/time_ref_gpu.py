@@ -114,6 +114,27 @@ def full_generator():
               f"max-abs diff vs reference: fp32 mode {diff32:.2e} (reference with TF32 convs, torch's default: {diff_tf32:.2e}), bf16 mode {diff16:.2e}" + ("" if B == 1 else "  (B > 1: reference quirk 5)"))
 
 
+def json_mode(gen, B, H, W):
+    """bench.py's `ref_gpu`: the unmodified reference generator on this GPU (its own DCN extension, PyTorch/cuDNN convs with
+    torch's default TF32 setting), same synthetic weights and inputs as the bench.  Imports nothing of the product package."""
+    import json
+    import bench
+    import ref_loader
+    from _synth import synth_inputs
+    cfg = dict(bench.CONFIGS["c3" if gen == "rdfc" else "c2"], H=H, W=W)
+    G = bench.build_reference(cfg, gpu=True).cuda()
+    rgb, stem, depth = (t.cuda() for t in synth_inputs(B, H, W, seed=0, Cs=cfg["cs"]))
+    with torch.no_grad():
+        t = timeit(lambda: bench.call_generator(G, cfg, rgb, stem, depth), reps=5)
+    print(json.dumps({"value": B / t * 1e3, "unit": "maps/s", "ms_per_step": t, "batch": B,
+                      "what": "unmodified reference generator (PyTorch/cuDNN fp32, TF32 convs allowed = torch default) + its own DCN "
+                              "CUDA extension compiled for sm_100a, same GPU, same weights / inputs; median of 5"}))
+
+
 if __name__ == "__main__":
-    main()
-    full_generator()
+    if len(sys.argv) > 1 and sys.argv[1] == "--json":
+        sys.path.insert(0, HERE)
+        json_mode(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+    else:
+        main()
+        full_generator()

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RDFC_ABI_VERSION 1
+#define RDFC_ABI_VERSION 2
 
 typedef enum {
     RDFC_OK = 0,
@@ -88,13 +88,36 @@ int rdfc_nlspn_affinity_forward(const float *guidance, const float *confidence, 
                                 const float *conv_b, const float *aff_scale, int affinity, int conf_prop,
                                 float *offset, float *aff, int B, int H, int W, void *stream);
 
+/* Optional output fusion applied by the LAST propagation iteration (rdf_generator.py:401-406): the result is clamped to [-1,1]
+ * (= depth_map_2, written to `out`) and  pred = softmax([c1, c2]) . [d1, clamp(result)]  is written as well.  All (B,1,H,W) fp32. */
+typedef struct {
+    const float *d1, *c1, *c2;
+    float *pred;
+} rdfc_fuse_out;
+
 /* feat_init (B,1,H,W); offset (B,18,H,W); aff (B,9,H,W); feat_fix (B,1,H,W) or NULL; out (B,1,H,W);
  * scratch: B*H*W floats (ping-pong buffer, may not alias anything else);
  * inter: NULL or prop_time*B*H*W floats receiving every iteration's result (the reference's list_feat).
- * clamp_out != 0 additionally clamps the final result to [-1,1] (rdf_generator.py:401). */
+ * preserve_input: every iteration reads feat blended with feat_fix where feat_fix > 0 (nlspn_model.py:159-160,169; folded into the
+ * kernel's staging).  clamp_out != 0 additionally clamps the final result to [-1,1] (rdf_generator.py:401); fuse: NULL or the
+ * output fusion above (implies the clamp). */
 int rdfc_nlspn_propagate_forward(const float *feat_init, const float *offset, const float *aff,
                                  const float *feat_fix, int preserve_input, float *out, float *scratch,
-                                 float *inter, int B, int H, int W, int prop_time, int clamp_out, void *stream);
+                                 float *inter, int B, int H, int W, int prop_time, int clamp_out,
+                                 const rdfc_fuse_out *fuse, void *stream);
+
+/* The same two stages over a PACKED fp16 stream instead of the fp32 offset / aff planes (bf16 inference mode): per pixel 24
+ * halves = (dy, dx) of the 8 non-centre taps + their 8 affinities (the centre tap's offset is zero and its affinity is
+ * 1 - sum of the rounded others, so every iteration stays an exact affine combination): 48 B instead of 100 B streamed per
+ * pixel and iteration.  Pixel g = b*H*W + y*W + x is stored as three 16-byte chunks at byte offset
+ * (g/32)*1536 + c*512 + (g%32)*16, c = 0..2.  `packed`: 16-byte aligned, rdfc_nlspn_packed_bytes(B,H,W) bytes. */
+size_t rdfc_nlspn_packed_bytes(int B, int H, int W);
+int rdfc_nlspn_affinity_forward_packed(const float *guidance, const float *confidence, const float *conv_w,
+                                       const float *conv_b, const float *aff_scale, int affinity, int conf_prop,
+                                       void *packed, int B, int H, int W, void *stream);
+int rdfc_nlspn_propagate_forward_packed(const float *feat_init, const void *packed, const float *feat_fix,
+                                        int preserve_input, float *out, float *scratch, int B, int H, int W,
+                                        int prop_time, int clamp_out, const rdfc_fuse_out *fuse, void *stream);
 
 /* Backward of rdfc_nlspn_affinity_forward up to the conv output (training): grad_offset (B,18,H,W), grad_aff (B,9,H,W) ->
  * grad_conv (B,24,H,W) = dL/d conv_offset_aff(guidance) (the caller back-propagates the 8 -> 24 channel conv itself),
@@ -249,6 +272,13 @@ int rdfc_norm_apply(const rdfc_view *x, const float *mean, const float *rstd, co
 int rdfc_depth_metric_nchunk(long long n);
 int rdfc_depth_metric_sums(const float *pred, const float *gt, const unsigned char *evaluate_mask, float std, float mean,
                            float t_valid, double *sums, double *partial, int B, long long n, void *stream);
+
+/* ------------------------------------------------------------------ development aids ------------------------- */
+/* Not part of the drop-in boundary.  rdfc_dev_set_knob overrides a development knob (the RDFC_* environment variables, which
+ * the library reads once per name); value INT64_MIN restores the default.  rdfc_dev_umma_timers copies the per-role cycle
+ * counters of the last conv launch made under RDFC_UMMA_DBG=1 (a -DRDFC_UMMA_TIMERS build) to `host`. */
+int rdfc_dev_set_knob(const char *name, long long value);
+int rdfc_dev_umma_timers(long long *host, int n);
 
 #ifdef __cplusplus
 }

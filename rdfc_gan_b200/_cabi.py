@@ -18,6 +18,10 @@ _DT = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
 c_int, c_void_p, c_float = ctypes.c_int, ctypes.c_void_p, ctypes.c_float
 
 
+class FuseOut(ctypes.Structure):
+    _fields_ = [("d1", c_void_p), ("c1", c_void_p), ("c2", c_void_p), ("pred", c_void_p)]
+
+
 class DcnShape(ctypes.Structure):
     _fields_ = [(n, c_int) for n in ("B", "Cin", "H", "W", "Cout", "kh", "kw", "sh", "sw", "ph", "pw", "dh", "dw",
                                      "group", "deformable_group", "im2col_step")]
@@ -63,7 +67,12 @@ def _load():
     lib.rdfc_dcn_out_size.argtypes = [ctypes.POINTER(DcnShape), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
     lib.rdfc_nlspn_affinity_forward.argtypes = [c_void_p] * 5 + [c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                                                 c_void_p]
-    lib.rdfc_nlspn_propagate_forward.argtypes = [c_void_p] * 4 + [c_int] + [c_void_p] * 3 + [c_int] * 5 + [c_void_p]
+    lib.rdfc_nlspn_propagate_forward.argtypes = [c_void_p] * 4 + [c_int] + [c_void_p] * 3 + [c_int] * 5 + [ctypes.POINTER(FuseOut), c_void_p]
+    lib.rdfc_nlspn_packed_bytes.argtypes = [c_int] * 3
+    lib.rdfc_nlspn_packed_bytes.restype = ctypes.c_size_t
+    lib.rdfc_nlspn_affinity_forward_packed.argtypes = [c_void_p] * 5 + [c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.rdfc_nlspn_propagate_forward_packed.argtypes = [c_void_p] * 3 + [c_int] + [c_void_p] * 2 + [c_int] * 5 + [ctypes.POINTER(FuseOut), c_void_p]
+    lib.rdfc_dev_set_knob.argtypes = [ctypes.c_char_p, ctypes.c_longlong]
     lib.rdfc_depth_metric_nchunk.argtypes = [ctypes.c_longlong]
     lib.rdfc_depth_metric_sums.argtypes = [c_void_p] * 3 + [ctypes.c_float] * 3 + [c_void_p] * 2 + [c_int, ctypes.c_longlong, c_void_p]
     lib.rdfc_nlspn_affinity_backward.argtypes = [c_void_p] * 5 + [c_int] * 2 + [c_void_p] * 6 + [c_int] * 3 + [c_void_p]
@@ -90,8 +99,19 @@ lib = _load()
 
 EXPORTS = ["rdfc_abi_version", "rdfc_last_error", "rdfc_launch_count", "rdfc_dcn_out_size", "rdfc_dcn_forward",
            "rdfc_dcn_backward", "rdfc_nlspn_affinity_forward", "rdfc_nlspn_propagate_forward", "rdfc_nlspn_propagate_backward", "rdfc_nlspn_affinity_backward",
+           "rdfc_nlspn_packed_bytes", "rdfc_nlspn_affinity_forward_packed", "rdfc_nlspn_propagate_forward_packed",
            "rdfc_fuse_depth_forward", "rdfc_conv_forward", "rdfc_heads_forward", "rdfc_instnorm_nchunk", "rdfc_instnorm_stats",
-           "rdfc_wadain_apply", "rdfc_adain_apply", "rdfc_norm_apply", "rdfc_depth_metric_nchunk", "rdfc_depth_metric_sums"]
+           "rdfc_wadain_apply", "rdfc_adain_apply", "rdfc_norm_apply", "rdfc_depth_metric_nchunk", "rdfc_depth_metric_sums", "rdfc_stem_forward", "rdfc_pack_stem_input",
+           "rdfc_wadain_tile", "rdfc_wadain_conv_forward", "rdfc_dev_set_knob", "rdfc_dev_umma_timers"]
+
+
+KNOB_UNSET = -(1 << 63)
+
+
+def set_knob(name, value=None):
+    """Development knobs (the RDFC_* environment variables, cached by the library on first use): override one at run time;
+    value None restores the default."""
+    check(lib.rdfc_dev_set_knob(name.encode(), KNOB_UNSET if value is None else int(value)))
 
 
 def check(rc):

@@ -40,6 +40,10 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 // number of SMs of the current device (cached)
 int sm_count();
 
+// development knob `name` (an RDFC_* environment variable, read once and cached; rdfc_dev_set_knob overrides it), or dflt
+constexpr long long KNOB_UNSET = (long long)0x8000000000000000ull;
+long long knob(const char *name, long long dflt);
+
 // ---- storage helpers: fp32 compute, fp32 / bf16 storage -------------------------------------------------------
 __device__ __forceinline__ float ldf(const float *p) { return __ldg(p); }
 __device__ __forceinline__ float ldf(const __nv_bfloat16 *p) { return __bfloat162float(*p); }

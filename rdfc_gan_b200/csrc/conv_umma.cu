@@ -1156,7 +1156,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     }
     if (k1 && P.CoutP % 256 == 0) bn_max = 256;                          // 1x1: the A stage feeds one tap only, so widen N
     if (wad) bn_max = wadain_tile(wad->x.C);
-    if (const char *e = getenv("RDFC_UMMA_BN")) bn_max = atoi(e);        // development knob
+    if (const long long e = knob("RDFC_UMMA_BN", KNOB_UNSET); e != KNOB_UNSET) bn_max = (int)e;        // development knob
     P.bn = P.CoutP < bn_max ? P.CoutP : bn_max;
     while (P.CoutP % P.bn) P.bn -= 16;   // largest multiple of 16 <= bn_max dividing the padded Cout
     P.n_tiles_n = P.CoutP / P.bn;
@@ -1176,9 +1176,9 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     }
     while (P.nacc > 1 && (P.Wt <= 8 * (P.nacc - 1) || pixels / (128 * P.nacc) * P.n_tiles_n < sm_count())) --P.nacc;
     if (d->stride == 2 && !d->transposed && k3 && P.nacc > 2) P.nacc = 2;   // four parity planes: keep the stage small
-    if (const char *e = getenv("RDFC_UMMA_NACC")) P.nacc = atoi(e);      // development knob
+    if (const long long e = knob("RDFC_UMMA_NACC", KNOB_UNSET); e != KNOB_UNSET) P.nacc = (int)e;      // development knob
     if (heads) P.nacc = 2;                                               // 16 x 16 pixel regions (see MODE_HEADS)
-    if (const char *e = getenv("RDFC_UMMA_NSETS")) P.nsets = atoi(e);    // development knob
+    if (const long long e = knob("RDFC_UMMA_NSETS", KNOB_UNSET); e != KNOB_UNSET) P.nsets = (int)e;    // development knob
     if (P.nsets * P.nacc * P.bn > 512) P.nsets = 1;
     // arrange the accumulators nax across x nay down so that the padded tile grid wastes the fewest pixels
     {
@@ -1191,7 +1191,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
             const long long score = area * 100 + (nax == nay ? 0 : area * 3);
             if (best < 0 || score < best) { best = score; P.nax = nax; }
         }
-        if (const char *e = getenv("RDFC_UMMA_NAX")) P.nax = atoi(e);    // development knob
+        if (const long long e = knob("RDFC_UMMA_NAX", KNOB_UNSET); e != KNOB_UNSET) P.nax = (int)e;    // development knob
         if (heads) P.nax = 2;
     }
     const int TW = 8 * P.nax, TH = rdfc::TH * (P.nacc / P.nax);
@@ -1205,7 +1205,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     // A operand through TMA tensor-map loads unless the producers have to build it (stem mode) or the driver entry
     // point is missing; RDFC_UMMA_TMA=0 forces the cp.async producers (development knob)
     P.a_tma = !stem && tmap_encoder() != nullptr;
-    if (const char *e = getenv("RDFC_UMMA_TMA")) P.a_tma = P.a_tma && atoi(e) != 0;
+    if (const long long e = knob("RDFC_UMMA_TMA", KNOB_UNSET); e != KNOB_UNSET) P.a_tma = P.a_tma && (int)e != 0;
     P.px16 = P.a_tma ? 4 : 1;
     // CTA pairs (tcgen05 cta_group::2, RDFC_UMMA_PAIR=1): each CTA stages half of every filter block and one stream of M = 256
     // MMAs issued by the leader covers both CTAs' pixel tiles.  Correct (tests/test_gpu_conv.py runs it) but OFF by default:
@@ -1213,9 +1213,9 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     // per M=256 N=128 MMA and 221 us, against 88 cycles per M=128 MMA and 166 us), and 1x1 / transposed convs lose 2x to the
     // extra barrier hops (a peer's TMA cannot complete on the leader's mbarrier, so its "full" signals are forwarded).
     P.pair = 0;
-    if (const char *e = getenv("RDFC_UMMA_PAIR")) P.pair = P.a_tma && P.bn % 32 == 0 && atoi(e) != 0;
+    if (const long long e = knob("RDFC_UMMA_PAIR", KNOB_UNSET); e != KNOB_UNSET) P.pair = P.a_tma && P.bn % 32 == 0 && (int)e != 0;
     P.dual = P.a_tma && !P.pair && P.nacc >= 2;
-    if (const char *e = getenv("RDFC_UMMA_DUAL")) P.dual = P.dual && atoi(e) != 0;      // development knob
+    if (const long long e = knob("RDFC_UMMA_DUAL", KNOB_UNSET); e != KNOB_UNSET) P.dual = P.dual && (int)e != 0;      // development knob
     P.ntiles = (P.pair ? (P.tiles_x * P.tiles_y + 1) / 2 : P.tiles_x * P.tiles_y) * P.B * P.nphases * P.n_tiles_n;   // pair mode: pairs of tiles
     Phase phases[4] = {};
     int base = 0;
@@ -1324,7 +1324,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     // not overlap (role timers: issue is blocking at the pipe's rate), so a 3x3 conv stages all nine taps of a k-block at once
     // when two such stages and two A stages fit.
     if (k3 && !d->transposed && !stem && 2 * a_stage + 2 * 9 * KCH * (P.pair ? P.bn / 2 : P.bn) * 16 + fixed <= budget) P.gtaps = 9;
-    if (const char *e = getenv("RDFC_UMMA_GTAPS")) P.gtaps = atoi(e);    // development knob (1, 3 or 9)
+    if (const long long e = knob("RDFC_UMMA_GTAPS", KNOB_UNSET); e != KNOB_UNSET) P.gtaps = (int)e;    // development knob (1, 3 or 9)
     const int b_stage = P.gtaps * KCH * (P.pair ? P.bn / 2 : P.bn) * 16;
     // A ring first (>= 2 stages: the producers publish k-block i while k-block i+1 is in flight), then B stages (2..6)
     // the filter stream is latency-bound: bytes in flight per SM = bandwidth x L2 latency (~2000 cycles), so keep
@@ -1337,33 +1337,35 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
         if (P.sb < 3) P.sb = P.gtaps == 9 ? 2 : 3;
         if (P.sb > 16) P.sb = 16;
     }
-    if (const char *e = getenv("RDFC_UMMA_SB")) P.sb = atoi(e);          // development knob (<= 16)
+    if (const long long e = knob("RDFC_UMMA_SB", KNOB_UNSET); e != KNOB_UNSET) P.sb = (int)e;          // development knob (<= 16)
     while (P.sb > 3 && 3 * a_stage + P.sb * b_stage + fixed > budget) --P.sb;     // prefer >= 3 A stages (2 in flight)
     while (P.sb > 2 && 2 * a_stage + P.sb * b_stage + fixed > budget) --P.sb;
     P.sa = (budget - fixed - P.sb * b_stage) / a_stage;
     if (P.sa > 6) P.sa = 6;
-    if (const char *e = getenv("RDFC_UMMA_SA")) P.sa = atoi(e) < P.sa ? atoi(e) : P.sa;
+    if (const long long e = knob("RDFC_UMMA_SA", KNOB_UNSET); e != KNOB_UNSET) P.sa = (int)e < P.sa ? (int)e : P.sa;
     RDFC_REQUIRE(P.sa >= 1 && P.sa <= 8 && P.sb >= 1 && P.sb <= 16, "UMMA conv: tile does not fit shared memory");
     const size_t smem = (size_t)P.sa * a_stage + (size_t)P.sb * b_stage + fixed + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                 // per device: the attribute belongs to the function ON a device
+    int dev_id = 0;
+    RDFC_CUDA(cudaGetDevice(&dev_id));
+    if (!attr_set[dev_id & 63]) {
 #define RDFC_SMEM_ATTR(M)                                                                                                      \
     RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));       \
     RDFC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
         RDFC_SMEM_ATTR(MODE_STD); RDFC_SMEM_ATTR(MODE_GENERAL); RDFC_SMEM_ATTR(MODE_WADAIN); RDFC_SMEM_ATTR(MODE_HEADS);
 #undef RDFC_SMEM_ATTR
-        attr_set = true;
+        attr_set[dev_id & 63] = true;
     }
-    if (const char *e = getenv("RDFC_UMMA_SKIP")) P.dbg_flags = atoi(e);
+    if (const long long e = knob("RDFC_UMMA_SKIP", KNOB_UNSET); e != KNOB_UNSET) P.dbg_flags = (int)e;
     static long long *dbg_buf = nullptr;
-    if (getenv("RDFC_UMMA_DBG")) {
+    if (knob("RDFC_UMMA_DBG", 0)) {
         if (!dbg_buf) RDFC_CUDA(cudaMalloc(&dbg_buf, 148 * 16 * sizeof(long long)));
         RDFC_CUDA(cudaMemsetAsync(dbg_buf, 0, 148 * 16 * sizeof(long long), st));
         P.dbg = dbg_buf;
         g_dbg_buf = dbg_buf;
     }
     int grid = P.ntiles < sm_count() ? P.ntiles : sm_count();
-    if (const char *e = getenv("RDFC_UMMA_GRID")) grid = atoi(e) < P.ntiles ? atoi(e) : P.ntiles;   // development knob
+    if (const long long e = knob("RDFC_UMMA_GRID", KNOB_UNSET); e != KNOB_UNSET) grid = (int)e < P.ntiles ? (int)e : P.ntiles;   // development knob
     const int mode = heads ? MODE_HEADS : wad ? MODE_WADAIN
                      : (P.planar || P.act > RDFC_ACT_LEAKY02 || !P.vec32 || P.Cout % 16 != 0) ? MODE_GENERAL : MODE_STD;
     void (*kern)(Params) = nullptr;
@@ -1376,7 +1378,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     if (P.pair) {
         // one cluster of two CTAs per tile pair (P.ntiles counts pairs; grid = 2 x min(pairs, #SMs / 2))
         int pairs = P.ntiles < sm_count() / 2 ? P.ntiles : sm_count() / 2;
-        if (const char *e = getenv("RDFC_UMMA_GRID")) pairs = atoi(e) / 2 < pairs ? (atoi(e) / 2 > 0 ? atoi(e) / 2 : 1) : pairs;
+        if (const long long e = knob("RDFC_UMMA_GRID", KNOB_UNSET); e != KNOB_UNSET) pairs = (int)e / 2 < pairs ? ((int)e / 2 > 0 ? (int)e / 2 : 1) : pairs;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -1388,7 +1390,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
         // measured with the two-lane graph: early launch of the next conv takes SMs the other lane's CTAs would have used, and the
         // step does not get faster (10.61 / 10.63 ms with, 10.58 / 10.47 ms without), so it is off by default
         static int pdl = -1;
-        if (pdl < 0) { const char *e = getenv("RDFC_UMMA_PDL"); pdl = e ? atoi(e) != 0 : 0; }
+        if (pdl < 0) pdl = knob("RDFC_UMMA_PDL", 0) != 0;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute attr[1];

@@ -4,10 +4,12 @@
 // with a 1x1 kernel and ~25 small ATen kernels) by ONE kernel, and nlspn_model.py:140-144,166-173 (prop_time x
 // {columns alloc, im2col, addmm(K=9,N=1), permute+contiguous}) by one gather kernel per iteration with no
 // intermediate buffer.  The propagation is HBM / L2 bound: per pixel and iteration it streams 16 offsets + 9
-// affinities (the centre tap's offsets are identically zero and are not read), gathers 36 feature corners through
-// L1, and writes one float.  The host wrapper walks the batch in L2-sized image groups so that iterations 2..T of a
-// group find their offset/affinity planes in the 126 MB L2 instead of HBM.
+// affinities (the centre tap's offsets are identically zero and are not read), gathers 36 feature corners from a
+// shared-memory band, and writes one float.  One launch per iteration over the whole batch (walking the batch in L2-sized
+// groups was measured slower: the launches get too small).
 #include <stdlib.h>
+
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -15,13 +17,6 @@ namespace rdfc {
 namespace {
 
 constexpr int TX = 32, TY = 8;   // pixel tile of a CTA (one warp = one 32-pixel row segment -> coalesced planes)
-
-// streaming load: read-only, do not allocate in L1 (keeps L1 for the gathered feature map)
-__device__ __forceinline__ float ld_stream(const float *p) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
 
 // bilinear sample with the DCN validity rule and per-corner zeroing (deformconv/src/cuda/modulated_deform_im2col_cuda.cuh:25-54,180)
 __device__ __forceinline__ float bilinear(const float *__restrict__ im, int H, int W, float y, float x) {
@@ -45,13 +40,16 @@ __device__ __forceinline__ float bilinear(const float *__restrict__ im, int H, i
 //   3. affinity: AS/ASS raw, TC tanh/scale, TGASS tanh/(scale+1e-8)                           (:82-87)
 //   4. conf_prop: aff_j *= bilinear(confidence, h + dy_j, w + dx_j)  (1x1 kernel, pad 0)       (:96-119)
 //   5. normalise by max(sum|aff| + 1e-4, 1) (ASS/TGASS) or sum|aff| + 1e-4 (AS); aff_ref = 1 - sum  (:122-136)
+//   6. output: fp32 planes offset (B,18,H,W) / aff (B,9,H,W) in the reference's layout, or (kPacked) the fp16 stream the
+//      packed propagation kernel reads: 24 halves per pixel, see below
+template <bool kPacked>
 __global__ void __launch_bounds__(TX *TY) nlspn_affinity_kernel(const float *__restrict__ guidance,
                                                                 const float *__restrict__ confidence,
                                                                 const float *__restrict__ conv_w,
                                                                 const float *__restrict__ conv_b,
                                                                 const float *__restrict__ aff_scale, int affinity,
                                                                 int conf_prop, float *__restrict__ offset,
-                                                                float *__restrict__ aff, int H, int W) {
+                                                                float *__restrict__ aff, uint4 *__restrict__ packed, int H, int W) {
     __shared__ __align__(16) float s_w[72 * 24];     // [(ci*9 + tap)][24 outputs]: one LDS.128 feeds 4 FMAs
     __shared__ float s_b[24];
     __shared__ float s_g[8][TY + 2][TX + 2];
@@ -111,6 +109,17 @@ __global__ void __launch_bounds__(TX *TY) nlspn_affinity_kernel(const float *__r
         sum += a[j];
     }
     const long long pix = (long long)y * W + x;
+    if (kPacked) {
+        // pixel g = b*P + pix lives in block g / 32 at lane g % 32: chunk 0 = (dy,dx) of neighbours 0..3, chunk 1 = neighbours
+        // 4..7, chunk 2 = the 8 affinities; chunks of a block are 512 bytes apart
+        const long long g = (long long)b * P + pix;
+        uint4 *p = packed + (g >> 5) * 96 + (g & 31);
+        auto h2 = [](float a_, float b_) { const __half2 h = __floats2half2_rn(a_, b_); return *reinterpret_cast<const uint32_t *>(&h); };
+        p[0] = make_uint4(h2(o[0], o[1]), h2(o[2], o[3]), h2(o[4], o[5]), h2(o[6], o[7]));
+        p[32] = make_uint4(h2(o[8], o[9]), h2(o[10], o[11]), h2(o[12], o[13]), h2(o[14], o[15]));
+        p[64] = make_uint4(h2(a[0], a[1]), h2(a[2], a[3]), h2(a[4], a[5]), h2(a[6], a[7]));
+        return;
+    }
     float *offp = offset + (long long)b * 18 * P + pix;
     float *affp = aff + (long long)b * 9 * P + pix;
 #pragma unroll
@@ -126,67 +135,66 @@ __global__ void __launch_bounds__(TX *TY) nlspn_affinity_kernel(const float *__r
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// One propagation iteration over images [0, nb) of the pointers given.  grid (ceil(W/TX), ceil(H/TY), nb).
-//   out(h,w) = sum_k aff_k(h,w) * bilinear(in, h - 1 + k/3 + dy_k, w - 1 + k%3 + dx_k)
-template <bool kClamp>
-__global__ void __launch_bounds__(TX *TY) nlspn_prop_kernel(const float *__restrict__ in,
-                                                            const float *__restrict__ offset,
-                                                            const float *__restrict__ aff, float *__restrict__ out,
-                                                            float *__restrict__ inter, int H, int W) {
-    const int x = blockIdx.x * TX + threadIdx.x, y = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
-    if (x >= W || y >= H) return;
-    const long long P = (long long)H * W, pix = (long long)y * W + x;
-    const float *offp = offset + (long long)b * 18 * P + pix;
-    const float *affp = aff + (long long)b * 9 * P + pix;
-    const float *im = in + (long long)b * P;
+// Propagation: out(h,w) = sum_k aff_k(h,w) * bilinear(in', h - 1 + k/3 + dy_k, w - 1 + k%3 + dx_k),  in' = in blended with
+// the sparse input where preserve_input asks for it (nlspn_model.py:159-160,169).
+//
+// A CTA owns a contiguous run of image rows (rows are dealt evenly over one wave of CTAs; a run may span images) and
+// walks it in sub-bands.  For a sub-band it first stages the feature rows its taps can reach (+- halo) in shared memory
+// with a zero border, so that
+//   * the 36 corner reads per pixel are LDS with NO bounds predicates: the DCN validity rule and per-corner zeroing
+//     (modulated_deform_im2col_cuda.cuh:25-54,180) fall out of clamping the sample position to [-1, H] x [-1, W] and
+//     reading zeros from the border;
+//   * the preserve_input blend happens while staging (no separate pass over the feature map);
+//   * the offset / affinity stream is read straight from HBM with 16- or 8-byte vectors (no L1 allocation);
+//   * taps that leave the staged band (|offset| > halo) take the global-memory path (rare).
+// Two stream formats:
+//   fp32 planes  offset (B,18,H,W) + aff (B,9,H,W), the reference's layout (fp32 parity mode, the Module API): 25 planes
+//                read per pixel (the centre tap's offsets are identically zero), two pixels per thread;
+//   packed fp16  24 halves per pixel (16 offsets + 8 affinities; centre affinity = 1 - sum of the rounded others, so the
+//                operator stays an exact affine combination), 48 B instead of 100 B per pixel and iteration, stored as
+//                three 16-byte chunks per pixel, chunk-planar within blocks of 32 pixels (every warp load is one
+//                contiguous 512-byte run), one pixel per thread (bf16 inference mode).
+// The last iteration can apply the generator's output fusion (rdf_generator.py:401-406: clamp, 2-way confidence softmax,
+// weighted sum) in its epilogue.
+struct FuseOut { const float *d1, *c1, *c2; float *pred; };
 
-    // issue all streaming loads first (25 independent requests in flight per thread)
-    float dy[9], dx[9], a[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        a[k] = ld_stream(affp + (long long)k * P);
-        if (k == 4) {
-            dy[k] = 0.f;
-            dx[k] = 0.f;
-        } else {
-            dy[k] = ld_stream(offp + (long long)(2 * k) * P);
-            dx[k] = ld_stream(offp + (long long)(2 * k + 1) * P);
-        }
+// feature value at linear image index i, with the preserve_input blend
+__device__ __forceinline__ float feat_at(const float *__restrict__ im, const float *__restrict__ fix, long long i) {
+    float v = __ldg(im + i);
+    if (fix) {
+        const float f = __ldg(fix + i);
+        v = f > 0.f ? f : v;
     }
-    float acc = 0.f;
-#pragma unroll
-    for (int k = 0; k < 9; ++k)
-        acc = fmaf(a[k], bilinear(im, H, W, (float)(y - 1 + k / 3) + dy[k], (float)(x - 1 + k % 3) + dx[k]), acc);
-    if (kClamp) acc = fminf(fmaxf(acc, -1.f), 1.f);
-    out[(long long)b * P + pix] = acc;
-    if (inter) inter[(long long)b * P + pix] = acc;
+    return v;
 }
 
+// bilinear sample from global memory (escape path and the fallback kernel), blend included
+__device__ __forceinline__ float bilinear_fix(const float *__restrict__ im, const float *__restrict__ fix, int H, int W, float y, float x) {
+    if (!(y > -1.f && x > -1.f && y < (float)H && x < (float)W)) return 0.f;
+    const float fy = floorf(y), fx = floorf(x);
+    const int yl = (int)fy, xl = (int)fx;
+    const float ly = y - fy, lx = x - fx, hy = 1.f - ly, hx = 1.f - lx;
+    const bool y0 = yl >= 0, y1 = yl + 1 <= H - 1, x0 = xl >= 0, x1 = xl + 1 <= W - 1;
+    const long long i = (long long)yl * W + xl;
+    const float v1 = (y0 && x0) ? feat_at(im, fix, i) : 0.f;
+    const float v2 = (y0 && x1) ? feat_at(im, fix, i + 1) : 0.f;
+    const float v3 = (y1 && x0) ? feat_at(im, fix, i + W) : 0.f;
+    const float v4 = (y1 && x1) ? feat_at(im, fix, i + W + 1) : 0.f;
+    return hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
+}
 
-// ------------------------------------------------------------------------------------------------------------------
-// Band kernel (the default): the thread-per-pixel kernel above is bound by the L1 tag stage (3.3 wavefronts per
-// gather request with 2-px offsets, 769 instructions per warp, DRAM only 41 % busy: profiles/).  Here a CTA owns a
-// contiguous run of image rows and first stages the feature rows its taps can reach (+- halo) in shared memory with
-// a zero border, so that
-//   * the 36 corner reads per pixel are LDS (bank-limited, no tag lookups) with NO bounds predicates: the DCN
-//     validity rule and per-corner zeroing (modulated_deform_im2col_cuda.cuh:25-54,180) fall out of clamping the
-//     sample position to [-1, H] x [-1, W] and reading zeros from the border;
-//   * the 25 streamed planes are read as 8-byte vectors, two pixels per thread, straight from HBM (no L1 allocation);
-//   * taps that leave the staged band (|offset| > halo) take the global-memory path of `bilinear` (rare).
-// Rows are dealt evenly over one wave of CTAs (a run may span two images).
-// Nine-tap gather from a staged band with the escape test hoisted out of the tap loop: the common case (no tap leaves
-// the band) is straight-line code with 36 independent LDS, so the loads of all taps overlap instead of serialising
-// behind a per-tap branch.  dy/dx/a: the pixel's 9 offsets and affinities; (y, x): the pixel.
 struct BandView {
     const float *tile;      // [nrows][pitch], tile row 0 = image row ty0, tile column tc = image column tc - 1
-    const float *im;        // the image in global memory (fallback path)
+    const float *im, *fix;  // the image (and the sparse input, or NULL) in global memory: escape path
     int pitch, ty0, nrows, H, W;
     float Hf, Wf;
 };
+
+// Nine-tap gather from a staged band with the escape test hoisted out of the tap loop: the common case (no tap leaves
+// the band) is straight-line code with 36 independent LDS.  dyf/dxf/af: the pixel's 9 offsets and affinities.
 template <typename FDy, typename FDx, typename FA>
 __device__ __forceinline__ float gather9(const BandView &v, FDy dyf, FDx dxf, FA af, int y, int x) {
-    // pass 1: does any tap leave the staged band?  (rows only: columns are staged over the full width)
-    float ymin = 1e30f, ymax = -1e30f;
+    float ymin = 1e30f, ymax = -1e30f;            // rows only: columns are staged over the full width
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         const float cy = fminf(fmaxf((float)(y - 1 + k / 3) + dyf(k), -1.f), v.Hf);
@@ -206,80 +214,91 @@ __device__ __forceinline__ float gather9(const BandView &v, FDy dyf, FDx dxf, FA
             const float *q = v.tile + (int)fmaf(fy - (float)v.ty0, (float)v.pitch, fx + 1.f);
             acc = fmaf(af(k), hy * hx * q[0] + hy * lx * q[1] + ly * hx * q[v.pitch] + ly * lx * q[v.pitch + 1], acc);
         }
-    } else {                     // some tap left the staged band: global-memory path
+    } else {
 #pragma unroll
         for (int k = 0; k < 9; ++k)
-            acc = fmaf(af(k), bilinear(v.im, v.H, v.W, (float)(y - 1 + k / 3) + dyf(k), (float)(x - 1 + k % 3) + dxf(k)), acc);
+            acc = fmaf(af(k), bilinear_fix(v.im, v.fix, v.H, v.W, (float)(y - 1 + k / 3) + dyf(k), (float)(x - 1 + k % 3) + dxf(k)), acc);
     }
     return acc;
 }
 
 constexpr int BAND_THREADS = 256;
 
+// stage image rows [ty0, ty0 + nrows) of `im` (blended with `fix`) into the tile, zero outside the image
+__device__ __forceinline__ void stage_band(float *tile, const float *__restrict__ im, const float *__restrict__ fix, int ty0, int nrows,
+                                           int pitch, int H, int W) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int tr = warp; tr < nrows; tr += BAND_THREADS / 32) {
+        const int iy = ty0 + tr;
+        const bool yok = iy >= 0 && iy < H;
+        const long long base = (long long)iy * W - 1;
+        float *dst = tile + tr * pitch;
+        for (int tc = lane; tc < pitch; tc += 32) dst[tc] = (yok && tc >= 1 && tc <= W) ? feat_at(im, fix, base + tc) : 0.f;
+    }
+}
+
+// epilogue of one output value at linear index o: store / clamp / fused output fusion
+template <bool kFinal>
+__device__ __forceinline__ float finish(float acc, int clamp, const FuseOut &fz, long long o) {
+    if (kFinal) {
+        if (clamp) acc = fminf(fmaxf(acc, -1.f), 1.f);
+        if (fz.pred) {
+            const float a = __ldg(fz.c1 + o), b = __ldg(fz.c2 + o), m = fmaxf(a, b);
+            const float e1 = expf(a - m), e2 = expf(b - m), inv = 1.f / (e1 + e2);
+            fz.pred[o] = __ldg(fz.d1 + o) * (e1 * inv) + acc * (e2 * inv);
+        }
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float ld_stream(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ float2 ld_stream2(const float *p) {
     float2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint4 ld_stream4(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 
-template <bool kClamp, int kPix, int kMinBlocks>
-__global__ void __launch_bounds__(BAND_THREADS, kMinBlocks) nlspn_prop_band_kernel(const float *__restrict__ in,
-                                                                          const float *__restrict__ offset,
-                                                                          const float *__restrict__ aff,
-                                                                          float *__restrict__ out, float *__restrict__ inter,
-                                                                          int B, int H, int W, int rows_per_cta, int halo, int prefetch,
-                                                                          int pre) {
+// ---- fp32 planes, kPix pixels per thread ------------------------------------------------------------------------------
+template <bool kFinal, int kPix, int kMinBlocks>
+__global__ void __launch_bounds__(BAND_THREADS, kMinBlocks)
+nlspn_prop_band_kernel(const float *__restrict__ in, const float *__restrict__ offset, const float *__restrict__ aff,
+                       const float *__restrict__ fixp, float *__restrict__ out, float *__restrict__ inter, FuseOut fz, int clamp,
+                       int B, int H, int W, int rows_per_cta, int sub_rows, int halo) {
     extern __shared__ float band_tile[];
     const int pitch = W + 4;                         // tile column tc <-> image column tc - 1 (-1 .. W + 2)
     const long long total = (long long)B * H, P = (long long)H * W;
     long long row = (long long)blockIdx.x * rows_per_cta;
     const long long row_end = row + rows_per_cta < total ? row + rows_per_cta : total;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Wp = W / kPix;
     const float Hf = (float)H, Wf = (float)W;
     // Programmatic dependent launch: the next iteration's grid may take SM slots as this grid's CTAs retire (its CTAs then
     // sit in griddepcontrol.wait until this grid has completed and flushed), which removes the launch gap and the CTA
-    // ramp-up between the 18 launches.  Nothing of the previous iteration is read before the wait; the offsets /
-    // affinities do not depend on it, so the lines of the thread's first `pre` items are sent on their way to L2 first.
-    if (pre && row < row_end) {
-        const int b = (int)(row / H), y_lo = (int)(row - (long long)b * H);
-        const int nr = (int)((row_end - row) < (long long)(H - y_lo) ? (row_end - row) : (long long)(H - y_lo));
-        for (int i = 0; i < pre; ++i) {
-            const int idx = threadIdx.x + i * BAND_THREADS;
-            if (idx < nr * Wp && (lane & 15) == 0) {         // one prefetch per 128-byte line (16 lanes x 8 bytes)
-                const int ry = idx / Wp, x = kPix * (idx - ry * Wp);
-                const long long pix = (long long)(y_lo + ry) * W + x;
-                const float *offp = offset + (long long)b * 18 * P + pix;
-                const float *affp = aff + (long long)b * 9 * P + pix;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(affp + (long long)k * P));
-                    if (k != 4) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(offp + (long long)(2 * k) * P));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(offp + (long long)(2 * k + 1) * P));
-                    }
-                }
-            }
-        }
-    }
+    // ramp-up between the launches.  Nothing of the previous iteration is read before the wait.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     while (row < row_end) {
         const int b = (int)(row / H), y_lo = (int)(row - (long long)b * H);
-        const int nr = (int)((row_end - row) < (long long)(H - y_lo) ? (row_end - row) : (long long)(H - y_lo));   // rows of this image
+        long long nrl = row_end - row;
+        if (nrl > H - y_lo) nrl = H - y_lo;          // rows of this image
+        if (nrl > sub_rows) nrl = sub_rows;          // ... that fit the tile
+        const int nr = (int)nrl;
         const int ty0 = y_lo - halo - 1;             // image row of tile row 0
         const int nrows = nr + 2 * halo + 3;
         const float *im = in + (long long)b * P;
+        const float *fix = fixp ? fixp + (long long)b * P : nullptr;
         __syncthreads();                              // previous sub-band is done with the tile
-        for (int tr = warp; tr < nrows; tr += BAND_THREADS / 32) {
-            const int iy = ty0 + tr;
-            const bool yok = iy >= 0 && iy < H;
-            const float *src = im + (long long)iy * W - 1;
-            float *dst = band_tile + tr * pitch;
-            for (int tc = lane; tc < pitch; tc += 32) dst[tc] = (yok && tc >= 1 && tc <= W) ? __ldg(src + tc) : 0.f;
-        }
+        stage_band(band_tile, im, fix, ty0, nrows, pitch, H, W);
         __syncthreads();
-        const BandView bv{band_tile, im, pitch, ty0, nrows, H, W, Hf, Wf};
+        const BandView bv{band_tile, im, fix, pitch, ty0, nrows, H, W, Hf, Wf};
         const int nitems = nr * Wp;
         for (int idx = threadIdx.x; idx < nitems; idx += BAND_THREADS) {
             const int ry = idx / Wp, x = kPix * (idx - ry * Wp), y = y_lo + ry;
@@ -287,19 +306,6 @@ __global__ void __launch_bounds__(BAND_THREADS, kMinBlocks) nlspn_prop_band_kern
             const float *offp = offset + (long long)b * 18 * P + pix;
             const float *affp = aff + (long long)b * 9 * P + pix;
             const long long o = (long long)b * P + pix;
-            if (prefetch && idx + BAND_THREADS < nitems) {
-                // the thread's next item: start its 25 plane lines on their way from HBM to L2 while this one is gathered
-                const int idn = idx + BAND_THREADS, ryn = idn / Wp;
-                const long long dpix = (long long)(y_lo + ryn) * W + kPix * (idn - ryn * Wp) - pix;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(affp + (long long)k * P + dpix));
-                    if (k != 4) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(offp + (long long)(2 * k) * P + dpix));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(offp + (long long)(2 * k + 1) * P + dpix));
-                    }
-                }
-            }
             if (kPix == 2) {
                 float2 a[9], dy[9], dx[9];
 #pragma unroll
@@ -314,10 +320,8 @@ __global__ void __launch_bounds__(BAND_THREADS, kMinBlocks) nlspn_prop_band_kern
                 }
                 float acc0 = gather9(bv, [&](int k) { return dy[k].x; }, [&](int k) { return dx[k].x; }, [&](int k) { return a[k].x; }, y, x);
                 float acc1 = gather9(bv, [&](int k) { return dy[k].y; }, [&](int k) { return dx[k].y; }, [&](int k) { return a[k].y; }, y, x + 1);
-                if (kClamp) {
-                    acc0 = fminf(fmaxf(acc0, -1.f), 1.f);
-                    acc1 = fminf(fmaxf(acc1, -1.f), 1.f);
-                }
+                acc0 = finish<kFinal>(acc0, clamp, fz, o);
+                acc1 = finish<kFinal>(acc1, clamp, fz, o + 1);
                 *reinterpret_cast<float2 *>(out + o) = make_float2(acc0, acc1);
                 if (inter) *reinterpret_cast<float2 *>(inter + o) = make_float2(acc0, acc1);
             } else {
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(BAND_THREADS, kMinBlocks) nlspn_prop_band_kern
                     }
                 }
                 float acc = gather9(bv, [&](int k) { return dy[k]; }, [&](int k) { return dx[k]; }, [&](int k) { return a[k]; }, y, x);
-                if (kClamp) acc = fminf(fmaxf(acc, -1.f), 1.f);
+                acc = finish<kFinal>(acc, clamp, fz, o);
                 out[o] = acc;
                 if (inter) inter[o] = acc;
             }
@@ -342,220 +346,101 @@ __global__ void __launch_bounds__(BAND_THREADS, kMinBlocks) nlspn_prop_band_kern
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Row-streaming propagation kernel (the default when W % 4 == 0): persistent CTAs, one image row per trip, one
-// thread per pixel.  The 25 offset/affinity planes of a row are staged in shared memory by TMA 1-D bulk copies
-// (cp.async.bulk, W*4 bytes each) onto an mbarrier, `stages` rows ahead of the compute, so HBM requests stay in
-// flight while the warps gather feature corners through L1.  A CTA owns a contiguous band of rows: the feature
-// rows its taps touch stay L1-resident from one trip to the next.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    for (;;) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) return;
-        if (clock64() - t0 > 8000000000ll) __trap();      // protocol bug: fail loudly instead of hanging the GPU
-    }
+// ---- packed fp16 stream, one pixel per thread -------------------------------------------------------------------------
+__device__ __forceinline__ float2 h2f(uint32_t u) {
+    const __half2 h = *reinterpret_cast<const __half2 *>(&u);
+    return __half22float2(h);
 }
 
-template <bool kClamp, int kMaxThreads, int kMinBlocks>
-__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) nlspn_prop_rows_kernel(const float *__restrict__ in,
-                                                               const float *__restrict__ offset,
-                                                               const float *__restrict__ aff, float *__restrict__ out,
-                                                               float *__restrict__ inter, int B, int H, int W,
-                                                               int stages, int rows_per_cta) {
-    extern __shared__ __align__(128) unsigned char nl_smem[];
-    float *stage_base = reinterpret_cast<float *>(nl_smem);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(nl_smem + (size_t)stages * 25 * W * sizeof(float));
-    const long long total = (long long)B * H, P = (long long)H * W;
-    const long long r0 = (long long)blockIdx.x * rows_per_cta;
-    const long long r1 = r0 + rows_per_cta < total ? r0 + rows_per_cta : total;
-    if (r0 >= r1) return;
-    const int x = threadIdx.x;
-    if (x == 0) {
-        for (int s = 0; s < stages; ++s)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const uint32_t row_bytes = (uint32_t)W * 4u;
-    // threads 0..24 each issue ONE plane's bulk copy (a single issuing thread serialises ~25 x 80 cycles per row)
-    auto issue = [&](long long row, int s) {
-        if (x >= 25) return;
-        const int b = (int)(row / H), y = (int)(row % H);
-        const uint32_t bar = smem_u32(bars + s);
-        if (x == 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(25u * row_bytes) : "memory");
-        const uint32_t dst = smem_u32(stage_base + (size_t)s * 25 * W) + (uint32_t)x * row_bytes;
-        const float *src;
-        if (x < 16) {
-            const int j = x >> 1, k = j < 4 ? j : j + 1;       // slot 2j / 2j+1 <- offset channels 2k / 2k+1
-            src = offset + ((long long)b * 18 + 2 * k + (x & 1)) * P + (long long)y * W;
-        } else {
-            src = aff + ((long long)b * 9 + (x - 16)) * P + (long long)y * W;
-        }
-        bulk_g2s(dst, src, row_bytes, bar);
-    };
-    for (int s = 0; s < stages; ++s)
-        if (r0 + s < r1) issue(r0 + s, s);
-
-    int it = 0;
-    for (long long row = r0; row < r1; ++row, ++it) {
-        const int s = it % stages;
-        mbar_wait_parity(smem_u32(bars + s), (uint32_t)((it / stages) & 1));
-        if (x < W) {
-            const int b = (int)(row / H), y = (int)(row % H);
-            const float *st = stage_base + (size_t)s * 25 * W + x;
-            const float *im = in + (long long)b * P;
-            float acc = 0.f;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const int j = k < 4 ? k : k - 1;
-                const float dy = k == 4 ? 0.f : st[(2 * j) * W], dx = k == 4 ? 0.f : st[(2 * j + 1) * W];
-                acc = fmaf(st[(16 + k) * W], bilinear(im, H, W, (float)(y - 1 + k / 3) + dy, (float)(x - 1 + k % 3) + dx), acc);
-            }
-            if (kClamp) acc = fminf(fmaxf(acc, -1.f), 1.f);
-            const long long o = (long long)b * P + (long long)y * W + x;
-            out[o] = acc;
-            if (inter) inter[o] = acc;
-        }
-        __syncthreads();                               // everyone is done reading stage s
-        if (row + stages < r1) issue(row + stages, s);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Ring kernel (the default when W % 4 == 0): the band kernel's shared-memory gathers + the row kernel's TMA stream,
-// warp-specialised so that neither waits for the other.  One persistent CTA per SM owns a contiguous run of rows:
-//   * producer warp: for every stage (G rows) 25 x G bulk copies (cp.async.bulk, one image row of one plane each)
-//     onto an mbarrier, S stages ahead, released by the consumer warps through an "empty" mbarrier;
-//   * consumer warps: stage the feature rows their taps can reach (+- halo, zero border) in shared memory once per
-//     sub-band, then per stage read the 25 streamed values of a pixel from shared memory (conflict-free) and gather
-//     the 36 corners with LDS; taps outside the staged band fall back to `bilinear` on global memory.
-// HBM requests therefore stay in flight during the gathers (the band kernel's load -> wait -> compute phases left DRAM
-// 47 % busy), and no thread holds the streamed values in registers.
-__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
-template <bool kClamp>
-__global__ void __launch_bounds__(992, 1) nlspn_prop_ring_kernel(const float *__restrict__ in, const float *__restrict__ offset,
-                                                                 const float *__restrict__ aff, float *__restrict__ out,
-                                                                 float *__restrict__ inter, int B, int H, int W,
-                                                                 int rows_per_cta, int halo, int G, int S, int nr_max) {
-    extern __shared__ __align__(128) unsigned char ring_smem[];
+template <bool kFinal>
+__global__ void __launch_bounds__(BAND_THREADS, 4)
+nlspn_prop_packed_kernel(const float *__restrict__ in, const uint4 *__restrict__ pk, const float *__restrict__ fixp,
+                         float *__restrict__ out, FuseOut fz, int clamp, int B, int H, int W, int rows_per_cta, int sub_rows, int halo) {
+    extern __shared__ float band_tile[];
     const int pitch = W + 4;
-    float *ring = reinterpret_cast<float *>(ring_smem);                                  // [S][G][25][W]
-    float *tile = ring + (size_t)S * G * 25 * W;                                         // [nr_max + 2 halo + 3][pitch]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tile + (size_t)(nr_max + 2 * halo + 3) * pitch);   // full[S], empty[S]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ncw = (blockDim.x >> 5) - 1;                                               // consumer warps; warp ncw produces
     const long long total = (long long)B * H, P = (long long)H * W;
-    const long long r0 = (long long)blockIdx.x * rows_per_cta;
-    const long long r1 = r0 + rows_per_cta < total ? r0 + rows_per_cta : total;
-    if (r0 >= r1) return;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + S + s)), "r"(ncw));
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const uint32_t row_bytes = (uint32_t)W * 4u;
-    if (warp == ncw) {
-        // ---------------- producer
-        int i = 0;
-        for (long long row = r0; row < r1; row += G, ++i) {
-            const int s = i % S;
-            const int ng = (int)((r1 - row) < G ? (r1 - row) : G);
-            mbar_wait_parity(smem_u32(bars + S + s), (uint32_t)(((i / S) & 1) ^ 1));      // consumers released the slot
-            const uint32_t full = smem_u32(bars + s);
-            if (lane == 0)
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(25u * row_bytes * (uint32_t)ng) : "memory");
-            __syncwarp();
-            for (int c = lane; c < 25 * ng; c += 32) {
-                const int g = c / 25, k = c - 25 * g;
-                const long long rg = row + g;
-                const int b = (int)(rg / H), y = (int)(rg - (long long)b * H);
-                const float *src;
-                if (k < 16) {
-                    const int j = k >> 1, kk = j < 4 ? j : j + 1;      // slot 2j / 2j+1 <- offset channels 2kk / 2kk+1
-                    src = offset + ((long long)b * 18 + 2 * kk + (k & 1)) * P + (long long)y * W;
-                } else {
-                    src = aff + ((long long)b * 9 + (k - 16)) * P + (long long)y * W;
-                }
-                bulk_g2s(smem_u32(ring + ((size_t)(s * G + g) * 25 + k) * W), src, row_bytes, full);
-            }
-        }
-        return;
-    }
-    // ---------------- consumers
-    const int nseg = (W + 31) >> 5;
+    long long row = (long long)blockIdx.x * rows_per_cta;
+    const long long row_end = row + rows_per_cta < total ? row + rows_per_cta : total;
     const float Hf = (float)H, Wf = (float)W;
-    const int nthr_c = ncw * 32;
-    int i = 0;
-    long long row = r0;
-    while (row < r1) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    while (row < row_end) {
         const int b = (int)(row / H), y_lo = (int)(row - (long long)b * H);
-        int nr = (int)((r1 - row) < (long long)(H - y_lo) ? (r1 - row) : (long long)(H - y_lo));
-        if (nr > nr_max) nr = nr_max;
-        const int ty0 = y_lo - halo - 1, nrows = nr + 2 * halo + 3;
+        long long nrl = row_end - row;
+        if (nrl > H - y_lo) nrl = H - y_lo;
+        if (nrl > sub_rows) nrl = sub_rows;
+        const int nr = (int)nrl;
+        const int ty0 = y_lo - halo - 1;
+        const int nrows = nr + 2 * halo + 3;
         const float *im = in + (long long)b * P;
-        asm volatile("bar.sync 1, %0;" ::"r"(nthr_c) : "memory");          // previous sub-band is done with the tile
-        for (int tr = warp; tr < nrows; tr += ncw) {
-            const int iy = ty0 + tr;
-            const bool yok = iy >= 0 && iy < H;
-            const float *src = im + (long long)iy * W - 1;
-            float *dst = tile + tr * pitch;
-            for (int tc = lane; tc < pitch; tc += 32) dst[tc] = (yok && tc >= 1 && tc <= W) ? __ldg(src + tc) : 0.f;
-        }
-        asm volatile("bar.sync 1, %0;" ::"r"(nthr_c) : "memory");
-        const BandView bv{tile, im, pitch, ty0, nrows, H, W, Hf, Wf};
-        for (int rr = 0; rr < nr; rr += G, ++i) {
-            const int s = i % S;
-            mbar_wait_parity(smem_u32(bars + s), (uint32_t)((i / S) & 1));
-            for (int seg = warp; seg < G * nseg; seg += ncw) {
-                const int g = seg / nseg, x = (seg - g * nseg) * 32 + lane, y = y_lo + rr + g;
-                if (rr + g < nr && x < W) {
-                    const float *st = ring + (size_t)(s * G + g) * 25 * W + x;
-                    float acc = gather9(bv,
-                                        [&](int k) { return k == 4 ? 0.f : st[(2 * (k < 4 ? k : k - 1)) * W]; },
-                                        [&](int k) { return k == 4 ? 0.f : st[(2 * (k < 4 ? k : k - 1) + 1) * W]; },
-                                        [&](int k) { return st[(16 + k) * W]; }, y, x);
-                    if (kClamp) acc = fminf(fmaxf(acc, -1.f), 1.f);
-                    const long long o = (long long)b * P + (long long)y * W + x;
-                    out[o] = acc;
-                    if (inter) inter[o] = acc;
-                }
+        const float *fix = fixp ? fixp + (long long)b * P : nullptr;
+        __syncthreads();
+        stage_band(band_tile, im, fix, ty0, nrows, pitch, H, W);
+        __syncthreads();
+        const BandView bv{band_tile, im, fix, pitch, ty0, nrows, H, W, Hf, Wf};
+        // linear pixel range of the sub-band; the walk starts at the enclosing 32-pixel block so that lane == g % 32
+        const long long g0 = (long long)b * P + (long long)y_lo * W, g1 = g0 + (long long)nr * W;
+        for (long long g = (g0 & ~31ll) + threadIdx.x; g < g1; g += BAND_THREADS) {
+            if (g < g0) continue;
+            const uint4 *p = pk + (g >> 5) * 96 + (g & 31);
+            const uint4 c0 = ld_stream4(p), c1 = ld_stream4(p + 32), c2 = ld_stream4(p + 64);
+            const int pix = (int)(g - (long long)b * P), y = pix / W, x = pix - y * W;
+            float dy[9], dx[9], a[9];
+            {
+                float2 t;
+                t = h2f(c0.x); dy[0] = t.x; dx[0] = t.y;
+                t = h2f(c0.y); dy[1] = t.x; dx[1] = t.y;
+                t = h2f(c0.z); dy[2] = t.x; dx[2] = t.y;
+                t = h2f(c0.w); dy[3] = t.x; dx[3] = t.y;
+                dy[4] = dx[4] = 0.f;
+                t = h2f(c1.x); dy[5] = t.x; dx[5] = t.y;
+                t = h2f(c1.y); dy[6] = t.x; dx[6] = t.y;
+                t = h2f(c1.z); dy[7] = t.x; dx[7] = t.y;
+                t = h2f(c1.w); dy[8] = t.x; dx[8] = t.y;
+                t = h2f(c2.x); a[0] = t.x; a[1] = t.y;
+                t = h2f(c2.y); a[2] = t.x; a[3] = t.y;
+                t = h2f(c2.z); a[5] = t.x; a[6] = t.y;
+                t = h2f(c2.w); a[7] = t.x; a[8] = t.y;
+                a[4] = 1.f - (((a[0] + a[1]) + (a[2] + a[3])) + ((a[5] + a[6]) + (a[7] + a[8])));
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cta(smem_u32(bars + S + s));        // this warp is done reading the stage
+            float acc = gather9(bv, [&](int k) { return dy[k]; }, [&](int k) { return dx[k]; }, [&](int k) { return a[k]; }, y, x);
+            acc = finish<kFinal>(acc, clamp, fz, g);
+            out[g] = acc;
         }
         row += nr;
     }
 }
 
-// feat = (1 - m) * feat + m * fix, m = fix > 0   (nlspn_model.py:159-160,169)
-__global__ void nlspn_preserve_kernel(const float *__restrict__ in, const float *__restrict__ fix,
-                                      float *__restrict__ out, long long n) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float f = __ldg(fix + i);
-        const float m = f > 0.f ? 1.f : 0.f;
-        out[i] = (1.f - m) * in[i] + m * f;
+// ---- fallback: one thread per pixel straight from global memory (images too wide for a shared-memory band) ---------
+template <bool kFinal>
+__global__ void __launch_bounds__(TX *TY) nlspn_prop_kernel(const float *__restrict__ in, const float *__restrict__ offset,
+                                                            const float *__restrict__ aff, const float *__restrict__ fixp,
+                                                            float *__restrict__ out, float *__restrict__ inter, FuseOut fz, int clamp,
+                                                            int H, int W) {
+    const int x = blockIdx.x * TX + threadIdx.x, y = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+    if (x >= W || y >= H) return;
+    const long long P = (long long)H * W, pix = (long long)y * W + x;
+    const float *offp = offset + (long long)b * 18 * P + pix;
+    const float *affp = aff + (long long)b * 9 * P + pix;
+    const float *im = in + (long long)b * P;
+    const float *fix = fixp ? fixp + (long long)b * P : nullptr;
+    float dy[9], dx[9], a[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        a[k] = ld_stream(affp + (long long)k * P);
+        dy[k] = k == 4 ? 0.f : ld_stream(offp + (long long)(2 * k) * P);
+        dx[k] = k == 4 ? 0.f : ld_stream(offp + (long long)(2 * k + 1) * P);
     }
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+        acc = fmaf(a[k], bilinear_fix(im, fix, H, W, (float)(y - 1 + k / 3) + dy[k], (float)(x - 1 + k % 3) + dx[k]), acc);
+    acc = finish<kFinal>(acc, clamp, fz, (long long)b * P + pix);
+    out[(long long)b * P + pix] = acc;
+    if (inter) inter[(long long)b * P + pix] = acc;
 }
 
+// feat = (1 - m) * feat + m * fix, m = fix > 0 is folded into the band staging; this kernel only serves prop_time == 0 callers
 __global__ void fuse_depth_kernel(const float *__restrict__ d1, const float *__restrict__ c1,
                                   const float *__restrict__ d2, const float *__restrict__ c2,
                                   float *__restrict__ d2c, float *__restrict__ pred, size_t n) {
@@ -568,199 +453,175 @@ __global__ void fuse_depth_kernel(const float *__restrict__ d1, const float *__r
     }
 }
 
+// launch geometry of the band kernels: CTAs per SM, rows per CTA, rows per sub-band (what fits the tile), shared memory
+struct BandGeom { int per_sm, rows_per_cta, sub_rows, nctas; size_t smem; bool ok; };
+static BandGeom band_geom(int B, int H, int W, int halo, int per_sm_max) {
+    BandGeom g{};
+    const long long total = (long long)B * H;
+    const size_t row_bytes = (size_t)(W + 4) * sizeof(float);
+    for (int per_sm = per_sm_max; per_sm >= 1; --per_sm) {
+        const size_t cap = (size_t)(220 * 1024) / per_sm - 1024;
+        int fit = (int)(cap / row_bytes) - 2 * halo - 3;                 // sub-band rows that fit beside the halo
+        if (const long long sub = knob("RDFC_NLSPN_SUB", 0); sub > 0 && fit > sub && per_sm == per_sm_max) fit = (int)sub;   // tests: force sub-bands
+        if (fit < (per_sm > 1 && knob("RDFC_NLSPN_SUB", 0) <= 0 ? 12 : 1)) continue;   // fewer CTAs per SM before tiny sub-bands
+        long long ctas = (long long)sm_count() * per_sm;
+        if (ctas > total) ctas = total;
+        g.per_sm = per_sm;
+        g.rows_per_cta = (int)((total + ctas - 1) / ctas);
+        g.sub_rows = fit < g.rows_per_cta ? fit : g.rows_per_cta;
+        if (g.sub_rows > H) g.sub_rows = H;
+        g.nctas = (int)((total + g.rows_per_cta - 1) / g.rows_per_cta);
+        g.smem = (size_t)(g.sub_rows + 2 * halo + 3) * row_bytes;
+        g.ok = true;
+        return g;
+    }
+    return g;
+}
+
+template <typename Kern, typename... Args>
+static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t st, int pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+static size_t packed_bytes(int B, int H, int W) { return (size_t)(((long long)B * H * W + 31) / 32) * 1536; }
+
 }  // namespace
 }  // namespace rdfc
 
 using namespace rdfc;
 
-extern "C" int rdfc_nlspn_affinity_forward(const float *guidance, const float *confidence, const float *conv_w,
-                                           const float *conv_b, const float *aff_scale, int affinity, int conf_prop,
-                                           float *offset, float *aff, int B, int H, int W, void *stream) {
-    RDFC_REQUIRE(guidance && conv_w && conv_b && aff_scale && offset && aff, "NULL pointer argument");
+static int affinity_check(const void *guidance, const void *confidence, const void *conv_w, const void *conv_b, const void *aff_scale,
+                          int affinity, int conf_prop, int B, int H, int W) {
+    RDFC_REQUIRE(guidance && conv_w && conv_b && aff_scale, "NULL pointer argument");
     RDFC_REQUIRE(!conf_prop || confidence, "conf_prop requires a confidence map (nlspn_model.py:150-151)");
     RDFC_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "bad shape (%d,%d,%d)", B, H, W);
     RDFC_REQUIRE(affinity >= RDFC_AFF_AS && affinity <= RDFC_AFF_TGASS, "unknown affinity mode %d", affinity);
+    return 0;
+}
+
+extern "C" int rdfc_nlspn_affinity_forward(const float *guidance, const float *confidence, const float *conv_w,
+                                           const float *conv_b, const float *aff_scale, int affinity, int conf_prop,
+                                           float *offset, float *aff, int B, int H, int W, void *stream) {
+    if (int rc = affinity_check(guidance, confidence, conv_w, conv_b, aff_scale, affinity, conf_prop, B, H, W)) return rc;
+    RDFC_REQUIRE(offset && aff, "NULL output pointer");
     dim3 grid(cdiv(W, TX), cdiv(H, TY), B), block(TX, TY);
-    nlspn_affinity_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(guidance, confidence, conv_w, conv_b, aff_scale,
-                                                                     affinity, conf_prop, offset, aff, H, W);
+    nlspn_affinity_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(guidance, confidence, conv_w, conv_b, aff_scale,
+                                                                            affinity, conf_prop, offset, aff, nullptr, H, W);
     RDFC_CHECK_LAUNCH("nlspn_affinity_kernel");
+    return 0;
+}
+
+extern "C" size_t rdfc_nlspn_packed_bytes(int B, int H, int W) { return (B > 0 && H > 0 && W > 0) ? packed_bytes(B, H, W) : 0; }
+
+extern "C" int rdfc_nlspn_affinity_forward_packed(const float *guidance, const float *confidence, const float *conv_w,
+                                                  const float *conv_b, const float *aff_scale, int affinity, int conf_prop,
+                                                  void *packed, int B, int H, int W, void *stream) {
+    if (int rc = affinity_check(guidance, confidence, conv_w, conv_b, aff_scale, affinity, conf_prop, B, H, W)) return rc;
+    RDFC_REQUIRE(packed && ((uintptr_t)packed % 16) == 0, "packed stream must be a 16-byte aligned buffer of rdfc_nlspn_packed_bytes()");
+    dim3 grid(cdiv(W, TX), cdiv(H, TY), B), block(TX, TY);
+    nlspn_affinity_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(guidance, confidence, conv_w, conv_b, aff_scale,
+                                                                           affinity, conf_prop, nullptr, nullptr, (uint4 *)packed, H, W);
+    RDFC_CHECK_LAUNCH("nlspn_affinity_kernel");
+    return 0;
+}
+
+// shared body of the two propagate entry points: `packed` != NULL selects the fp16 stream
+static int propagate(const float *feat_init, const float *offset, const float *aff, const void *packed, const float *feat_fix,
+                     int preserve_input, float *out, float *scratch, float *inter, int B, int H, int W, int prop_time, int clamp_out,
+                     const rdfc_fuse_out *fuse, cudaStream_t st) {
+    RDFC_REQUIRE(feat_init && out && scratch, "NULL pointer argument");
+    RDFC_REQUIRE(!preserve_input || feat_fix, "preserve_input requires feat_fix (nlspn_model.py:157-158)");
+    RDFC_REQUIRE(B > 0 && H > 0 && W > 0 && prop_time >= 0, "bad shape (%d,%d,%d) x %d", B, H, W, prop_time);
+    RDFC_REQUIRE(!fuse || (fuse->d1 && fuse->c1 && fuse->c2 && fuse->pred), "fuse: NULL pointer");
+    const long long P = (long long)H * W;
+    const FuseOut fz = fuse ? FuseOut{fuse->d1, fuse->c1, fuse->c2, fuse->pred} : FuseOut{nullptr, nullptr, nullptr, nullptr};
+    const int clamp = (clamp_out || fuse) ? 1 : 0;          // the output fusion reads clamp(depth_map_2) (rdf_generator.py:401)
+    if (prop_time == 0) {
+        if (fuse) {
+            const int nblk = (int)min((long long)cdiv(B * P, 256), (long long)sm_count() * 8);
+            fuse_depth_kernel<<<nblk, 256, 0, st>>>(fuse->d1, fuse->c1, feat_init, fuse->c2, out, fuse->pred, (size_t)(B * P));
+            RDFC_CHECK_LAUNCH("fuse_depth_kernel");
+        } else {
+            RDFC_CUDA(cudaMemcpyAsync(out, feat_init, sizeof(float) * B * P, cudaMemcpyDeviceToDevice, st));
+        }
+        return 0;
+    }
+    const float *fix = preserve_input ? feat_fix : nullptr;
+    // band halo rows: taps beyond it take the global path (measured at sigma = 2.2 px offsets: 8 -> 49.5, 6 -> 47.8, 4 -> 47.2 us)
+    const int halo = (int)knob("RDFC_NLSPN_HALO", 6);
+    const int pdl = knob("RDFC_NLSPN_PDL", 1) != 0;         // programmatic dependent launch between the iterations
+    const bool simple = knob("RDFC_NLSPN_SIMPLE", 0) != 0;
+    // pixels per thread of the fp32-plane kernel: 2 -> 3 CTAs / SM (measured best), 1 (odd widths) -> 5 CTAs / SM
+    const int pix = (!packed && W % 2 == 0 && P % 2 == 0 && ((uintptr_t)offset % 8) == 0 && ((uintptr_t)aff % 8) == 0 &&
+                     ((uintptr_t)out % 8) == 0 && ((uintptr_t)scratch % 8) == 0 && (!inter || ((uintptr_t)inter % 8) == 0)) ? 2 : 1;
+    const int per_sm_max = (int)knob("RDFC_NLSPN_PER_SM", packed ? 4 : (pix == 2 ? 3 : 5));
+    const BandGeom g = band_geom(B, H, W, halo, per_sm_max);
+    const bool band = g.ok && !simple;
+    RDFC_REQUIRE(band || !packed, "packed NLSPN stream: image too wide for the band kernel (W = %d)", W);
+    if (band) {
+        if (packed) {
+            RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        } else if (pix == 2) {
+            RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_band_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_band_kernel<true, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        } else {
+            RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_band_kernel<false, 1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_band_kernel<true, 1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        }
+    }
+    float *bufs[2] = {scratch, out};
+    const float *cur = feat_init;
+    for (int t = 0; t < prop_time; ++t) {
+        float *dst = bufs[(prop_time - 1 - t) % 2 == 0 ? 1 : 0];      // ping-pong parity: the last iteration lands in `out`
+        float *it = inter ? inter + (long long)t * B * P : nullptr;
+        const bool last = t == prop_time - 1;
+        const FuseOut none{nullptr, nullptr, nullptr, nullptr};
+        if (band && packed) {
+            if (last) RDFC_CUDA(launch_pdl(nlspn_prop_packed_kernel<true>, g.nctas, BAND_THREADS, g.smem, st, pdl, cur, (const uint4 *)packed, fix, dst, fz, clamp, B, H, W, g.rows_per_cta, g.sub_rows, halo));
+            else RDFC_CUDA(launch_pdl(nlspn_prop_packed_kernel<false>, g.nctas, BAND_THREADS, g.smem, st, pdl, cur, (const uint4 *)packed, fix, dst, none, 0, B, H, W, g.rows_per_cta, g.sub_rows, halo));
+            RDFC_CHECK_LAUNCH("nlspn_prop_packed_kernel");
+        } else if (band) {
+#define RDFC_BAND(FIN, PX, MB, FZ, CL)                                                                                            \
+    RDFC_CUDA(launch_pdl(nlspn_prop_band_kernel<FIN, PX, MB>, g.nctas, BAND_THREADS, g.smem, st, pdl, cur, offset, aff, fix, dst, it, \
+                         FZ, CL, B, H, W, g.rows_per_cta, g.sub_rows, halo))
+            if (pix == 2) { if (last) RDFC_BAND(true, 2, 3, fz, clamp); else RDFC_BAND(false, 2, 3, none, 0); }
+            else { if (last) RDFC_BAND(true, 1, 5, fz, clamp); else RDFC_BAND(false, 1, 5, none, 0); }
+#undef RDFC_BAND
+            RDFC_CHECK_LAUNCH("nlspn_prop_band_kernel");
+        } else {
+            RDFC_REQUIRE(B <= 65535, "batch too large for the fallback kernel");
+            dim3 grid(cdiv(W, TX), cdiv(H, TY), B), block(TX, TY);
+            if (last) nlspn_prop_kernel<true><<<grid, block, 0, st>>>(cur, offset, aff, fix, dst, it, fz, clamp, H, W);
+            else nlspn_prop_kernel<false><<<grid, block, 0, st>>>(cur, offset, aff, fix, dst, it, none, 0, H, W);
+            RDFC_CHECK_LAUNCH("nlspn_prop_kernel");
+        }
+        cur = dst;
+    }
     return 0;
 }
 
 extern "C" int rdfc_nlspn_propagate_forward(const float *feat_init, const float *offset, const float *aff,
                                             const float *feat_fix, int preserve_input, float *out, float *scratch,
                                             float *inter, int B, int H, int W, int prop_time, int clamp_out,
-                                            void *stream) {
-    RDFC_REQUIRE(feat_init && offset && aff && out && scratch, "NULL pointer argument");
-    RDFC_REQUIRE(!preserve_input || feat_fix, "preserve_input requires feat_fix (nlspn_model.py:157-158)");
-    RDFC_REQUIRE(B > 0 && H > 0 && W > 0 && prop_time >= 0, "bad shape (%d,%d,%d) x %d", B, H, W, prop_time);
-    cudaStream_t st = (cudaStream_t)stream;
-    const long long P = (long long)H * W;
-    if (prop_time == 0) {
-        RDFC_CUDA(cudaMemcpyAsync(out, feat_init, sizeof(float) * B * P, cudaMemcpyDeviceToDevice, st));
-        return 0;
-    }
-    // L2 blocking: offset+aff of a group (27 planes, 25 read) should stay L2 resident across the iterations.
-    const long long bytes_per_img = 27 * P * 4;
-    // Measured on B200 (profiles/): walking the batch in L2-sized groups does NOT pay -- a 60 MB group still misses
-    // L2 (21 % hit rate, LRU thrash) and small launches lose more to launch/tail effects -- so the default is one
-    // launch per iteration over the whole batch.  RDFC_NLSPN_GROUP_MB re-enables grouping for experiments.
-    long long budget = 1ll << 40;
-    if (const char *e = getenv("RDFC_NLSPN_GROUP_MB")) budget = (long long)atoi(e) << 20;
-    long long gsz = budget / bytes_per_img;
-    if (gsz < 1) gsz = 1;
-    if (gsz > 65535) gsz = 65535;
-    // extra buffer for preserve_input (blend result); reuse: blend writes into the buffer not being read
-    for (long long b0 = 0; b0 < B; b0 += gsz) {
-        const int nb = (int)((B - b0) < gsz ? (B - b0) : gsz);
-        dim3 grid(cdiv(W, TX), cdiv(H, TY), nb), block(TX, TY);
-        const float *off_g = offset + b0 * 18 * P, *aff_g = aff + b0 * 9 * P;
-        const float *fix_g = feat_fix ? feat_fix + b0 * P : nullptr;
-        float *bufs[2] = {scratch + b0 * P, out + b0 * P};
-        // choose ping-pong parity so that the last iteration lands in `out`
-        const float *cur = feat_init + b0 * P;
-        for (int t = 0; t < prop_time; ++t) {
-            float *dst = bufs[(prop_time - 1 - t) % 2 == 0 ? 1 : 0];
-            if (preserve_input) {
-                // blend into dst's sibling is unsafe (cur may live there); blend in place needs cur writable:
-                // iteration 0 reads feat_init (const) -> blend into the other buffer first.
-                float *tmp = (dst == bufs[0]) ? bufs[1] : bufs[0];
-                const int nblk = (int)min((long long)cdiv(nb * P, 256), (long long)sm_count() * 8);
-                nlspn_preserve_kernel<<<nblk, 256, 0, st>>>(cur, fix_g, tmp, nb * P);
-                RDFC_CHECK_LAUNCH("nlspn_preserve_kernel");
-                cur = tmp;
-            }
-            float *it = inter ? inter + ((long long)t * B + b0) * P : nullptr;
-            const bool clamp = clamp_out && t == prop_time - 1;
-            // row-streaming kernel: needs 16-byte row granularity for the bulk copies
-            const size_t stage_bytes = (size_t)25 * W * sizeof(float);
-            const int nt = (W + 31) / 32 * 32;
-            // many small CTAs per SM (1 stage each) hide the bulk-copy latency by interleaving; wide rows get 2 stages
-            int stages = 2;
-            if (const char *e = getenv("RDFC_NLSPN_STAGES")) stages = atoi(e);
-            while (stages > 1 && stages * stage_bytes + 64 > 200 * 1024) --stages;
-            const size_t smem = stages * stage_bytes + 64;
-            // ring kernel: TMA row stream + shared-memory band gathers, one persistent CTA per SM
-            {
-                int halo_r = 8;
-                if (const char *e = getenv("RDFC_NLSPN_HALO")) halo_r = atoi(e);
-                const int nseg = (W + 31) / 32;
-                int G = (H % 3 == 0 && nseg <= 10) ? 3 : ((H % 2 == 0 && nseg <= 15) ? 2 : 1);   // rows per stage ~ 30 warps of work
-                if (const char *e = getenv("RDFC_NLSPN_G")) G = atoi(e);
-                int ncw = G * nseg > 30 ? 30 : G * nseg;
-                if (const char *e = getenv("RDFC_NLSPN_NCW")) ncw = atoi(e);
-                const size_t stage_b = (size_t)G * 25 * W * 4;
-                int S = stage_b >= 48 * 1024 ? 2 : 3;
-                if (const char *e = getenv("RDFC_NLSPN_STAGES")) S = atoi(e);
-                const long long total_rows = (long long)nb * H;
-                long long nctas = sm_count();
-                if (const char *e = getenv("RDFC_NLSPN_RING_CTAS")) nctas = atoll(e);
-                long long rpc = (total_rows + nctas - 1) / nctas;
-                rpc = (rpc + G - 1) / G * G;
-                const long long left = 220 * 1024 - (long long)S * stage_b - 2 * S * 8 - 128;
-                long long nr_max = left / ((W + 4) * 4) - 2 * halo_r - 3;
-                if (nr_max > rpc) nr_max = rpc;
-                nr_max = nr_max / G * G;
-                const bool ring_ok = getenv("RDFC_NLSPN_RING") && !getenv("RDFC_NLSPN_SIMPLE") && !getenv("RDFC_NLSPN_ROWS") &&
-                                     W % 4 == 0 && H % G == 0 && nr_max >= G && nr_max >= 4 && ncw >= 1 && ncw <= 30 &&
-                                     ((uintptr_t)off_g % 16) == 0 && ((uintptr_t)aff_g % 16) == 0 && (P % 4) == 0;
-                if (ring_ok) {
-                    const size_t smem = (size_t)S * stage_b + (size_t)(nr_max + 2 * halo_r + 3) * (W + 4) * 4 + 2 * S * 8 + 128;
-                    const int grid_r = (int)((total_rows + rpc - 1) / rpc);
-                    if (clamp) {
-                        RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                        nlspn_prop_ring_kernel<true><<<grid_r, (ncw + 1) * 32, smem, st>>>(cur, off_g, aff_g, dst, it, nb, H, W, (int)rpc, halo_r, G, S, (int)nr_max);
-                    } else {
-                        RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                        nlspn_prop_ring_kernel<false><<<grid_r, (ncw + 1) * 32, smem, st>>>(cur, off_g, aff_g, dst, it, nb, H, W, (int)rpc, halo_r, G, S, (int)nr_max);
-                    }
-                    RDFC_CHECK_LAUNCH("nlspn_prop_ring_kernel");
-                    cur = dst;
-                    continue;
-                }
-            }
-            // band kernel: even W (8-byte plane vectors), tile must fit shared memory
-            int halo = 6;      // rows of band halo: taps beyond it take the global path (measured at sigma = 2.2 px offsets: 8 -> 49.5, 6 -> 47.8, 4 -> 47.2 us per launch)
-            if (const char *e = getenv("RDFC_NLSPN_HALO")) halo = atoi(e);
-            const long long total_rows_b = (long long)nb * H;
-            int band_pix = 2;                      // pixels per thread: 2 -> 3 CTAs / SM (measured best), 1 -> 5 CTAs / SM
-            if (W % 2 != 0) band_pix = 1;
-            if (const char *e = getenv("RDFC_NLSPN_PIX")) band_pix = atoi(e);
-            const int band_per_sm = band_pix == 2 ? 3 : 5;
-            int band_prefetch = 0;        // measured: L2 prefetch of the next item costs more LSU slots than it hides (1058 vs 957 us)
-            if (const char *e = getenv("RDFC_NLSPN_PREFETCH")) band_prefetch = atoi(e);
-            int band_pdl = 1;             // programmatic dependent launch between the iterations (see the kernel)
-            if (const char *e = getenv("RDFC_NLSPN_PDL")) band_pdl = atoi(e) != 0;
-            int band_pre = 0;             // items per thread whose offset / affinity lines are prefetched to L2 before the wait
-            if (const char *e = getenv("RDFC_NLSPN_PRE")) band_pre = atoi(e);
-            long long band_ctas = (long long)sm_count() * band_per_sm;
-            if (const char *e = getenv("RDFC_NLSPN_BAND_CTAS")) band_ctas = atoll(e);
-            if (band_ctas > total_rows_b) band_ctas = total_rows_b;
-            const int band_rpc = (int)((total_rows_b + band_ctas - 1) / band_ctas);
-            const size_t band_smem = (size_t)(band_rpc + 2 * halo + 3) * (W + 4) * sizeof(float);
-            const size_t band_smem_max = (size_t)(220 * 1024) / band_per_sm;
-            const bool band_ok = !getenv("RDFC_NLSPN_SIMPLE") && !getenv("RDFC_NLSPN_ROWS") && W % band_pix == 0 && band_smem <= band_smem_max &&
-                                 ((uintptr_t)off_g % 8) == 0 && ((uintptr_t)aff_g % 8) == 0 && ((uintptr_t)dst % 8) == 0 &&
-                                 (!it || ((uintptr_t)it % 8) == 0) && (P % 2) == 0;
-            if (band_ok) {
-                const int nctas = (int)((total_rows_b + band_rpc - 1) / band_rpc);
-#define RDFC_BAND(CL, PX, MB)                                                                                                  \
-    do {                                                                                                                       \
-        RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_band_kernel<CL, PX, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)); \
-        cudaLaunchConfig_t cfg = {};                                                                                       \
-        cfg.gridDim = dim3(nctas); cfg.blockDim = dim3(BAND_THREADS); cfg.dynamicSmemBytes = band_smem; cfg.stream = st;       \
-        cudaLaunchAttribute attr[1];                                                                                           \
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                       \
-        attr[0].val.programmaticStreamSerializationAllowed = band_pdl;                                                         \
-        cfg.attrs = attr; cfg.numAttrs = 1;                                                                                    \
-        RDFC_CUDA(cudaLaunchKernelEx(&cfg, nlspn_prop_band_kernel<CL, PX, MB>, (const float *)cur, (const float *)off_g,       \
-                                     (const float *)aff_g, (float *)dst, (float *)it, (int)nb, H, W, band_rpc, halo, band_prefetch, \
-                                     band_pre));                                                                               \
-    } while (0)
-                if (band_pix == 2) { if (clamp) RDFC_BAND(true, 2, 3); else RDFC_BAND(false, 2, 3); }
-                else { if (clamp) RDFC_BAND(true, 1, 5); else RDFC_BAND(false, 1, 5); }
-#undef RDFC_BAND
-                RDFC_CHECK_LAUNCH("nlspn_prop_band_kernel");
-                cur = dst;
-                continue;
-            }
-            const bool rows_ok = getenv("RDFC_NLSPN_ROWS") && W % 4 == 0 && W <= 1024 && smem <= 200 * 1024 &&
-                                 ((uintptr_t)off_g % 16) == 0 && ((uintptr_t)aff_g % 16) == 0;
-            if (rows_ok) {
-                int per_sm = (int)((226 * 1024) / (smem + 1024));
-                if (per_sm * nt > 2048) per_sm = 2048 / nt;
-                if (nt <= 320 && per_sm > 3) per_sm = 3;       // register budget of the <320,3> instantiation (64 regs)
-                if (per_sm < 1) per_sm = 1;
-                if (const char *e = getenv("RDFC_NLSPN_CTAS_PER_SM")) per_sm = atoi(e);
-                const long long total_rows = (long long)nb * H;
-                long long nctas = (long long)sm_count() * per_sm;
-                if (nctas > total_rows) nctas = total_rows;
-                const int rpc = (int)((total_rows + nctas - 1) / nctas);
-                nctas = (total_rows + rpc - 1) / rpc;
-#define RDFC_ROWS(CL, MT, MB)                                                                                        \
-    do {                                                                                                             \
-        RDFC_CUDA(cudaFuncSetAttribute(nlspn_prop_rows_kernel<CL, MT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       200 * 1024));                                                                 \
-        nlspn_prop_rows_kernel<CL, MT, MB><<<(int)nctas, nt, smem, st>>>(cur, off_g, aff_g, dst, it, nb, H, W, stages, rpc); \
-    } while (0)
-                if (nt <= 320) {
-                    if (clamp) RDFC_ROWS(true, 320, 3); else RDFC_ROWS(false, 320, 3);
-                } else {
-                    if (clamp) RDFC_ROWS(true, 1024, 1); else RDFC_ROWS(false, 1024, 1);
-                }
-#undef RDFC_ROWS
-                RDFC_CHECK_LAUNCH("nlspn_prop_rows_kernel");
-            } else {
-                if (clamp)
-                    nlspn_prop_kernel<true><<<grid, block, 0, st>>>(cur, off_g, aff_g, dst, it, H, W);
-                else
-                    nlspn_prop_kernel<false><<<grid, block, 0, st>>>(cur, off_g, aff_g, dst, it, H, W);
-                RDFC_CHECK_LAUNCH("nlspn_prop_kernel");
-            }
-            cur = dst;
-        }
-    }
-    return 0;
+                                            const rdfc_fuse_out *fuse, void *stream) {
+    RDFC_REQUIRE(offset && aff, "NULL pointer argument");
+    return propagate(feat_init, offset, aff, nullptr, feat_fix, preserve_input, out, scratch, inter, B, H, W, prop_time, clamp_out,
+                     fuse, (cudaStream_t)stream);
+}
+
+extern "C" int rdfc_nlspn_propagate_forward_packed(const float *feat_init, const void *packed, const float *feat_fix,
+                                                   int preserve_input, float *out, float *scratch, int B, int H, int W,
+                                                   int prop_time, int clamp_out, const rdfc_fuse_out *fuse, void *stream) {
+    RDFC_REQUIRE(packed && ((uintptr_t)packed % 16) == 0, "packed stream must be 16-byte aligned");
+    return propagate(feat_init, nullptr, nullptr, packed, feat_fix, preserve_input, out, scratch, nullptr, B, H, W, prop_time,
+                     clamp_out, fuse, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

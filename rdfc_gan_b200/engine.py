@@ -38,7 +38,7 @@ class _Packed:
             cur = getattr(self, name)
             if val is None:
                 setattr(self, name, None)
-            elif cur is None or cur.shape != val.shape or cur.dtype != val.dtype:
+            elif cur is None or cur.shape != val.shape or cur.dtype != val.dtype or cur.device != val.device:
                 setattr(self, name, val.contiguous().clone())
             else:
                 cur.copy_(val)
@@ -111,10 +111,20 @@ class GeneratorEngine:
         self.gen = gen
         self.precision = 'fp32'
         self.use_cuda_graph = True
-        self._plans = {}
+        self.max_plans = 4       # plans (activation buffers + a captured graph each) kept per engine, least recently used first out
+        self._plans = {}         # (B, H, W, Cs, device, precision) -> Plan, in LRU order
         self._packed = {}        # (precision, layer name) -> _Packed
         self._wver = {}          # precision -> parameter version stamp
         self._recipes = {}       # (precision, layer name) -> (sources, umma, transposed) for in-place re-packing
+        self._device = None      # packed weights and plans live on ONE device; moving the module drops them
+
+    def clear_plans(self, precision=None):
+        """Drop cached plans (their activation buffers, descriptors and CUDA graphs) -- all of them, or one precision's.
+        Plans are also evicted least-recently-used beyond `max_plans`.  A plan's fixed I/O buffers are shared by every call
+        that hits it: calls must be issued from one stream / thread at a time (the reference's modules have the same
+        single-stream contract through cuDNN workspaces)."""
+        for key in [k for k in self._plans if precision is None or k[5] == precision]:
+            del self._plans[key]
 
     # ------------------------------------------------------------------------------------------- weights --------
     def _stamp(self):
@@ -180,8 +190,8 @@ class GeneratorEngine:
         adt = torch.bfloat16 if bf16 else torch.float32
         plan = Plan()
         plan.precision = precision
-        def new(*shape, dtype=adt):
-            t = torch.empty(shape, dtype=dtype, device=device)
+        def new(*shape, dtype=None):
+            t = torch.empty(shape, dtype=dtype or adt, device=device)
             plan.keep.append(t)          # descriptors hold raw pointers: every buffer must live as long as the plan
             return t
 
@@ -364,27 +374,52 @@ class GeneratorEngine:
         n = B * H * W
         if has_gd:
             pl = g.nlspn_refine_module.prop_layer
-            plan.offset, plan.aff, plan.scratch, plan.d2raw = f32(B, 18, H, W), f32(B, 9, H, W), f32(B, 1, H, W), f32(B, 1, H, W)
+            plan.scratch, plan.d2raw = f32(B, 1, H, W), f32(B, 1, H, W)
             pw = self._pack_nlspn(precision)
             plan.keep.append(pw)
             aff_mode, conf_prop, preserve, T = C.AFFINITY[pl.affinity], int(bool(pl.conf_prop)), int(bool(pl.preserve_input)), pl.prop_time
+            fix = C.ptr(plan.depth) if preserve else None
+            fz = C.FuseOut(plan.d1.data_ptr(), plan.c1.data_ptr(), plan.conf.data_ptr(), plan.pred.data_ptr())
+            plan.keep.append(fz)
             plan.names.append('nlspn_affinity')
-            plan.steps.append(lambda s: C.check(C.lib.rdfc_nlspn_affinity_forward(
-                C.ptr(plan.guide), C.ptr(plan.conf), C.ptr(pw.weight), C.ptr(pw.shift), C.ptr(pw.scale), aff_mode, conf_prop,
-                C.ptr(plan.offset), C.ptr(plan.aff), B, H, W, s)))
-            plan.names.append(f'nlspn_propagate x{T}')
-            plan.steps.append(lambda s: C.check(C.lib.rdfc_nlspn_propagate_forward(
-                C.ptr(plan.pred_init), C.ptr(plan.offset), C.ptr(plan.aff), C.ptr(plan.depth) if preserve else None, preserve,
-                C.ptr(plan.d2raw), C.ptr(plan.scratch), None, B, H, W, T, 0, s)))
-            plan.n_launch += 1 + T * (2 if preserve else 1)
-            d2src = plan.d2raw
+            if bf16:
+                # bf16 mode: offsets / affinities as a packed fp16 stream (48 B instead of 100 B per pixel and iteration)
+                plan.packed = new(C.lib.rdfc_nlspn_packed_bytes(B, H, W), dtype=torch.uint8)
+                plan.steps.append(lambda s: C.check(C.lib.rdfc_nlspn_affinity_forward_packed(
+                    C.ptr(plan.guide), C.ptr(plan.conf), C.ptr(pw.weight), C.ptr(pw.shift), C.ptr(pw.scale), aff_mode, conf_prop,
+                    C.ptr(plan.packed), B, H, W, s)))
+
+                def prop(src, dst, iters, fuse):
+                    return lambda s: C.check(C.lib.rdfc_nlspn_propagate_forward_packed(
+                        C.ptr(src), C.ptr(plan.packed), fix, preserve, C.ptr(dst), C.ptr(plan.scratch), B, H, W, iters, 0,
+                        ctypes.byref(fz) if fuse else None, s))
+            else:
+                plan.offset, plan.aff = f32(B, 18, H, W), f32(B, 9, H, W)
+                plan.steps.append(lambda s: C.check(C.lib.rdfc_nlspn_affinity_forward(
+                    C.ptr(plan.guide), C.ptr(plan.conf), C.ptr(pw.weight), C.ptr(pw.shift), C.ptr(pw.scale), aff_mode, conf_prop,
+                    C.ptr(plan.offset), C.ptr(plan.aff), B, H, W, s)))
+
+                def prop(src, dst, iters, fuse):
+                    return lambda s: C.check(C.lib.rdfc_nlspn_propagate_forward(
+                        C.ptr(src), C.ptr(plan.offset), C.ptr(plan.aff), fix, preserve, C.ptr(dst), C.ptr(plan.scratch), None,
+                        B, H, W, iters, 0, ctypes.byref(fz) if fuse else None, s))
+            # iterations 1..T-1 beside the RGB heads; the last one applies the output fusion (clamp, confidence softmax, weighted
+            # sum) in its epilogue and therefore waits for the RGB heads' d1 / c1
+            src = plan.pred_init
+            if T > 1:
+                plan.names.append(f'nlspn_propagate x{T - 1}')
+                plan.steps.append(prop(src, plan.d2raw, T - 1, False))
+                src = plan.d2raw
+            plan.join()
+            plan.names.append('nlspn_propagate (last) + fuse_depth' if T > 0 else 'fuse_depth')
+            plan.steps.append(prop(src, plan.d2, min(T, 1), True))
+            plan.n_launch += 1 + max(T, 1)
         else:
-            d2src = plan.pred_init
-        plan.join()
-        plan.names.append('fuse_depth')
-        plan.steps.append(lambda s: C.check(C.lib.rdfc_fuse_depth_forward(
-            C.ptr(plan.d1), C.ptr(plan.c1), C.ptr(d2src), C.ptr(plan.conf), C.ptr(plan.d2), C.ptr(plan.pred), n, s)))
-        plan.n_launch += 1
+            plan.join()
+            plan.names.append('fuse_depth')
+            plan.steps.append(lambda s: C.check(C.lib.rdfc_fuse_depth_forward(
+                C.ptr(plan.d1), C.ptr(plan.c1), C.ptr(plan.pred_init), C.ptr(plan.conf), C.ptr(plan.d2), C.ptr(plan.pred), n, s)))
+            plan.n_launch += 1
         plan.outputs = (plan.d1, plan.c1, plan.d2, plan.conf, plan.pred)
         return plan
 
@@ -563,11 +598,24 @@ class GeneratorEngine:
         if H < 16 or W < 16:
             raise RuntimeError("inputs smaller than 16x16 do not survive the four stride-2 stages")
         dev = stem_in.device
+        pdev = next(g.parameters()).device
+        if pdev != dev or depth.device != dev:
+            raise RuntimeError(f"generator parameters are on {pdev}, inputs on {dev} / {depth.device}: move the module with .to(device)")
+        if self._device != dev:          # first use, or the module moved: packed weights / plans of the old device are stale
+            self._plans.clear()
+            self._packed.clear()
+            self._recipes.clear()
+            self._wver.clear()
+            self._device = dev
         key = (B, H, W, Cs, dev, self.precision)
         with torch.cuda.device(dev), torch.no_grad():
             stamp = self._stamp()
-            plan = self._plans.get(key)
+            plan = self._plans.pop(key, None)
+            if plan is not None:
+                self._plans[key] = plan                     # most recently used last
             if plan is None:
+                while len(self._plans) >= self.max_plans:
+                    del self._plans[next(iter(self._plans))]
                 plan = self._plans[key] = self._build_plan(B, H, W, Cs, dev, self.precision)   # packs the weights too
                 self._wver[self.precision] = stamp
                 plan.stem_in.copy_(stem_in)

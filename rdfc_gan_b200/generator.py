@@ -101,14 +101,34 @@ class _GeneratorBase(nn.Module):
         self.engine(precision)
         return self
 
-    def _run(self, stem_in, depth):
-        for t in (stem_in, depth):
+    def _check_inference(self, *tensors):
+        for t in tensors:
             if not t.is_cuda:
                 raise RuntimeError("rdfc_gan_b200 generators run on CUDA (sm_100a) tensors only; there is no CPU path")
-        if self.training and torch.is_grad_enabled():
-            raise RuntimeError("training-mode forward (batch-statistics BatchNorm + autograd) is not implemented yet; "
-                               "call .eval() and run under torch.no_grad()")
+        if self.training:
+            # the reference would use batch-statistics BatchNorm and update the running stats here, whatever the grad mode
+            raise RuntimeError("training-mode forward (batch-statistics BatchNorm + autograd) is not implemented by the inference "
+                               "engine; call .eval()")
+        if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+            raise RuntimeError("the eval-mode forward is inference-only and returns detached tensors: an input requires grad; "
+                               "run under torch.no_grad() or detach the inputs")
+
+    def _run(self, stem_in, depth):
+        self._check_inference(stem_in, depth)
         return self.engine().forward(stem_in, depth)
+
+    _OUTPUTS = ('depth_map_1', 'confidence_map_1', 'depth_map_2', 'confidence_map_2', 'pred_depth')
+
+    def _stream(self, pairs, outputs):
+        """Pipelined inference over HOST (stem input, depth) batches: engine.forward_stream."""
+        want = tuple(self._OUTPUTS.index(k) for k in outputs)
+        dev = next(self.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError("rdfc_gan_b200 generators run on CUDA (sm_100a) devices only; move the module first")
+        if self.training:
+            raise RuntimeError("stream() is an inference API: call .eval()")
+        for res in self.engine().forward_stream(pairs, dev, want):
+            yield dict(zip(outputs, res))
 
 
 class RDFGenerator(_GeneratorBase):
@@ -132,20 +152,12 @@ class RDFGenerator(_GeneratorBase):
         self.use_pretrained_global_guidance_module = False
         self.pretrained_on_imagenet = pretrained_on_imagenet
 
-    def stream(self, batches, outputs=('depth_map_1', 'confidence_map_1', 'depth_map_2', 'confidence_map_2', 'pred_depth')):
+    def stream(self, batches, outputs=_GeneratorBase._OUTPUTS):
         """Pipelined inference for a stream of HOST batches: ``batches`` yields ``(rgb, depth, normal)`` CPU tensors
         (pinned memory makes the copies asynchronous); yields one dict of pinned CPU tensors per batch, in order, with
         the keys in ``outputs``.  Host->device and device->host copies overlap the forward of the neighbouring batches
         (engine.forward_stream); the arithmetic is exactly ``forward``'s.  A yielded dict is reused two batches later."""
-        names = ('depth_map_1', 'confidence_map_1', 'depth_map_2', 'confidence_map_2', 'pred_depth')
-        want = tuple(names.index(k) for k in outputs)
-        dev = next(self.parameters()).device
-        if dev.type != 'cuda':
-            raise RuntimeError("rdfc_gan_b200 generators run on CUDA (sm_100a) devices only; move the module first")
-        if self.training and torch.is_grad_enabled():
-            raise RuntimeError("stream() is an inference API: call .eval() and run under torch.no_grad()")
-        for res in self.engine().forward_stream(((normal, depth) for _, depth, normal in batches), dev, want):
-            yield dict(zip(outputs, res))
+        return self._stream(((normal, depth) for _, depth, normal in batches), outputs)
 
     def forward(self, rgb, depth, normal):
         """rdf_generator.py:280-414: both stems read ``normal`` (:286,289); ``rgb`` is unused by the reference too."""
@@ -177,6 +189,14 @@ class DCVGANGenerator(_GeneratorBase):
         self.use_nlpsn_refine = use_nlpsn_refine
         self.global_guidance_module = global_guidance_module
         self._build_tail(ce, cd, de, dd, True, nlspn_configs)               # gd_dec* always exist (:73-76)
+
+    def stream(self, batches, outputs=_GeneratorBase._OUTPUTS):
+        """As RDFGenerator.stream for ``(rgb, depth)`` HOST batches; needs ``global_guidance_module`` None / Identity (the stem
+        input is then ``rgb`` itself, e.g. a precomputed 40-channel guidance map): a guidance network runs on the device and
+        belongs in front of ``forward``."""
+        if not (self.global_guidance_module is None or isinstance(self.global_guidance_module, nn.Identity)):
+            raise RuntimeError("stream() needs the guidance map as input (global_guidance_module None or nn.Identity)")
+        return self._stream(((rgb, depth) for rgb, depth in batches), outputs)
 
     def forward(self, rgb, depth):
         """rdf_gan_generator.py:233-361 -> (depth_map_1, confidence_map_1, depth_map_2, confidence_map_2, final)"""

@@ -3,22 +3,23 @@
 Same constructor arguments, parameter names / shapes (state_dict compatible: ``aff_scale_const``, ``w``, ``b``,
 ``w_conf``, ``conv_offset_aff.{weight,bias}``), asserts and return tuples.  The forward pass runs two fused sm_100a
 kernels through the C ABI (rdfc_nlspn_affinity_forward, rdfc_nlspn_propagate_forward) instead of the reference's
-26 DCN calls + ~25 ATen kernels.  When gradients are required it falls back to the reference's *composition*
-(still on the GPU, through ModulatedDeformConvFunction -> rdfc_dcn_forward/backward); there is no CPU path.
+26 DCN calls + ~25 ATen kernels; with gradients enabled the same two stages run as two differentiable ops whose
+backwards are fused kernels as well (rdfc_nlspn_affinity_backward, rdfc_nlspn_propagate_backward).  There is no CPU
+path and no re-statement of the reference's per-call composition: configurations the fused kernels do not cover
+(``prop_kernel != 3``, guidance with other than 8 channels, non-fp32 tensors) raise.
 """
 import torch
 import torch.nn as nn
 
 from . import _cabi as C
-from .dcn.functions import ModulatedDeformConvFunction
 
 
 class _PropagateFused(torch.autograd.Function):
     """The T propagation iterations as one differentiable op: forward = rdfc_nlspn_propagate_forward (keeping every
     iteration's result), backward = rdfc_nlspn_propagate_backward (the transposed gather as a scatter per iteration, then ONE
     pass for grad_offset / grad_aff).  Replaces the reference's prop_time ModulatedDeformConvFunction calls and their
-    backwards (nlspn_model.py:140-175); feat_fix gets no gradient path worth keeping (the reference detaches the mask only,
-    the m * fix term's gradient is returned as well)."""
+    backwards (nlspn_model.py:140-175).  Returns (result, inter) with inter (T,B,1,H,W) = the reference's list_feat stacked;
+    gradients arriving through either output are honoured."""
 
     @staticmethod
     def forward(ctx, feat_init, offset, aff, feat_fix, prop_time, preserve_input):
@@ -27,32 +28,34 @@ class _PropagateFused(torch.autograd.Function):
         fix = feat_fix.contiguous() if (preserve_input and feat_fix is not None) else None
         out = torch.empty_like(feat_init)
         scratch = torch.empty_like(feat_init)
-        inter = torch.empty((max(prop_time, 1),) + tuple(feat_init.shape), dtype=torch.float32, device=feat_init.device)
+        inter = torch.empty((prop_time,) + tuple(feat_init.shape), dtype=torch.float32, device=feat_init.device)
         with torch.cuda.device(feat_init.device):
             C.check(C.lib.rdfc_nlspn_propagate_forward(
                 C.ptr(feat_init), C.ptr(offset), C.ptr(aff), C.ptr(fix), int(bool(preserve_input)), C.ptr(out),
-                C.ptr(scratch), C.ptr(inter), B, H, W, prop_time, 0, C.stream_ptr(feat_init.device)))
+                C.ptr(scratch), C.ptr(inter) if prop_time > 0 else None, B, H, W, prop_time, 0, None,
+                C.stream_ptr(feat_init.device)))
         ctx.save_for_backward(feat_init, offset, aff, fix if fix is not None else feat_init.new_empty(0), inter)
         ctx.cfg = (prop_time, bool(preserve_input), fix is not None)
-        return out
+        return out, inter
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, grad_out, grad_inter):
         feat_init, offset, aff, fix, inter = ctx.saved_tensors
         prop_time, preserve, has_fix = ctx.cfg
+        if has_fix and ctx.needs_input_grad[3]:
+            raise NotImplementedError("gradient w.r.t. feat_fix (the sparse input depth) is not provided by the fused NLSPN backward")
         B, _, H, W = feat_init.shape
         grad_out = grad_out.contiguous()
+        # autograd hands over a dense zero tensor for an unused output; an all-zero grad_inter just adds zeros in the kernel
+        g_inter = grad_inter.contiguous() if (grad_inter is not None and prop_time > 0) else None
         g_feat, g_off, g_aff = torch.empty_like(feat_init), torch.empty_like(offset), torch.empty_like(aff)
         scratch = torch.empty((prop_time + 1,) + tuple(feat_init.shape), dtype=torch.float32, device=feat_init.device)
         with torch.cuda.device(feat_init.device):
             C.check(C.lib.rdfc_nlspn_propagate_backward(
-                C.ptr(grad_out), None, C.ptr(feat_init), C.ptr(inter), C.ptr(offset), C.ptr(aff),
+                C.ptr(grad_out), C.ptr(g_inter), C.ptr(feat_init), C.ptr(inter), C.ptr(offset), C.ptr(aff),
                 C.ptr(fix) if has_fix else None, int(preserve), C.ptr(g_feat), C.ptr(g_off), C.ptr(g_aff), C.ptr(scratch),
                 B, H, W, prop_time, C.stream_ptr(feat_init.device)))
-        g_fix = None
-        if has_fix and ctx.needs_input_grad[3]:
-            raise NotImplementedError("gradient w.r.t. feat_fix (the sparse input depth) is not provided by the fused NLSPN backward")
-        return g_feat, g_off, g_aff, g_fix, None, None
+        return g_feat, g_off, g_aff, None, None, None
 
 
 class _AffinityFused(torch.autograd.Function):
@@ -145,146 +148,72 @@ class NLPSN(nn.Module):
         self.deformable_groups = 1
         self.im2col_step = 64
         self.return_intermediates = True
-        self.fused_backward = True          # False: always differentiate through the reference's composition
 
-    # ---- fused inference path --------------------------------------------------------------------------------
-    def _fused_ok(self, *tensors):
-        if self.k_f != 3 or self.k_g != 3:
-            return False
-        if torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in tensors) or
-                                        any(p.requires_grad for p in self.conv_offset_aff.parameters())):
-            return False
-        return all(t is None or t.dtype == torch.float32 for t in tensors)
+    def _require_supported(self, *tensors):
+        """The fused kernels hard-code the reference's only setting: a 3x3 propagation kernel fed by 8 guidance channels through
+        a 3x3 conv_offset_aff, fp32 tensors on a CUDA device."""
+        if self.k_f != 3 or self.k_g != 3 or self.channels_g != 8:
+            raise NotImplementedError(
+                f"rdfc_gan_b200 NLSPN kernels cover prop_kernel = 3 with 8 guidance channels (the reference's only configuration, "
+                f"F/lib/tools/config.py:70); got k_f={self.k_f}, k_g={self.k_g}, channels_g={self.channels_g}")
+        C.require_cuda(*tensors, self.conv_offset_aff.weight)
+        for t in tensors:
+            if t is not None and t.dtype != torch.float32:
+                raise RuntimeError(f"rdfc_gan_b200 NLSPN runs on float32 tensors, got {t.dtype}")
+            if t is not None and t.device != self.conv_offset_aff.weight.device:
+                raise RuntimeError(f"NLSPN parameters are on {self.conv_offset_aff.weight.device}, an input is on {t.device}")
 
-    def _fused_train_ok(self, feat_init, offset, aff, feat_fix):
-        """Gradients are needed: the fused forward + backward pair covers k_f = 3, fp32, no list_feat consumer and no
-        gradient into feat_fix; everything else takes the reference's composition below."""
-        if self.k_f != 3 or self.return_intermediates or not self.fused_backward:
-            return False
-        if self.preserve_input and feat_fix is not None and feat_fix.requires_grad:
-            return False
-        return all(t is None or t.dtype == torch.float32 for t in (feat_init, offset, aff, feat_fix))
+    def _wants_grad(self, *tensors):
+        return torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in tensors) or
+                                            any(p.requires_grad for p in self.conv_offset_aff.parameters()) or
+                                            self.aff_scale_const.requires_grad)
 
-    def _get_offset_affinity_fused(self, guidance, confidence):
+    def _get_offset_affinity(self, guidance, confidence=None, rgb=None):
+        """nlspn_model.py:68-138 -> offset (B,18,H,W), aff (B,9,H,W)"""
+        conf = confidence if self.conf_prop else None
+        self._require_supported(guidance, conf)
+        if self._wants_grad(guidance, conf):
+            return _AffinityFused.apply(guidance, conf, self.conv_offset_aff.weight, self.conv_offset_aff.bias,
+                                        self.aff_scale_const, self.affinity, self.conf_prop)
         B, _, H, W = guidance.shape
         guidance = guidance.contiguous()
-        confidence = None if confidence is None else confidence.contiguous()
-        offset = torch.empty((B, 2 * (self.num + 1), H, W), dtype=torch.float32, device=guidance.device)
-        aff = torch.empty((B, self.num + 1, H, W), dtype=torch.float32, device=guidance.device)
+        conf = None if conf is None else conf.contiguous()
+        offset = torch.empty((B, 18, H, W), dtype=torch.float32, device=guidance.device)
+        aff = torch.empty((B, 9, H, W), dtype=torch.float32, device=guidance.device)
         with torch.cuda.device(guidance.device):
             C.check(C.lib.rdfc_nlspn_affinity_forward(
-                C.ptr(guidance), C.ptr(confidence), C.ptr(self.conv_offset_aff.weight.detach().contiguous()),
+                C.ptr(guidance), C.ptr(conf), C.ptr(self.conv_offset_aff.weight.detach().contiguous()),
                 C.ptr(self.conv_offset_aff.bias.detach().contiguous()), C.ptr(self.aff_scale_const.detach()),
                 C.AFFINITY[self.affinity], int(bool(self.conf_prop)), C.ptr(offset), C.ptr(aff), B, H, W,
                 C.stream_ptr(guidance.device)))
         return offset, aff
 
-    def _propagate_fused(self, feat_init, offset, aff, feat_fix, want_inter):
-        B, _, H, W = feat_init.shape
-        feat_init = feat_init.contiguous()
-        out = torch.empty_like(feat_init)
-        scratch = torch.empty_like(feat_init)
-        inter = (torch.empty((self.prop_time,) + tuple(feat_init.shape), dtype=torch.float32, device=feat_init.device)
-                 if want_inter and self.prop_time > 0 else None)
-        fix = feat_fix.contiguous() if (self.preserve_input and feat_fix is not None) else None
-        with torch.cuda.device(feat_init.device):
-            C.check(C.lib.rdfc_nlspn_propagate_forward(
-                C.ptr(feat_init), C.ptr(offset), C.ptr(aff), C.ptr(fix), int(bool(self.preserve_input)), C.ptr(out),
-                C.ptr(scratch), C.ptr(inter), B, H, W, self.prop_time, 0, C.stream_ptr(feat_init.device)))
-        return out, ([] if inter is None else list(inter.unbind(0)))
-
-    # ---- reference composition (autograd) ----------------------------------------------------------------------
-    def _get_offset_affinity(self, guidance, confidence=None, rgb=None):
-        """nlspn_model.py:68-138"""
-        C.require_cuda(guidance, confidence)
-        if self._fused_ok(guidance, confidence):
-            return self._get_offset_affinity_fused(guidance, confidence if self.conf_prop else None)
-        if (self.fused_backward and self.k_f == 3 and self.k_g == 3 and guidance.dtype == torch.float32 and
-                (confidence is None or confidence.dtype == torch.float32)):
-            # training: one differentiable op (see _AffinityFused)
-            return _AffinityFused.apply(guidance, confidence if self.conf_prop else None, self.conv_offset_aff.weight,
-                                        self.conv_offset_aff.bias, self.aff_scale_const, self.affinity, self.conf_prop)
-        B, _, H, W = guidance.shape
-        offset_aff = self.conv_offset_aff(guidance)
-        o1, o2, aff = torch.chunk(offset_aff, 3, dim=1)
-        offset = torch.cat((o1, o2), dim=1).view(B, self.num, 2, H, W)
-        list_offset = list(torch.chunk(offset, self.num, dim=1))
-        list_offset.insert(self.idx_ref, torch.zeros((B, 1, 2, H, W)).type_as(offset))
-        offset = torch.cat(list_offset, dim=1).view(B, -1, H, W)
-        if self.affinity in ['AS', 'ASS']:
-            pass
-        elif self.affinity == 'TC':
-            aff = torch.tanh(aff) / self.aff_scale_const
-        elif self.affinity == 'TGASS':
-            aff = torch.tanh(aff) / (self.aff_scale_const + 1e-8)
-        else:
-            raise NotImplementedError
-        if self.conf_prop:
-            list_conf = []
-            offset_each = torch.chunk(offset, self.num + 1, dim=1)
-            modulation_dummy = torch.ones((B, 1, H, W)).type_as(offset).detach()
-            for idx_off in range(0, self.num + 1):
-                ww = idx_off % self.k_f
-                hh = idx_off // self.k_f
-                if ww == (self.k_f - 1) / 2 and hh == (self.k_f - 1) / 2:
-                    continue
-                offset_tmp = offset_each[idx_off].detach()
-                conf_tmp = ModulatedDeformConvFunction.apply(confidence, offset_tmp, modulation_dummy, self.w_conf,
-                                                             self.b, self.stride, 0, self.dilation, self.groups,
-                                                             self.deformable_groups, self.im2col_step)
-                list_conf.append(conf_tmp)
-            conf_aff = torch.cat(list_conf, dim=1)
-            aff = aff * conf_aff.contiguous()
-        aff_abs = torch.abs(aff)
-        aff_abs_sum = torch.sum(aff_abs, dim=1, keepdim=True) + 1e-4
-        if self.affinity in ['ASS', 'TGASS']:
-            aff_abs_sum = torch.clamp(aff_abs_sum, min=1.0)     # == aff_abs_sum[aff_abs_sum < 1.0] = 1.0 (:126)
-        if self.affinity in ['AS', 'ASS', 'TGASS']:
-            aff = aff / aff_abs_sum
-        aff_sum = torch.sum(aff, dim=1, keepdim=True)
-        aff_ref = 1.0 - aff_sum
-        list_aff = list(torch.chunk(aff, self.num, dim=1))
-        list_aff.insert(self.idx_ref, aff_ref)
-        aff = torch.cat(list_aff, dim=1)
-        return offset, aff
-
-    def _propagate_once(self, feat, offset, aff):
-        """nlspn_model.py:140-144"""
-        return ModulatedDeformConvFunction.apply(feat, offset, aff, self.w, self.b, self.stride, self.padding,
-                                                 self.dilation, self.groups, self.deformable_groups, self.im2col_step)
-
     def forward(self, feat_init, guidance, confidence=None, feat_fix=None, rgb=None):
         """nlspn_model.py:146-175 -> (feat_result, list_feat, offset, aff, aff_scale_const.data)"""
         assert self.channels_g == guidance.shape[1]
         assert self.channels_f == feat_init.shape[1]
-        C.require_cuda(feat_init, guidance, confidence)
         if self.conf_prop:
             assert confidence is not None
-            offset, aff = self._get_offset_affinity(guidance, confidence, rgb)
-        else:
-            offset, aff = self._get_offset_affinity(guidance, None, rgb)
+        offset, aff = self._get_offset_affinity(guidance, confidence, rgb)
         if self.preserve_input:
             assert feat_init.shape == feat_fix.shape
-        if self._fused_ok(feat_init, offset, aff):
-            feat_result, list_feat = self._propagate_fused(feat_init, offset.contiguous(), aff.contiguous(), feat_fix,
-                                                           self.return_intermediates)
-            return feat_result, list_feat, offset, aff, self.aff_scale_const.data
-        if self._fused_train_ok(feat_init, offset, aff, feat_fix):
-            # training: the propagation as ONE differentiable op with a fused backward (list_feat is not returned, as
-            # NLSPNRefineModule drops it anyway, nlspn_model.py:193-197)
-            feat_result = _PropagateFused.apply(feat_init, offset, aff, feat_fix if self.preserve_input else None,
-                                                self.prop_time, self.preserve_input)
-            return feat_result, [], offset, aff, self.aff_scale_const.data
-        if self.preserve_input:
-            mask_fix = torch.sum(feat_fix > 0.0, dim=1, keepdim=True).detach()
-            mask_fix = (mask_fix > 0.0).type_as(feat_fix)
-        feat_result = feat_init
-        list_feat = []
-        for k in range(1, self.prop_time + 1):
-            if self.preserve_input:
-                feat_result = (1.0 - mask_fix) * feat_result + mask_fix * feat_fix
-            feat_result = self._propagate_once(feat_result, offset, aff)
-            list_feat.append(feat_result)
+        fix = feat_fix if self.preserve_input else None
+        self._require_supported(feat_init, fix)
+        T = self.prop_time
+        if self._wants_grad(feat_init, offset, aff):
+            feat_result, inter = _PropagateFused.apply(feat_init, offset, aff, fix, T, self.preserve_input)
+        else:
+            B, _, H, W = feat_init.shape
+            feat_init = feat_init.contiguous()
+            feat_result, scratch = torch.empty_like(feat_init), torch.empty_like(feat_init)
+            inter = (torch.empty((T,) + tuple(feat_init.shape), dtype=torch.float32, device=feat_init.device)
+                     if self.return_intermediates and T > 0 else None)
+            with torch.cuda.device(feat_init.device):
+                C.check(C.lib.rdfc_nlspn_propagate_forward(
+                    C.ptr(feat_init), C.ptr(offset.contiguous()), C.ptr(aff.contiguous()), C.ptr(None if fix is None else fix.contiguous()),
+                    int(bool(self.preserve_input)), C.ptr(feat_result), C.ptr(scratch), C.ptr(inter), B, H, W, T, 0, None,
+                    C.stream_ptr(feat_init.device)))
+        list_feat = list(inter.unbind(0)) if (self.return_intermediates and inter is not None and T > 0) else []
         return feat_result, list_feat, offset, aff, self.aff_scale_const.data
 
 

@@ -29,7 +29,11 @@ class ShardedGenerator:
     def __call__(self, rgb, depth, normal, gather=False):
         world, rank = _world()
         lo, hi = shard_bounds(rgb.shape[0], world, rank)
+        if hi == lo:
+            raise RuntimeError(f"rank {rank} of {world} owns no image of a batch of {rgb.shape[0]}: use at most one rank per image")
         out = self.generator(rgb[lo:hi], depth[lo:hi], normal[lo:hi])
+        if isinstance(out, tuple):              # DCVGANGenerator-style 5-tuple
+            out = dict(zip(('depth_map_1', 'confidence_map_1', 'depth_map_2', 'confidence_map_2', 'pred_depth'), out))
         if not gather or world == 1:
             return out
         sizes = [shard_bounds(rgb.shape[0], world, r) for r in range(world)]
@@ -44,23 +48,87 @@ class ShardedGenerator:
         return merged
 
 
+class GradientBucket:
+    """ONE pre-flattened gradient buffer per dtype for a FIXED parameter list: every ``p.grad`` is a view into it, so the
+    all-reduce needs no ``torch.cat`` and no copy-back, and every rank reduces the same number of elements whatever subset of
+    parameters received a gradient this step (parameters that got none contribute zeros -- DDP's find_unused_parameters
+    behaviour; fuse_layer5 and the frozen NLSPN dummies never get one).  Replaces DistributedDataParallel's
+    25 MB buckets (C/lib/models/rdfc_gan.py:102-119)."""
+
+    def __init__(self, parameters):
+        self.params = [p for p in parameters if p.requires_grad]
+        self.flat = {}
+        by_dtype = {}
+        for p in self.params:
+            by_dtype.setdefault((p.dtype, p.device), []).append(p)
+        for key, ps in by_dtype.items():
+            buf = torch.zeros(sum(p.numel() for p in ps), dtype=key[0], device=key[1])
+            off = 0
+            for p in ps:
+                p.grad = buf[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self.flat[key] = buf
+
+    def numel(self):
+        return sum(b.numel() for b in self.flat.values())
+
+    def zero(self):
+        """Instead of optimizer.zero_grad(set_to_none=True), which would detach the views."""
+        for b in self.flat.values():
+            b.zero_()
+
+    def _rebind(self):
+        # autograd may have replaced a .grad (e.g. after zero_grad(set_to_none=True)): copy it back into its slot
+        for (dtype, dev), buf in self.flat.items():
+            off = 0
+            for p in (q for q in self.params if (q.dtype, q.device) == (dtype, dev)):
+                view = buf[off:off + p.numel()].view_as(p)
+                if p.grad is None:
+                    view.zero_()
+                    p.grad = view
+                elif p.grad.data_ptr() != view.data_ptr():
+                    view.copy_(p.grad)
+                    p.grad = view
+                off += p.numel()
+
+    def allreduce(self, average=True):
+        """Sum (then / world) over the ranks, in place.  Returns the number of elements reduced."""
+        world, _ = _world()
+        self._rebind()
+        if world > 1:
+            for buf in self.flat.values():
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                if average:
+                    buf.div_(world)
+        return self.numel()
+
+
 def allreduce_gradients(parameters, average=True):
-    """ONE all-reduce over the flattened gradients of the parameters that received one (fuse_layer5 and the frozen
-    NLSPN dummies never do), instead of DDP's 25 MB buckets.  Returns the number of elements reduced."""
+    """One-shot form of GradientBucket for callers that do not keep a bucket: reduces over the FIXED list of parameters that
+    require grad (missing gradients count as zeros, so all ranks agree on the size), one all-reduce per dtype."""
     world, _ = _world()
-    grads = [p.grad for p in parameters if p.grad is not None]
-    if not grads or world == 1:
-        return sum(g.numel() for g in grads)
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    if average:
-        flat.div_(world)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
-    return off
+    params = [p for p in parameters if p.requires_grad]
+    groups = {}
+    for p in params:
+        groups.setdefault((p.dtype, p.device), []).append(p)
+    total = 0
+    for ps in groups.values():
+        total += sum(p.numel() for p in ps)
+        if world == 1:
+            continue
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in ps])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if average:
+            flat.div_(world)
+        off = 0
+        for p in ps:
+            n = p.numel()
+            if p.grad is None:
+                p.grad = flat[off:off + n].view_as(p).clone()
+            else:
+                p.grad.copy_(flat[off:off + n].view_as(p))
+            off += n
+    return total
 
 
 def reduce_losses(losses):

@@ -69,7 +69,7 @@ def nlspn(B=32, H=228, W=304, T=18):
     out, scratch = torch.empty_like(f), torch.empty_like(f)
     s = C.stream_ptr()
     ms = time_it(lambda: C.check(C.lib.rdfc_nlspn_propagate_forward(C.ptr(f), C.ptr(off), C.ptr(aff), None, 0, C.ptr(out),
-                                                                     C.ptr(scratch), None, B, H, W, T, 0, s)))
+                                                                     C.ptr(scratch), None, B, H, W, T, 0, None, s)))
     gbs = 116.0 * B * H * W * T / ms / 1e6
     print(f"nlspn B={B} T={T}: {ms*1e3:.1f} us total, {gbs:.0f} GB/s algorithmic ({gbs/6550.4:.3f} of measured HBM peak) "
           f"env={ {k_: v for k_, v in os.environ.items() if k_.startswith('RDFC_')} }")

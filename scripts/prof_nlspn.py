@@ -1,6 +1,11 @@
-"""Development aid: time of the 18-iteration NLSPN propagation alone (CUDA graph of the launches, L2 flushed between reps).
-    python scripts/prof_nlspn.py [B]          (RDFC_NLSPN_* knobs apply)
-"""
+"""NLSPN micro-benchmark (development aid): the propagation kernels alone, both stream formats, knob sweeps.
+
+    python scripts/prof_nlspn.py [B] [H W] [--sweep]
+
+Per configuration: the T = 18 launches as a CUDA graph, L2 flushed between repetitions, median / min of 30 repetitions;
+prints us per launch and GB/s on the 116 B per pixel and iteration algorithmic figure and on the bytes the kernel
+actually streams (fp32 planes 106 B incl. feature read / write, packed fp16 56 B)."""
+import ctypes
 import os
 import statistics
 import sys
@@ -10,84 +15,85 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-import bench  # noqa: E402
 from rdfc_gan_b200 import _cabi as C  # noqa: E402
-from _synth import synth_inputs  # noqa: E402
+
+T = 18
 
 
-def main():
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-    dev = torch.device("cuda", 0)
-    G = bench.build_generator().to(dev).set_precision("bf16")
-    rgb, normal, depth = synth_inputs(B, bench.H, bench.W, seed=0)
-    with torch.no_grad():
-        G(rgb.to(dev), depth.to(dev), normal.to(dev))
-    plan = next(iter(G.engine()._plans.values()))
-    T, H, W = 18, bench.H, bench.W
-    if os.environ.get("OFFSCALE"):          # how does the band halo behave with larger offsets?
-        plan.offset.mul_(float(os.environ["OFFSCALE"]))
-        print("offset std now", float(plan.offset.std()))
-
-    def prop():
-        C.check(C.lib.rdfc_nlspn_propagate_forward(C.ptr(plan.pred_init), C.ptr(plan.offset), C.ptr(plan.aff), None, 0,
-                                                   C.ptr(plan.d2raw), C.ptr(plan.scratch), None, B, H, W, T, 0, C.stream_ptr()))
+def bench(fn, flush, reps=30):
     for _ in range(3):
-        prop()
+        fn()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        prop()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ts = []
-    for _ in range(12):
+        fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
         flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         g.replay()
         b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    ms = statistics.median(ts)
-    print(f"NLSPN x{T} B={B}: {ms*1e3:.1f} us total, {ms*1e3/T:.2f} us / launch, "
-          f"{116.0*B*H*W*T/ms/1e6:.0f} GB/s algorithmic")
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    return statistics.median(ts), ts[0]
 
 
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    B = int(args[0]) if args else 32
+    H, W = (int(args[1]), int(args[2])) if len(args) >= 3 else (228, 304)
+    dev = "cuda"
+    gen = torch.Generator(device=dev).manual_seed(0)
+    guide = torch.randn(B, 8, H, W, device=dev, generator=gen)
+    conf = torch.rand(B, 1, H, W, device=dev, generator=gen)
+    init = torch.rand(B, 1, H, W, device=dev, generator=gen) * 2 - 1
+    w = torch.cat([0.25 * torch.randn(16, 8, 3, 3, device=dev, generator=gen), 0.02 * torch.randn(8, 8, 3, 3, device=dev, generator=gen)])
+    bias = torch.cat([torch.rand(16, device=dev, generator=gen) * 3 - 1.5, torch.rand(8, device=dev, generator=gen) * 1.7 + 0.3])
+    w = w * float(os.environ.get("OFFSCALE", "0.32"))          # 0.32: sigma ~ 0.73 px like bench.py's weights; 1.0: sigma ~ 2.2 px
+    scale = torch.tensor([4.0], device=dev)
+    off, aff = torch.empty(B, 18, H, W, device=dev), torch.empty(B, 9, H, W, device=dev)
+    packed = torch.empty(C.lib.rdfc_nlspn_packed_bytes(B, H, W), dtype=torch.uint8, device=dev)
+    s = C.stream_ptr()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    aff_args = (C.ptr(guide), C.ptr(conf), C.ptr(w), C.ptr(bias), C.ptr(scale), 3, 1)
+    f_aff32 = lambda: C.check(C.lib.rdfc_nlspn_affinity_forward(*aff_args, C.ptr(off), C.ptr(aff), B, H, W, C.stream_ptr()))
+    f_aff16 = lambda: C.check(C.lib.rdfc_nlspn_affinity_forward_packed(*aff_args, C.ptr(packed), B, H, W, C.stream_ptr()))
+    f_aff32(); f_aff16()
+    print(f"B={B} {H}x{W}  offset sigma {float(off[:, :8].std()):.2f} px")
+    for name, f in (("affinity fp32 planes", f_aff32), ("affinity packed fp16", f_aff16)):
+        med, mn = bench(f, flush)
+        print(f"{name:28s} {med * 1e3:8.1f} us (min {mn * 1e3:.1f})")
+    out, scratch, pred = torch.empty_like(init), torch.empty_like(init), torch.empty_like(init)
+    d1, c1 = torch.rand_like(init), torch.rand_like(init)
+    fz = C.FuseOut(d1.data_ptr(), c1.data_ptr(), conf.data_ptr(), pred.data_ptr())
+    f32 = lambda: C.check(C.lib.rdfc_nlspn_propagate_forward(C.ptr(init), C.ptr(off), C.ptr(aff), None, 0, C.ptr(out), C.ptr(scratch), None,
+                                                             B, H, W, T, 0, ctypes.byref(fz), C.stream_ptr()))
+    f16 = lambda: C.check(C.lib.rdfc_nlspn_propagate_forward_packed(C.ptr(init), C.ptr(packed), None, 0, C.ptr(out), C.ptr(scratch),
+                                                                    B, H, W, T, 0, ctypes.byref(fz), C.stream_ptr()))
+    P = B * H * W
 
+    def report(name, f, actual):
+        med, mn = bench(f, flush)
+        us = med * 1e3 / T
+        print(f"{name:44s} {us:7.2f} us/launch (min {mn * 1e3 / T:6.2f})  {116 * P / us / 1e3:7.0f} GB/s on 116 B/px  "
+              f"{actual * P / us / 1e3:6.0f} GB/s streamed ({actual} B/px)")
+    report("propagate fp32 planes (default)", f32, 108)
+    report("propagate packed fp16 (default)", f16, 56)
+    if "--sweep" in sys.argv:
+        for per_sm in (2, 3, 4, 5, 6):
+            for halo in (4, 6):
+                C.set_knob("RDFC_NLSPN_PER_SM", per_sm)
+                C.set_knob("RDFC_NLSPN_HALO", halo)
+                report(f"packed per_sm={per_sm} halo={halo}", f16, 56)
+        C.set_knob("RDFC_NLSPN_PER_SM", None)
+        C.set_knob("RDFC_NLSPN_HALO", None)
+        for pdl in (0, 1):
+            C.set_knob("RDFC_NLSPN_PDL", pdl)
+            report(f"packed pdl={pdl}", f16, 56)
+        C.set_knob("RDFC_NLSPN_PDL", None)
 
-def train_timing(B=8):
-    """fused forward + backward of the propagation against the reference's composition (prop_time DCN Function calls):
-        python scripts/prof_nlspn.py --train [B]"""
-    from rdfc_gan_b200.nlspn import NLSPNRefineModule
-    from _synth import nlspn_stress_inputs
-    H, W = bench.H, bench.W
-    x = nlspn_stress_inputs(B, H, W, 1)
-    t = {k: torch.from_numpy(v).cuda() for k, v in x.items()}
-    gout = torch.randn(B, 1, H, W, device="cuda")
-    for fused in (True, False):
-        mod = NLSPNRefineModule(prop_kernel=3, prop_time=18, affinity="TGASS", affinity_gamma=0.5, conf_prop=True).cuda().train()
-        mod.prop_layer.conv_offset_aff.weight.data.copy_(t["conv_w"])
-        mod.prop_layer.conv_offset_aff.bias.data.copy_(t["conv_b"])
-        mod.prop_layer.fused_backward = fused
-        ts = []
-        for rep in range(5):
-            g = t["guidance"].clone().requires_grad_(True)
-            p = t["pred_init"].clone().requires_grad_(True)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            y, _ = mod(p, g, t["confidence"], t["feat_fix"])
-            y.backward(gout)
-            b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
-        print(f"NLSPN forward+backward B={B} 228x304 x18, {'fused propagate fwd/bwd' if fused else 'composition (18 DCN Function calls)'}: "
-              f"{statistics.median(ts[1:]):.2f} ms")
-
-
-if __name__ == "__main__" and "--train" in sys.argv:
-    sys.argv.remove("--train")
-    train_timing(int(sys.argv[1]) if len(sys.argv) > 1 else 8)
-    sys.exit(0)
 
 if __name__ == "__main__":
     main()

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Generate tests/golden/*.npz by running the REFERENCE's own Python (needs /root/reference; build container only).
 
-    python tests/golden/make_golden.py [dcn] [nlspn] [generator]
+    python tests/golden/make_golden.py [dcn] [nlspn] [generator] [generator_v2]
 
 * dcn_<case>.npz        reference ModulatedDeformConvFunction / DeformConvFunction forward (the Function's call into
                         ``DCN`` is served by torchvision.ops.deform_conv2d, see _ref_import.py) and the five gradients
@@ -50,6 +50,51 @@ GEN_CASES = {
     "as12_preserve": (dict(use_nlspn_refine=True, nlspn_configs=dict(_NL, affinity="AS", prop_time=12, preserve_input=True)),
                       1, 36, 52, 3, "scaled", True, 8),
 }
+
+
+# Batched / full-size / RDF-GAN cases (round 2).  `store`: per output map (stride, image indices or None = all); maps that
+# are not listed are not stored.  cls "rdfc" = RDFC-GAN's RDFGenerator, "rdf" = RDF-GAN's DCVGANGenerator (the F/ class itself,
+# imported through baseline/ref_loader.py with the nlspn alias of SURVEY 8c; global_guidance_module = nn.Identity()).
+_ALL5 = ("depth_map_1", "confidence_map_1", "depth_map_2", "confidence_map_2", "pred_depth")
+GEN_CASES_V2 = {
+    # the bench's own weights and inputs (init recipe + NLSPN stress, seed 0) at B = 4 and B = 32, 228x304
+    "rdfc_full_b4": dict(cls="rdfc", kw=dict(use_nlspn_refine=True, nlspn_configs=_NL), B=4, H=228, W=304, Cs=3, recipe="init",
+                         stress=True, seed=0, store={k: (4, None) for k in _ALL5}, full=("pred_depth", 3)),
+    "rdfc_full_b32": dict(cls="rdfc", kw=dict(use_nlspn_refine=True, nlspn_configs=_NL), B=32, H=228, W=304, Cs=3, recipe="init",
+                          stress=True, seed=0, store={k: (8, None) for k in ("depth_map_1", "depth_map_2", "pred_depth")},
+                          full=("pred_depth", 31)),
+    "dcvgan_r34": dict(cls="rdf", kw=dict(encoder_rgb="resnet34", encoder_depth="resnet34", semantic_channels_in=40, adain_weighting=True,
+                                          use_nlpsn_refine=True, nlspn_configs=_NL), B=1, H=40, W=56, Cs=40, recipe="scaled",
+                       stress=True, seed=9, store={k: (1, None) for k in _ALL5}),
+    "dcvgan_r18_b2": dict(cls="rdf", kw=dict(semantic_channels_in=40, use_nlpsn_refine=True, nlspn_configs=_NL), B=2, H=36, W=52, Cs=40,
+                          recipe="scaled", stress=True, seed=10, store={k: (1, None) for k in _ALL5}),
+}
+
+
+def make_generator_v2():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "baseline"))
+    import ref_loader
+    assert ref_loader.install(), "reference checkout not present"
+    for name, c in GEN_CASES_V2.items():
+        torch.manual_seed(0)
+        if c["cls"] == "rdfc":
+            G = ref_loader.load_rdfc()(pretrained_on_imagenet=False, **c["kw"]).eval()
+        else:
+            G = ref_loader.load_rdf_gan()[0](torch.nn.Identity(), pretrained_on_imagenet=False, **c["kw"]).eval()
+        sd = synth_state_dict(G, seed=c["seed"], recipe=c["recipe"], nlspn_stress=c["stress"])
+        G.load_state_dict(sd, strict=True)
+        rgb, stem, depth = synth_inputs(c["B"], c["H"], c["W"], seed=c["seed"], Cs=c["Cs"])
+        with torch.no_grad():
+            out = G(rgb, depth, stem) if c["cls"] == "rdfc" else dict(zip(_ALL5, G(stem, depth)))
+        res = {"digest": np.array([state_dict_digest(sd)], np.int64)}
+        for k, (stride, imgs) in c["store"].items():
+            v = out[k].numpy()
+            res[k] = (v if imgs is None else v[list(imgs)])[:, :, ::stride, ::stride]
+        if "full" in c:
+            k, i = c["full"]
+            res[f"full_{k}_{i}"] = out[k][i].numpy()
+        np.savez_compressed(os.path.join(HERE, f"generator_{name}.npz"), **res)
+        print("generator", name, {k: (float(v.min()), float(v.max())) for k, v in out.items()})
 
 
 def make_dcn():
@@ -128,3 +173,5 @@ if __name__ == "__main__":
         make_nlspn()
     if "generator" in what:
         make_generator()
+    if "generator_v2" in what:
+        make_generator_v2()

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     exported = set(re.findall(r" T (rdfc_[a-z0-9_]+)", nm))
     assert declared <= exported, declared - exported
     assert set(C.EXPORTS) <= exported
-    assert C.lib.rdfc_abi_version() == 1
+    assert C.lib.rdfc_abi_version() == 2
 
 
 def test_host_side_validation_without_gpu():

@@ -276,19 +276,21 @@ def test_pack_stem_input(B, H, W, C0, Cpad, with_in1):
 
 @pytest.mark.parametrize("shape", [(2, 64, 64, 40, 40, 3, 1, False), (1, 128, 128, 57, 76, 3, 1, False), (2, 64, 128, 40, 40, 3, 2, False),
                                    (1, 64, 64, 20, 20, 3, 2, True), (2, 96, 192, 33, 21, 1, 1, False)])
-def test_cta_pair_mode_matches(shape, monkeypatch):
+def test_cta_pair_mode_matches(shape):
     """RDFC_UMMA_PAIR=1 (tcgen05 cta_group::2: two CTAs, one M=256 MMA stream, half the filter staged per CTA) gives the
     same result as the default single-CTA kernel, bit for bit, and both match the torch reference."""
+    from rdfc_gan_b200 import _cabi as C
     B, Cin, Cout, H, W, k, stride, transposed = shape
     g = torch.Generator().manual_seed(sum(shape[:6]))
     x = torch.randn(B, Cin, H, W, generator=g)
     w = torch.randn(*((Cin, Cout, k, k) if transposed else (Cout, Cin, k, k)), generator=g) / math.sqrt(Cin * k * k)
     scale, shift = 1 + 0.1 * torch.randn(Cout, generator=g), 0.1 * torch.randn(Cout, generator=g)
     kw = dict(stride=stride, pad=(1 if transposed else k // 2), act=1, transposed=transposed, bf16=True)
-    monkeypatch.setenv("RDFC_UMMA_PAIR", "0")
+    C.set_knob("RDFC_UMMA_PAIR", 0)
     single = _run_conv(x, w, scale, shift, **kw)
-    monkeypatch.setenv("RDFC_UMMA_PAIR", "1")
+    C.set_knob("RDFC_UMMA_PAIR", 1)
     pair = _run_conv(x, w, scale, shift, **kw)
+    C.set_knob("RDFC_UMMA_PAIR", None)
     assert torch.equal(single, pair)
     ref = _ref_conv(x, w, scale, shift, **kw)
     assert float((pair - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
@@ -296,19 +298,21 @@ def test_cta_pair_mode_matches(shape, monkeypatch):
 
 @pytest.mark.parametrize("shape", [(2, 64, 64, 40, 40, 3, 1, False), (2, 64, 128, 40, 40, 3, 2, False), (1, 64, 64, 20, 20, 3, 2, True),
                                    (2, 96, 192, 33, 21, 1, 2, False)])
-def test_cp_async_producer_fallback_matches(shape, monkeypatch):
+def test_cp_async_producer_fallback_matches(shape):
     """RDFC_UMMA_TMA=0 (six producer warps staging the halo with 16-byte cp.async into the no-swizzle layout; the path the
     fused stems also use) gives the same result as the default TMA tensor-map path, bit for bit."""
+    from rdfc_gan_b200 import _cabi as C
     B, Cin, Cout, H, W, k, stride, transposed = shape
     g = torch.Generator().manual_seed(sum(shape[:6]) + 1)
     x = torch.randn(B, Cin, H, W, generator=g)
     w = torch.randn(*((Cin, Cout, k, k) if transposed else (Cout, Cin, k, k)), generator=g) / math.sqrt(Cin * k * k)
     scale, shift = 1 + 0.1 * torch.randn(Cout, generator=g), 0.1 * torch.randn(Cout, generator=g)
     kw = dict(stride=stride, pad=(1 if transposed else k // 2), act=2, transposed=transposed, bf16=True)
-    monkeypatch.setenv("RDFC_UMMA_TMA", "1")
+    C.set_knob("RDFC_UMMA_TMA", 1)
     tma = _run_conv(x, w, scale, shift, **kw)
-    monkeypatch.setenv("RDFC_UMMA_TMA", "0")
+    C.set_knob("RDFC_UMMA_TMA", 0)
     cpasync = _run_conv(x, w, scale, shift, **kw)
+    C.set_knob("RDFC_UMMA_TMA", None)
     assert torch.equal(tma, cpasync)
 
 

@@ -91,6 +91,34 @@ def test_generator_oracle_matches_reference(name, golden_dir):
         assert np.abs(v - g).max() <= 2e-5, k
 
 
+@pytest.mark.parametrize("name", ["dcvgan_r34", "dcvgan_r18_b2", "rdfc_full_b4"])
+def test_generator_oracle_matches_round2_goldens(name, golden_dir):
+    """The oracle restatement against the round-2 goldens: RDF-GAN's DCVGANGenerator class itself (same body over a 40-channel
+    stem input) and the bench recipe at B = 4, 228x304."""
+    from make_golden import GEN_CASES_V2
+    from oracle import generator as ogen
+    from _synth import synth_inputs, synth_state_dict
+    c = GEN_CASES_V2[name]
+    gold = np.load(f"{golden_dir}/generator_{name}.npz")
+    # state-dict keys and shapes of both generators are those of the product's parameter containers (pinned against the
+    # reference's key list in test_cabi_and_layout.py); the digest proves the weights are the golden's
+    from rdfc_gan_b200.generator import DCVGANGenerator, RDFGenerator
+    import torch
+    G = (RDFGenerator(pretrained_on_imagenet=False, **c["kw"]) if c["cls"] == "rdfc" else
+         DCVGANGenerator(torch.nn.Identity(), pretrained_on_imagenet=False, **c["kw"]))
+    sd = synth_state_dict(G, seed=c["seed"], recipe=c["recipe"], nlspn_stress=c["stress"])
+    from _synth import state_dict_digest
+    assert state_dict_digest(sd) == int(gold["digest"][0])
+    rgb, stem, depth = synth_inputs(c["B"], c["H"], c["W"], seed=c["seed"], Cs=c["Cs"])
+    torch.set_num_threads(8)
+    out = ogen.generator_forward(sd, stem, depth, adain_weighting=c["kw"].get("adain_weighting", False), use_nlspn_refine=True,
+                                 nlspn_configs=c["kw"]["nlspn_configs"])
+    for k, (stride, imgs) in c["store"].items():
+        v = out[k].numpy()
+        v = (v if imgs is None else v[list(imgs)])[:, :, ::stride, ::stride]
+        assert np.abs(v - gold[k]).max() <= 2e-5, (k, np.abs(v - gold[k]).max())
+
+
 def test_oracle_nlspn_backward_matches_finite_differences():
     """oracle.nlspn.nlspn_propagate_backward (the reference's reverse loop on the C DCN oracle) against central finite
     differences of the oracle forward: pins the checker the GPU backward is compared with."""

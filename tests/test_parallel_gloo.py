@@ -39,6 +39,26 @@ def _worker(rank, world, port, q):
         for i, p in enumerate(p for p in net.parameters() if p.grad is not None):
             expect = sum(g[i] for g in gathered) / world
             assert torch.allclose(p.grad, expect, atol=1e-6)
+        # GradientBucket: grads are views of one flat buffer; a parameter that got no grad on ONE rank must not desynchronise
+        from rdfc_gan_b200.parallel import GradientBucket
+        torch.manual_seed(1)
+        net2 = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+        bucket = GradientBucket(net2.parameters())
+        for step in range(2):
+            bucket.zero()
+            x = torch.full((2, 4), float(rank + 1 + step))
+            y = net2[0](x) if rank == 0 else net2[1](net2[0](x))          # rank 0 never touches net2[1] ("unused branch")
+            y.sum().backward()
+            local = [p.grad.clone() for p in net2.parameters()]
+            assert all(p.grad.data_ptr() >= bucket.flat[(p.dtype, p.device)].data_ptr() for p in net2.parameters())
+            assert bucket.allreduce() == 4 * 3 + 3 + 3 * 2 + 2
+            gathered = [None] * world
+            dist.all_gather_object(gathered, local)
+            for i, p in enumerate(net2.parameters()):
+                assert torch.allclose(p.grad, sum(g[i] for g in gathered) / world, atol=1e-6), (step, i)
+        if rank == 1:                                   # world 2, one image: rank 1 owns nothing and must say so
+            with pytest.raises(RuntimeError):
+                ShardedGenerator(Fake())(rgb[:1], depth[:1], normal[:1])
         red = reduce_losses({"loss_G": torch.tensor(float(rank)), "loss_D": 2.0})
         assert abs(red["loss_G"] - 0.5) < 1e-6 and abs(red["loss_D"] - 2.0) < 1e-6
         q.put((rank, "ok"))
