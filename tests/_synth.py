@@ -17,6 +17,13 @@ import numpy as np
 import torch
 
 
+# Stated bf16 tolerances (RMSE, max-abs) against the fp32 results, normalised depth units, per synthetic-weight recipe: twice what
+# was measured on B200 (gpurun_out/parity_measured.jsonl, round 2: init 7.4e-4 / 4.9e-3 over 256 images; scaled ResNet-18
+# 4.4e-3 / 3.5e-2; scaled ResNet-34 + adain_weighting 1.3e-2 / 1.9e-1 -- that recipe drives the tanh heads into saturation, so
+# single pixels move a lot).  tests, smoke() and bench.py all read this table.
+BF16_BOUND = {"init": (1.5e-3, 1e-2), "scaled_r18": (1e-2, 7e-2), "scaled_r34": (2.7e-2, 3.9e-1)}
+
+
 def _rng(seed, name):
     return np.random.Generator(np.random.PCG64([seed, zlib.crc32(name.encode())]))
 

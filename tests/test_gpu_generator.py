@@ -1,12 +1,13 @@
 """-m gpu: the whole generator (RDFGenerator / DCVGANGenerator drop-ins on the sm_100a kernels) against the golden
 outputs of the reference's own generator and against the CPU oracle, on identical synthetic weights and inputs.
-Tolerances (BASELINE.json north_star): fp32 max-abs <= 1e-4 on every output map; bf16: RMSE <= 2e-3 and max-abs <= 2e-2
-in normalised depth units (the survey measured RMSE 5.6e-4 / max-abs 3.3e-3 for an all-bf16 forward)."""
+Tolerances (BASELINE.json north_star): fp32 max-abs <= 1e-4 on every output map; bf16: the stated per-recipe bounds of
+tests/_synth.py BF16_BOUND (bench recipe: RMSE <= 1.5e-3 and max-abs <= 1e-2 in normalised depth units; the survey measured
+RMSE 5.6e-4 / max-abs 3.3e-3 for an all-bf16 forward of one image)."""
 import numpy as np
 import pytest
 import torch
 
-from _synth import state_dict_digest, synth_inputs, synth_state_dict
+from _synth import BF16_BOUND, state_dict_digest, synth_inputs, synth_state_dict
 from make_golden import GEN_CASES, GEN_CASES_V2
 
 pytestmark = pytest.mark.gpu
@@ -68,8 +69,8 @@ def test_bf16_tensor_core_path(name, golden_dir):
         out = G(rgb.cuda(), depth.cuda(), stem.cuda())
     errs = _cmp(out, gold)
     _dump(f"bf16:{name}", errs)
-    scaled = "init" not in name     # O(1) activations through 40 layers: bf16 storage noise accumulates
-    rmse_tol, max_tol = (2e-2, 2e-1) if scaled else (2e-3, 2e-2)
+    # "scaled" recipes: O(1) activations through 40+ layers, bf16 storage noise accumulates
+    rmse_tol, max_tol = BF16_BOUND["init" if "init" in name else ("scaled_r34" if "r34" in name else "scaled_r18")]
     assert all(e[1] <= rmse_tol and e[0] <= max_tol for e in errs.values()), errs
 
 
@@ -100,10 +101,6 @@ def _cmp_v2(out, gold, c):
     return errs
 
 
-# the ONE stated bf16 tolerance of the bench recipe (init_weights + trained-magnitude NLSPN offsets), normalised depth units;
-# bench.py asserts the same numbers in-run (PARITY_RMSE / PARITY_MAXABS)
-BF16_RMSE, BF16_MAXABS = 2e-3, 2e-2
-
 
 @pytest.mark.parametrize("name", list(GEN_CASES_V2))
 def test_batched_and_rdfgan_goldens(name, golden_dir):
@@ -125,8 +122,8 @@ def test_batched_and_rdfgan_goldens(name, golden_dir):
     errs16 = _cmp_v2(out16, gold, c)
     _dump(f"bf16:{name}", errs16)
     _dump(f"fp32:{name}", errs)
-    scaled = c["recipe"] != "init"
-    rmse_tol, max_tol = (2e-2, 2e-1) if scaled else (BF16_RMSE, BF16_MAXABS)
+    # the bench recipe (init) has ONE stated bound, asserted by bench.py in-run as well (tests/_synth.py BF16_BOUND)
+    rmse_tol, max_tol = BF16_BOUND["init" if c["recipe"] == "init" else ("scaled_r34" if "r34" in name else "scaled_r18")]
     assert all(e[1] <= rmse_tol and e[0] <= max_tol for e in errs16.values()), errs16
     for k in KEYS:                                    # every image, every pixel: bf16 against fp32 mode
         d = (out16[k].float() - out32[k]).cpu().numpy()
@@ -235,4 +232,4 @@ def test_sunrgbd_shape_480x640_oracle_and_bf16():
         out16 = G(rgb.cuda(), depth.cuda(), stem.cuda())
     for k in KEYS:
         d = (out16[k].float() - out32[k]).cpu().numpy()
-        assert np.sqrt(np.mean(d ** 2)) <= 2e-3 and np.abs(d).max() <= 2e-2, (k, np.sqrt(np.mean(d ** 2)), np.abs(d).max())
+        assert np.sqrt(np.mean(d ** 2)) <= BF16_BOUND["init"][0] and np.abs(d).max() <= BF16_BOUND["init"][1], (k, np.sqrt(np.mean(d ** 2)), np.abs(d).max())
