@@ -53,7 +53,8 @@ constexpr int MMA_WARP = 6, BLOAD_WARP = 7, EPI_WARP0 = 8, NEPI_WARPS = 8;
 constexpr int MMA2_WARP = 5;       // second MMA issuer (TMA mode only, where warps 1-5 have no staging work); another scheduler than MMA_WARP
 constexpr int NTHREADS = 16 * 32;
 constexpr int MAX_PLANES = 4, MAX_TAPS = 9;
-constexpr int BAR_BYTES = (3 * 8 + 3 * 16 + 4) * 8 + 16;   // mbarriers for <= 8 A stages, <= 16 B stages, 2+2 accumulator sets; TMEM slot
+constexpr int BAR_BYTES = (3 * 8 + 3 * 16 + 4 + 4) * 8 + 16;   // mbarriers for <= 8 A stages, <= 16 B stages, 2+2 accumulator sets, 4 residual slabs; TMEM slot
+constexpr int EPI_SLAB_BYTES = 128 * 64;      // one staged epilogue slab: 128 pixels x 32 bf16 channels
 
 struct Plane {
     int ystep, yoff, xstep, xoff;  // input pixel = (ystep*(ty0+r) + yoff, xstep*(tx0+c) + xoff)
@@ -71,6 +72,13 @@ struct Params {
     // A operand through TMA (a_tma != 0): one 4-D tensor map (C, W, H, B) over the NHWC input view; box = 32 channels x
     // plane columns x plane rows, SWIZZLE_64B, zero fill outside the image = the conv padding
     alignas(64) CUtensorMap tmap_a;
+    // Epilogue through TMA (tma_out != 0, MODE_STD only): 4-D tensor maps (C, W, H, B) over the NHWC output view and the
+    // residual view; box = 32 channels x 8 x 16 pixels (one accumulator's 128 MMA rows), SWIZZLE_64B.  The epilogue stages
+    // 32-channel slabs [pixel][64 B] in shared memory and writes them with cp.async.bulk.tensor stores (out-of-range pixels and
+    // channels are clipped by the TMA unit); residual slabs arrive the same way through tensor loads.
+    alignas(64) CUtensorMap tmap_out;
+    alignas(64) CUtensorMap tmap_res;
+    int tma_out;
     int dual;                      // two MMA issuer warps (MMA_WARP and MMA2_WARP), each owning a subset of the accumulators
     int pair;                      // cta_group::2: two CTAs (a cluster) work on two pixel tiles with ONE stream of M = 256 MMAs; each
                                    // holds its own A stages and HALF of every filter stage (per-SM shared-memory reads per MMA: 4 KB + N*16 B)
@@ -359,7 +367,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     // stages start on a 1 KB boundary (the SWIZZLE_64B pattern the TMA writes repeats every 1 KB; the host adds the slack)
     unsigned char *sA = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     unsigned char *sB = sA + (size_t)P.sa * a_stage_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)P.sb * b_stage_bytes);
+    // epilogue staging (tma_out): [2 groups][2 buffers] output slabs, then [2 groups][2 buffers] residual slabs; 1 KB aligned
+    // because every stage size is a multiple of 1 KB
+    unsigned char *sE = sB + (size_t)P.sb * b_stage_bytes;
+    const int epi_bytes = P.tma_out ? (P.res ? 8 : 4) * EPI_SLAB_BYTES : 0;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sE + epi_bytes);
     // barrier map: a_full[sa] a_empty[sa] b_full[sb] b_empty[sb] acc_full[2] acc_empty[2]
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -369,8 +381,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
     const int A_FULL = 0, A_EMPTY = sa_k, B_FULL = 2 * sa_k, B_EMPTY = B_FULL + sb_k, ACC_FULL = B_EMPTY + sb_k,
               ACC_EMPTY = ACC_FULL + 2, PEER_A = ACC_EMPTY + 2, PEER_B = PEER_A + P.sa;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + PEER_B + P.sb);
+    const int RES_FULL = PEER_B + P.sb + 1;           // [group][buffer]: a residual slab has landed
     // per-channel epilogue vectors, padded to CoutP with (1, 0): 16-byte aligned after the barrier block
-    float *s_scale = reinterpret_cast<float *>(sB + (size_t)P.sb * b_stage_bytes + BAR_BYTES);
+    float *s_scale = reinterpret_cast<float *>(sE + epi_bytes + BAR_BYTES);
     float *s_shift = s_scale + P.CoutP;
     uint2 *s_tap = reinterpret_cast<uint2 *>(s_shift + P.CoutP);      // [phase][tap] A-descriptor words (lo, hi)
     float *s_stat = reinterpret_cast<float *>(s_tap + 4 * MAX_TAPS);   // W-AdaIN: mean[C], rstd[C] of the current image; stem: input patch;
@@ -393,6 +406,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
             for (int i = 0; i < P.sa; ++i) mbar_init(BAR(PEER_A + i), 1);
             for (int i = 0; i < P.sb; ++i) mbar_init(BAR(PEER_B + i), 1);
         }
+        for (int i = 0; i < 4; ++i) mbar_init(BAR(RES_FULL + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
@@ -817,14 +831,121 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         const int G = bn >> 4;
         int it = 0, wad_b = -1;
         long long t_accfull = 0, t_epi = 0;
+        // TMA epilogue (P.tma_out): per group of 4 warps (= one accumulator of 128 pixels at a time) two output slab buffers
+        // and two residual slab buffers, indexed by a slab counter that runs across accumulators and tiles.  My pixel's row in
+        // a slab is m = 32 wq + lane ([m][64 B]); SWIZZLE_64B puts 16-byte chunk k at position k ^ ((m >> 1) & 3), which also
+        // makes the 16-byte shared-memory accesses of a quarter warp conflict-free.
+        const bool tma_epi = kMode == MODE_STD && P.tma_out;
+        const uint32_t ebuf = smem_u32(sE) + (uint32_t)grp * 2u * EPI_SLAB_BYTES;
+        const uint32_t rbuf = smem_u32(sE) + 4u * EPI_SLAB_BYTES + (uint32_t)grp * 2u * EPI_SLAB_BYTES;
+        const bool leader = wq == 0 && lane == 0;
+        const uint32_t row_off = (uint32_t)(32 * wq + lane) * 64u, swz = (uint32_t)(((32 * wq + lane) >> 1) & 3);
+        uint32_t ctr = 0;
         for (int tile = tile0; tile < P.ntiles; tile += tile_step, ++it) {
             const Tile t = decode_tile<kPair>(P, tile, rank);
             const int oyo = P.oyo[t.z], oxo = P.oxo[t.z];
             const int set = nsets == 2 ? (it & 1) : 0;
             const int use = nsets == 2 ? (it >> 1) : it;
+            const long long _te = DBG_ON ? clock64() : 0;
+            if (tma_epi) {
+                // ---- epilogue through shared memory + TMA: per 32-channel slab of an accumulator
+                //   TMEM -> registers -> y = act(acc*scale + shift + residual slab) -> bf16 slab in shared memory -> one
+                //   cp.async.bulk.tensor store of the 8 x 16 pixel box (the TMA unit clips pixels / channels outside the tensor).
+                // Slab `ctr` uses buffers ctr & 1.  Before the group barrier of slab ctr the leader has waited until the store of
+                // slab ctr - 1 has read its buffer, so after the barrier buffer (ctr + 1) & 1 is free for the next slab; the
+                // residual slab of ctr + 2 is requested after the barrier (everybody has read slab ctr's residual by then).
+                const int nslab = bn >> 5, nitems = ((nacc - grp + 1) >> 1) * nslab;
+                auto coords = [&](int q, int &c0, int &x, int &y) {
+                    const int j = grp + 2 * (q / nslab), sl = q - (q / nslab) * nslab;
+                    c0 = t.n0 + 32 * sl; x = oxs * (t.tx0 + 8 * (j % nax)) + oxo; y = oys * (t.ty0 + 16 * (j / nax)) + oyo;
+                };
+                auto issue_res = [&](int q, uint32_t cq) {           // leader only
+                    int c0, x, y;
+                    coords(q, c0, x, y);
+                    const uint32_t bar = BAR(RES_FULL + 2 * grp + (int)(cq & 1u));
+                    mbar_expect_tx(bar, (uint32_t)EPI_SLAB_BYTES);
+                    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                                     rbuf + (cq & 1u) * (uint32_t)EPI_SLAB_BYTES),
+                                 "l"(&P.tmap_res), "r"(c0), "r"(x), "r"(y), "r"(t.b), "r"(bar)
+                                 : "memory");
+                };
+                // this tile's first two residual slabs do not depend on the MMAs: request them before waiting for the accumulators
+                // (every lane of the group is past the previous tile's last barrier, i.e. done reading the residual buffers)
+                if (res && leader) {
+                    if (nitems > 0) issue_res(0, ctr);
+                    if (nitems > 1) issue_res(1, ctr + 1);
+                }
+                { DBG_T0(); mbar_wait<true>(BAR(ACC_FULL + set), use & 1); DBG_ACC(t_accfull); }
+                tc_fence_after();
+                for (int q = 0; q < nitems; ++q, ++ctr) {
+                    const int j = grp + 2 * (q / nslab), sl = q - (q / nslab) * nslab;
+                    const uint32_t trow = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(set * set_cols + j * bn + 32 * sl);
+                    uint32_t va[16], vb[16];
+                    tc_ld16_issue(trow, va);
+                    tc_ld16_issue(trow + 16u, vb);
+                    const uint32_t eb = ebuf + (ctr & 1u) * (uint32_t)EPI_SLAB_BYTES + row_off;
+                    const uint32_t rb = rbuf + (ctr & 1u) * (uint32_t)EPI_SLAB_BYTES + row_off;
+                    if (res) mbar_wait(BAR(RES_FULL + 2 * grp + (int)(ctr & 1u)), (ctr >> 1) & 1u);
+                    tc_wait_ld(va);
+                    tc_wait_ld(vb);
+                    const int nb = t.n0 + 32 * sl;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {                    // 16 channels = two 16-byte chunks
+                        const uint32_t (&v)[16] = h ? vb : va;
+                        float f[16];
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const float4 sc = *reinterpret_cast<const float4 *>(s_scale + nb + 16 * h + 4 * q4);
+                            const float4 sh = *reinterpret_cast<const float4 *>(s_shift + nb + 16 * h + 4 * q4);
+                            f[4 * q4 + 0] = fmaf(__uint_as_float(v[4 * q4 + 0]), sc.x, sh.x);
+                            f[4 * q4 + 1] = fmaf(__uint_as_float(v[4 * q4 + 1]), sc.y, sh.y);
+                            f[4 * q4 + 2] = fmaf(__uint_as_float(v[4 * q4 + 2]), sc.z, sh.z);
+                            f[4 * q4 + 3] = fmaf(__uint_as_float(v[4 * q4 + 3]), sc.w, sh.w);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const uint32_t chunk = ((uint32_t)(2 * h + k) ^ swz) << 4;
+                            if (res) {
+                                uint32_t rr[4];
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]) : "r"(rb + chunk));
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 p2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr[e]));
+                                    f[8 * k + 2 * e] += p2.x;
+                                    f[8 * k + 2 * e + 1] += p2.y;
+                                }
+                            }
+                            uint32_t o[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float y0 = f[8 * k + 2 * e], y1 = f[8 * k + 2 * e + 1];
+                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(y0, slope * y0), fmaxf(y1, slope * y1));
+                                o[e] = *reinterpret_cast<const uint32_t *>(&h2);
+                            }
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(eb + chunk), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                        }
+                    }
+                    fence_proxy_async();                              // my slab rows -> visible to the TMA unit
+                    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // store ctr - 1 has read its buffer
+                    if (grp == 0) asm volatile("bar.sync 4, 128;" ::: "memory"); else asm volatile("bar.sync 5, 128;" ::: "memory");
+                    if (leader) {
+                        int c0, x, y;
+                        coords(q, c0, x, y);
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&P.tmap_out),
+                                     "r"(c0), "r"(x), "r"(y), "r"(t.b), "r"(ebuf + (ctr & 1u) * (uint32_t)EPI_SLAB_BYTES)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        if (res && q + 2 < nitems) issue_res(q + 2, ctr + 2);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + set));
+                if (DBG_ON) t_epi += clock64() - _te;
+                continue;
+            }
             { DBG_T0(); mbar_wait<true>(BAR(ACC_FULL + set), use & 1); DBG_ACC(t_accfull); }
             tc_fence_after();
-            const long long _te = DBG_ON ? clock64() : 0;
             if (kMode == MODE_HEADS) {
                 // ---- decode heads (rdf_generator.py:372-398), shift-add form.  The GEMM gave Y[p, t * ncols + q] =
                 // W_t[q, :] . X[p, :] for the 16 x 16 pixel region; head q at pixel p is act(bias_q + sum_t Y[p + d_t, t, q]).
@@ -1036,6 +1157,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
             if (lane == 0) { if (kPair && rank != 0) mbar_arrive_remote(BAR(ACC_EMPTY + set), 0); else mbar_arrive(BAR(ACC_EMPTY + set)); }
             if (DBG_ON) t_epi += clock64() - _te;
         }
+        if (tma_epi && leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // my stores have been written
         if (DBG_ON && warp == EPI_WARP0 && lane == 0) { P.dbg[blockIdx.x * 16 + 9] = t_accfull; P.dbg[blockIdx.x * 16 + 10] = t_epi; }
 #undef planar
 #undef vec32
@@ -1318,7 +1440,34 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     const int a_stage = P.a_tma ? P.nplanes * P.a_plane_bytes : (KCH * P.npix_pad * 16 + 1023) / 1024 * 1024;
     const int stem_patch = stem ? 2 * ((P.stem_k / 9) * (TH + 2) * (TW + 2) + 4) * 4 : 0;  // two fp32 input patches of a tile (stem mode)
     const int heads_y = heads ? 256 * (P.bn + 1) * 4 : 0;                                   // shift-add heads: Y of a region
-    const int fixed = BAR_BYTES + 2 * P.CoutP * 4 + 4 * MAX_TAPS * 8 + 2 * P.wad_C * 4 + stem_patch + heads_y + 256;   // barriers, (scale, shift) and tap tables, slack
+    // Epilogue through TMA stores (and TMA residual loads): hot variant only (bf16 NHWC, 32-byte aligned slices, whole
+    // 32-channel slabs), single-CTA tiles.  Measured per layer at B = 32 (gpurun_out/r2_plan_tmaout*.txt): it pays where the
+    // per-lane 32-byte residual loads + stores were the bottleneck -- stride-1 residual layers with N <= 128 (64 -> 64 + residual
+    // @228x304: 269 -> 230 us, 230 -> 218 us; 128 -> 128 + residual: 154 -> 150 us) -- and costs elsewhere (the slabs take 32-64 KB
+    // from the operand stages: stride-2 convs 121 -> 138 us, 256-wide + residual 144 -> 168 us, 128 -> 160 719 -> 769 us), so it
+    // is selected per layer.  RDFC_UMMA_TMAOUT: 0 = never, 1 = where it pays (default), 2 = every eligible layer, transposed convs
+    // (element-strided store boxes) included -- the tests run all three.
+    const int mode_std = !heads && !wad && !(P.planar || P.act > RDFC_ACT_LEAKY02 || !P.vec32 || P.Cout % 16 != 0);
+    const long long tmaout_knob = knob("RDFC_UMMA_TMAOUT", 1);
+    const bool tmaout_pays = d->residual.ptr && P.bn <= 128 && !d->transposed && d->stride == 1;
+    P.tma_out = mode_std && P.a_tma && !P.pair && !P.out2 && !stem && P.bn % 32 == 0 &&
+                (tmaout_knob >= 2 || (tmaout_knob == 1 && tmaout_pays));
+    if (P.tma_out) {
+        const int es = d->transposed ? 2 : 1;
+        const cuuint32_t box[4] = {32, (cuuint32_t)(es * 7 + 1), (cuuint32_t)(es * 15 + 1), 1};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+        auto encode = [&](CUtensorMap *tm, const void *ptr, int C, int stride) {
+            const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)P.Wo, (cuuint64_t)P.Ho, (cuuint64_t)P.B};
+            const cuuint64_t gstr[3] = {(cuuint64_t)stride * 2, (cuuint64_t)P.Wo * stride * 2, (cuuint64_t)P.Ho * P.Wo * stride * 2};
+            return tmap_encoder()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        };
+        CUresult r = encode(&P.tmap_out, d->out.ptr, d->out.C, d->out.pix_stride);
+        if (r == CUDA_SUCCESS && d->residual.ptr) r = encode(&P.tmap_res, d->residual.ptr, d->residual.C, d->residual.pix_stride);
+        RDFC_REQUIRE(r == CUDA_SUCCESS, "UMMA conv: cuTensorMapEncodeTiled (epilogue) failed (%d)", (int)r);
+    }
+    const int epi_stage = P.tma_out ? (d->residual.ptr ? 8 : 4) * EPI_SLAB_BYTES : 0;
+    const int fixed = BAR_BYTES + 2 * P.CoutP * 4 + 4 * MAX_TAPS * 8 + 2 * P.wad_C * 4 + stem_patch + heads_y + 256 + epi_stage;   // barriers, (scale, shift) and tap tables, slack, epilogue slabs
     const int budget = 219 * 1024;
     // The issuing warp pays ~1000 cycles per filter stage (barrier wait, commits, ring bookkeeping) that the tensor pipe does
     // not overlap (role timers: issue is blocking at the pipe's rate), so a 3x3 conv stages all nine taps of a k-block at once

@@ -22,10 +22,11 @@ def main():
     prec = args[1] if len(args) > 1 else "bf16"
     out_json = sys.argv[sys.argv.index("--json") + 1] if "--json" in sys.argv else None
     dev = torch.device("cuda", 0)
-    G = bench.build_generator().to(dev).set_precision(prec)
-    rgb, normal, depth = synth_inputs(B, bench.H, bench.W, seed=0)
+    cfg = bench.CONFIGS[os.environ.get("CONFIG", "c3")]
+    G = bench.build_product(cfg).to(dev).set_precision(prec)
+    rgb, normal, depth = synth_inputs(B, cfg["H"], cfg["W"], seed=0, Cs=cfg["cs"])
     with torch.no_grad():
-        G(rgb.to(dev), depth.to(dev), normal.to(dev))
+        bench.call_generator(G, cfg, rgb.to(dev), normal.to(dev), depth.to(dev))
     plan = next(iter(G.engine()._plans.values()))
     assert len(plan.names) == len(plan.steps), (len(plan.names), len(plan.steps))
     s = C.stream_ptr()

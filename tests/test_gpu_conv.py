@@ -316,6 +316,33 @@ def test_cp_async_producer_fallback_matches(shape):
     assert torch.equal(tma, cpasync)
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 64, 40, 44, 3, 1, False, True), (3, 128, 128, 29, 38, 3, 1, False, True),
+                                   (2, 64, 128, 41, 40, 3, 2, False, False), (1, 128, 160, 30, 52, 3, 1, False, False),
+                                   (2, 192, 64, 20, 27, 3, 2, True, False), (2, 96, 192, 33, 21, 1, 2, False, False),
+                                   (1, 256, 256, 19, 26, 3, 1, False, True)])
+def test_tma_store_epilogue_matches_direct_stores(shape):
+    """RDFC_UMMA_TMAOUT: the epilogue that stages 32-channel slabs in shared memory and writes them with cp.async.bulk.tensor
+    stores (residual slabs through tensor loads) does the same arithmetic as the per-lane global stores: bit-identical outputs,
+    clipped tiles, odd sizes, strided (transposed) store boxes and N = 160 / 256 tiles included; both match the torch reference."""
+    from rdfc_gan_b200 import _cabi as C
+    B, Cin, Cout, H, W, k, stride, transposed, with_res = shape
+    g = torch.Generator().manual_seed(sum(shape[:6]) + 7)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(*((Cin, Cout, k, k) if transposed else (Cout, Cin, k, k)), generator=g) / math.sqrt(Cin * k * k)
+    scale, shift = 1 + 0.1 * torch.randn(Cout, generator=g), 0.1 * torch.randn(Cout, generator=g)
+    kw = dict(stride=stride, pad=(1 if transposed else k // 2), act=2, transposed=transposed, bf16=True)
+    if with_res:
+        kw["residual"] = torch.randn(B, Cout, H, W, generator=g)
+    outs = []
+    for mode in (0, 2, 1):
+        C.set_knob("RDFC_UMMA_TMAOUT", mode)
+        outs.append(_run_conv(x, w, scale, shift, **kw))
+    C.set_knob("RDFC_UMMA_TMAOUT", None)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = _ref_conv(x, w, scale, shift, **kw)
+    assert float((outs[1] - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+
+
 @pytest.mark.parametrize("case", [(2, 64, 64, 36, 52, 1), (2, 64, 128, 37, 50, 2), (1, 128, 256, 30, 44, 2), (2, 256, 256, 19, 26, 1)])
 def test_conv_input_grad_on_the_forward_kernel(case):
     """rdfc_gan_b200.conv_grad: dgrad of the generator's 3x3 convs as stride-1 / transposed convs on the tensor-core kernel,
