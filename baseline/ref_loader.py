@@ -26,7 +26,10 @@ def install():
         return False
     os.makedirs(REFD, exist_ok=True)
     jobs = [(os.path.join(c, "lib/models/generator/rdf_generator"), "rdf_generator"),
-            (os.path.join(f, "lib/models"), "rdf_gan_lib/lib/models")]      # imported as `lib.models...`, like F/ does
+            (os.path.join(f, "lib/models"), "rdf_gan_lib/lib/models"),      # imported as `lib.models...`, like F/ does
+            (os.path.join(c, "lib/models/module"), "rdfc_lib/lib/models/module"),             # the training step's pieces of RDFC-GAN
+            (os.path.join(c, "lib/models/discriminator"), "rdfc_lib/lib/models/discriminator"),
+            (os.path.join(c, "lib/losses"), "rdfc_lib/lib/losses")]
     for src, dst in jobs:
         if os.path.isdir(src):
             out = os.path.join(REFD, dst)
@@ -115,6 +118,36 @@ def load_rdf_gan(gpu=False):
     gen = importlib.import_module(base + ".rdf_gan_generator").DCVGANGenerator
     esa = importlib.import_module("lib.models.segmentator.esa_net.esa_net_one_modality").ESANetOneModality
     return gen, esa
+
+
+def load_rdfc_training():
+    """-> (PatchGANDiscriminator, GANLoss, L1_loss) of RDFC-GAN (C/lib/models/discriminator/patch_gan_discriminator.py,
+    C/lib/losses/gan_loss.py), imported as ``lib...`` through package shells (the discriminator package's __init__ imports a
+    build_discriminator file the checkout lacks).  Call in a process that has not imported RDF-GAN's ``lib``."""
+    root = os.path.join(REFD, "rdfc_lib", "lib")
+    for name, sub in (("lib", ""), ("lib.models", "models"), ("lib.models.module", "models/module"),
+                      ("lib.models.discriminator", "models/discriminator"), ("lib.losses", "losses")):
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [os.path.join(root, sub)]
+        sys.modules[name] = pkg
+    D = importlib.import_module("lib.models.discriminator.patch_gan_discriminator").PatchGANDiscriminator
+    gl = importlib.import_module("lib.losses.gan_loss")
+    return D, gl.GANLoss, gl.L1_loss
+
+
+def differentiable_dcn_on_cpu():
+    """The reference's ModulatedDeformConvFunction calls the extension's backward, which has no CPU kernel: for a TRAINING step
+    on the CPU, ``apply`` is served by torchvision.ops.deform_conv2d at that boundary (its autograd is the reference's col2im
+    arithmetic).  Call after load_rdfc()."""
+    from torchvision.ops import deform_conv2d
+    nm = importlib.import_module("rdf_generator.nlspn.nlspn_model")
+
+    class Shim:
+        @staticmethod
+        def apply(inp, offset, mask, weight, bias, stride, padding, dilation, groups, dg, step):
+            return deform_conv2d(inp, offset.contiguous(), weight, bias, stride=stride, padding=padding, dilation=dilation,
+                                 mask=mask.contiguous())
+    nm.ModulatedDeformConvFunction = Shim
 
 
 def load_single(fname, modname):

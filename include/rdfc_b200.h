@@ -273,6 +273,43 @@ int rdfc_depth_metric_nchunk(long long n);
 int rdfc_depth_metric_sums(const float *pred, const float *gt, const unsigned char *evaluate_mask, float std, float mean,
                            float t_valid, double *sums, double *partial, int B, long long n, void *stream);
 
+/* ------------------------------------------------------------------ training step ---------------------------- */
+/* Batch-statistics BatchNorm fused with the activation and the residual add, and the conv filter gradient: what the
+ * reference's train() mode leaves to nn.BatchNorm2d / cuDNN inside conv_bn_relu / convt_bn_relu / BasicBlock
+ * (encoder_decoder/common.py:29-61, encoder_decoder/encoder_decoder.py:39-59; training step lib/models/rdf_gan.py:135-207).
+ * Activations: bf16 NHWC views over npix = B*H*W pixels; statistics and parameter gradients fp32; deterministic reductions. */
+
+/* floats of workspace for rdfc_bn_stats / rdfc_bn_act_backward */
+int rdfc_bn_workspace_floats(long long npix, int C);
+/* per-channel mean and BIASED variance of x over npix pixels (Chan-combined partials, fixed order) */
+int rdfc_bn_stats(const rdfc_view *x, long long npix, float *workspace, float *mean, float *var, void *stream);
+/* out = act(x * scale[c] + shift[c] + residual)   (scale = gamma * rstd, shift = beta - mean * scale; residual may be NULL;
+ * act: none / ReLU / LeakyReLU(0.2)) */
+int rdfc_affine_act_forward(const rdfc_view *x, const float *scale, const float *shift, const rdfc_view *residual, int act,
+                            const rdfc_view *out, long long npix, void *stream);
+/* Backward of out = act(gamma * (y - mean) * rstd + beta + residual) with batch statistics (mean, rstd) of y:
+ *   dz = dout * act'(out)  (act' from the sign of `out`),   sum_dz[c] = sum dz (= d beta),   sum_dz_xhat[c] = sum dz * xhat (= d gamma),
+ *   dy = gamma * rstd * (dz - sum_dz / npix - xhat * sum_dz_xhat / npix),   dres = dz (written when dres is not NULL). */
+int rdfc_bn_act_backward(const rdfc_view *dout, const rdfc_view *out, const rdfc_view *y, const float *mean, const float *rstd,
+                         const float *gamma, int act, const rdfc_view *dy, const rdfc_view *dres, float *workspace,
+                         float *sum_dz, float *sum_dz_xhat, long long npix, void *stream);
+
+/* Filter gradient of y = conv2d(input, W (O, I, k, k), stride, padding (k-1)/2):
+ *   grad_weight[o][i][ky][kx] = sum_{b,py,px} grad_out[b,py,px,o] * input[b, stride*py - pad + ky, stride*px - pad + kx, i]
+ * (fp32, torch's (O, I, kh, kw) layout, overwritten).  A ConvTranspose2d(k3, s2, p1, op1) layer's filter gradient (Cin, Cout, 3, 3)
+ * is the same sum with grad_out := the layer's INPUT and input := the gradient w.r.t. its (uncropped) output.
+ * workspace: rdfc_conv_wgrad_workspace_floats(d) floats (split-K partials, reduced in a fixed order). */
+typedef struct {
+    int B;
+    int Hg, Wg;             /* grid of grad_out */
+    int Hi, Wi;             /* grid of input */
+    int k, stride, pad;     /* k in {1, 3}, stride in {1, 2}, pad = (k - 1) / 2 */
+    rdfc_view grad_out;     /* bf16 NHWC, O channels */
+    rdfc_view input;        /* bf16 NHWC, I channels */
+} rdfc_wgrad_desc;
+long long rdfc_conv_wgrad_workspace_floats(const rdfc_wgrad_desc *d);
+int rdfc_conv_wgrad(const rdfc_wgrad_desc *d, float *grad_weight, float *workspace, void *stream);
+
 /* ------------------------------------------------------------------ development aids ------------------------- */
 /* Not part of the drop-in boundary.  rdfc_dev_set_knob overrides a development knob (the RDFC_* environment variables, which
  * the library reads once per name); value INT64_MIN restores the default.  rdfc_dev_umma_timers copies the per-role cycle

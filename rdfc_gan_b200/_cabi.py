@@ -53,6 +53,11 @@ class WadainConvDesc(ctypes.Structure):
                 ("bias", c_void_p), ("mean", c_void_p), ("rstd", c_void_p), ("gwbw", View)]
 
 
+class WgradDesc(ctypes.Structure):
+    _fields_ = [("B", c_int), ("Hg", c_int), ("Wg", c_int), ("Hi", c_int), ("Wi", c_int), ("k", c_int), ("stride", c_int),
+                ("pad", c_int), ("grad_out", View), ("input", View)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -73,6 +78,15 @@ def _load():
     lib.rdfc_nlspn_affinity_forward_packed.argtypes = [c_void_p] * 5 + [c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.rdfc_nlspn_propagate_forward_packed.argtypes = [c_void_p] * 3 + [c_int] + [c_void_p] * 2 + [c_int] * 5 + [ctypes.POINTER(FuseOut), c_void_p]
     lib.rdfc_dev_set_knob.argtypes = [ctypes.c_char_p, ctypes.c_longlong]
+    VP = ctypes.POINTER(View)
+    lib.rdfc_bn_workspace_floats.argtypes = [ctypes.c_longlong, c_int]
+    lib.rdfc_bn_stats.argtypes = [VP, ctypes.c_longlong, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.rdfc_affine_act_forward.argtypes = [VP, c_void_p, c_void_p, VP, c_int, VP, ctypes.c_longlong, c_void_p]
+    lib.rdfc_bn_act_backward.argtypes = [VP, VP, VP, c_void_p, c_void_p, c_void_p, c_int, VP, VP, c_void_p, c_void_p, c_void_p,
+                                         ctypes.c_longlong, c_void_p]
+    lib.rdfc_conv_wgrad_workspace_floats.argtypes = [ctypes.POINTER(WgradDesc)]
+    lib.rdfc_conv_wgrad_workspace_floats.restype = ctypes.c_longlong
+    lib.rdfc_conv_wgrad.argtypes = [ctypes.POINTER(WgradDesc), c_void_p, c_void_p, c_void_p]
     lib.rdfc_depth_metric_nchunk.argtypes = [ctypes.c_longlong]
     lib.rdfc_depth_metric_sums.argtypes = [c_void_p] * 3 + [ctypes.c_float] * 3 + [c_void_p] * 2 + [c_int, ctypes.c_longlong, c_void_p]
     lib.rdfc_nlspn_affinity_backward.argtypes = [c_void_p] * 5 + [c_int] * 2 + [c_void_p] * 6 + [c_int] * 3 + [c_void_p]
@@ -102,7 +116,9 @@ EXPORTS = ["rdfc_abi_version", "rdfc_last_error", "rdfc_launch_count", "rdfc_dcn
            "rdfc_nlspn_packed_bytes", "rdfc_nlspn_affinity_forward_packed", "rdfc_nlspn_propagate_forward_packed",
            "rdfc_fuse_depth_forward", "rdfc_conv_forward", "rdfc_heads_forward", "rdfc_instnorm_nchunk", "rdfc_instnorm_stats",
            "rdfc_wadain_apply", "rdfc_adain_apply", "rdfc_norm_apply", "rdfc_depth_metric_nchunk", "rdfc_depth_metric_sums", "rdfc_stem_forward", "rdfc_pack_stem_input",
-           "rdfc_wadain_tile", "rdfc_wadain_conv_forward", "rdfc_dev_set_knob", "rdfc_dev_umma_timers"]
+           "rdfc_wadain_tile", "rdfc_wadain_conv_forward", "rdfc_dev_set_knob", "rdfc_dev_umma_timers",
+           "rdfc_bn_workspace_floats", "rdfc_bn_stats", "rdfc_affine_act_forward", "rdfc_bn_act_backward",
+           "rdfc_conv_wgrad_workspace_floats", "rdfc_conv_wgrad"]
 
 
 KNOB_UNSET = -(1 << 63)

@@ -105,15 +105,17 @@ class _GeneratorBase(nn.Module):
         for t in tensors:
             if not t.is_cuda:
                 raise RuntimeError("rdfc_gan_b200 generators run on CUDA (sm_100a) tensors only; there is no CPU path")
-        if self.training:
-            # the reference would use batch-statistics BatchNorm and update the running stats here, whatever the grad mode
-            raise RuntimeError("training-mode forward (batch-statistics BatchNorm + autograd) is not implemented by the inference "
-                               "engine; call .eval()")
         if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
             raise RuntimeError("the eval-mode forward is inference-only and returns detached tensors: an input requires grad; "
                                "run under torch.no_grad() or detach the inputs")
 
     def _run(self, stem_in, depth):
+        if self.training:
+            # train(): batch-statistics BatchNorm (running stats updated) and autograd, whatever the grad mode -- as the reference
+            from .train_forward import generator_forward_train
+            if self.bn is not True or self.fuse_kind not in ('WAdaIN', 'AdaIN', 'IN'):
+                raise NotImplementedError("training-mode forward covers bn=True generators")
+            return generator_forward_train(self, stem_in, depth)
         self._check_inference(stem_in, depth)
         return self.engine().forward(stem_in, depth)
 

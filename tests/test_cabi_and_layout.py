@@ -100,3 +100,11 @@ def test_dcn_shim_installs_as_module():
         sys.modules.pop("DCN", None)
         if saved is not None:
             sys.modules["DCN"] = saved
+
+
+def test_patchgan_state_dict_matches_reference(golden_dir):
+    """tests/golden/patchgan_state_dict_keys.json was dumped from the reference's PatchGANDiscriminator(in_channels=1)."""
+    from rdfc_gan_b200.discriminator import PatchGANDiscriminator
+    want = json.load(open(os.path.join(golden_dir, "patchgan_state_dict_keys.json")))
+    got = {k: list(v.shape) for k, v in PatchGANDiscriminator(in_channels=1).state_dict().items()}
+    assert got == want
