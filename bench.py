@@ -19,7 +19,8 @@ a barrier + synchronize and the max over ranks is taken.  Rank 0 prints ONE JSON
              memory), H2D + D2H inside the timed region.
   parity     the timed bf16 outputs of the first batch against this repo's fp32 mode (<= 1e-4 from the reference, tests/) on
              the same images: RMSE / max-abs per map; the run FAILS above PARITY_RMSE / PARITY_MAXABS.
-  value_fp32 maps/s of the fp32 parity mode (measured while computing `parity`).
+  value_fp32 maps/s of the strict fp32 parity mode (CUDA cores; measured while computing `parity`); value_fp32_tc: the fp32 mode
+             on the tensor cores (split fp16 operands) with its max-abs distance from the strict mode.
   ref_gpu    the unmodified reference (PyTorch/cuDNN + its own DCN CUDA extension, baseline/_ref) on the same GPU, maps/s.
   roofline   the NLSPN propagation kernel timed alone (CUDA events on its launch stream, >= 50 repetitions, min / median):
              achieved = 116 B x pixels per launch / launch time, against MEASURED_PEAKS.json hbm_gbs.
@@ -327,7 +328,7 @@ def main():
     d2h = sum(t.numel() * 4 for t in outs_h.values())
 
     # ---------------- parity of what was timed: bf16 outputs vs this repo's fp32 mode, image chunk by image chunk
-    parity, value_fp32 = None, None
+    parity, value_fp32, value_fp32_tc = None, None, None
     if args.precision == "bf16" and not args.no_parity:
         chunk = min(cfg["fp32_chunk"], B)
         with torch.no_grad():
@@ -355,6 +356,27 @@ def main():
                 se[i] += float((d * d).sum())
                 mx[i] = max(mx[i], float(d.abs().max()))
         eng.clear_plans(precision="fp32")
+        # the tensor-core fp32 mode (split fp16 operands) on the first chunk: throughput and its distance from the strict fp32 mode
+        G.set_precision("fp32_tc")
+        with torch.no_grad():
+            o32 = call_generator(G, cfg, rgb_d[:chunk], stem_d[:chunk], depth_d[:chunk])          # strict reference of this chunk
+            G.set_precision("fp32")
+            ref32 = {k: v.clone() for k, v in call_generator(G, cfg, rgb_d[:chunk], stem_d[:chunk], depth_d[:chunk]).items()}
+            G.set_precision("fp32_tc")
+            ttc = []
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                o32 = call_generator(G, cfg, rgb_d[:chunk], stem_d[:chunk], depth_d[:chunk])
+                b.record()
+                torch.cuda.synchronize()
+                ttc.append(a.elapsed_time(b))
+        tc_err = max(float((o32[k] - ref32[k]).abs().max()) for k in KEYS)
+        value_fp32_tc = {"value": chunk * world / (statistics.median(ttc) / 1e3), "unit": "maps/s", "batch_per_gpu": chunk,
+                         "max_abs_vs_fp32": maxreduce(tc_err),
+                         "note": "fp32 tensors, contractions on tcgen05 with split fp16 operands (x_hi W_hi + x_hi W_lo + x_lo W_hi)"}
+        eng.clear_plans(precision="fp32")
+        eng.clear_plans(precision="fp32_tc")
         G.set_precision("bf16")
         parity = {k: {"rmse": (maxreduce(se[i]) / (B * H * W)) ** 0.5, "max_abs": maxreduce(mx[i])} for i, k in enumerate(KEYS)}
         parity["against"] = "fp32 mode of this repo (<= 1e-4 from the reference's goldens, tests/test_gpu_generator.py)"
@@ -363,7 +385,7 @@ def main():
         parity["images"] = args.batch
         if t32:
             value_fp32 = {"value": chunk * world / (statistics.median(t32) / 1e3), "unit": "maps/s", "batch_per_gpu": chunk,
-                          "note": "fp32 parity mode (module call incl. input copies and output clones)"}
+                          "note": "strict fp32 parity mode, CUDA cores (module call incl. input copies and output clones)"}
         bad = {k: v for k, v in parity.items() if k in KEYS and (v["rmse"] > tol_rmse or v["max_abs"] > tol_max)}
         if bad:
             print(json.dumps({"error": "bf16 outputs outside the stated tolerance", "parity": parity}), file=sys.stderr)
@@ -447,7 +469,7 @@ def main():
             "dtype": args.precision if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(cfg, args, world, B), "clocks": clocks,
             "e2e": {"value": e2e, "unit": "maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": plan.n_launch * args.steps, "parity": parity, "value_fp32": value_fp32, "ref_gpu": ref_gpu,
+            "gpu_launches": plan.n_launch * args.steps, "parity": parity, "value_fp32": value_fp32, "value_fp32_tc": value_fp32_tc, "ref_gpu": ref_gpu,
             "roofline": roofline, "roofline_dense": roofline_dense, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "librdfc_b200.so")
 
 F32, F64, BF16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH, ACT_SIGMOID = range(5)
-PATH_SIMT_F32, PATH_UMMA_BF16 = 0, 1
+PATH_SIMT_F32, PATH_UMMA_BF16, PATH_UMMA_F32X3 = 0, 1, 2
 AFFINITY = {"AS": 0, "ASS": 1, "TC": 2, "TGASS": 3}
 _DT = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
 
@@ -35,12 +35,13 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [("B", c_int), ("Hi", c_int), ("Wi", c_int), ("Ho", c_int), ("Wo", c_int), ("kh", c_int), ("kw", c_int),
                 ("stride", c_int), ("pad", c_int), ("transposed", c_int), ("act", c_int), ("path", c_int),
                 ("inp", View), ("in2", View), ("out", View), ("residual", View), ("weight", c_void_p),
-                ("scale", c_void_p), ("shift", c_void_p)]
+                ("scale", c_void_p), ("shift", c_void_p), ("workspace", c_void_p), ("workspace_bytes", ctypes.c_size_t)]
 
 
 class HeadsDesc(ctypes.Structure):
     _fields_ = [("B", c_int), ("H", c_int), ("W", c_int), ("inp", View), ("weight", c_void_p), ("shift", c_void_p),
-                ("ncols", c_int), ("act", c_int * 16), ("out", c_void_p * 16), ("out_bstride", ctypes.c_longlong * 16)]
+                ("ncols", c_int), ("act", c_int * 16), ("out", c_void_p * 16), ("out_bstride", ctypes.c_longlong * 16),
+                ("workspace", c_void_p), ("workspace_bytes", ctypes.c_size_t)]
 
 
 class StemDesc(ctypes.Structure):

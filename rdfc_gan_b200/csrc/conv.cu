@@ -4,7 +4,8 @@
 namespace rdfc {
 int conv_simt_forward(const rdfc_conv_desc *d, cudaStream_t st);
 int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads, const rdfc_stem_desc *stem,
-                      const rdfc_wadain_conv_desc *wad);
+                      const rdfc_wadain_conv_desc *wad, int split_c);
+int split_f32_forward(const rdfc_view *x, void *out_bf16, long long npix, cudaStream_t st);
 int wadain_tile(int C);
 int conv_umma_read_dbg(long long *host, int n);
 }  // namespace rdfc
@@ -26,8 +27,23 @@ extern "C" int rdfc_conv_forward(const rdfc_conv_desc *d, void *stream) {
     RDFC_REQUIRE(d->in.nchw || d->in.pix_stride >= d->in.C, "conv: input pixel stride smaller than its channel count");
     RDFC_REQUIRE(d->out.nchw || d->out.pix_stride >= d->out.C, "conv: output pixel stride smaller than its channel count");
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->path == RDFC_PATH_UMMA_BF16) return conv_umma_forward(d, st, nullptr, nullptr, nullptr);
+    if (d->path == RDFC_PATH_UMMA_BF16) return conv_umma_forward(d, st, nullptr, nullptr, nullptr, 0);
     if (d->path == RDFC_PATH_SIMT_F32) return conv_simt_forward(d, st);
+    if (d->path == RDFC_PATH_UMMA_F32X3) {
+        // fp32-faithful contraction on the bf16 tensor cores: split the fp32 input into [hi | lo] bf16 halves (one HBM pass into the
+        // caller's workspace), then the tcgen05 kernel walks x_hi W_hi + x_hi W_lo + x_lo W_hi and writes fp32
+        RDFC_REQUIRE(d->in.dtype == RDFC_F32 && d->out.dtype == RDFC_F32 && !d->in.nchw && !d->out.nchw && !d->in2.ptr,
+                     "conv (fp32 on tensor cores): single fp32 NHWC source and fp32 NHWC output");
+        RDFC_REQUIRE(d->in.C % 32 == 0, "conv (fp32 on tensor cores): Cin (%d) must be a multiple of 32", d->in.C);
+        const long long npix = (long long)d->B * d->Hi * d->Wi;
+        RDFC_REQUIRE(d->workspace && d->workspace_bytes >= (size_t)npix * d->in.C * 4 && ((uintptr_t)d->workspace % 128) == 0,
+                     "conv (fp32 on tensor cores): workspace of B*Hi*Wi*Cin*4 bytes (128-byte aligned) required");
+        if (int rc = split_f32_forward(&d->in, d->workspace, npix, st)) return rc;
+        rdfc_conv_desc e = *d;
+        e.in.ptr = d->workspace; e.in.dtype = RDFC_BF16; e.in.C = 2 * d->in.C; e.in.pix_stride = 2 * d->in.C;
+        e.path = RDFC_PATH_UMMA_BF16;
+        return conv_umma_forward(&e, st, nullptr, nullptr, nullptr, d->in.C);
+    }
     return fail(RDFC_ERR_INVALID, "conv: unknown path %d", d->path);
 }
 
@@ -42,7 +58,18 @@ extern "C" int rdfc_heads_forward(const rdfc_heads_desc *h, void *stream) {
     d.in = h->in;
     d.out.ptr = h->out[0]; d.out.dtype = RDFC_F32; d.out.C = (9 * h->ncols + 15) / 16 * 16; d.out.pix_stride = d.out.C;
     d.weight = h->weight; d.scale = nullptr; d.shift = h->shift;
-    return conv_umma_forward(&d, (cudaStream_t)stream, h, nullptr, nullptr);
+    int split_c = 0;
+    if (h->in.dtype == RDFC_F32) {
+        // fp32 input (the tensor-core fp32 mode): split it into [hi | lo] fp16 halves first; the filter bank then holds 3 x C channels
+        const long long npix = (long long)h->B * h->H * h->W;
+        RDFC_REQUIRE(!h->in.nchw && h->in.C % 32 == 0, "heads (fp32 input): NHWC view with C %% 32 == 0");
+        RDFC_REQUIRE(h->workspace && h->workspace_bytes >= (size_t)npix * h->in.C * 4 && ((uintptr_t)h->workspace % 128) == 0,
+                     "heads (fp32 input): workspace of B*H*W*C*4 bytes (128-byte aligned) required");
+        if (int rc = split_f32_forward(&h->in, h->workspace, npix, (cudaStream_t)stream)) return rc;
+        split_c = h->in.C;
+        d.in.ptr = h->workspace; d.in.dtype = RDFC_BF16; d.in.C = 2 * split_c; d.in.pix_stride = 2 * split_c;
+    }
+    return conv_umma_forward(&d, (cudaStream_t)stream, h, nullptr, nullptr, split_c);
 }
 
 extern "C" int rdfc_stem_forward(const rdfc_stem_desc *m, void *stream) {
@@ -60,7 +87,7 @@ extern "C" int rdfc_stem_forward(const rdfc_stem_desc *m, void *stream) {
     d.in.ptr = (void *)m->in0; d.in.dtype = RDFC_F32; d.in.C = 64; d.in.pix_stride = 64;      // the virtual im2col matrix
     d.out = m->out;
     d.weight = m->weight; d.scale = m->scale; d.shift = m->shift;
-    return conv_umma_forward(&d, (cudaStream_t)stream, nullptr, m, nullptr);
+    return conv_umma_forward(&d, (cudaStream_t)stream, nullptr, m, nullptr, 0);
 }
 
 extern "C" int rdfc_wadain_tile(int C) { return wadain_tile(C); }
@@ -83,7 +110,7 @@ extern "C" int rdfc_wadain_conv_forward(const rdfc_wadain_conv_desc *w, void *st
     d.kh = d.kw = 1; d.stride = 1; d.pad = 0; d.act = RDFC_ACT_NONE; d.path = RDFC_PATH_UMMA_BF16;
     d.in = w->style; d.out = w->out;
     d.weight = w->weight; d.scale = nullptr; d.shift = w->bias;
-    return conv_umma_forward(&d, (cudaStream_t)stream, nullptr, nullptr, w);
+    return conv_umma_forward(&d, (cudaStream_t)stream, nullptr, nullptr, w, 0);
 }
 
 // development aid (not part of the public ABI): role timers of the last conv_umma launch under RDFC_UMMA_DBG=1

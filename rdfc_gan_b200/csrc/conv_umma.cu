@@ -79,6 +79,13 @@ struct Params {
     alignas(64) CUtensorMap tmap_out;
     alignas(64) CUtensorMap tmap_res;
     int tma_out;
+    // fp32-faithful contraction on the 16-bit tensor cores ("3 x fp16"): the input is a split tensor [hi(C) | lo(C)] per pixel
+    // (hi = fp16(x), lo = fp16(x - hi): 22 mantissa bits together) and the filter bank is packed as [W_hi ; W_lo ; W_hi] along
+    // Cin, so that the K loop computes x_hi W_hi + x_hi W_lo + x_lo W_hi with fp32 accumulation (the dropped x_lo W_lo term is
+    // 2^-22 relative).  A bf16 split (8 + 8 bits) was measured first: 1.3e-4 max-abs on the O(1)-activation goldens, not enough.
+    // k-block i reads input channels split_ch(i); out_f32: fp32 NHWC output / residual (MODE_GENERAL).
+    int split_c;                   // C (input channels of the layer) when split, else 0
+    int out_f32;
     int dual;                      // two MMA issuer warps (MMA_WARP and MMA2_WARP), each owning a subset of the accumulators
     int pair;                      // cta_group::2: two CTAs (a cluster) work on two pixel tiles with ONE stream of M = 256 MMAs; each
                                    // holds its own A stages and HALF of every filter stage (per-SM shared-memory reads per MMA: 4 KB + N*16 B)
@@ -444,7 +451,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         // RDFC_UMMA_SKIP & 4: issue every MMA with N = 16 (wrong results): is the loop bound by issue or by the tensor pipe?
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(((P.dbg_flags & 4) ? 16 : P.bn) >> 3) << 17) | ((kPair ? 16u : 8u) << 24);
 #else
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((kPair ? 16u : 8u) << 24);
+        // operand format: bf16 (1), or fp16 (0) for the split fp32-faithful mode (11 + 11 mantissa bits per operand)
+        const uint32_t fmt = P.split_c ? 0u : 1u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((kPair ? 16u : 8u) << 24);
 #endif
         // one k-step = 16 channels: two chunk planes further in the [cin/8][pixel][16 B] layout, 32 bytes in [pixel][64 B]
         const uint32_t a_kstep = keep(P.a_tma ? 2u : 2u * (uint32_t)P.npix_pad), b_kstep = keep(2u * (uint32_t)bn_cta);
@@ -580,12 +589,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                     if (P.dbg_flags & 8) { mbar_arrive(full); if (++s == sa_n) { s = 0; par ^= 1u; } continue; }
 #endif
                     mbar_expect_tx(full, (uint32_t)P.a_tx_bytes);
+                    // input channel of k-block i: plain convs walk the channels; split inputs walk hi, hi again, then lo
+                    int a_ch = i * BK;
+                    if (P.split_c) a_ch = a_ch < P.split_c ? a_ch : (a_ch < 2 * P.split_c ? a_ch - P.split_c : a_ch - P.split_c);
                     for (int pl = 0; pl < npl; ++pl) {
                         const Plane &q = P.planes[pl];
                         asm volatile(
                             "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
                                 sA0 + (uint32_t)s * (uint32_t)a_stage_bytes + (uint32_t)pl * plane_b),
-                            "l"(&P.tmap_a), "r"(i * BK), "r"(q.xstep * t.tx0 + q.xoff), "r"(q.ystep * t.ty0 + q.yoff), "r"(t.b), "r"(full)
+                            "l"(&P.tmap_a), "r"(a_ch), "r"(q.xstep * t.tx0 + q.xoff), "r"(q.ystep * t.ty0 + q.yoff), "r"(t.b), "r"(full)
                             : "memory");
                     }
                     if (++s == sa_n) { s = 0; par ^= 1u; }
@@ -826,7 +838,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
 #define vec32 (kMode == MODE_STD || (flags & 2))      // MODE_STD: the host guarantees 32-byte aligned slices and Cout % 16 == 0
 #define skip (flags >> 2)
         const float slope = act == RDFC_ACT_RELU ? 0.f : (act == RDFC_ACT_LEAKY02 ? 0.2f : 1.f);
-        const __nv_bfloat16 *res = P.res;
+        const __nv_bfloat16 *res = (kGeneral && P.out_f32) ? nullptr : P.res;            // fp32 mode: the residual is read as floats below
+        const float *res32 = (kGeneral && P.out_f32) ? reinterpret_cast<const float *>(P.res) : nullptr;
         __nv_bfloat16 *const outp = P.out;
         const int G = bn >> 4;
         int it = 0, wad_b = -1;
@@ -1076,6 +1089,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                         f[4 * q4 + 2] = fmaf(__uint_as_float(v[4 * q4 + 2]), sc.z, sh.z);
                         f[4 * q4 + 3] = fmaf(__uint_as_float(v[4 * q4 + 3]), sc.w, sh.w);
                     }
+                    if (kGeneral && P.out_f32) {
+                        // fp32-faithful mode: fp32 NHWC output (and residual), 16 channels = 64 bytes per lane
+                        float *op = reinterpret_cast<float *>(P.out) + opix * out_stride + n0 + n;
+                        const float *rp = res32 ? res32 + opix * res_stride + n0 + n : nullptr;
+                        const int nvalid = Cout - n0 - n;
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            if (4 * q4 + 4 <= nvalid) {
+                                float4 y = make_float4(f[4 * q4], f[4 * q4 + 1], f[4 * q4 + 2], f[4 * q4 + 3]);
+                                if (rp) {
+                                    const float4 r4 = __ldg(reinterpret_cast<const float4 *>(rp) + q4);
+                                    y.x += r4.x; y.y += r4.y; y.z += r4.z; y.w += r4.w;
+                                }
+                                if (act <= RDFC_ACT_LEAKY02) {
+                                    y.x = fmaxf(y.x, slope * y.x); y.y = fmaxf(y.y, slope * y.y); y.z = fmaxf(y.z, slope * y.z); y.w = fmaxf(y.w, slope * y.w);
+                                } else {
+                                    y.x = apply_act(y.x, act); y.y = apply_act(y.y, act); y.z = apply_act(y.z, act); y.w = apply_act(y.w, act);
+                                }
+                                reinterpret_cast<float4 *>(op)[q4] = y;
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (4 * q4 + e < nvalid) {
+                                        float y = f[4 * q4 + e] + (rp ? __ldg(rp + 4 * q4 + e) : 0.f);
+                                        op[4 * q4 + e] = act <= RDFC_ACT_LEAKY02 ? fmaxf(y, slope * y) : apply_act(y, act);
+                                    }
+                            }
+                        }
+                        return;
+                    }
                     if (planar) {
                         // fused decode heads: column q -> its own fp32 plane with its own activation
 #pragma unroll
@@ -1211,17 +1254,22 @@ static TmapEncodeFn tmap_encoder() {
 
 int wadain_tile(int C) { return (2 * C) % 256 == 0 ? 256 : 128; }
 
+// split_c != 0: `d->in` is a split bf16 tensor [hi(split_c) | lo(split_c)] (see Params::split_c) and the filter bank holds
+// 3 * split_c input channels; the output (and residual) may then be fp32 NHWC.
 int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads, const rdfc_stem_desc *stem,
-                      const rdfc_wadain_conv_desc *wad) {
-    RDFC_REQUIRE((stem || d->in.dtype == RDFC_BF16) && (heads || d->out.dtype == RDFC_BF16), "UMMA conv: bf16 in/out only");
+                      const rdfc_wadain_conv_desc *wad, int split_c) {
+    RDFC_REQUIRE((stem || d->in.dtype == RDFC_BF16) && (heads || d->out.dtype == RDFC_BF16 || (split_c && d->out.dtype == RDFC_F32)),
+                 "UMMA conv: bf16 in/out only");
     RDFC_REQUIRE(!d->in.nchw && !d->out.nchw && !d->in2.ptr, "UMMA conv: single NHWC source / NHWC output only");
     RDFC_REQUIRE(d->in.C % BK == 0, "UMMA conv: Cin (%d) must be a multiple of %d", d->in.C, BK);
     RDFC_REQUIRE((stem || (d->in.pix_stride % 8 == 0 && ((uintptr_t)d->in.ptr % 16) == 0)) && ((uintptr_t)d->weight % 16) == 0 &&
                      (heads || (d->out.pix_stride % 8 == 0 && ((uintptr_t)d->out.ptr % 16) == 0)),
                  "UMMA conv: views must be 16-byte aligned with pixel strides that are multiples of 8 elements");
-    RDFC_REQUIRE(!d->residual.ptr || (d->residual.dtype == RDFC_BF16 && d->residual.pix_stride % 8 == 0 &&
+    RDFC_REQUIRE(!d->residual.ptr || (d->residual.dtype == d->out.dtype && d->residual.pix_stride % 8 == 0 &&
                                       ((uintptr_t)d->residual.ptr % 16) == 0),
-                 "UMMA conv: residual must be an aligned bf16 NHWC view");
+                 "UMMA conv: residual must be an aligned NHWC view of the output's dtype");
+    RDFC_REQUIRE(!split_c || (!stem && !wad && d->in.C == 2 * split_c && split_c % BK == 0),
+                 "UMMA conv (split input): [hi | lo] view with 2 x %d channels expected", split_c);
     RDFC_REQUIRE((!d->scale || ((uintptr_t)d->scale % 16) == 0) && (!d->shift || ((uintptr_t)d->shift % 16) == 0),
                  "UMMA conv: scale / shift vectors must be 16-byte aligned");
     const bool k3 = d->kh == 3 && d->kw == 3, k1 = d->kh == 1 && d->kw == 1;
@@ -1236,6 +1284,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     P.w = (const __nv_bfloat16 *)d->weight;
     P.Cout = d->out.C; P.CoutP = (P.Cout + 15) / 16 * 16;
     P.cin_chunks = d->in.C / 8; P.nkb = d->in.C / BK;
+    if (split_c) { P.split_c = split_c; P.cin_chunks = 3 * split_c / 8; P.nkb = 3 * split_c / BK; P.out_f32 = d->out.dtype == RDFC_F32; }
     P.out = (__nv_bfloat16 *)d->out.ptr; P.out_stride = d->out.pix_stride; P.Ho = d->Ho; P.Wo = d->Wo;
     P.res = (const __nv_bfloat16 *)d->residual.ptr; P.res_stride = d->residual.pix_stride;
     P.scale = d->scale; P.shift = d->shift; P.act = d->act;
@@ -1437,6 +1486,8 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     P.vec32 = !heads && ((uintptr_t)d->out.ptr % 32) == 0 && d->out.pix_stride % 16 == 0 &&
               (!P.out2 || (((uintptr_t)P.out2 % 32) == 0 && P.out2_stride % 16 == 0 && P.split % 16 == 0)) &&
               (!d->residual.ptr || (((uintptr_t)d->residual.ptr % 32) == 0 && d->residual.pix_stride % 16 == 0));
+    if (P.out_f32) P.vec32 = 0;                    // fp32 output: the general epilogue variant
+    RDFC_REQUIRE(!split_c || P.a_tma, "UMMA conv (split input) needs the TMA producer");
     const int a_stage = P.a_tma ? P.nplanes * P.a_plane_bytes : (KCH * P.npix_pad * 16 + 1023) / 1024 * 1024;
     const int stem_patch = stem ? 2 * ((P.stem_k / 9) * (TH + 2) * (TW + 2) + 4) * 4 : 0;  // two fp32 input patches of a tile (stem mode)
     const int heads_y = heads ? 256 * (P.bn + 1) * 4 : 0;                                   // shift-add heads: Y of a region

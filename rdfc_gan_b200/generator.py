@@ -96,8 +96,9 @@ class _GeneratorBase(nn.Module):
         return self._engine
 
     def set_precision(self, precision):
-        """'fp32' (CUDA-core fp32 contraction, the <=1e-4 parity mode) or 'bf16' (tcgen05 tensor cores)."""
-        assert precision in ('fp32', 'bf16')
+        """'fp32' (CUDA-core fp32 contraction, the strict <=1e-4 parity mode), 'fp32_tc' (fp32 tensors, contractions on the
+        tcgen05 tensor cores with split fp16 operands) or 'bf16' (tcgen05 tensor cores, the throughput mode)."""
+        assert precision in ('fp32', 'fp32_tc', 'bf16')
         self.engine(precision)
         return self
 
