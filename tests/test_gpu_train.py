@@ -233,3 +233,35 @@ def test_training_step_against_reference_gradients(golden_dir):
     stats = model.optimize_parameters()
     assert set(stats) == {"loss_D", "loss_D_real", "loss_D_fake", "loss_G_GAN", "loss_L1_rgb_branch", "loss_L1_depth_branch", "loss_L1_fusion"}
     assert all(math.isfinite(v) for v in stats.values())
+
+
+def test_resnet_generator_against_reference(golden_dir):
+    """G_B2A (C/lib/models/generator/resnet_generator.py): train() and eval() outputs and the parameter gradients of a linear probe
+    against the reference class on the CPU (tests/golden/resnet_generator.npz).  bf16 activations: outputs to 3e-2, gradient
+    direction to the bf16 noise floor (see test_generator_backward_matches_bf16_emulation)."""
+    from make_train_golden import RESNET_CASE, grad_sample_index, resnet_inputs
+    from _synth import synth_state_dict
+    from rdfc_gan_b200.resnet_generator import ResnetGenerator
+    gold = np.load(f"{golden_dir}/resnet_generator.npz")
+    G = ResnetGenerator(**RESNET_CASE["kw"])
+    G.load_state_dict(synth_state_dict(G, seed=RESNET_CASE["seed"], recipe="scaled"))
+    G = G.cuda().train()
+    x, probe = (t.cuda() for t in resnet_inputs())
+    y = G(x)
+    assert tuple(y.shape) == tuple(gold["out_train"].shape)
+    assert float((y.detach().cpu() - torch.from_numpy(gold["out_train"])).abs().max()) <= 3e-2
+    (y * probe).sum().backward()
+    cos = {}
+    for n, p in G.named_parameters():
+        if p.numel() < 8:
+            continue
+        idx = torch.from_numpy(grad_sample_index(n, p.numel()))
+        got, want = p.grad.detach().reshape(-1).cpu()[idx].double(), torch.from_numpy(gold[f"grad_{n}"]).double()
+        cos[n] = float((got * want).sum() / (got.norm() * want.norm() + 1e-30))
+    assert min(cos.values()) >= 0.85 and float(np.median(list(cos.values()))) >= 0.95, sorted((c, n) for n, c in cos.items())[:6]
+    G.eval()
+    with torch.no_grad():
+        ye = G(x)
+    assert float((ye.cpu() - torch.from_numpy(gold["out_eval"])).abs().max()) <= 3e-2
+    with pytest.raises(RuntimeError):
+        G(x.cpu())
