@@ -317,6 +317,29 @@ typedef struct {
 long long rdfc_conv_wgrad_workspace_floats(const rdfc_wgrad_desc *d);
 int rdfc_conv_wgrad(const rdfc_wgrad_desc *d, float *grad_weight, float *workspace, void *stream);
 
+/* ------------------------------------------------------------------ ESANet guidance glue ---------------------- */
+/* The non-GEMM layers of RDF-GAN's global_guidance_module (F/lib/models/segmentator/esa_net/esa_net_one_modality.py:145-172,
+ * decoder.py:137-191, model_utils.py:34-49,99-134; F = /root/reference/RDF-GAN); its GEMM-shaped layers go through
+ * rdfc_conv_forward.  All views bf16 NHWC. */
+
+/* encoder.conv1 + folded bn1 + ReLU: k x k (<= 7) conv, any stride, from fp32 NCHW x (B, Cin <= 4, Hi, Wi); weight (Cout, Cin, k, k) fp32 */
+int rdfc_first_conv_forward(const float *x_nchw, int B, int Cin, int Hi, int Wi, const float *weight, int k, int stride, int pad,
+                            const float *scale, const float *shift, int relu, const rdfc_view *out, void *stream);
+/* F.max_pool2d(kernel 3, stride 2, padding 1) */
+int rdfc_maxpool3x3s2_forward(const rdfc_view *x, const rdfc_view *out, int B, int Hi, int Wi, void *stream);
+/* SqueezeAndExcitation.fc on the per-image channel means (B, C) -> weights (B, C): sigmoid(W2 relu(W1 m + b1) + b2), W1 (R, C), W2 (C, R);
+ * the scaling x * w is rdfc_norm_apply with mean = 0, rstd = w */
+int rdfc_se_weights(const float *mean, const float *w1, const float *b1, const float *w2, const float *b2, float *out, int B, int C, int R,
+                    void *stream);
+/* nn.AdaptiveAvgPool2d(bins) -> out (B, bins, bins, C) */
+int rdfc_adaptive_avgpool_forward(const rdfc_view *x, const rdfc_view *out, int B, int H, int W, int bins, void *stream);
+/* F.interpolate(mode='nearest') of a (hs, ws) map to (H, W), written into `out` (a channel slice of a concat buffer) */
+int rdfc_upsample_nearest_forward(const rdfc_view *x, const rdfc_view *out, int B, int hs, int ws, int H, int W, void *stream);
+/* Upsample('learned-3x3-zeropad'): nearest resize (Hi, Wi) -> (Ho, Wo), depth-wise 3x3 conv (weight (C, 1, 3, 3), bias (C)) with zero
+ * padding, + skip (or NULL); result to `out` (bf16 NHWC) or, when out_nchw != NULL, to fp32 NCHW (B, C, Ho, Wo) */
+int rdfc_upsample_dw_forward(const rdfc_view *x, const float *weight, const float *bias, const rdfc_view *skip, const rdfc_view *out,
+                             float *out_nchw, int B, int Hi, int Wi, int Ho, int Wo, void *stream);
+
 /* ------------------------------------------------------------------ development aids ------------------------- */
 /* Not part of the drop-in boundary.  rdfc_dev_set_knob overrides a development knob (the RDFC_* environment variables, which
  * the library reads once per name); value INT64_MIN restores the default.  rdfc_dev_umma_timers copies the per-role cycle

@@ -88,6 +88,12 @@ def _load():
     lib.rdfc_conv_wgrad_workspace_floats.argtypes = [ctypes.POINTER(WgradDesc)]
     lib.rdfc_conv_wgrad_workspace_floats.restype = ctypes.c_longlong
     lib.rdfc_conv_wgrad.argtypes = [ctypes.POINTER(WgradDesc), c_void_p, c_void_p, c_void_p]
+    lib.rdfc_first_conv_forward.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, VP, c_void_p]
+    lib.rdfc_maxpool3x3s2_forward.argtypes = [VP, VP, c_int, c_int, c_int, c_void_p]
+    lib.rdfc_se_weights.argtypes = [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p]
+    lib.rdfc_adaptive_avgpool_forward.argtypes = [VP, VP, c_int, c_int, c_int, c_int, c_void_p]
+    lib.rdfc_upsample_nearest_forward.argtypes = [VP, VP, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.rdfc_upsample_dw_forward.argtypes = [VP, c_void_p, c_void_p, VP, VP, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.rdfc_depth_metric_nchunk.argtypes = [ctypes.c_longlong]
     lib.rdfc_depth_metric_sums.argtypes = [c_void_p] * 3 + [ctypes.c_float] * 3 + [c_void_p] * 2 + [c_int, ctypes.c_longlong, c_void_p]
     lib.rdfc_nlspn_affinity_backward.argtypes = [c_void_p] * 5 + [c_int] * 2 + [c_void_p] * 6 + [c_int] * 3 + [c_void_p]
@@ -119,7 +125,8 @@ EXPORTS = ["rdfc_abi_version", "rdfc_last_error", "rdfc_launch_count", "rdfc_dcn
            "rdfc_wadain_apply", "rdfc_adain_apply", "rdfc_norm_apply", "rdfc_depth_metric_nchunk", "rdfc_depth_metric_sums", "rdfc_stem_forward", "rdfc_pack_stem_input",
            "rdfc_wadain_tile", "rdfc_wadain_conv_forward", "rdfc_dev_set_knob", "rdfc_dev_umma_timers",
            "rdfc_bn_workspace_floats", "rdfc_bn_stats", "rdfc_affine_act_forward", "rdfc_bn_act_backward",
-           "rdfc_conv_wgrad_workspace_floats", "rdfc_conv_wgrad"]
+           "rdfc_conv_wgrad_workspace_floats", "rdfc_conv_wgrad", "rdfc_first_conv_forward", "rdfc_maxpool3x3s2_forward", "rdfc_se_weights",
+           "rdfc_adaptive_avgpool_forward", "rdfc_upsample_nearest_forward", "rdfc_upsample_dw_forward"]
 
 
 KNOB_UNSET = -(1 << 63)

@@ -102,6 +102,8 @@ class ResnetGenerator(nn.Module):
                 x = via_torch(m, x.float()).to(torch.bfloat16)           # 7x7 / thin convs, eval-mode or instance normalisation: fp32 PyTorch
             elif isinstance(m, nn.LeakyReLU):                            # not in place: the producer saved its output for backward
                 x = F.leaky_relu(x, m.negative_slope)
+            elif isinstance(m, nn.PReLU):                                # fp32 slope parameter: evaluate in fp32
+                x = via_torch(m, x.float()).to(torch.bfloat16)
             else:                                                        # pads, PReLU / Tanh, dropout: element-wise PyTorch
                 x = via_torch(m, x)
         return x

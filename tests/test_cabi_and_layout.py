@@ -108,3 +108,14 @@ def test_patchgan_state_dict_matches_reference(golden_dir):
     want = json.load(open(os.path.join(golden_dir, "patchgan_state_dict_keys.json")))
     got = {k: list(v.shape) for k, v in PatchGANDiscriminator(in_channels=1).state_dict().items()}
     assert got == want
+
+
+def test_esanet_state_dict_matches_reference(golden_dir):
+    """tests/golden/esanet_r34_state_dict_keys.json was dumped from the reference's ESANetOneModality (F/bash/test_nyuv2_Ts2T.sh flags)."""
+    from make_esanet_golden import ESANET_CASES
+    from rdfc_gan_b200.esanet import ESANetOneModality
+    want = json.load(open(os.path.join(golden_dir, "esanet_r34_state_dict_keys.json")))
+    got = {k: list(v.shape) for k, v in ESANetOneModality(**ESANET_CASES["r34_full"]["kw"]).state_dict().items()}
+    assert got == want
+    with pytest.raises(NotImplementedError):
+        ESANetOneModality(pretrained_on_imagenet=False, encoder='resnet50')
