@@ -55,9 +55,9 @@ CONFIGS = {
                name="BASELINE config 3: RDFC-GAN RDFGenerator inference (ResNet-18 x2, W-AdaIN, NLSPN TGASS 18 it.), global batch 256 "
                     "@228x304, batch-sharded"),
     # c2's weights are fan-in scaled (O(1) activations through ~70 layers, outputs span [-1, 1]): its own, wider, stated bound
-    "c2": dict(gen="rdf", batch=32, H=228, W=304, gflop=393.3, fp32_chunk=16, cs=40, parity=BF16_BOUND["scaled_r34"],
-               name="BASELINE config 2: RDF-GAN DCVGANGenerator forward (ResNet-34 x2, 40-channel guidance stem, W-AdaIN + "
-                    "adain_weighting, NLSPN TGASS 18 it.), batch 32 @228x304"),
+    "c2": dict(gen="rdf", batch=32, H=228, W=304, gflop=415.8, fp32_chunk=16, cs=3, parity=BF16_BOUND["scaled_r34"],
+               name="BASELINE config 2: RDF-GAN DCVGANGenerator forward (ESANet-34 guidance network -> 40-channel stems, ResNet-34 x2, "
+                    "W-AdaIN + adain_weighting, NLSPN TGASS 18 it.), batch 32 @228x304"),
     "c5": dict(gen="rdfc", batch=64, H=480, W=640, gflop=976.9, fp32_chunk=8, cs=3, parity=(PARITY_RMSE, PARITY_MAXABS),
                name="BASELINE config 5: RDFGenerator inference @480x640 (SUN RGB-D shape), NLSPN 18 it., bf16, global batch 64, "
                     "batch-sharded"),
@@ -121,9 +121,18 @@ def synth_weights(module, cfg):
     return synth_state_dict(module, seed=0, recipe=recipe, nlspn_stress=True)
 
 
+ESANET_KW = dict(num_classes=40, pretrained_on_imagenet=False, encoder="resnet34", encoder_block="BasicBlock",
+                 channels_decoder=[512, 256, 128], nr_decoder_blocks=[3, 3, 3], encoder_decoder_fusion="add", context_module="ppm",
+                 weighting_in_encoder="SE-add", upsampling="learned-3x3-zeropad", pyramid_supervision=False)      # F/bash/test_nyuv2_Ts2T.sh:7-16
+
+
 def build_product(cfg):
     from rdfc_gan_b200.generator import DCVGANGenerator, RDFGenerator
-    G = (RDFGenerator(**gen_kwargs(cfg)) if cfg["gen"] == "rdfc" else DCVGANGenerator(None, **gen_kwargs(cfg))).eval()
+    if cfg["gen"] == "rdfc":
+        G = RDFGenerator(**gen_kwargs(cfg)).eval()
+    else:
+        from rdfc_gan_b200.esanet import ESANetOneModality
+        G = DCVGANGenerator(ESANetOneModality(height=cfg["H"], width=cfg["W"], **ESANET_KW), **gen_kwargs(cfg)).eval()
     G.load_state_dict(synth_weights(G, cfg))
     return G
 
@@ -134,17 +143,18 @@ def build_reference(cfg, gpu=False):
     if cfg["gen"] == "rdfc":
         G = ref_loader.load_rdfc(gpu)(**gen_kwargs(cfg)).eval()
     else:
-        import torch
-        G = ref_loader.load_rdf_gan(gpu)[0](torch.nn.Identity(), **gen_kwargs(cfg)).eval()
+        DCV, ESA = ref_loader.load_rdf_gan(gpu)
+        G = DCV(ESA(height=cfg["H"], width=cfg["W"], **ESANET_KW), **gen_kwargs(cfg)).eval()
     G.load_state_dict(synth_weights(G, cfg))
     return G
 
 
 def call_generator(G, cfg, rgb, stem, depth):
-    """RDFGenerator.forward(rgb, depth, normal) -> dict; DCVGANGenerator.forward(guidance-as-rgb, depth) -> 5-tuple."""
+    """RDFGenerator.forward(rgb, depth, normal) -> dict; DCVGANGenerator.forward(rgb, depth) -> 5-tuple (its guidance network
+    maps rgb to the 40-channel stem input)."""
     if cfg["gen"] == "rdfc":
         return G(rgb, depth, stem)
-    return dict(zip(KEYS, G(stem, depth)))
+    return dict(zip(KEYS, G(rgb, depth)))
 
 
 def reference_cpu(cfg, n_images, reps, warmup=1):
@@ -270,6 +280,19 @@ def main():
     eng = G.engine()
     plan = next(iter(eng._plans.values()))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    esa_plan, n_launch = None, plan.n_launch
+    if cfg["gen"] == "rdf":              # config 2: the ESANet guidance network's own plan (graph) runs in front of the generator's
+        esa = G.global_guidance_module
+        esa_plan = next(iter(esa._plans.values()))
+        n_launch += len(esa_plan["steps"])
+        with torch.no_grad():
+            stem_d = esa(rgb_d)          # the 40-channel map the stems read (used by the parity section below)
+
+    def run_step():
+        if esa_plan is not None:
+            esa_plan["graph"].replay()
+            plan.stem_in.copy_(esa_plan["out"])
+        plan.run()
 
     def barrier():
         torch.cuda.synchronize()
@@ -285,18 +308,18 @@ def main():
 
     # ---------------- value: inputs resident, graph replay, per-step CUDA events, L2 flush between steps
     for _ in range(args.warmup):
-        plan.run()
+        run_step()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.15)                         # let nvidia-smi start streaming; the GPU keeps running warm-up work meanwhile
     for _ in range(2):
-        plan.run()
+        run_step()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in evs:
         flush.zero_()
         a.record()
-        plan.run()
+        run_step()
         b.record()
     barrier()
     clocks = sampler.summary()
@@ -309,13 +332,22 @@ def main():
 
     def host_batches(n):
         for _ in range(n):
-            yield (rgb_h, depth_h, stem_h) if cfg["gen"] == "rdfc" else (stem_h, depth_h)
+            yield (rgb_h, depth_h, stem_h)
 
     def e2e_run(n):
-        # G.stream() overlaps the H2D copy of batch i+1 and the D2H read of batch i-1 with the forward of batch i
-        for o in G.stream(host_batches(n), outputs=KEYS):
-            for k in KEYS:
-                outs_h[k].copy_(o[k])                     # host-side use of the result (pinned -> pinned)
+        if cfg["gen"] == "rdfc":
+            # G.stream() overlaps the H2D copy of batch i+1 and the D2H read of batch i-1 with the forward of batch i
+            for o in G.stream(host_batches(n), outputs=KEYS):
+                for k in KEYS:
+                    outs_h[k].copy_(o[k])                 # host-side use of the result (pinned -> pinned)
+        else:
+            # RDF-GAN: the module call G(rgb, depth) (guidance network + generator) on batches copied from / to pinned host memory
+            with torch.no_grad():
+                for _ in range(n):
+                    o = G(rgb_h.to(dev, non_blocking=True), depth_h.to(dev, non_blocking=True))
+                    for k, t in zip(KEYS, o):
+                        outs_h[k].copy_(t, non_blocking=True)
+                    torch.cuda.synchronize()
     e2e_run(3)
     barrier()
     t0 = time.perf_counter()
@@ -324,7 +356,7 @@ def main():
     e2e = args.batch * args.steps / maxreduce(time.perf_counter() - t0)
     # RDFGenerator's stems read `normal` and `depth` only (rdf_generator.py:286-292: `rgb` is unused), so those are the
     # tensors stream() copies; DCVGANGenerator without a guidance module reads the 40-channel map + depth
-    h2d = stem_h.numel() * 4 + depth_h.numel() * 4
+    h2d = (stem_h if cfg["gen"] == "rdfc" else rgb_h).numel() * 4 + depth_h.numel() * 4
     d2h = sum(t.numel() * 4 for t in outs_h.values())
 
     # ---------------- parity of what was timed: bf16 outputs vs this repo's fp32 mode, image chunk by image chunk
@@ -379,7 +411,8 @@ def main():
         eng.clear_plans(precision="fp32_tc")
         G.set_precision("bf16")
         parity = {k: {"rmse": (maxreduce(se[i]) / (B * H * W)) ** 0.5, "max_abs": maxreduce(mx[i])} for i, k in enumerate(KEYS)}
-        parity["against"] = "fp32 mode of this repo (<= 1e-4 from the reference's goldens, tests/test_gpu_generator.py)"
+        parity["against"] = "fp32 mode of this repo (<= 1e-4 from the reference's goldens, tests/test_gpu_generator.py)" + (
+            "" if esa_plan is None else "; the ESANet guidance network has one (bf16) mode and is common to both sides")
         tol_rmse, tol_max = cfg["parity"]
         parity["bound"] = {"rmse": tol_rmse, "max_abs": tol_max}
         parity["images"] = args.batch
@@ -469,7 +502,7 @@ def main():
             "dtype": args.precision if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(cfg, args, world, B), "clocks": clocks,
             "e2e": {"value": e2e, "unit": "maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": plan.n_launch * args.steps, "parity": parity, "value_fp32": value_fp32, "value_fp32_tc": value_fp32_tc, "ref_gpu": ref_gpu,
+            "gpu_launches": n_launch * args.steps, "parity": parity, "value_fp32": value_fp32, "value_fp32_tc": value_fp32_tc, "ref_gpu": ref_gpu,
             "roofline": roofline, "roofline_dense": roofline_dense, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()

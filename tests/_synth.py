@@ -77,6 +77,14 @@ def synth_state_dict(module, seed=0, recipe="init", nlspn_stress=False):
         else:
             raise KeyError(f"no synthetic recipe for {key} {shape}")
         out[key] = torch.from_numpy(np.ascontiguousarray(v))
+    # an ESANet guidance sub-network (RDF-GAN's global_guidance_module): damp the last BatchNorm of every residual branch and the
+    # logits, or 25 residual blocks in front of non-tracking eval-mode BatchNorms blow the 40-channel map up to 1e7
+    for k in out:
+        if "global_guidance_module." in k and recipe != "init":
+            if k.endswith("bn2.weight"):
+                out[k] = out[k] * 0.25
+            elif k.endswith("decoder.conv_out.weight"):
+                out[k] = out[k] * 0.1
     if nlspn_stress:
         kw, kb = [k for k in out if k.endswith("conv_offset_aff.weight")], [k for k in out if k.endswith("conv_offset_aff.bias")]
         for k in kw:
