@@ -201,9 +201,11 @@ def test_dcvgan_signature_and_errors():
     R = RDFGenerator(pretrained_on_imagenet=False).eval()
     with pytest.raises(RuntimeError, match="CUDA"):
         R(torch.zeros(1, 3, 32, 32), torch.zeros(1, 1, 32, 32), torch.zeros(1, 3, 32, 32))
-    R = R.cuda().train()
-    with pytest.raises(RuntimeError, match="training"):
-        R(torch.zeros(1, 3, 32, 32).cuda(), torch.zeros(1, 1, 32, 32).cuda(), torch.zeros(1, 3, 32, 32).cuda())
+    R = R.cuda().eval()
+    with pytest.raises(RuntimeError, match="inference-only"):          # eval mode returns detached maps: a grad-requiring input must not pass silently
+        R(torch.zeros(1, 3, 32, 32).cuda(), torch.zeros(1, 1, 32, 32).cuda().requires_grad_(True), torch.zeros(1, 3, 32, 32).cuda())
+    out = R.train()(torch.zeros(1, 3, 32, 32).cuda(), torch.zeros(1, 1, 32, 32).cuda(), torch.zeros(1, 3, 32, 32).cuda())
+    assert out["pred_depth"].requires_grad and out["pred_depth"].shape == (1, 1, 32, 32)      # train(): the autograd path (tests/test_gpu_train.py)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
