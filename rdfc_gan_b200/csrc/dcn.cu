@@ -5,9 +5,13 @@
 // no `columns` buffer and no per-im2col_step chunking: a CTA samples a strip of output pixels once into shared
 // memory and contracts it against the filter bank in registers.  The NLSPN-shaped calls (Cin = Cout = 1) never come
 // here from the generator -- they run in nlspn.cu -- but the Function / Module API does.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace rdfc {
+int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads, const rdfc_stem_desc *stem,
+                      const rdfc_wadain_conv_desc *wad, int split_c);
 namespace {
 
 constexpr int TP = 32;        // output pixels per CTA strip (one warp lane per pixel in the contraction)
@@ -289,6 +293,122 @@ int fwd(const void *input, const void *weight, const void *bias, const void *off
     return 0;
 }
 
+// ---------------------------------------------------------------- forward on the tensor cores ------------------
+// out = W . (mask * deform_im2col(x, offset)) + b as the reference factors it (modulated_deform_conv_cuda.cu:78-118): the sampled
+// columns are materialised -- here as fp16 halves [hi | lo] per (pixel, group), so that the contraction can run on tcgen05 with
+// split operands at fp32 fidelity (conv_umma.cu, Params::split_c) -- then ONE 1x1 implicit GEMM per group contracts them with
+// the filter bank packed [W_hi ; W_lo ; W_hi], and a transposition returns the NCHW layout of the DCN boundary.
+// cols[pixel][group][2 * Kg] with Kg = (Cin / group) * kh * kw, k = ci_local * K + tap (the filter's own flattening).
+// grid (ceil(P / 32), B), 8 warps.  Per chunk of 64 rows kk = ci * K + tap: sampling with one lane per PIXEL (offset / mask planes
+// and the image rows are read coalesced, as in the reference's im2col), the values go through a shared-memory tile, and the
+// write-out runs with one warp per pixel and the lanes along kk, so that every pixel's column block leaves as 128-byte rows.
+template <bool kMask>
+__global__ void __launch_bounds__(NT) dcn_im2col_split_kernel(const float *__restrict__ input, const float *__restrict__ offset,
+                                                              const float *__restrict__ mask, __half *__restrict__ cols, Geo g) {
+    __shared__ float tile[64][33];
+    const int K = g.kh * g.kw, P = g.Ho * g.Wo, Kg = (g.Cin / g.group) * K, cpd = g.Cin / g.dg, KT = g.Cin * K;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y, p0 = blockIdx.x * 32;
+    const int p = p0 + lane, ho = p / g.Wo, wo = p - ho * g.Wo;
+    const float *img = input + (long long)b * g.Cin * g.H * g.W;
+    for (int k0 = 0; k0 < KT; k0 += 64) {
+        for (int r = warp; r < 64; r += NT / 32) {
+            const int kk = k0 + r;
+            float v = 0.f;
+            if (kk < KT && p < P) {
+                const int ci = kk / K, tap = kk - ci * K, dgi = ci / cpd, ky = tap / g.kw, kx = tap - ky * g.kw;
+                const float *offp = offset + ((long long)b * g.dg * 2 * K + (long long)dgi * 2 * K + 2 * tap) * P + p;
+                const float y = (float)(ho * g.sh - g.ph + ky * g.dh) + __ldg(offp), x = (float)(wo * g.sw - g.pw + kx * g.dw) + __ldg(offp + P);
+                v = sample<float>(img + (long long)ci * g.H * g.W, g.H, g.W, y, x);
+                if (kMask) v *= __ldg(mask + ((long long)b * g.dg * K + (long long)dgi * K + tap) * P + p);
+            }
+            tile[r][lane] = v;
+        }
+        __syncthreads();
+        for (int px = warp; px < 32; px += NT / 32) {
+            const int pp = p0 + px, kk = k0 + 2 * lane;                  // two consecutive rows per lane (kk even, Kg even: same group)
+            if (pp < P && kk < KT) {
+                const float v0 = tile[2 * lane][px], v1 = tile[2 * lane + 1][px];
+                const int grp = kk / Kg, kl = kk - grp * Kg;
+                __half *row = cols + (((long long)b * P + pp) * g.group + grp) * (2 * Kg);
+                const __half2 hi = __floats2half2_rn(v0, v1);
+                const float2 hf = __half22float2(hi);
+                *reinterpret_cast<__half2 *>(row + kl) = hi;
+                *reinterpret_cast<__half2 *>(row + Kg + kl) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// filter bank of one group -> UMMA packing [1 tap][3 Kg / 8][CoutP][8] of [W_hi ; W_lo ; W_hi] (fp16)
+__global__ void __launch_bounds__(NT) dcn_pack_x3_kernel(const float *__restrict__ w, __half *__restrict__ packed, int Cog, int CoutP, int Kg) {
+    const int total = 3 * Kg * CoutP;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int e = i & 7, co = (i >> 3) % CoutP, ch = i / (8 * CoutP);
+        const int kk = ch * 8 + e, k = kk % Kg, part = kk / Kg;
+        float v = 0.f;
+        if (co < Cog) {
+            const float x = __ldg(w + (long long)co * Kg + k);
+            const float hi = __half2float(__float2half_rn(x));
+            v = part == 1 ? x - hi : hi;
+        }
+        packed[i] = __float2half_rn(v);
+    }
+}
+
+__global__ void __launch_bounds__(NT) nhwc_to_nchw_kernel(const float *__restrict__ x, float *__restrict__ out, int B, int C, int P) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += NT / 32)
+        if (p0 + r < P && c0 + tx < C) tile[r][tx] = x[((long long)b * P + p0 + r) * C + c0 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += NT / 32)
+        if (c0 + r < C && p0 + tx < P) out[((long long)b * C + c0 + r) * P + p0 + tx] = tile[tx][r];
+}
+
+bool fwd_tc_ok(const Geo &g) {
+    const int Kg = (g.Cin / g.group) * g.kh * g.kw, Cog = g.Cout / g.group;
+    return Kg % 32 == 0 && Cog >= 16 && Cog % 8 == 0 && knob("RDFC_DCN_TC", 1) != 0;
+}
+
+int fwd_tc(const float *input, const float *weight, const float *bias, const float *offset, const float *mask, float *output,
+           const Geo &g, cudaStream_t st) {
+    const int K = g.kh * g.kw, P = g.Ho * g.Wo, Kg = (g.Cin / g.group) * K, Cog = g.Cout / g.group, CoutP = (Cog + 15) / 16 * 16;
+    const long long npix = (long long)g.B * P;
+    __half *cols = nullptr, *packed = nullptr;
+    float *tmp = nullptr;
+    const size_t cols_bytes = (size_t)npix * g.group * 2 * Kg * sizeof(__half), pk_bytes = (size_t)3 * Kg * CoutP * sizeof(__half);
+    RDFC_CUDA(cudaMallocAsync((void **)&cols, cols_bytes, st));
+    RDFC_CUDA(cudaMallocAsync((void **)&packed, pk_bytes * g.group, st));
+    RDFC_CUDA(cudaMallocAsync((void **)&tmp, (size_t)npix * g.Cout * sizeof(float), st));
+    int rc = 0;
+    {
+        const dim3 grid(cdiv(P, 32), g.B);
+        if (mask) dcn_im2col_split_kernel<true><<<grid, NT, 0, st>>>(input, offset, mask, cols, g);
+        else dcn_im2col_split_kernel<false><<<grid, NT, 0, st>>>(input, offset, nullptr, cols, g);
+        count_launch();
+    }
+    for (int grp = 0; grp < g.group && rc == 0; ++grp) {
+        __half *pk = packed + (size_t)grp * 3 * Kg * CoutP;
+        dcn_pack_x3_kernel<<<cdiv(3 * Kg * CoutP, NT), NT, 0, st>>>(weight + (long long)grp * Cog * Kg, pk, Cog, CoutP, Kg);
+        count_launch();
+        rdfc_conv_desc d{};
+        d.B = g.B; d.Hi = d.Ho = g.Ho; d.Wi = d.Wo = g.Wo;
+        d.kh = d.kw = 1; d.stride = 1; d.pad = 0; d.act = RDFC_ACT_NONE; d.path = RDFC_PATH_UMMA_BF16;
+        d.in.ptr = cols + (size_t)grp * 2 * Kg; d.in.dtype = RDFC_BF16; d.in.C = 2 * Kg; d.in.pix_stride = g.group * 2 * Kg;
+        d.out.ptr = tmp + (size_t)grp * Cog; d.out.dtype = RDFC_F32; d.out.C = Cog; d.out.pix_stride = g.Cout;
+        d.weight = pk; d.scale = nullptr; d.shift = bias ? bias + (size_t)grp * Cog : nullptr;
+        rc = conv_umma_forward(&d, st, nullptr, nullptr, nullptr, Kg);
+    }
+    if (rc == 0) {
+        nhwc_to_nchw_kernel<<<dim3(cdiv(P, 32), cdiv(g.Cout, 32), g.B), NT, 0, st>>>(tmp, output, g.B, g.Cout, P);
+        count_launch();
+        if (cudaGetLastError() != cudaSuccess) rc = fail(RDFC_ERR_CUDA, "dcn forward (tensor cores): kernel launch failed");
+    }
+    cudaFreeAsync(cols, st); cudaFreeAsync(packed, st); cudaFreeAsync(tmp, st);
+    return rc;
+}
+
 template <typename T>
 int bwd(const void *input, const void *weight, const void *offset, const void *mask, const void *gout, void *gin,
         void *goff, void *gmask, void *gw, void *gb, const Geo &g, cudaStream_t st) {
@@ -344,6 +464,10 @@ extern "C" int rdfc_dcn_forward(const void *input, const void *weight, const voi
     if (int rc = check_shape(s, g)) return rc;
     RDFC_REQUIRE(input && weight && offset && output, "input / weight / offset / output must not be NULL");
     cudaStream_t st = (cudaStream_t)stream;
+    // GEMM-sized layers: sampled columns + tcgen05 contraction at fp32 fidelity (split fp16 operands); thin layers: the strip kernel
+    if (dtype == RDFC_F32 && fwd_tc_ok(g))
+        return fwd_tc((const float *)input, (const float *)weight, (const float *)bias, (const float *)offset, (const float *)mask,
+                      (float *)output, g, st);
     if (dtype == RDFC_F32) return fwd<float>(input, weight, bias, offset, mask, output, g, st);
     if (dtype == RDFC_F64) return fwd<double>(input, weight, bias, offset, mask, output, g, st);
     return fail(RDFC_ERR_UNSUPPORTED, "rdfc_dcn_forward: dtype %d not supported (fp32 / fp64 only, as the reference)",

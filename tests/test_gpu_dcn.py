@@ -167,3 +167,41 @@ def test_example_pack_modules():                           # test.py:506-530
         assert (out.double().cpu() - ref).abs().max() < 1e-3
         out.mean().backward()
         assert m.weight.grad is not None and torch.isfinite(m.weight.grad).all()
+
+
+@pytest.mark.parametrize("case", [
+    # B, Cin, Cout, H, W, k, s, p, d, groups, dg, mask      (first: the reference's timing shape, deformconv/test.py:519-530)
+    (2, 64, 128, 128, 128, 3, 1, 1, 1, 1, 2, True), (2, 64, 64, 37, 45, 3, 2, 1, 1, 2, 4, True), (1, 32, 48, 20, 33, 3, 1, 2, 2, 1, 1, False),
+    (3, 128, 256, 19, 26, 1, 1, 0, 1, 1, 2, True)])
+def test_forward_on_tensor_cores_matches_strip_kernel(case):
+    """GEMM-sized DCN layers ((Cin / groups) * kh * kw a multiple of 32, >= 16 outputs per group) take the tcgen05 path: sampled
+    columns as split fp16 halves + one 1x1 implicit GEMM per group at fp32 fidelity.  It must agree with the CUDA-core strip
+    kernel (RDFC_DCN_TC = 0, the path the golden / oracle tests above pin) to fp32 accumulation noise, and -- at the first,
+    smaller-batch shape -- with the fp64 C oracle."""
+    from oracle import dcn as odcn
+    from rdfc_gan_b200 import _cabi as C
+    from rdfc_gan_b200.dcn import DCN
+    B, Cin, Cout, H, W, k, s, p, d, g, dg, with_mask = case
+    gen = torch.Generator(device="cuda").manual_seed(sum(case[:11]))
+    Ho, Wo = (H + 2 * p - (d * (k - 1) + 1)) // s + 1, (W + 2 * p - (d * (k - 1) + 1)) // s + 1
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=gen)
+    w = torch.randn(Cout, Cin // g, k, k, device="cuda", generator=gen) * 0.1
+    b = torch.randn(Cout, device="cuda", generator=gen) * 0.1
+    off = torch.randn(B, dg * 2 * k * k, Ho, Wo, device="cuda", generator=gen) * 2.0
+    m = torch.rand(B, dg * k * k, Ho, Wo, device="cuda", generator=gen) if with_mask else None
+    geo = (k, k, s, s, p, p, d, d, g, dg, 64)
+    outs = []
+    for tc in (1, 0):
+        C.set_knob("RDFC_DCN_TC", tc)
+        n0 = C.launch_count()
+        outs.append(DCN.modulated_deform_conv_forward(x, w, b, off, m, *geo) if with_mask else DCN.deform_conv_forward(x, w, b, off, *geo))
+        launches = C.launch_count() - n0
+        assert (launches >= 3 + g) == bool(tc), (tc, launches)          # im2col + per-group (pack + GEMM [+ split]) + transpose vs one strip kernel
+    C.set_knob("RDFC_DCN_TC", None)
+    scale = float(outs[1].abs().max())
+    assert outs[0].shape == (B, Cout, Ho, Wo) and outs[0].is_contiguous()
+    assert float((outs[0] - outs[1]).abs().max()) <= 3e-5 * scale, float((outs[0] - outs[1]).abs().max()) / scale
+    if H * W <= 2000:
+        ref = odcn.modulated_deform_conv_forward(x.cpu().numpy().astype(np.float64), w.cpu().numpy().astype(np.float64), b.cpu().numpy().astype(np.float64),
+                                                 off.cpu().numpy().astype(np.float64), None if m is None else m.cpu().numpy().astype(np.float64), *geo)
+        assert np.abs(outs[0].cpu().numpy() - ref).max() <= 3e-5 * scale
