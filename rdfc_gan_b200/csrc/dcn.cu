@@ -298,57 +298,80 @@ int fwd(const void *input, const void *weight, const void *bias, const void *off
 // columns are materialised -- here as fp16 halves [hi | lo] per (pixel, group), so that the contraction can run on tcgen05 with
 // split operands at fp32 fidelity (conv_umma.cu, Params::split_c) -- then ONE 1x1 implicit GEMM per group contracts them with
 // the filter bank packed [W_hi ; W_lo ; W_hi], and a transposition returns the NCHW layout of the DCN boundary.
-// cols[pixel][group][2 * Kg] with Kg = (Cin / group) * kh * kw, k = ci_local * K + tap (the filter's own flattening).
-// grid (ceil(P / 32), B), 8 warps.  Per chunk of 64 rows kk = ci * K + tap: sampling with one lane per PIXEL (offset / mask planes
-// and the image rows are read coalesced, as in the reference's im2col), the values go through a shared-memory tile, and the
-// write-out runs with one warp per pixel and the lanes along kk, so that every pixel's column block leaves as 128-byte rows.
+// cols[pixel][group][2 * Kg] with Kg = (Cin / group) * kh * kw, TAP-MAJOR: k = tap * (Cin / group) + ci_local (the filter pack below
+// follows), so that a chunk of 64 rows is one tap over 64 channels and the sampling position, the four bilinear weights (corner
+// zeroing folded in, modulated_deform_im2col_cuda.cuh:25-54) and the mask are computed once per (pixel, tap, deformable group)
+// instead of once per sample.  grid (ceil(P / 32), B), 8 warps.  Sampling runs with one lane per PIXEL (offset / mask planes and
+// the image rows are read coalesced, as in the reference's im2col), the values go through a shared-memory tile, and the write-out
+// runs with one warp per pixel and the lanes along the channels, so that every pixel's column block leaves as 128-byte rows.
 template <bool kMask>
 __global__ void __launch_bounds__(NT) dcn_im2col_split_kernel(const float *__restrict__ input, const float *__restrict__ offset,
                                                               const float *__restrict__ mask, __half *__restrict__ cols, Geo g) {
     __shared__ float tile[64][33];
-    const int K = g.kh * g.kw, P = g.Ho * g.Wo, Kg = (g.Cin / g.group) * K, cpd = g.Cin / g.dg, KT = g.Cin * K;
+    const int K = g.kh * g.kw, P = g.Ho * g.Wo, Cg = g.Cin / g.group, Kg = Cg * K, cpd = g.Cin / g.dg;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y, p0 = blockIdx.x * 32;
     const int p = p0 + lane, ho = p / g.Wo, wo = p - ho * g.Wo;
-    const float *img = input + (long long)b * g.Cin * g.H * g.W;
-    for (int k0 = 0; k0 < KT; k0 += 64) {
-        for (int r = warp; r < 64; r += NT / 32) {
-            const int kk = k0 + r;
-            float v = 0.f;
-            if (kk < KT && p < P) {
-                const int ci = kk / K, tap = kk - ci * K, dgi = ci / cpd, ky = tap / g.kw, kx = tap - ky * g.kw;
-                const float *offp = offset + ((long long)b * g.dg * 2 * K + (long long)dgi * 2 * K + 2 * tap) * P + p;
-                const float y = (float)(ho * g.sh - g.ph + ky * g.dh) + __ldg(offp), x = (float)(wo * g.sw - g.pw + kx * g.dw) + __ldg(offp + P);
-                v = sample<float>(img + (long long)ci * g.H * g.W, g.H, g.W, y, x);
-                if (kMask) v *= __ldg(mask + ((long long)b * g.dg * K + (long long)dgi * K + tap) * P + p);
+    const long long HW = (long long)g.H * g.W;
+    const float *img = input + (long long)b * g.Cin * HW;
+    for (int grp = 0; grp < g.group; ++grp)
+        for (int tap = 0; tap < K; ++tap) {
+            const int ky = tap / g.kw, kx = tap - ky * g.kw;
+            for (int c0 = 0; c0 < Cg; c0 += 64) {
+                int cur_dg = -1, i1 = 0, i2 = 0, i3 = 0, i4 = 0;
+                float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f, mk = 1.f;
+#pragma unroll 1
+                for (int r = warp * 8; r < warp * 8 + 8; ++r) {
+                    const int cl = c0 + r;
+                    float v = 0.f;
+                    if (cl < Cg && p < P) {
+                        const int ci = grp * Cg + cl, dgi = ci / cpd;
+                        if (dgi != cur_dg) {
+                            cur_dg = dgi;
+                            const float *offp = offset + ((long long)b * g.dg * 2 * K + (long long)dgi * 2 * K + 2 * tap) * P + p;
+                            const float y = (float)(ho * g.sh - g.ph + ky * g.dh) + __ldg(offp), x = (float)(wo * g.sw - g.pw + kx * g.dw) + __ldg(offp + P);
+                            if (kMask) mk = __ldg(mask + ((long long)b * g.dg * K + (long long)dgi * K + tap) * P + p);
+                            w1 = w2 = w3 = w4 = 0.f; i1 = i2 = i3 = i4 = 0;
+                            if (y > -1.f && x > -1.f && y < (float)g.H && x < (float)g.W) {
+                                const int yl = (int)floorf(y), xl = (int)floorf(x), yh = yl + 1, xh = xl + 1;
+                                const float ly = y - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
+                                if (yl >= 0 && xl >= 0) { w1 = hy * hx; i1 = yl * g.W + xl; }
+                                if (yl >= 0 && xh <= g.W - 1) { w2 = hy * lx; i2 = yl * g.W + xh; }
+                                if (yh <= g.H - 1 && xl >= 0) { w3 = ly * hx; i3 = yh * g.W + xl; }
+                                if (yh <= g.H - 1 && xh <= g.W - 1) { w4 = ly * lx; i4 = yh * g.W + xh; }
+                            }
+                        }
+                        const float *im = img + (long long)ci * HW;
+                        v = w1 * __ldg(im + i1) + w2 * __ldg(im + i2) + w3 * __ldg(im + i3) + w4 * __ldg(im + i4);
+                        if (kMask) v *= mk;
+                    }
+                    tile[r][lane] = v;
+                }
+                __syncthreads();
+                for (int px = warp; px < 32; px += NT / 32) {
+                    const int pp = p0 + px, cl = c0 + 2 * lane;              // two consecutive channels per lane (Cg even)
+                    if (pp < P && cl < Cg) {
+                        const float v0 = tile[2 * lane][px], v1 = tile[2 * lane + 1][px];
+                        __half *row = cols + (((long long)b * P + pp) * g.group + grp) * (2 * Kg) + tap * Cg + cl;
+                        const __half2 hi = __floats2half2_rn(v0, v1);
+                        const float2 hf = __half22float2(hi);
+                        *reinterpret_cast<__half2 *>(row) = hi;
+                        *reinterpret_cast<__half2 *>(row + Kg) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                    }
+                }
+                __syncthreads();
             }
-            tile[r][lane] = v;
         }
-        __syncthreads();
-        for (int px = warp; px < 32; px += NT / 32) {
-            const int pp = p0 + px, kk = k0 + 2 * lane;                  // two consecutive rows per lane (kk even, Kg even: same group)
-            if (pp < P && kk < KT) {
-                const float v0 = tile[2 * lane][px], v1 = tile[2 * lane + 1][px];
-                const int grp = kk / Kg, kl = kk - grp * Kg;
-                __half *row = cols + (((long long)b * P + pp) * g.group + grp) * (2 * Kg);
-                const __half2 hi = __floats2half2_rn(v0, v1);
-                const float2 hf = __half22float2(hi);
-                *reinterpret_cast<__half2 *>(row + kl) = hi;
-                *reinterpret_cast<__half2 *>(row + Kg + kl) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-            }
-        }
-        __syncthreads();
-    }
 }
 
-// filter bank of one group -> UMMA packing [1 tap][3 Kg / 8][CoutP][8] of [W_hi ; W_lo ; W_hi] (fp16)
-__global__ void __launch_bounds__(NT) dcn_pack_x3_kernel(const float *__restrict__ w, __half *__restrict__ packed, int Cog, int CoutP, int Kg) {
-    const int total = 3 * Kg * CoutP;
+// filter bank of one group -> UMMA packing [1 tap][3 Kg / 8][CoutP][8] of [W_hi ; W_lo ; W_hi] (fp16), rows tap-major as the columns
+__global__ void __launch_bounds__(NT) dcn_pack_x3_kernel(const float *__restrict__ w, __half *__restrict__ packed, int Cog, int CoutP, int Cg, int K) {
+    const int Kg = Cg * K, total = 3 * Kg * CoutP;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int e = i & 7, co = (i >> 3) % CoutP, ch = i / (8 * CoutP);
-        const int kk = ch * 8 + e, k = kk % Kg, part = kk / Kg;
+        const int kk = ch * 8 + e, k = kk % Kg, part = kk / Kg, tap = k / Cg, cl = k - tap * Cg;
         float v = 0.f;
         if (co < Cog) {
-            const float x = __ldg(w + (long long)co * Kg + k);
+            const float x = __ldg(w + (long long)co * Kg + cl * K + tap);
             const float hi = __half2float(__float2half_rn(x));
             v = part == 1 ? x - hi : hi;
         }
@@ -368,7 +391,7 @@ __global__ void __launch_bounds__(NT) nhwc_to_nchw_kernel(const float *__restric
 
 bool fwd_tc_ok(const Geo &g) {
     const int Kg = (g.Cin / g.group) * g.kh * g.kw, Cog = g.Cout / g.group;
-    return Kg % 32 == 0 && Cog >= 16 && Cog % 8 == 0 && knob("RDFC_DCN_TC", 1) != 0;
+    return Kg % 32 == 0 && (g.Cin / g.group) % 2 == 0 && Cog >= 16 && Cog % 8 == 0 && knob("RDFC_DCN_TC", 1) != 0;
 }
 
 int fwd_tc(const float *input, const float *weight, const float *bias, const float *offset, const float *mask, float *output,
@@ -390,7 +413,7 @@ int fwd_tc(const float *input, const float *weight, const float *bias, const flo
     }
     for (int grp = 0; grp < g.group && rc == 0; ++grp) {
         __half *pk = packed + (size_t)grp * 3 * Kg * CoutP;
-        dcn_pack_x3_kernel<<<cdiv(3 * Kg * CoutP, NT), NT, 0, st>>>(weight + (long long)grp * Cog * Kg, pk, Cog, CoutP, Kg);
+        dcn_pack_x3_kernel<<<cdiv(3 * Kg * CoutP, NT), NT, 0, st>>>(weight + (long long)grp * Cog * Kg, pk, Cog, CoutP, g.Cin / g.group, K);
         count_launch();
         rdfc_conv_desc d{};
         d.B = g.B; d.Hi = d.Ho = g.Ho; d.Wi = d.Wo = g.Wo;
