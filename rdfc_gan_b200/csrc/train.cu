@@ -538,8 +538,19 @@ static int wgrad_geom(const rdfc_wgrad_desc *d, WgGeom *g) {
     return 0;
 }
 
+namespace rdfc {
+bool wgrad_umma_ok(const rdfc_wgrad_desc *d);                       // wgrad_umma.cu: 3x3 filter gradients on tcgen05
+long long wgrad_umma_workspace_floats(const rdfc_wgrad_desc *d);
+int wgrad_umma(const rdfc_wgrad_desc *d, float *grad_weight, float *workspace, cudaStream_t st);
+}  // namespace rdfc
+
 extern "C" long long rdfc_conv_wgrad_workspace_floats(const rdfc_wgrad_desc *d) {
     WgGeom g;
+    if (wgrad_geom(d, &g) != 0) return -1;
+    if (wgrad_umma_ok(d)) {                                         // either path may serve the call (knob): size for both
+        const long long u = wgrad_umma_workspace_floats(d);
+        return u > g.ws_floats ? u : g.ws_floats;
+    }
     return wgrad_geom(d, &g) == 0 ? g.ws_floats : -1;
 }
 
@@ -550,6 +561,7 @@ extern "C" int rdfc_conv_wgrad(const rdfc_wgrad_desc *d, float *grad_weight, flo
     if (int rc = check_view(&d->grad_out, d->grad_out.C, "wgrad grad_out")) return rc;
     if (int rc = check_view(&d->input, d->input.C, "wgrad input")) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (wgrad_umma_ok(d)) return wgrad_umma(d, grad_weight, workspace, st);
     WgradParams P{};
     P.G = (const __nv_bfloat16 *)d->grad_out.ptr; P.I = (const __nv_bfloat16 *)d->input.ptr;
     P.g_stride = d->grad_out.pix_stride; P.i_stride = d->input.pix_stride; P.O = d->grad_out.C; P.Ich = d->input.C;

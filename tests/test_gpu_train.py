@@ -20,7 +20,8 @@ def _rel(a, b):
 @pytest.mark.parametrize("case", [
     # B, Cin, Cout, H, W, k, stride
     (2, 64, 64, 36, 52, 3, 1), (3, 64, 128, 37, 50, 3, 2), (2, 128, 32, 19, 45, 3, 1), (1, 192, 384, 29, 38, 1, 1),
-    (2, 64, 128, 40, 41, 1, 2), (2, 96, 160, 17, 23, 3, 1), (1, 512, 512, 15, 19, 3, 1), (4, 64, 64, 228, 304, 3, 1)])
+    (2, 64, 128, 40, 41, 1, 2), (2, 96, 160, 17, 23, 3, 1), (1, 512, 512, 15, 19, 3, 1), (4, 64, 64, 228, 304, 3, 1),
+    (2, 192, 64, 29, 38, 3, 2), (1, 128, 256, 58, 77, 3, 2), (2, 256, 80, 9, 100, 3, 1)])
 def test_filter_gradient_against_torch(case):
     from rdfc_gan_b200.train_ops import _wgrad
     B, Cin, Cout, H, W, k, s = case
@@ -35,6 +36,23 @@ def test_filter_gradient_against_torch(case):
     assert _rel(got, want) <= 2e-5, _rel(got, want)          # fp32 accumulation of exact bf16 products
     again = _wgrad(gy, x, k, s)
     assert torch.equal(got, again), "the split-K reduction must be deterministic"
+    if k == 3:
+        # 3x3 filter gradients run on tcgen05 (csrc/wgrad_umma.cu); every tile width of that kernel and the mma.sync kernel
+        # (RDFC_WGRAD_UMMA = 0, also the 1x1 path) must give the same sums
+        from rdfc_gan_b200 import _cabi as C
+        try:
+            for knobs in ({"RDFC_WGRAD_TW": 16}, {"RDFC_WGRAD_TW": 32}, {"RDFC_WGRAD_UMMA": 0}):
+                for name, v in knobs.items():
+                    C.set_knob(name, v)
+                n0 = C.launch_count()
+                other = _wgrad(gy, x, k, s)
+                assert C.launch_count() - n0 == 2
+                assert _rel(other, want) <= 2e-5, (knobs, _rel(other, want))
+                for name in knobs:
+                    C.set_knob(name, None)
+        finally:
+            for name in ("RDFC_WGRAD_TW", "RDFC_WGRAD_UMMA"):
+                C.set_knob(name, None)
 
 
 @pytest.mark.parametrize("case", [(2, 64, 64, 20, 28, 3, 1, False), (2, 64, 128, 21, 27, 3, 2, False), (2, 128, 64, 10, 13, 3, 2, True),
