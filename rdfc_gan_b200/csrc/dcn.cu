@@ -12,6 +12,8 @@
 namespace rdfc {
 int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads_desc *heads, const rdfc_stem_desc *stem,
                       const rdfc_wadain_conv_desc *wad, int split_c);
+long long wgrad_umma_workspace_floats(const rdfc_wgrad_desc *d);
+int wgrad_umma_partials(const rdfc_wgrad_desc *d, float *workspace, int fp16, cudaStream_t st, int *nchunk);
 namespace {
 
 constexpr int TP = 32;        // output pixels per CTA strip (one warp lane per pixel in the contraction)
@@ -304,10 +306,41 @@ int fwd(const void *input, const void *weight, const void *bias, const void *off
 // instead of once per sample.  grid (ceil(P / 32), B), 8 warps.  Sampling runs with one lane per PIXEL (offset / mask planes and
 // the image rows are read coalesced, as in the reference's im2col), the values go through a shared-memory tile, and the write-out
 // runs with one warp per pixel and the lanes along the channels, so that every pixel's column block leaves as 128-byte rows.
+// Split-precision operands are fp16 halves, and fp16 has a narrow exponent range: every tensor that gets split is first scaled by a
+// power of two chosen from its largest magnitude (hi < 2048, so lo = x - hi keeps 11 significant bits down to ~3e-5 of the largest
+// element), and the GEMM epilogue multiplies the exact inverse back.  The maxima live on the device (no host synchronisation):
+// am[0] = max |input|, am[1] = max |mask| (1 when there is none), am[2] = max |weight|, am[3] = max |grad_output|, as the bit
+// patterns of non-negative floats (which order like unsigned integers).
+struct AmaxArgs { const float *p[4]; long long n[4]; };
+__global__ void __launch_bounds__(NT) dcn_amax_kernel(AmaxArgs a, unsigned *am) {
+    const int seg = blockIdx.y;
+    const float *x = a.p[seg];
+    if (!x) return;
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < a.n[seg]; i += (long long)gridDim.x * NT) m = fmaxf(m, fabsf(__ldg(x + i)));
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sft));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(am + seg, __float_as_uint(m));
+}
+// power of two s with amax * s in [1024, 2048); 1 for an all-zero (or non-finite) tensor
+__device__ __forceinline__ float pow2_scale(float amax) {
+    if (!(amax > 0.f) || !(amax < 3.0e38f)) return 1.f;
+    int ex;
+    frexpf(amax, &ex);                       // amax = f * 2^ex, f in [0.5, 1)
+    ex = 11 - ex;
+    ex = ex > 100 ? 100 : (ex < -100 ? -100 : ex);
+    return exp2f((float)ex);
+}
+__device__ __forceinline__ float scale_cols(const unsigned *am) { return pow2_scale(__uint_as_float(am[0]) * (am[1] ? __uint_as_float(am[1]) : 1.f)); }
+__device__ __forceinline__ float scale_w(const unsigned *am) { return pow2_scale(__uint_as_float(am[2])); }
+__device__ __forceinline__ float scale_g(const unsigned *am) { return pow2_scale(__uint_as_float(am[3])); }
+
 template <bool kMask>
 __global__ void __launch_bounds__(NT) dcn_im2col_split_kernel(const float *__restrict__ input, const float *__restrict__ offset,
-                                                              const float *__restrict__ mask, __half *__restrict__ cols, Geo g) {
+                                                              const float *__restrict__ mask, __half *__restrict__ cols, Geo g,
+                                                              const unsigned *__restrict__ am) {
     __shared__ float tile[64][33];
+    const float sx = scale_cols(am);
     const int K = g.kh * g.kw, P = g.Ho * g.Wo, Cg = g.Cin / g.group, Kg = Cg * K, cpd = g.Cin / g.dg;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y, p0 = blockIdx.x * 32;
     const int p = p0 + lane, ho = p / g.Wo, wo = p - ho * g.Wo;
@@ -350,7 +383,7 @@ __global__ void __launch_bounds__(NT) dcn_im2col_split_kernel(const float *__res
                 for (int px = warp; px < 32; px += NT / 32) {
                     const int pp = p0 + px, cl = c0 + 2 * lane;              // two consecutive channels per lane (Cg even)
                     if (pp < P && cl < Cg) {
-                        const float v0 = tile[2 * lane][px], v1 = tile[2 * lane + 1][px];
+                        const float v0 = tile[2 * lane][px] * sx, v1 = tile[2 * lane + 1][px] * sx;
                         __half *row = cols + (((long long)b * P + pp) * g.group + grp) * (2 * Kg) + tap * Cg + cl;
                         const __half2 hi = __floats2half2_rn(v0, v1);
                         const float2 hf = __half22float2(hi);
@@ -364,14 +397,18 @@ __global__ void __launch_bounds__(NT) dcn_im2col_split_kernel(const float *__res
 }
 
 // filter bank of one group -> UMMA packing [1 tap][3 Kg / 8][CoutP][8] of [W_hi ; W_lo ; W_hi] (fp16), rows tap-major as the columns
-__global__ void __launch_bounds__(NT) dcn_pack_x3_kernel(const float *__restrict__ w, __half *__restrict__ packed, int Cog, int CoutP, int Cg, int K) {
+// vec[co] = 1 / (scale of the columns * scale of the filters): the GEMM epilogue's per-channel factor
+__global__ void __launch_bounds__(NT) dcn_pack_x3_kernel(const float *__restrict__ w, __half *__restrict__ packed, int Cog, int CoutP, int Cg, int K,
+                                                         const unsigned *__restrict__ am, float *__restrict__ vec) {
     const int Kg = Cg * K, total = 3 * Kg * CoutP;
+    const float sw = scale_w(am);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CoutP; i += gridDim.x * blockDim.x) vec[i] = 1.f / (sw * scale_cols(am));
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int e = i & 7, co = (i >> 3) % CoutP, ch = i / (8 * CoutP);
         const int kk = ch * 8 + e, k = kk % Kg, part = kk / Kg, tap = k / Cg, cl = k - tap * Cg;
         float v = 0.f;
         if (co < Cog) {
-            const float x = __ldg(w + (long long)co * Kg + cl * K + tap);
+            const float x = __ldg(w + (long long)co * Kg + cl * K + tap) * sw;
             const float hi = __half2float(__float2half_rn(x));
             v = part == 1 ? x - hi : hi;
         }
@@ -394,33 +431,56 @@ bool fwd_tc_ok(const Geo &g) {
     return Kg % 32 == 0 && (g.Cin / g.group) % 2 == 0 && Cog >= 16 && Cog % 8 == 0 && knob("RDFC_DCN_TC", 1) != 0;
 }
 
+// device scratch of one call: am[4] (maxima), then the epilogue vector
+struct Aux { unsigned *am; float *vec; };
+int aux_alloc(Aux *a, int nvec, cudaStream_t st) {
+    void *p = nullptr;
+    RDFC_CUDA(cudaMallocAsync(&p, 16 + sizeof(float) * (size_t)nvec, st));
+    RDFC_CUDA(cudaMemsetAsync(p, 0, 16, st));
+    a->am = (unsigned *)p; a->vec = (float *)((char *)p + 16);
+    return 0;
+}
+int amax_launch(const Aux &a, const float *x, long long nx, const float *mask, long long nm, const float *w, long long nw, const float *go, long long ng,
+                cudaStream_t st) {
+    AmaxArgs args{{x, mask, w, go}, {nx, nm, nw, ng}};
+    long long nmax = nx > ng ? nx : ng;
+    const int blocks = (int)min((long long)cdiv(nmax, NT * 8), (long long)sm_count() * 4);
+    dcn_amax_kernel<<<dim3(blocks, 4), NT, 0, st>>>(args, a.am);
+    RDFC_CHECK_LAUNCH("dcn_amax_kernel");
+    return 0;
+}
+
 int fwd_tc(const float *input, const float *weight, const float *bias, const float *offset, const float *mask, float *output,
            const Geo &g, cudaStream_t st) {
     const int K = g.kh * g.kw, P = g.Ho * g.Wo, Kg = (g.Cin / g.group) * K, Cog = g.Cout / g.group, CoutP = (Cog + 15) / 16 * 16;
     const long long npix = (long long)g.B * P;
     __half *cols = nullptr, *packed = nullptr;
     float *tmp = nullptr;
+    Aux aux{};
     const size_t cols_bytes = (size_t)npix * g.group * 2 * Kg * sizeof(__half), pk_bytes = (size_t)3 * Kg * CoutP * sizeof(__half);
     RDFC_CUDA(cudaMallocAsync((void **)&cols, cols_bytes, st));
     RDFC_CUDA(cudaMallocAsync((void **)&packed, pk_bytes * g.group, st));
     RDFC_CUDA(cudaMallocAsync((void **)&tmp, (size_t)npix * g.Cout * sizeof(float), st));
-    int rc = 0;
-    {
+    int rc = aux_alloc(&aux, CoutP, st);
+    if (rc == 0)
+        rc = amax_launch(aux, input, (long long)g.B * g.Cin * g.H * g.W, mask, mask ? (long long)g.B * g.dg * K * P : 0, weight,
+                         (long long)g.Cout * Kg, nullptr, 0, st);
+    if (rc == 0) {
         const dim3 grid(cdiv(P, 32), g.B);
-        if (mask) dcn_im2col_split_kernel<true><<<grid, NT, 0, st>>>(input, offset, mask, cols, g);
-        else dcn_im2col_split_kernel<false><<<grid, NT, 0, st>>>(input, offset, nullptr, cols, g);
+        if (mask) dcn_im2col_split_kernel<true><<<grid, NT, 0, st>>>(input, offset, mask, cols, g, aux.am);
+        else dcn_im2col_split_kernel<false><<<grid, NT, 0, st>>>(input, offset, nullptr, cols, g, aux.am);
         count_launch();
     }
     for (int grp = 0; grp < g.group && rc == 0; ++grp) {
         __half *pk = packed + (size_t)grp * 3 * Kg * CoutP;
-        dcn_pack_x3_kernel<<<cdiv(3 * Kg * CoutP, NT), NT, 0, st>>>(weight + (long long)grp * Cog * Kg, pk, Cog, CoutP, g.Cin / g.group, K);
+        dcn_pack_x3_kernel<<<cdiv(3 * Kg * CoutP, NT), NT, 0, st>>>(weight + (long long)grp * Cog * Kg, pk, Cog, CoutP, g.Cin / g.group, K, aux.am, aux.vec);
         count_launch();
         rdfc_conv_desc d{};
         d.B = g.B; d.Hi = d.Ho = g.Ho; d.Wi = d.Wo = g.Wo;
         d.kh = d.kw = 1; d.stride = 1; d.pad = 0; d.act = RDFC_ACT_NONE; d.path = RDFC_PATH_UMMA_BF16;
         d.in.ptr = cols + (size_t)grp * 2 * Kg; d.in.dtype = RDFC_BF16; d.in.C = 2 * Kg; d.in.pix_stride = g.group * 2 * Kg;
         d.out.ptr = tmp + (size_t)grp * Cog; d.out.dtype = RDFC_F32; d.out.C = Cog; d.out.pix_stride = g.Cout;
-        d.weight = pk; d.scale = nullptr; d.shift = bias ? bias + (size_t)grp * Cog : nullptr;
+        d.weight = pk; d.scale = aux.vec; d.shift = bias ? bias + (size_t)grp * Cog : nullptr;
         rc = conv_umma_forward(&d, st, nullptr, nullptr, nullptr, Kg);
     }
     if (rc == 0) {
@@ -429,6 +489,248 @@ int fwd_tc(const float *input, const float *weight, const float *bias, const flo
         if (cudaGetLastError() != cudaSuccess) rc = fail(RDFC_ERR_CUDA, "dcn forward (tensor cores): kernel launch failed");
     }
     cudaFreeAsync(cols, st); cudaFreeAsync(packed, st); cudaFreeAsync(tmp, st);
+    if (aux.am) cudaFreeAsync(aux.am, st);
+    return rc;
+}
+
+// ---------------------------------------------------------------- backward on the tensor cores -----------------
+// The reference's backward (modulated_deform_conv_cuda.cu:124-280) is: columns' gradient = W^T . grad_output (GEMM), col2im_coord /
+// col2im over it, and grad_weight = grad_output . columns^T (GEMM with K = pixels).  Here both GEMMs run on tcgen05 at fp32 fidelity:
+//   gsplit  = grad_output as fp16 halves [hi | lo] per (pixel, group)                              (dcn_gout_split_kernel)
+//   gcols   = 1x1 implicit GEMM of gsplit with the filter bank transposed, fp32 [pixel][group][tap-major k]   (conv_umma, split operands)
+//   grad_input / grad_offset / grad_mask from gcols in one pass                                    (dcn_col2im_coord_kernel)
+//   grad_weight = sum over pixels gsplit^T . cols: the filter-gradient kernel of wgrad_umma.cu (K = pixels, MN-major operands) run for
+//   the three split products hi.hi + hi.lo + lo.hi into consecutive chunk ranges of one workspace    (dcn_wgrad_reduce_kernel)
+
+// grad_output NCHW fp32 -> [pixel][group][hi (Cog) | lo (Cog)] fp16, scaled
+__global__ void __launch_bounds__(NT) dcn_gout_split_kernel(const float *__restrict__ gout, __half *__restrict__ gs, int Cout, int Cog, int P,
+                                                            const unsigned *__restrict__ am) {
+    __shared__ float tile[32][33];
+    const float sg = scale_g(am);
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += NT / 32)
+        if (c0 + r < Cout && p0 + tx < P) tile[r][tx] = __ldg(gout + ((long long)b * Cout + c0 + r) * P + p0 + tx) * sg;
+    __syncthreads();
+    for (int r = ty; r < 32; r += NT / 32) {
+        const int c = c0 + tx, pp = p0 + r;
+        if (c < Cout && pp < P) {
+            const int grp = c / Cog, cl = c - grp * Cog;
+            const float v = tile[tx][r];
+            const __half hi = __float2half_rn(v);
+            __half *row = gs + (((long long)b * P + pp) * (Cout / Cog) + grp) * (2 * Cog);
+            row[cl] = hi;
+            row[Cog + cl] = __float2half_rn(v - __half2float(hi));
+        }
+    }
+}
+
+// filter bank of one group, transposed -> UMMA packing [3 Cog / 8][KgP][8] of [W_hi ; W_lo ; W_hi] along the OUTPUT channels of the layer
+// (the GEMM's input channels); GEMM column k = tap * Cg + ci_local.  vec[k] = 1 / (scale of grad_output * scale of the filters).
+__global__ void __launch_bounds__(NT) dcn_pack_t_x3_kernel(const float *__restrict__ w, __half *__restrict__ packed, int Cog, int KgP, int Cg, int K,
+                                                           const unsigned *__restrict__ am, float *__restrict__ vec) {
+    const int Kg = Cg * K, total = 3 * Cog * KgP;
+    const float sw = scale_w(am);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < KgP; i += gridDim.x * blockDim.x) vec[i] = 1.f / (sw * scale_g(am));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int e = i & 7, k = (i >> 3) % KgP, ch = i / (8 * KgP);
+        const int kk = ch * 8 + e, c = kk % Cog, part = kk / Cog, tap = k / Cg, cl = k - tap * Cg;
+        float v = 0.f;
+        if (k < Kg) {
+            const float x = __ldg(w + (long long)c * Kg + cl * K + tap) * sw;
+            const float hi = __half2float(__float2half_rn(x));
+            v = part == 1 ? x - hi : hi;
+        }
+        packed[i] = __float2half_rn(v);
+    }
+}
+
+// grad_input (col2im, modulated_deform_im2col_cuda.cuh:197-254), grad_offset / grad_mask (col2im_coord, cuh:257-328) from the columns'
+// gradient gcols[pixel][group][tap * Cg + ci_local] (fp32).  grid (ceil(P / 32), B), 8 warps; the mirror image of the im2col kernel: a chunk
+// of 64 channels of one tap is read with the lanes along the channels, goes through a shared-memory tile, and is consumed with one lane per
+// PIXEL (coalesced image reads and atomics), the position / bilinear weights computed once per (pixel, tap, deformable group); the per-pixel
+// sums over the channels of a deformable group are combined through shared memory in a fixed order.
+constexpr int MAXDG = 16;
+template <bool kMask>
+__global__ void __launch_bounds__(NT) dcn_col2im_coord_kernel(const float *__restrict__ input, const float *__restrict__ offset, const float *__restrict__ mask,
+                                                              const float *__restrict__ gcols, float *__restrict__ gin, float *__restrict__ goff,
+                                                              float *__restrict__ gmask, Geo g) {
+    __shared__ float tile[64][33];
+    __shared__ float part[NT / 32][3][32];
+    __shared__ float acc[MAXDG][3][32];
+    __shared__ int part_dg[NT / 32];
+    const int K = g.kh * g.kw, P = g.Ho * g.Wo, Cg = g.Cin / g.group, Kg = Cg * K, cpd = g.Cin / g.dg;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y, p0 = blockIdx.x * 32;
+    const int p = p0 + lane, ho = p / g.Wo, wo = p - ho * g.Wo;
+    const long long HW = (long long)g.H * g.W;
+    const float *img = input + (long long)b * g.Cin * HW;
+    float *gimg = gin ? gin + (long long)b * g.Cin * HW : nullptr;
+    for (int tap = 0; tap < K; ++tap) {
+        const int ky = tap / g.kw, kx = tap - ky * g.kw;
+        for (int i = threadIdx.x; i < g.dg * 96; i += NT) (&acc[0][0][0])[i] = 0.f;
+        for (int grp = 0; grp < g.group; ++grp)
+            for (int c0 = 0; c0 < Cg; c0 += 64) {
+                __syncthreads();                                           // previous chunk's tile / part consumed, acc zeroed
+                for (int px = warp; px < 32; px += NT / 32) {
+                    const int pp = p0 + px, cl = c0 + 2 * lane;
+                    float2 v = make_float2(0.f, 0.f);
+                    if (pp < P && cl < Cg) v = __ldg(reinterpret_cast<const float2 *>(gcols + ((long long)b * P + pp) * ((long long)g.group * Kg) + (long long)grp * Kg + tap * Cg + cl));
+                    tile[2 * lane][px] = v.x;
+                    tile[2 * lane + 1][px] = v.y;
+                }
+                __syncthreads();
+                float sm = 0.f, sy = 0.f, sx = 0.f;
+                const int cfirst = c0 + warp * 8;
+                const int dgi = (grp * Cg + (cfirst < Cg ? cfirst : 0)) / cpd;
+                if (cfirst < Cg && p < P) {
+                    const float *offp = offset + ((long long)b * g.dg * 2 * K + (long long)dgi * 2 * K + 2 * tap) * P + p;
+                    const float y = (float)(ho * g.sh - g.ph + ky * g.dh) + __ldg(offp), x = (float)(wo * g.sw - g.pw + kx * g.dw) + __ldg(offp + P);
+                    const float mk = kMask ? __ldg(mask + ((long long)b * g.dg * K + (long long)dgi * K + tap) * P + p) : 1.f;
+                    if (y > -1.f && x > -1.f && y < (float)g.H && x < (float)g.W) {
+                        const int yl = (int)floorf(y), xl = (int)floorf(x), yh = yl + 1, xh = xl + 1;
+                        const float ly = y - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
+                        const bool f1 = yl >= 0 && xl >= 0, f2 = yl >= 0 && xh <= g.W - 1, f3 = yh <= g.H - 1 && xl >= 0, f4 = yh <= g.H - 1 && xh <= g.W - 1;
+                        const int i1 = f1 ? yl * g.W + xl : 0, i2 = f2 ? yl * g.W + xh : 0, i3 = f3 ? yh * g.W + xl : 0, i4 = f4 ? yh * g.W + xh : 0;
+#pragma unroll 1
+                        for (int r = warp * 8; r < warp * 8 + 8; ++r) {
+                            const int cl = c0 + r;
+                            if (cl >= Cg) break;
+                            const long long pl = (long long)(grp * Cg + cl) * HW;
+                            const float *im = img + pl;
+                            const float gcol = tile[r][lane];
+                            const float v1 = f1 ? __ldg(im + i1) : 0.f, v2 = f2 ? __ldg(im + i2) : 0.f, v3 = f3 ? __ldg(im + i3) : 0.f, v4 = f4 ? __ldg(im + i4) : 0.f;
+                            const float val = hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
+                            sm += gcol * val;
+                            sy += gcol * mk * (hx * (v3 - v1) + lx * (v4 - v2));
+                            sx += gcol * mk * (hy * (v2 - v1) + ly * (v4 - v3));
+                            if (gimg) {
+                                const float top = gcol * mk;
+                                float *gi = gimg + pl;
+                                if (f1) atomicAdd(gi + i1, hy * hx * top);
+                                if (f2) atomicAdd(gi + i2, hy * lx * top);
+                                if (f3) atomicAdd(gi + i3, ly * hx * top);
+                                if (f4) atomicAdd(gi + i4, ly * lx * top);
+                            }
+                        }
+                    }
+                }
+                part[warp][0][lane] = sm; part[warp][1][lane] = sy; part[warp][2][lane] = sx;
+                if (lane == 0) part_dg[warp] = cfirst < Cg ? dgi : -1;
+                __syncthreads();
+                if (threadIdx.x < 96) {
+                    const int comp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+                    for (int w = 0; w < NT / 32; ++w)
+                        if (part_dg[w] >= 0) acc[part_dg[w]][comp][ln] += part[w][comp][ln];
+                }
+            }
+        __syncthreads();
+        for (int i = threadIdx.x; i < g.dg * 96; i += NT) {
+            const int dgi = i / 96, comp = (i / 32) % 3, ln = i & 31, pp = p0 + ln;
+            if (pp >= P) continue;
+            const float v = acc[dgi][comp][ln];
+            if (comp == 0) { if (kMask && gmask) gmask[((long long)b * g.dg * K + (long long)dgi * K + tap) * P + pp] = v; }
+            else if (goff) goff[((long long)b * g.dg * 2 * K + (long long)dgi * 2 * K + 2 * tap + (comp - 1)) * P + pp] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// grad_weight[co][ci_local][tap] = inv * sum over the (3 * nchunk) partial blocks [Cog][Kg] (tap-major k) of one group
+__global__ void __launch_bounds__(NT) dcn_wgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ gw, int Cog, int Cg, int K, int nblocks,
+                                                              const unsigned *__restrict__ am) {
+    const int Kg = Cg * K;
+    const long long total = (long long)Cog * Kg;
+    const float inv = 1.f / (scale_g(am) * scale_cols(am));
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(e / Kg), k = (int)(e - (long long)o * Kg), tap = k / Cg, cl = k - tap * Cg;
+        float s = 0.f;
+        for (int c = 0; c < nblocks; ++c) s += __ldg(partial + (long long)c * total + e);
+        gw[(long long)o * Kg + cl * K + tap] = s * inv;
+    }
+}
+
+bool bwd_tc_ok(const Geo &g) {
+    const int Cg = g.Cin / g.group, Kg = Cg * g.kh * g.kw, Cog = g.Cout / g.group, cpd = g.Cin / g.dg;
+    return Kg % 32 == 0 && Cg % 8 == 0 && cpd % 8 == 0 && Cog % 32 == 0 && g.dg <= MAXDG && knob("RDFC_DCN_TC", 1) != 0;
+}
+
+int bwd_tc(const float *input, const float *weight, const float *offset, const float *mask, const float *gout, float *gin, float *goff, float *gmask,
+           float *gw, float *gb, const Geo &g, cudaStream_t st) {
+    const int K = g.kh * g.kw, P = g.Ho * g.Wo, Cg = g.Cin / g.group, Kg = Cg * K, Cog = g.Cout / g.group, KgP = (Kg + 15) / 16 * 16;
+    const long long npix = (long long)g.B * P;
+    __half *gs = nullptr, *cols = nullptr, *packed = nullptr;
+    float *gcols = nullptr, *ws = nullptr;
+    Aux aux{};
+    const bool need_data = gin || goff || gmask;
+    int rc = aux_alloc(&aux, KgP, st);
+    if (rc == 0)
+        rc = amax_launch(aux, input, (long long)g.B * g.Cin * g.H * g.W, mask, mask ? (long long)g.B * g.dg * K * P : 0, weight, (long long)g.Cout * Kg, gout,
+                         npix * g.Cout, st);
+    if (rc) return rc;
+    if (gin) RDFC_CUDA(cudaMemsetAsync(gin, 0, sizeof(float) * (size_t)g.B * g.Cin * g.H * g.W, st));
+    RDFC_CUDA(cudaMallocAsync((void **)&gs, (size_t)npix * g.group * 2 * Cog * sizeof(__half), st));
+    dcn_gout_split_kernel<<<dim3(cdiv(P, 32), cdiv(g.Cout, 32), g.B), NT, 0, st>>>(gout, gs, g.Cout, Cog, P, aux.am);
+    count_launch();
+    if (need_data) {
+        RDFC_CUDA(cudaMallocAsync((void **)&gcols, (size_t)npix * g.group * Kg * sizeof(float), st));
+        RDFC_CUDA(cudaMallocAsync((void **)&packed, (size_t)3 * Cog * KgP * sizeof(__half), st));
+        for (int grp = 0; grp < g.group && rc == 0; ++grp) {
+            dcn_pack_t_x3_kernel<<<cdiv(3 * Cog * KgP, NT), NT, 0, st>>>(weight + (long long)grp * Cog * Kg, packed, Cog, KgP, Cg, K, aux.am, aux.vec);
+            count_launch();
+            rdfc_conv_desc d{};
+            d.B = g.B; d.Hi = d.Ho = g.Ho; d.Wi = d.Wo = g.Wo;
+            d.kh = d.kw = 1; d.stride = 1; d.pad = 0; d.act = RDFC_ACT_NONE; d.path = RDFC_PATH_UMMA_BF16;
+            d.in.ptr = gs + (size_t)grp * 2 * Cog; d.in.dtype = RDFC_BF16; d.in.C = 2 * Cog; d.in.pix_stride = g.group * 2 * Cog;
+            d.out.ptr = gcols + (size_t)grp * Kg; d.out.dtype = RDFC_F32; d.out.C = Kg; d.out.pix_stride = g.group * Kg;
+            d.weight = packed; d.scale = aux.vec; d.shift = nullptr;
+            rc = conv_umma_forward(&d, st, nullptr, nullptr, nullptr, Cog);
+        }
+        if (rc == 0) {
+            const dim3 grid(cdiv(P, 32), g.B);
+            if (mask) dcn_col2im_coord_kernel<true><<<grid, NT, 0, st>>>(input, offset, mask, gcols, gin, goff, gmask, g);
+            else dcn_col2im_coord_kernel<false><<<grid, NT, 0, st>>>(input, offset, nullptr, gcols, gin, goff, nullptr, g);
+            count_launch();
+        }
+    }
+    if (gw && rc == 0) {
+        RDFC_CUDA(cudaMallocAsync((void **)&cols, (size_t)npix * g.group * 2 * Kg * sizeof(__half), st));
+        const dim3 grid(cdiv(P, 32), g.B);
+        if (mask) dcn_im2col_split_kernel<true><<<grid, NT, 0, st>>>(input, offset, mask, cols, g, aux.am);
+        else dcn_im2col_split_kernel<false><<<grid, NT, 0, st>>>(input, offset, nullptr, cols, g, aux.am);
+        count_launch();
+        rdfc_wgrad_desc wd{};
+        wd.B = g.B; wd.Hg = wd.Hi = g.Ho; wd.Wg = wd.Wi = g.Wo; wd.k = 1; wd.stride = 1; wd.pad = 0;
+        wd.grad_out.dtype = RDFC_BF16; wd.grad_out.C = Cog; wd.grad_out.pix_stride = g.group * 2 * Cog;
+        wd.input.dtype = RDFC_BF16; wd.input.C = Kg; wd.input.pix_stride = g.group * 2 * Kg;
+        wd.grad_out.ptr = gs; wd.input.ptr = cols;
+        const long long per = wgrad_umma_workspace_floats(&wd);
+        if (per < 0) rc = RDFC_ERR_INVALID;
+        if (rc == 0) RDFC_CUDA(cudaMallocAsync((void **)&ws, (size_t)per * 3 * sizeof(float), st));
+        for (int grp = 0; grp < g.group && rc == 0; ++grp) {
+            int nchunk = 0, nc = 0;
+            const long long blk = (long long)Cog * Kg;
+            for (int t = 0; t < 3 && rc == 0; ++t) {                      // hi.hi, hi.lo, lo.hi
+                wd.grad_out.ptr = gs + (size_t)grp * 2 * Cog + (t == 2 ? Cog : 0);
+                wd.input.ptr = cols + (size_t)grp * 2 * Kg + (t == 1 ? Kg : 0);
+                rc = wgrad_umma_partials(&wd, ws + (long long)nchunk * blk, 1, st, &nc);
+                nchunk += nc;
+            }
+            if (rc == 0) {
+                dcn_wgrad_reduce_kernel<<<(int)min((long long)cdiv(blk, NT), (long long)sm_count() * 8), NT, 0, st>>>(ws, gw + (long long)grp * blk, Cog, Cg, K, nchunk, aux.am);
+                count_launch();
+            }
+        }
+    }
+    if (gb && rc == 0) {
+        dcn_bwd_bias_kernel<float><<<g.Cout, NT, 0, st>>>(gout, gb, g.B, g.Cout, P);
+        count_launch();
+    }
+    if (rc == 0 && cudaGetLastError() != cudaSuccess) rc = fail(RDFC_ERR_CUDA, "dcn backward (tensor cores): kernel launch failed");
+    if (gs) cudaFreeAsync(gs, st);
+    if (gcols) cudaFreeAsync(gcols, st);
+    if (packed) cudaFreeAsync(packed, st);
+    if (cols) cudaFreeAsync(cols, st);
+    if (ws) cudaFreeAsync(ws, st);
+    cudaFreeAsync(aux.am, st);
     return rc;
 }
 
@@ -506,6 +808,10 @@ extern "C" int rdfc_dcn_backward(const void *input, const void *weight, const vo
     RDFC_REQUIRE(input && weight && offset && grad_output, "input / weight / offset / grad_output must not be NULL");
     RDFC_REQUIRE(mask || !grad_mask, "grad_mask requested without a mask (DCN v1 has none)");
     cudaStream_t st = (cudaStream_t)stream;
+    // GEMM-sized layers: both contractions of the backward on tcgen05 at fp32 fidelity; thin layers / fp64: the CUDA-core kernels
+    if (dtype == RDFC_F32 && bwd_tc_ok(g))
+        return bwd_tc((const float *)input, (const float *)weight, (const float *)offset, (const float *)mask, (const float *)grad_output,
+                      (float *)grad_input, (float *)grad_offset, (float *)grad_mask, (float *)grad_weight, (float *)grad_bias, g, st);
     if (dtype == RDFC_F32)
         return bwd<float>(input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask, grad_weight,
                           grad_bias, g, st);

@@ -1,4 +1,4 @@
-// Filter gradient of the 3x3 convolutions on tcgen05 (the training step's largest kernel; reference: autograd of nn.Conv2d /
+// Filter gradient of the 3x3 (and 1x1: one tap, the input box is the pixels themselves) convolutions on tcgen05 (the training step's largest kernel; reference: autograd of nn.Conv2d /
 // nn.ConvTranspose2d in RDFC-GAN/lib/models/generator/rdf_generator/encoder_decoder/common.py:29-61 -> cuDNN wgrad).
 //
 //   dW[o][i][ky][kx] = sum over (b, py, px) of  G[b, py, px, o] * I[b, s*py - 1 + ky, s*px - 1 + kx, i]
@@ -33,7 +33,8 @@ constexpr int WU_MAXST = 6;
 struct WuParams {
     alignas(64) CUtensorMap tmG;
     alignas(64) CUtensorMap tmI;
-    int B, Hg, Wg, s, TR, TW, NB, nob, nib, O, Ich;
+    int B, Hg, Wg, s, pad, ntap, npair, TR, TW, NB, nob, nib, O, Ich;
+    int fp16;                   // operands are fp16 (the DCN path's split halves) instead of bf16
     int groups_per_img, groups_per_cta, total_groups, nst;
     uint32_t g_box_bytes, g_boxes, i_plane_bytes, i_planes, i_off, stage_bytes, tx_bytes, rpitch, ncol;
     uint32_t toff[9];           // byte offset of tap t's pixel (row 0, column 0 of the tile) inside the staged input region
@@ -99,8 +100,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(const __grid_constan
                 const uint32_t st = sbase + (uint32_t)s * P.stage_bytes, fb = smem_u32(&full[s]);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(P.tx_bytes) : "memory");
                 for (uint32_t bx = 0; bx < P.g_boxes; ++bx) tma4d(st + bx * P.g_box_bytes, &P.tmG, ob * P.NB + 64 * (int)bx, gx0, gy0, b, fb);
-                if (P.s == 1) {
-                    tma4d(st + P.i_off, &P.tmI, ib * 64, gx0 - 1, gy0 - 1, b, fb);
+                if (P.i_planes == 1) {
+                    tma4d(st + P.i_off, &P.tmI, ib * 64, P.s * gx0 - P.pad, P.s * gy0 - P.pad, b, fb);
                 } else {
                     for (int py = 0; py < 2; ++py)
                         for (int px = 0; px < 2; ++px)
@@ -112,11 +113,11 @@ __global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(const __grid_constan
         __syncwarp();
     } else if (warp == 1) {
         // instruction descriptor: fp32 accumulate, bf16 x bf16, both operands MN-major, M = 128, N = NB
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(P.NB >> 3) << 17) | (8u << 24);
+        const uint32_t idesc = (1u << 4) | (P.fp16 ? 0u : (1u << 7) | (1u << 10)) | (1u << 15) | (1u << 16) | ((uint32_t)(P.NB >> 3) << 17) | (8u << 24);
         const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);            // SBO = 1024, version 1, SWIZZLE_128B
         uint32_t a_lo[5];                                                                  // per pair: tap a's offset (16-byte units) | LBO
 #pragma unroll
-        for (int j = 0; j < 5; ++j) a_lo[j] = (P.toff[P.pa[j]] >> 4) | (((P.toff[P.pb[j]] - P.toff[P.pa[j]]) >> 4) << 16);
+        for (int j = 0; j < 5; ++j) a_lo[j] = j < P.npair ? (P.toff[P.pa[j]] >> 4) | (((P.toff[P.pb[j]] - P.toff[P.pa[j]]) >> 4) << 16) : 0u;
         const uint32_t b_lbo = (P.g_box_bytes >> 4) << 16;
         const int hsteps = P.TW / 16;
         for (int t = 0; t < ntiles; ++t) {
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(const __grid_constan
                         const uint32_t acc = (t | r | h) ? 1u : 0u;
 #pragma unroll
                         for (int j = 0; j < 5; ++j) {
+                            if (j >= P.npair) break;
                             const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo[j] + ia);
                             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(
                                              tmem + (uint32_t)j * P.ncol),
@@ -151,10 +153,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(const __grid_constan
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3, m = 32 * q + lane, second = m >> 6, i = ib * 64 + (m & 63);
         const bool i_ok = i < P.Ich;
-        for (int j = 0; j < 5; ++j) {
-            if (j == 4 && second) break;                                   // warp-uniform: the last pair is tap 8 twice
+        for (int j = 0; j < P.npair; ++j) {
+            if (second && P.pb[j] == P.pa[j]) break;                       // warp-uniform: the last pair is one tap twice
             const int tap = second ? P.pb[j] : P.pa[j];
-            float *dst = P.partial + (((long long)chunk * 9 + tap) * P.O) * P.Ich + i;
+            float *dst = P.partial + (((long long)chunk * P.ntap + tap) * P.O) * P.Ich + i;
             for (int c0 = 0; c0 < P.NB; c0 += 16) {
                 uint32_t v[16];
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -176,14 +178,15 @@ __global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(const __grid_constan
 }
 
 // dW[o][i][tap] (torch's (O, I, 3, 3)) = sum over chunks of partial[chunk][tap][o][i], in chunk order
-__global__ void __launch_bounds__(256) wgrad_umma_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int O, int Ich, int nchunk) {
-    const long long per = (long long)O * Ich, total = 9 * per;
+__global__ void __launch_bounds__(256) wgrad_umma_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int O, int Ich, int nchunk,
+                                                                int ntap) {
+    const long long per = (long long)O * Ich, total = ntap * per;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int tap = (int)(e / per);
         const long long oi = e - (long long)tap * per;
         float s = 0.f;
         for (int c = 0; c < nchunk; ++c) s += __ldg(partial + (long long)c * total + e);
-        dw[oi * 9 + tap] = s;
+        dw[oi * ntap + tap] = s;
     }
 }
 
@@ -204,9 +207,9 @@ TmapEncodeFn tmap_encoder() {
 
 }  // namespace
 
-// the tcgen05 path takes every 3x3 filter gradient whose channel counts are multiples of 16 (RDFC_WGRAD_UMMA = 0 keeps the mma.sync kernel)
+// the tcgen05 path takes every 3x3 / 1x1 filter gradient whose channel counts are multiples of 16 (RDFC_WGRAD_UMMA = 0 keeps the mma.sync kernel)
 bool wgrad_umma_ok(const rdfc_wgrad_desc *d) {
-    return d->k == 3 && d->pad == 1 && (d->stride == 1 || d->stride == 2) && d->grad_out.C % 16 == 0 && d->grad_out.C >= 16 && d->input.C % 8 == 0 &&
+    return (d->k == 3 || d->k == 1) && d->pad == (d->k - 1) / 2 && (d->stride == 1 || d->stride == 2) && d->grad_out.C % 16 == 0 && d->grad_out.C >= 16 && d->input.C % 8 == 0 &&
            d->input.pix_stride % 8 == 0 && d->grad_out.pix_stride % 8 == 0 && knob("RDFC_WGRAD_UMMA", 1) != 0 && tmap_encoder() != nullptr;
 }
 
@@ -214,11 +217,12 @@ struct WuGeom { WuParams P; int nchunk; size_t smem; long long ws_floats; };
 
 static int wgrad_umma_geom(const rdfc_wgrad_desc *d, WuGeom *g) {
     WuParams &P = g->P;
-    P.B = d->B; P.Hg = d->Hg; P.Wg = d->Wg; P.s = d->stride; P.O = d->grad_out.C; P.Ich = d->input.C;
+    P.B = d->B; P.Hg = d->Hg; P.Wg = d->Wg; P.s = d->stride; P.pad = d->pad; P.O = d->grad_out.C; P.Ich = d->input.C;
+    P.ntap = d->k * d->k; P.npair = (P.ntap + 1) / 2;
     // tile: 32-pixel rows unless 16-pixel rows waste fewer columns; rows per tile so that a stage stays near 45-60 KB
     const int w32 = cdiv(P.Wg, 32) * 32, w16 = cdiv(P.Wg, 16) * 16;
     P.TW = (int)knob("RDFC_WGRAD_TW", w16 < w32 ? 16 : 32);
-    P.TR = P.s == 1 ? (P.TW == 32 ? 4 : 8) : (P.TW == 32 ? 2 : 4);
+    P.TR = (P.s == 1 || d->k == 1) ? (P.TW == 32 ? 4 : 8) : (P.TW == 32 ? 2 : 4);
     if (P.TR > P.Hg) P.TR = P.Hg;
     P.nob = cdiv(P.O, 96);
     P.NB = cdiv(cdiv(P.O, P.nob), 16) * 16;
@@ -228,22 +232,28 @@ static int wgrad_umma_geom(const rdfc_wgrad_desc *d, WuGeom *g) {
     P.g_box_bytes = (uint32_t)(P.TR * P.TW * 128);
     P.i_off = P.g_boxes * P.g_box_bytes;
     int prow, pcol;                                   // rows / columns of one staged input plane
-    if (P.s == 1) { P.i_planes = 1; prow = P.TR + 2; pcol = P.TW + 2; } else { P.i_planes = 4; prow = P.TR + 1; pcol = P.TW + 1; }
+    if (d->k == 1) { P.i_planes = 1; prow = P.TR; pcol = P.TW; }                           // 1x1: the pixels themselves (every s-th)
+    else if (P.s == 1) { P.i_planes = 1; prow = P.TR + 2; pcol = P.TW + 2; }
+    else { P.i_planes = 4; prow = P.TR + 1; pcol = P.TW + 1; }
     P.i_plane_bytes = (uint32_t)((prow * pcol * 128 + 1023) / 1024 * 1024);
     P.rpitch = (uint32_t)pcol * 128u;
     P.stage_bytes = P.i_off + P.i_planes * P.i_plane_bytes;
     P.tx_bytes = P.g_boxes * P.g_box_bytes + P.i_planes * (uint32_t)(prow * pcol * 128);
-    for (int ky = 0; ky < 3; ++ky)
-        for (int kx = 0; kx < 3; ++kx) {
-            if (P.s == 1) {
+    for (int t = 0; t < 9; ++t) P.toff[t] = 0;
+    for (int ky = 0; ky < d->k; ++ky)
+        for (int kx = 0; kx < d->k; ++kx) {
+            if (d->k == 1) {
+                P.toff[0] = 0;
+            } else if (P.s == 1) {
                 P.toff[ky * 3 + kx] = (uint32_t)(ky * pcol + kx) * 128u;
             } else {    // row 2 gy - 1 + ky: ky = 0 -> plane 0 (rows -1, 1, ..) row gy; ky = 1 -> plane 1 (rows 0, 2, ..) row gy; ky = 2 -> plane 0 row gy + 1
                 const int py = ky == 1, dy = ky == 2, px = kx == 1, dx = kx == 2;
                 P.toff[ky * 3 + kx] = (uint32_t)(py * 2 + px) * P.i_plane_bytes + (uint32_t)(dy * pcol + dx) * 128u;
             }
         }
-    for (int j = 0; j < 5; ++j) {
-        int a = 2 * j, b = j == 4 ? 8 : 2 * j + 1;
+    for (int j = 0; j < 5; ++j) { P.pa[j] = P.pb[j] = 0; }
+    for (int j = 0; j < P.npair; ++j) {
+        int a = 2 * j, b = 2 * j + 1 < P.ntap ? 2 * j + 1 : 2 * j;
         if (P.toff[a] > P.toff[b]) { const int t = a; a = b; b = t; }
         P.pa[j] = a; P.pb[j] = b;
         RDFC_REQUIRE(P.toff[b] - P.toff[a] < (1u << 18), "wgrad (tcgen05): tap distance exceeds the descriptor's LBO field");
@@ -259,7 +269,7 @@ static int wgrad_umma_geom(const rdfc_wgrad_desc *d, WuGeom *g) {
     if (want < 1) want = 1;
     P.groups_per_cta = cdiv(P.total_groups, want);
     g->nchunk = cdiv(P.total_groups, P.groups_per_cta);
-    g->ws_floats = (long long)g->nchunk * 9 * P.O * P.Ich;
+    g->ws_floats = (long long)g->nchunk * P.ntap * P.O * P.Ich;
     return 0;
 }
 
@@ -268,11 +278,14 @@ long long wgrad_umma_workspace_floats(const rdfc_wgrad_desc *d) {
     return wgrad_umma_geom(d, &g) == 0 ? g.ws_floats : -1;
 }
 
-int wgrad_umma(const rdfc_wgrad_desc *d, float *grad_weight, float *workspace, cudaStream_t st) {
+// the split-K partials only: workspace[chunk][tap][O][Ich] for chunk < *nchunk (callers that combine several products -- the DCN
+// filter gradient's split-precision terms -- reduce them themselves); fp16 != 0: the views hold fp16 values
+int wgrad_umma_partials(const rdfc_wgrad_desc *d, float *workspace, int fp16, cudaStream_t st, int *nchunk) {
     WuGeom g;
     if (int rc = wgrad_umma_geom(d, &g)) return rc;
     WuParams &P = g.P;
     P.partial = workspace;
+    P.fp16 = fp16;
     RDFC_REQUIRE(((uintptr_t)d->grad_out.ptr % 16) == 0 && ((uintptr_t)d->input.ptr % 16) == 0, "wgrad (tcgen05): 16-byte aligned tensors");
     {
         const cuuint64_t gdim[4] = {(cuuint64_t)P.O, (cuuint64_t)d->Wg, (cuuint64_t)d->Hg, (cuuint64_t)d->B};
@@ -287,7 +300,7 @@ int wgrad_umma(const rdfc_wgrad_desc *d, float *grad_weight, float *workspace, c
         const cuuint64_t gdim[4] = {(cuuint64_t)P.Ich, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->B};
         const cuuint64_t ps = (cuuint64_t)d->input.pix_stride * 2;
         const cuuint64_t gstr[3] = {ps, ps * d->Wi, ps * d->Wi * d->Hi};
-        const int prow = P.s == 1 ? P.TR + 2 : P.TR + 1, pcol = P.s == 1 ? P.TW + 2 : P.TW + 1;
+        const int prow = d->k == 1 ? P.TR : (P.s == 1 ? P.TR + 2 : P.TR + 1), pcol = d->k == 1 ? P.TW : (P.s == 1 ? P.TW + 2 : P.TW + 1);
         const cuuint32_t box[4] = {64, (cuuint32_t)(P.s * (pcol - 1) + 1), (cuuint32_t)(P.s * (prow - 1) + 1), 1};
         const cuuint32_t estr[4] = {1, (cuuint32_t)P.s, (cuuint32_t)P.s, 1};
         const CUresult r = tmap_encoder()(&P.tmI, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)d->input.ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -303,9 +316,17 @@ int wgrad_umma(const rdfc_wgrad_desc *d, float *grad_weight, float *workspace, c
     }
     wgrad_umma_kernel<<<dim3(P.nob * P.nib, g.nchunk), 192, g.smem, st>>>(P);
     RDFC_CHECK_LAUNCH("wgrad_umma_kernel");
-    const long long total = 9ll * P.O * P.Ich;
+    *nchunk = g.nchunk;
+    return 0;
+}
+
+int wgrad_umma(const rdfc_wgrad_desc *d, float *grad_weight, float *workspace, cudaStream_t st) {
+    int nchunk = 0;
+    if (int rc = wgrad_umma_partials(d, workspace, 0, st, &nchunk)) return rc;
+    const int ntap = d->k * d->k;
+    const long long total = (long long)ntap * d->grad_out.C * d->input.C;
     const int nblk = (int)min((long long)cdiv(total, 256), (long long)sm_count() * 8);
-    wgrad_umma_reduce_kernel<<<nblk, 256, 0, st>>>(workspace, grad_weight, P.O, P.Ich, g.nchunk);
+    wgrad_umma_reduce_kernel<<<nblk, 256, 0, st>>>(workspace, grad_weight, d->grad_out.C, d->input.C, nchunk, ntap);
     RDFC_CHECK_LAUNCH("wgrad_umma_reduce_kernel");
     return 0;
 }

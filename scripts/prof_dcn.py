@@ -39,3 +39,13 @@ for B in (2, 16):
         y_ref = ref.modulated_deform_conv_forward(x, w, b, off, m, *geo)
         line += f" | reference extension {t_ref:.3f} ms | max-abs vs reference: tcgen05 {float((res[1][1] - y_ref).abs().max()):.2e}, strip {float((res[0][1] - y_ref).abs().max()):.2e}"
     print(line)
+    # backward (input / offset / mask / weight / bias gradients)
+    go = torch.randn(B, 128, 128, 128, device="cuda", generator=g) * 0.01
+    t_b = timeit(lambda: DCN.modulated_deform_conv_backward(x, w, b, off, m, go, *geo), reps=10)
+    line = f"DCNv2 backward B={B}: this repo {t_b:.3f} ms"
+    if os.path.exists(so):
+        t_rb = timeit(lambda: ref.modulated_deform_conv_backward(x, w, b, off, m, go, *geo), reps=10)
+        mine, theirs = DCN.modulated_deform_conv_backward(x, w, b, off, m, go, *geo), ref.modulated_deform_conv_backward(x, w, b, off, m, go, *geo)
+        errs = ", ".join(f"{float((a - r).abs().max() / r.abs().max().clamp_min(1e-30)):.1e}" for a, r in zip(mine, theirs))
+        line += f" | reference extension {t_rb:.3f} ms | relative max-abs differences (input, offset, mask, weight, bias): {errs}"
+    print(line)

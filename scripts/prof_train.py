@@ -31,3 +31,8 @@ tot = sum(r[0] for r in rows.values())
 print(f"B={B}: {tot/1e3:.1f} ms of GPU kernel time in one step")
 for n, (t, c) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:40]:
     print(f"{t/1e3:9.2f} ms {100*t/tot:5.1f}%  x{c:4d}  {n}")
+if os.environ.get("OPS", "1") == "1":
+    # the PyTorch ops behind the at::native kernels: self device time by (op, input shapes)
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof2:
+        m.set_input(data); m.optimize_parameters(); torch.cuda.synchronize()
+    print(prof2.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=40, max_shapes_column_width=70))

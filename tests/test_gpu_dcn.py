@@ -205,3 +205,53 @@ def test_forward_on_tensor_cores_matches_strip_kernel(case):
         ref = odcn.modulated_deform_conv_forward(x.cpu().numpy().astype(np.float64), w.cpu().numpy().astype(np.float64), b.cpu().numpy().astype(np.float64),
                                                  off.cpu().numpy().astype(np.float64), None if m is None else m.cpu().numpy().astype(np.float64), *geo)
         assert np.abs(outs[0].cpu().numpy() - ref).max() <= 3e-5 * scale
+
+
+@pytest.mark.parametrize("case", [
+    # B, Cin, Cout, H, W, k, s, p, d, groups, dg, mask, magnitude of the input / grad_output
+    (2, 64, 128, 128, 128, 3, 1, 1, 1, 1, 2, True, 1.0), (2, 64, 64, 37, 45, 3, 2, 1, 1, 2, 4, True, 1.0), (1, 32, 64, 20, 33, 3, 1, 2, 2, 1, 1, False, 1.0),
+    (3, 128, 256, 19, 26, 1, 1, 0, 1, 1, 2, True, 1.0), (2, 64, 64, 23, 31, 3, 1, 1, 1, 1, 2, True, 1e-4), (2, 64, 64, 23, 31, 3, 1, 1, 1, 1, 2, True, 3e3)])
+def test_backward_on_tensor_cores_matches_cuda_core_kernels(case):
+    """GEMM-sized DCN layers run both contractions of the backward on tcgen05 (columns' gradient = W^T . grad_output through conv_umma,
+    grad_weight = grad_output . columns^T through the filter-gradient kernel, split fp16 operands scaled by a power of two of each tensor's
+    maximum).  All five gradients must agree with the CUDA-core kernels (RDFC_DCN_TC = 0, the path the goldens / gradcheck pin) to fp32
+    accumulation noise -- also for tensors far from unit magnitude (fp16's exponent range) -- and, at small sizes, with the fp64 C oracle."""
+    from oracle import dcn as odcn
+    from rdfc_gan_b200 import _cabi as C
+    from rdfc_gan_b200.dcn import DCN
+    B, Cin, Cout, H, W, k, s, p, d, g, dg, with_mask, mag = case
+    gen = torch.Generator(device="cuda").manual_seed(sum(case[:11]) + 7)
+    Ho, Wo = (H + 2 * p - (d * (k - 1) + 1)) // s + 1, (W + 2 * p - (d * (k - 1) + 1)) // s + 1
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=gen) * mag
+    w = torch.randn(Cout, Cin // g, k, k, device="cuda", generator=gen) * 0.1
+    b = torch.randn(Cout, device="cuda", generator=gen) * 0.1
+    off = torch.randn(B, dg * 2 * k * k, Ho, Wo, device="cuda", generator=gen) * 2.0
+    m = torch.rand(B, dg * k * k, Ho, Wo, device="cuda", generator=gen) if with_mask else None
+    go = torch.randn(B, Cout, Ho, Wo, device="cuda", generator=gen) * mag
+    geo = (k, k, s, s, p, p, d, d, g, dg, 64)
+    res = []
+    for tc in (1, 0):
+        C.set_knob("RDFC_DCN_TC", tc)
+        n0 = C.launch_count()
+        res.append(DCN.modulated_deform_conv_backward(x, w, b, off, m, go, *geo) if with_mask else DCN.deform_conv_backward(x, w, b, off, go, *geo))
+        launches = C.launch_count() - n0
+        assert (launches >= 8) == bool(tc), (tc, launches)
+        if tc:                                   # forward at this magnitude too
+            y_tc = DCN.modulated_deform_conv_forward(x, w, b, off, m, *geo) if with_mask else DCN.deform_conv_forward(x, w, b, off, *geo)
+        else:
+            y_cc = DCN.modulated_deform_conv_forward(x, w, b, off, m, *geo) if with_mask else DCN.deform_conv_forward(x, w, b, off, *geo)
+    C.set_knob("RDFC_DCN_TC", None)
+    names = ("input", "offset", "mask", "weight", "bias") if with_mask else ("input", "offset", "weight", "bias")
+    assert float((y_tc - y_cc).abs().max()) <= 3e-5 * float(y_cc.abs().max())
+    for name, a, r in zip(names, res[0], res[1]):
+        assert a.shape == r.shape and a.is_contiguous()
+        scale = float(r.abs().max())
+        tol = 2e-4 if name == "input" else 5e-5              # grad_input sums atomics in a different order
+        assert float((a - r).abs().max()) <= tol * scale, (name, float((a - r).abs().max()) / scale)
+    if H * W <= 1000:
+        f64 = lambda t: None if t is None else t.cpu().numpy().astype(np.float64)
+        ref = odcn.modulated_deform_conv_backward(f64(x), f64(w), f64(b), f64(off), f64(m), f64(go), *geo)
+        ref = [r for r in ref if r is not None]
+        for name, a, r in zip(names, res[0], ref):
+            scale = float(np.abs(r).max())
+            assert np.abs(a.cpu().numpy() - r).max() <= 1e-4 * scale, (name, np.abs(a.cpu().numpy() - r).max() / scale)
