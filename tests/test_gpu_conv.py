@@ -86,6 +86,10 @@ CASES = [
     (8, 256, 256, 57, 76, 3, 1, False, 1, True, None),
     (4, 64, 64, 228, 304, 3, 1, False, 1, True, None),
     (2, 192, 64, 114, 152, 3, 2, True, 2, False, None),
+    # stride 2 through the dense plane (SWIZZLE_128B pixel-pair rows): odd sizes, wide N, 1x1
+    (3, 256, 512, 57, 75, 3, 2, False, 1, False, None),
+    (2, 128, 256, 29, 38, 1, 2, False, 0, False, None),
+    (2, 512, 512, 29, 38, 3, 2, False, 1, False, None),
 ]
 
 
