@@ -204,7 +204,7 @@ def main(args, rank, world, local):
             "allreduce": {"ms_per_step": ar_ms, "share": ar_ms / (t_ms / args.steps), "elements": model.bucket_G.numel() + model.bucket_D.numel(),
                           "backend": "nccl" if world > 1 else "none (1 rank)"},
             "losses": {k: float(v) for k, v in stats.items()},
-            "roofline": {"kernel": "conv forward / dgrad (conv_umma_kernel, tcgen05) + wgrad (wgrad_kernel, mma.sync): whole dense part",
+            "roofline": {"kernel": "conv forward / dgrad (conv_umma_kernel) + filter gradient (wgrad_umma_kernel), all tcgen05: whole dense part",
                          "bound": "tensor", "achieved": tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": tflops / pk["bf16_sustained"], "traffic": None, "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
                          "note": "3 x 221.4 GFLOP per image (forward, data gradient, filter gradient) over the whole step time"},

@@ -35,7 +35,8 @@ struct WuParams {
     alignas(64) CUtensorMap tmI;
     int B, Hg, Wg, s, pad, ntap, npair, TR, TW, NB, nob, nib, O, Ich;
     int fp16;                   // operands are fp16 (the DCN path's split halves) instead of bf16
-    int groups_per_img, groups_per_cta, total_groups, nst;
+    int groups_per_img, total_groups, tiles_per_cta, total_tiles, nst;
+    int dbg;                    // development knob RDFC_WGRAD_DBG: 1 = stage nothing, 2 = issue no MMAs (wrong results; what bounds the kernel?)
     uint32_t g_box_bytes, g_boxes, i_plane_bytes, i_planes, i_off, stage_bytes, tx_bytes, rpitch, ncol;
     uint32_t toff[9];           // byte offset of tap t's pixel (row 0, column 0 of the tile) inside the staged input region
     int pa[5], pb[5];           // tap pairs, toff[pa] <= toff[pb]
@@ -87,17 +88,19 @@ __global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(const __grid_constan
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
     const int ob = blockIdx.x / P.nib, ib = blockIdx.x - ob * P.nib, chunk = blockIdx.y;
-    const int g0 = chunk * P.groups_per_cta, g1 = min(g0 + P.groups_per_cta, P.total_groups);
-    const int xtiles = (P.Wg + P.TW - 1) / P.TW, ntiles = (g1 - g0) * xtiles;
+    // split K by TILES (row group x column tile), a contiguous run per CTA
+    const int xtiles = (P.Wg + P.TW - 1) / P.TW;
+    const int t_begin = chunk * P.tiles_per_cta, ntiles = min(t_begin + P.tiles_per_cta, P.total_tiles) - t_begin;
 
     if (warp == 0) {
         if (elect_one()) {
-            int grp = g0, xt = 0;
+            int grp = t_begin / xtiles, xt = t_begin - grp * xtiles;
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % P.nst;
                 if (t >= P.nst) wait_bar(smem_u32(&empty[s]), (uint32_t)((t / P.nst - 1) & 1));
                 const int b = grp / P.groups_per_img, gy0 = (grp - b * P.groups_per_img) * P.TR, gx0 = xt * P.TW;
                 const uint32_t st = sbase + (uint32_t)s * P.stage_bytes, fb = smem_u32(&full[s]);
+                if (P.dbg & 1) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory"); if (++xt == xtiles) { xt = 0; ++grp; } continue; }
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(P.tx_bytes) : "memory");
                 for (uint32_t bx = 0; bx < P.g_boxes; ++bx) tma4d(st + bx * P.g_box_bytes, &P.tmG, ob * P.NB + 64 * (int)bx, gx0, gy0, b, fb);
                 if (P.i_planes == 1) {
@@ -112,41 +115,63 @@ __global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(const __grid_constan
         }
         __syncwarp();
     } else if (warp == 1) {
-        // instruction descriptor: fp32 accumulate, bf16 x bf16, both operands MN-major, M = 128, N = NB
-        const uint32_t idesc = (1u << 4) | (P.fp16 ? 0u : (1u << 7) | (1u << 10)) | (1u << 15) | (1u << 16) | ((uint32_t)(P.NB >> 3) << 17) | (8u << 24);
-        const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);            // SBO = 1024, version 1, SWIZZLE_128B
-        uint32_t a_lo[5];                                                                  // per pair: tap a's offset (16-byte units) | LBO
+        // One lane issues; what it costs per MMA bounds the kernel once the operands are staged (a first version recomputed the
+        // descriptors from kernel parameters -- re-read from the constant bank after every asm volatile -- and ran at 88 cycles per MMA
+        // against the pipe's 48): everything the loop needs sits in registers (an opaque zero keeps ptxas from re-materialising the
+        // parameters), descriptors advance by one 32-bit add, the pair loop is unrolled for the 9-tap and the 1-tap case.
+        uint32_t kz;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(kz));
+        kz >>= 31;
+        // instruction descriptor: fp32 accumulate, bf16 (or fp16) operands, both MN-major, M = 128, N = NB
+        const uint32_t idesc = ((1u << 4) | (P.fp16 ? 0u : (1u << 7) | (1u << 10)) | (1u << 15) | (1u << 16) | ((uint32_t)(P.NB >> 3) << 17) | (8u << 24)) + kz;
+        const uint32_t desc_hi = ((uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29)) + kz;      // SBO = 1024, version 1, SWIZZLE_128B
+        uint32_t a_lo[5], d_col[5];                                                         // per pair: tap a's offset (16-byte units) | LBO; accumulator
 #pragma unroll
-        for (int j = 0; j < 5; ++j) a_lo[j] = j < P.npair ? (P.toff[P.pa[j]] >> 4) | (((P.toff[P.pb[j]] - P.toff[P.pa[j]]) >> 4) << 16) : 0u;
-        const uint32_t b_lbo = (P.g_box_bytes >> 4) << 16;
-        const int hsteps = P.TW / 16;
+        for (int j = 0; j < 5; ++j) {
+            a_lo[j] = (j < P.npair ? (P.toff[P.pa[j]] >> 4) | (((P.toff[P.pb[j]] - P.toff[P.pa[j]]) >> 4) << 16) : 0u) + kz;
+            d_col[j] = tmem + (uint32_t)j * P.ncol + kz;
+        }
+        const uint32_t b_lbo = ((P.g_box_bytes >> 4) << 16) + kz;
+        const int hsteps = P.TW / 16 + (int)kz, TR = P.TR + (int)kz, nst = P.nst + (int)kz, nine = (P.npair == 5) + (int)kz, dbg2 = (P.dbg & 2) + (int)kz;
+        const uint32_t rstep_i = (P.rpitch >> 4) + kz, rstep_g = ((uint32_t)(P.TW * 128) >> 4) + kz, stage16 = (P.stage_bytes >> 4) + kz;
+        const uint32_t i_off16 = (P.i_off >> 4) + kz, base16 = ((sbase & 0x3FFFFu) >> 4) + kz;
+        const uint32_t full0 = smem_u32(&full[0]) + kz, empty0 = smem_u32(&empty[0]) + kz, done_b = smem_u32(&done) + kz;
+        int s = 0;
+        uint32_t par = 0;
         for (int t = 0; t < ntiles; ++t) {
-            const int s = t % P.nst;
-            wait_bar(smem_u32(&full[s]), (uint32_t)((t / P.nst) & 1));
+            wait_bar(full0 + 8u * (uint32_t)s, par);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
-                const uint32_t st = sbase + (uint32_t)s * P.stage_bytes;
-                const uint32_t gI = ((st + P.i_off) & 0x3FFFFu) >> 4, gG = (st & 0x3FFFFu) >> 4;
-                for (int r = 0; r < P.TR; ++r)
+                const uint32_t gG = base16 + (uint32_t)s * stage16;
+                uint32_t ia_r = gG + i_off16, ga_r = gG | b_lbo;
+                uint32_t acc = t ? 1u : 0u;
+                for (int r = 0; r < (dbg2 ? (t == 0) : TR); ++r) {
+                    uint32_t ia = ia_r, ga = ga_r;
                     for (int h = 0; h < hsteps; ++h) {
-                        const uint32_t ia = gI + (((uint32_t)r * P.rpitch + (uint32_t)h * 2048u) >> 4);
-                        const uint32_t ga = gG + (((uint32_t)(r * P.TW + h * 16) * 128u) >> 4);
-                        const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(ga | b_lbo);
-                        const uint32_t acc = (t | r | h) ? 1u : 0u;
+                        if (nine) {
 #pragma unroll
-                        for (int j = 0; j < 5; ++j) {
-                            if (j >= P.npair) break;
-                            const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo[j] + ia);
-                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(
-                                             tmem + (uint32_t)j * P.ncol),
-                                         "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                            for (int j = 0; j < 5; ++j) {
+                                asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+                                             "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_col[j]),
+                                             "r"(a_lo[j] + ia), "r"(ga), "r"(desc_hi), "r"(idesc), "r"(acc)
+                                             : "memory");
+                            }
+                        } else {
+                            asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+                                         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_col[0]),
+                                         "r"(a_lo[0] + ia), "r"(ga), "r"(desc_hi), "r"(idesc), "r"(acc)
                                          : "memory");
                         }
+                        acc = 1u;
+                        ia += 128u; ga += 128u;                              // 16 pixels = 2048 bytes
                     }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
-                if (t == ntiles - 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done)) : "memory");
+                    ia_r += rstep_i; ga_r += rstep_g;
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8u * (uint32_t)s) : "memory");
+                if (t == ntiles - 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(done_b) : "memory");
             }
             __syncwarp();
+            if (++s == nst) { s = 0; par ^= 1u; }
         }
     } else {
         wait_bar(smem_u32(&done), 0);
@@ -267,8 +292,10 @@ static int wgrad_umma_geom(const rdfc_wgrad_desc *d, WuGeom *g) {
     const int nblk = P.nob * P.nib;
     int want = sm_count() / nblk;                      // one CTA per SM (each allocates all of TMEM): about one wave in total
     if (want < 1) want = 1;
-    P.groups_per_cta = cdiv(P.total_groups, want);
-    g->nchunk = cdiv(P.total_groups, P.groups_per_cta);
+    P.total_tiles = P.total_groups * cdiv(P.Wg, P.TW);
+    P.tiles_per_cta = cdiv(P.total_tiles, want);
+    g->nchunk = cdiv(P.total_tiles, P.tiles_per_cta);
+    P.dbg = (int)knob("RDFC_WGRAD_DBG", 0);
     g->ws_floats = (long long)g->nchunk * P.ntap * P.O * P.Ich;
     return 0;
 }

@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(128) pair_kernel(const __grid_constant__ CUten
 }
 
 // rate: n_iter x 8 MMAs of shape (M, N, 16), both operands MN-major SW128, start addresses walking like a wgrad K loop
-__global__ void __launch_bounds__(128) rate_kernel(int n_iter, int M, int N, int nacc, int mn_major, long long *out) {
+__global__ void __launch_bounds__(128) rate_kernel(int n_iter, int M, int N, int nacc, int mn_major, long long *out, uint32_t a_shift = 0, uint32_t a_lbo = 16384,
+                                                   uint32_t b_shift = 128) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
@@ -194,8 +195,8 @@ __global__ void __launch_bounds__(128) rate_kernel(int n_iter, int M, int N, int
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 // MN-major: 16 pixels = 2048 B per K step, LBO 16 KB between channel blocks; K-major SW128: 8-row groups 1024 B apart
-                const uint64_t da = mn_major ? make_desc(a0 + (uint32_t)(u & 7) * 2048u, 16384, 1024, 2, 0) : make_desc(a0 + (uint32_t)(u & 3) * 32u, 16, 1024, 2, 0);
-                const uint64_t db = mn_major ? make_desc(b0 + (uint32_t)(u & 7) * 2048u + 128u * (uint32_t)(u % 3), 16384, 1024, 2, 0)
+                const uint64_t da = mn_major ? make_desc(a0 + (uint32_t)(u & 7) * 2048u + a_shift * (uint32_t)(1 + u % 3), a_lbo, 1024, 2, 0) : make_desc(a0 + (uint32_t)(u & 3) * 32u, 16, 1024, 2, 0);
+                const uint64_t db = mn_major ? make_desc(b0 + (uint32_t)(u & 7) * 2048u + b_shift * (uint32_t)(u % 3), 16384, 1024, 2, 0)
                                              : make_desc(b0 + (uint32_t)(u & 3) * 32u, 16, 1024, 2, 0);
                 mma(tmem + (uint32_t)((u % nacc) * N), da, db, idesc, (it | (u >= nacc)) ? 1u : 0u);
             }
@@ -325,5 +326,18 @@ int main() {
                     cudaMemcpy(&h_cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
                     printf("rate %s M=%d N=%d nacc=%d: %.1f cycles / MMA (math at full rate: %d)\n", mn ? "MN-major" : "K-major ", M, N, nacc, (double)h_cyc / (400 * 8), M * N / 256);
                 }
+    // operand alignment: tap shifts move the start address off the 1024-byte swizzle atom; LBO = 128 overlaps the two halves of A
+    struct V { const char *name; uint32_t a_shift, a_lbo, b_shift; };
+    const V vs[] = {{"A aligned, LBO 16 KB, B aligned", 0, 16384, 0}, {"A aligned, LBO 16 KB, B shifted 128", 0, 16384, 128}, {"A shifted 128, LBO 16 KB, B aligned", 128, 16384, 0},
+                    {"A aligned, LBO 128, B aligned", 0, 128, 0}, {"A shifted 128, LBO 128, B aligned", 128, 128, 0}, {"A shifted 128, LBO 4352, B aligned", 128, 4352, 0},
+                    {"A shifted 512, LBO 16 KB, B aligned", 512, 16384, 0}, {"A shifted 1024, LBO 1024, B aligned", 1024, 1024, 0}};
+    for (const V &v : vs)
+        for (int N : {64, 96}) {
+            rate_kernel<<<148, 128, 160 * 1024>>>(400, 128, N, 3, 1, d_cyc, v.a_shift, v.a_lbo, v.b_shift);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("rate variant: %s\n", cudaGetErrorString(e)); return 1; }
+            cudaMemcpy(&h_cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
+            printf("rate MN-major M=128 N=%d, %s: %.1f cycles / MMA\n", N, v.name, (double)h_cyc / (400 * 8));
+        }
     return 0;
 }
