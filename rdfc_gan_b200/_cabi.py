@@ -176,8 +176,22 @@ def view(t, C=None, c0=0, nchw=False):
     if nchw:
         assert t.is_contiguous()
         return View(t.data_ptr(), dtype_code(t), t.shape[1], 0, 1)
-    assert t.is_contiguous() and t.dim() == 4
+    assert t.dim() == 4 and nhwc_viewable(t), "NHWC tensor (or a channel slice of one) expected"
     ctot = t.shape[3]
     C = ctot - c0 if C is None else C
     assert 0 <= c0 and c0 + C <= ctot
-    return View(t.data_ptr() + c0 * t.element_size(), dtype_code(t), C, ctot, 0)
+    return View(t.data_ptr() + c0 * t.element_size(), dtype_code(t), C, ctot if t.is_contiguous() else t.stride(2), 0)
+
+
+def nhwc_viewable(t):
+    """True if ``t`` (B,H,W,C) is a dense NHWC tensor or a CHANNEL SLICE of one (what autograd hands back for the inputs of a
+    torch.cat along the channels): channels contiguous, one pixel pitch S >= C for the three outer dimensions.  Such tensors go to
+    the kernels as (pointer, C, pixel stride) views -- no .contiguous() copy."""
+    if t.dim() != 4:
+        return False
+    if t.is_contiguous():
+        return True
+    B, H, W, Cc = t.shape
+    sb, sh, sw, sc = t.stride()
+    return (sc == 1 and sw >= Cc and sw % 8 == 0 and (H == 1 or sh == W * sw) and (B == 1 or sb == H * W * sw) and W > 1
+            and t.data_ptr() % 16 == 0)

@@ -39,8 +39,9 @@ def _basic_block(x, blk):
 def _small_conv(x_nhwc, conv, act=None):
     """A conv too thin for the tensor-core kernel (<= 8 output channels): torch, on the NHWC tensor viewed as channels-last NCHW.
     -> fp32 NCHW"""
-    x = x_nhwc.permute(0, 3, 1, 2)
-    y = F.conv2d(x, conv.weight.to(BF), None if conv.bias is None else conv.bias.to(BF), stride=1, padding=1).float()
+    x = x_nhwc.permute(0, 3, 1, 2)                      # channels-last view; channels-last filters keep cuDNN from converting layouts
+    w = conv.weight.to(BF).contiguous(memory_format=torch.channels_last)
+    y = F.conv2d(x, w, None if conv.bias is None else conv.bias.to(BF), stride=1, padding=1).float()
     if act == 'tanh':
         y = torch.tanh(y)
     elif act == 'sigmoid':
@@ -97,8 +98,8 @@ def generator_forward_train(g, stem_in, depth):
     C.require_cuda(stem_in, depth)
     L = C.ACT_LEAKY02
     # ---- stems (rdf_generator.py:286-292): 3 / 1 input channels, bias, LeakyReLU -- torch
-    def stem(x, seq):
-        return _nhwc(F.leaky_relu(F.conv2d(x, seq[0].weight, seq[0].bias, padding=1), 0.2)).to(BF)
+    def stem(x, seq):                                   # fp32 conv (cuDNN's NCHW fp32 kernels), cast BEFORE the layout change (half the bytes)
+        return _nhwc(F.leaky_relu(F.conv2d(x, seq[0].weight, seq[0].bias, padding=1), 0.2).to(BF))
     fe1 = {'r': stem(stem_in, g.rgb_branch_en1),
            'd': torch.cat([stem(stem_in, g.depth_branch_en1_rgb), stem(depth, g.depth_branch_en1_depth)], 3)}
     # ---- encoders

@@ -41,6 +41,12 @@ def _conv_umma(x, w_oihw, k, stride, transposed, out_hw):
     return out
 
 
+def _dense(t):
+    """The tensor itself when the kernels can read it as a (pointer, channels, pixel stride) view -- dense NHWC or a channel slice of a
+    dense NHWC tensor, which is what autograd returns for the operands of a channel concatenation -- else a contiguous copy."""
+    return t if C.nhwc_viewable(t) else t.contiguous()
+
+
 def _wgrad(grad_out, inp, k, stride):
     """sum_p grad_out[p, o] * inp[stride * p - pad + tap, i] -> (O, I, k, k) fp32."""
     B, Hg, Wg, O = grad_out.shape
@@ -62,7 +68,7 @@ class _Conv2dNHWC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, k, stride, transposed):
         C.require_cuda(x, weight)
-        x = x.contiguous()
+        x = _dense(x)
         B, H, W, _ = x.shape
         if transposed:                      # ConvTranspose2d(k3, s2, p1, op1): weight (Cin, Cout, 3, 3), output exactly 2x
             out_hw = (2 * H, 2 * W)
@@ -79,7 +85,7 @@ class _Conv2dNHWC(torch.autograd.Function):
     def backward(ctx, gy):
         x, weight = ctx.saved_tensors
         k, stride, transposed = ctx.cfg
-        gy = gy.contiguous()
+        gy = _dense(gy)
         B, H, W, Cin = x.shape
         w = weight.detach()
         gx = gw = None
@@ -114,7 +120,7 @@ def conv2d_nhwc(x, weight, k=3, stride=1, transposed=False):
 class _BNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, gamma, beta, residual, act, eps, bn):
-        y = y.contiguous()
+        y = _dense(y)
         B, H, W, Cc = y.shape
         npix = B * H * W
         dev = y.device
@@ -126,8 +132,8 @@ class _BNAct(torch.autograd.Function):
         rstd = torch.rsqrt(var + eps)
         scale = (gamma.detach().float() * rstd).contiguous()
         shift = (beta.detach().float() - mean * scale).contiguous()
-        out = torch.empty_like(y)
-        res = residual.contiguous() if residual is not None else None
+        out = torch.empty(y.shape, dtype=y.dtype, device=y.device)
+        res = _dense(residual) if residual is not None else None
         vo, vr = C.view(out), C.view(res)
         with torch.cuda.device(dev):
             C.check(C.lib.rdfc_affine_act_forward(ctypes.byref(vy), C.ptr(scale), C.ptr(shift), ctypes.byref(vr) if res is not None else None,
@@ -146,12 +152,12 @@ class _BNAct(torch.autograd.Function):
     def backward(ctx, gout):
         y, out, mean, rstd, gamma = ctx.saved_tensors
         act, has_res = ctx.cfg
-        gout = gout.contiguous()
+        gout = _dense(gout)
         B, H, W, Cc = y.shape
         npix = B * H * W
         dev = y.device
-        dy = torch.empty_like(y)
-        dres = torch.empty_like(y) if (has_res and ctx.needs_input_grad[3]) else None
+        dy = torch.empty(y.shape, dtype=y.dtype, device=y.device)
+        dres = torch.empty(y.shape, dtype=y.dtype, device=y.device) if (has_res and ctx.needs_input_grad[3]) else None
         ws = torch.empty(C.lib.rdfc_bn_workspace_floats(npix, Cc), dtype=torch.float32, device=dev)
         s_dz, s_dzx = torch.empty(Cc, device=dev), torch.empty(Cc, device=dev)
         g32 = gamma.detach().float().contiguous()
