@@ -35,4 +35,8 @@ if os.environ.get("OPS", "1") == "1":
     # the PyTorch ops behind the at::native kernels: self device time by (op, input shapes)
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof2:
         m.set_input(data); m.optimize_parameters(); torch.cuda.synchronize()
-    print(prof2.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=40, max_shapes_column_width=70))
+    rows2 = [(e.self_device_time_total, e.count, e.key, str(e.input_shapes)[:110]) for e in prof2.key_averages(group_by_input_shape=True)
+             if e.key.startswith("aten::") and e.self_device_time_total > 0]
+    print("PyTorch ops by self device time (op, input shapes):")
+    for t, c, k, shp in sorted(rows2, reverse=True)[:60]:
+        print(f"{t/1e3:8.2f} ms  x{c:4d}  {k:34s} {shp}")
