@@ -44,6 +44,85 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const float *__restrict
     }
 }
 
+// ---- the same for the case ESANet runs (7 x 7, stride 2, pad 3, 64 outputs): register-tiled --------------------------------------------
+// A CTA computes 8 x 16 output pixels x 64 channels: the input patch (Cin x 21 x 37, zero padded) and the whole filter bank ([tap][ci][cout],
+// 37 KB at Cin = 3) sit in shared memory; a warp owns one output row, a lane 4 adjacent pixels x 8 channels (32 accumulators).  Per (ci, ky)
+// the lane reads the 13 patch values its four pixels touch once (three 16-byte loads + one) and per kx eight filter values (two 16-byte,
+// warp-broadcast loads): 224 FMAs per 18 shared-memory loads instead of 1 per 2 in the kernel above (7.1 ms -> 0.3 ms at B = 32, 228 x 304).
+constexpr int FC_TY = 8, FC_TX = 16, FC_PR = 2 * FC_TY + 5, FC_PC = 40;
+__global__ void __launch_bounds__(256) first_conv7s2_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ scale,
+                                                            const float *__restrict__ shift, __nv_bfloat16 *__restrict__ out, int out_stride, int B,
+                                                            int Cin, int Hi, int Wi, int Ho, int Wo, int relu) {
+    extern __shared__ __align__(16) float fsm[];
+    float *sw = fsm;                                    // [49 * Cin][64]
+    float *patch = fsm + 49 * Cin * 64;                 // [Cin][FC_PR][FC_PC]
+    for (int e = threadIdx.x; e < 49 * Cin * 64; e += 256) {
+        const int co = e & 63, t = e >> 6, ci = t % Cin, kk = t / Cin;          // torch layout w[co][ci][ky][kx]
+        sw[e] = w[((long long)co * Cin + ci) * 49 + kk];
+    }
+    const int tiles_x = (Wo + FC_TX - 1) / FC_TX, tiles_y = (Ho + FC_TY - 1) / FC_TY;
+    const long long ntiles = (long long)B * tiles_y * tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cg = lane & 7, pg = lane >> 3;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { sc[c] = scale[cg * 8 + c]; sh[c] = shift[cg * 8 + c]; }
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y), b = (int)(tile / ((long long)tiles_x * tiles_y));
+        const int oy0 = ty * FC_TY, ox0 = tx * FC_TX, iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
+        __syncthreads();                                // the previous tile's patch has been consumed (and the filters are in place)
+        for (int e = threadIdx.x; e < Cin * FC_PR * FC_PC; e += 256) {
+            const int c = e % FC_PC, r = (e / FC_PC) % FC_PR, ci = e / (FC_PC * FC_PR);
+            const int iy = iy0 + r, ix = ix0 + c;
+            patch[e] = (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) ? __ldg(x + (((long long)b * Cin + ci) * Hi + iy) * Wi + ix) : 0.f;
+        }
+        __syncthreads();
+        float acc[4][8];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[p][c] = 0.f;
+        for (int ci = 0; ci < Cin; ++ci)
+#pragma unroll 1
+            for (int ky = 0; ky < 7; ++ky) {
+                const float *prow = patch + (ci * FC_PR + 2 * warp + ky) * FC_PC + 8 * pg;
+                float in[13];
+                {
+                    const float4 a = *reinterpret_cast<const float4 *>(prow), b4 = *reinterpret_cast<const float4 *>(prow + 4),
+                                 c4 = *reinterpret_cast<const float4 *>(prow + 8);
+                    in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w; in[4] = b4.x; in[5] = b4.y; in[6] = b4.z; in[7] = b4.w;
+                    in[8] = c4.x; in[9] = c4.y; in[10] = c4.z; in[11] = c4.w; in[12] = prow[12];
+                }
+#pragma unroll
+                for (int kx = 0; kx < 7; ++kx) {
+                    const float *wp = sw + ((ky * 7 + kx) * Cin + ci) * 64 + cg * 8;
+                    const float4 w0 = *reinterpret_cast<const float4 *>(wp), w1 = *reinterpret_cast<const float4 *>(wp + 4);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[p][c] = fmaf(in[2 * p + kx], wv[c], acc[p][c]);
+                }
+            }
+        const int oy = oy0 + warp;
+        if (oy < Ho) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int ox = ox0 + 4 * pg + p;
+                if (ox >= Wo) continue;
+                uint32_t o[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float y0 = fmaf(acc[p][2 * c], sc[2 * c], sh[2 * c]), y1 = fmaf(acc[p][2 * c + 1], sc[2 * c + 1], sh[2 * c + 1]);
+                    if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                    o[c] = *reinterpret_cast<const uint32_t *>(&h);
+                }
+                *reinterpret_cast<uint4 *>(out + (((long long)b * Ho + oy) * Wo + ox) * out_stride + cg * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
 // ---- max pooling 3x3 / stride 2 / pad 1 over bf16 NHWC, 8 channels per thread -------------------------------------------
 __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16 *__restrict__ x, int x_stride, __nv_bfloat16 *__restrict__ out,
                                                       int out_stride, int B, int C, int Hi, int Wi, int Ho, int Wo) {
@@ -172,6 +251,120 @@ __global__ void __launch_bounds__(256) upsample_dw_kernel(const __nv_bfloat16 *_
     }
 }
 
+// The two shapes ESANet runs, restructured (the kernel above stays as the general fallback; same arithmetic order, identical results):
+// (1) fp32 NCHW result (the network's last up-sampling, 40 planes at full resolution): with x fastest across the lanes the plain kernel reads
+// 2 bytes out of a different pixel per lane and tap.  Here a CTA owns 64 output pixels of one row x all channels: the (<= 3) source rows are
+// staged in shared memory with coalesced channel-fastest reads, the outputs leave as 256-byte runs per plane (1.36 ms -> ~0.1 ms at B = 32).
+constexpr int UP_TX = 64, UP_NCOL = 70;
+__global__ void __launch_bounds__(256) upsample_dw_nchw_kernel(const __nv_bfloat16 *__restrict__ x, int x_stride, const float *__restrict__ w,
+                                                               const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ skip, int skip_stride,
+                                                               float *__restrict__ out, int C, int Hi, int Wi, int Ho, int Wo) {
+    extern __shared__ float usrc[];                     // [3][UP_NCOL][CP]
+    const int CP = C | 1;
+    const float fy = (float)Hi / Ho, fx = (float)Wi / Wo;
+    const int oy = blockIdx.y, ox0 = blockIdx.x * UP_TX, b = blockIdx.z;
+    int sy[3];
+    bool vy[3];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int uy = oy - 1 + ky;
+        vy[ky] = uy >= 0 && uy < Ho;
+        sy[ky] = vy[ky] ? min((int)floorf(uy * fy), Hi - 1) : 0;
+    }
+    const int ux_lo = max(ox0 - 1, 0), ux_hi = min(ox0 + UP_TX, Wo - 1);
+    const int sx_lo = min((int)floorf(ux_lo * fx), Wi - 1), ncol = min((int)floorf(ux_hi * fx), Wi - 1) - sx_lo + 1;
+    const int cgs = C >> 3;                             // 16-byte loads: eight channels per thread
+    for (int e = threadIdx.x; e < 3 * ncol * cgs; e += 256) {
+        const int cg = e % cgs, col = (e / cgs) % ncol, ky = e / (cgs * ncol);
+        float *dst = usrc + (ky * UP_NCOL + col) * CP + cg * 8;
+        if (vy[ky]) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(x + (((long long)b * Hi + sy[ky]) * Wi + sx_lo + col) * x_stride + cg * 8);
+            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); dst[2 * q] = f.x; dst[2 * q + 1] = f.y; }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = 0.f;
+        }
+    }
+    __syncthreads();
+    const int ox = ox0 + (threadIdx.x & (UP_TX - 1));
+    if (ox >= Wo) return;
+    int scol[3];
+    bool vx[3];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+        const int ux = ox - 1 + kx;
+        vx[kx] = ux >= 0 && ux < Wo;
+        scol[kx] = vx[kx] ? min((int)floorf(ux * fx), Wi - 1) - sx_lo : 0;
+    }
+    for (int c = threadIdx.x / UP_TX; c < C; c += 256 / UP_TX) {
+        float acc = bias[c];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            if (!vy[ky]) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+                if (vx[kx]) acc = fmaf(w[c * 9 + ky * 3 + kx], usrc[(ky * UP_NCOL + scol[kx]) * CP + c], acc);
+        }
+        if (skip) acc += __bfloat162float(skip[(((long long)b * Ho + oy) * Wo + ox) * skip_stride + c]);
+        out[(((long long)b * C + c) * Ho + oy) * Wo + ox] = acc;
+    }
+}
+
+// (2) bf16 NHWC result: eight channels per thread (16-byte loads / stores), the depth-wise filters in shared memory as [tap][channel]
+__global__ void __launch_bounds__(256) upsample_dw_nhwc8_kernel(const __nv_bfloat16 *__restrict__ x, int x_stride, const float *__restrict__ w,
+                                                                const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ skip, int skip_stride,
+                                                                __nv_bfloat16 *__restrict__ out, int out_stride, int B, int C, int Hi, int Wi, int Ho,
+                                                                int Wo) {
+    extern __shared__ float usw[];                      // [9][C] then bias[C]
+    for (int e = threadIdx.x; e < 9 * C; e += 256) usw[e] = w[(e % C) * 9 + e / C];
+    for (int e = threadIdx.x; e < C; e += 256) usw[9 * C + e] = bias[e];
+    __syncthreads();
+    const int cgs = C >> 3;
+    const long long total = (long long)B * Ho * Wo * cgs;
+    const float fy = (float)Hi / Ho, fx = (float)Wi / Wo;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cgs) * 8;
+        const long long p = i / cgs;
+        const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho), b = (int)(p / ((long long)Wo * Ho));
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = usw[9 * C + c0 + q];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int uy = oy - 1 + ky;
+            if (uy < 0 || uy >= Ho) continue;
+            const int sy = min((int)floorf(uy * fy), Hi - 1);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ux = ox - 1 + kx;
+                if (ux < 0 || ux >= Wo) continue;
+                const int sx = min((int)floorf(ux * fx), Wi - 1);
+                const uint4 v = *reinterpret_cast<const uint4 *>(x + (((long long)b * Hi + sy) * Wi + sx) * x_stride + c0);
+                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+                const float *wt = usw + (ky * 3 + kx) * C + c0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = __bfloat1622float2(h[q]);
+                    acc[2 * q] = fmaf(wt[2 * q], f.x, acc[2 * q]);
+                    acc[2 * q + 1] = fmaf(wt[2 * q + 1], f.y, acc[2 * q + 1]);
+                }
+            }
+        }
+        if (skip) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(skip + p * skip_stride + c0);
+            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); acc[2 * q] += f.x; acc[2 * q + 1] += f.y; }
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]); o[q] = *reinterpret_cast<const uint32_t *>(&h2); }
+        *reinterpret_cast<uint4 *>(out + p * out_stride + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 int grid_for(long long total) { return (int)min((long long)cdiv(total, 256), (long long)sm_count() * 16); }
 
 }  // namespace
@@ -192,6 +385,22 @@ extern "C" int rdfc_first_conv_forward(const float *x_nchw, int B, int Cin, int 
     RDFC_REQUIRE(B > 0 && Cin >= 1 && Cin <= 4 && k >= 1 && k <= 7 && stride >= 1 && out->C <= 256 && 256 % out->C == 0,
                  "first conv: Cin <= 4, k <= 7, Cout a divisor of 256");
     const int Ho = (Hi + 2 * pad - k) / stride + 1, Wo = (Wi + 2 * pad - k) / stride + 1;
+    if (k == 7 && stride == 2 && pad == 3 && out->C == 64 && knob("RDFC_FIRSTCONV_FAST", 1) != 0) {     // ESANet's stem: the register-tiled kernel
+        const size_t fsmem = (size_t)(49 * Cin * 64 + Cin * FC_PR * FC_PC) * sizeof(float);
+        static bool attr[64] = {};
+        int dev = 0;
+        RDFC_CUDA(cudaGetDevice(&dev));
+        if (!attr[dev & 63]) {
+            RDFC_CUDA(cudaFuncSetAttribute(first_conv7s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+            attr[dev & 63] = true;
+        }
+        const long long ntiles = (long long)B * cdiv(Ho, FC_TY) * cdiv(Wo, FC_TX);
+        const int grid = (int)min(ntiles, (long long)sm_count() * 3);
+        first_conv7s2_kernel<<<grid, 256, fsmem, (cudaStream_t)stream>>>(x_nchw, weight, scale, shift, (__nv_bfloat16 *)out->ptr, out->pix_stride, B, Cin,
+                                                                         Hi, Wi, Ho, Wo, relu);
+        RDFC_CHECK_LAUNCH("first_conv7s2_kernel");
+        return 0;
+    }
     const size_t smem = (size_t)k * k * Cin * out->C * sizeof(float);
     RDFC_REQUIRE(smem <= 48 * 1024, "first conv: filter bank exceeds 48 KB of shared memory");
     const long long npix = (long long)B * Ho * Wo;
@@ -256,12 +465,20 @@ extern "C" int rdfc_upsample_dw_forward(const rdfc_view *x, const float *weight,
         sk = (const __nv_bfloat16 *)skip->ptr; sk_stride = skip->pix_stride;
     }
     const long long total = (long long)B * Ho * Wo * x->C;
-    if (out_nchw) {
+    const bool fast = knob("RDFC_UPSAMPLE_FAST", 1) != 0;
+    if (out_nchw && fast && Hi <= Ho && Wi <= Wo && (size_t)3 * UP_NCOL * (x->C | 1) * 4 <= 48 * 1024 && B <= 65535 && Ho <= 65535) {
+        upsample_dw_nchw_kernel<<<dim3(cdiv(Wo, UP_TX), Ho, B), 256, (size_t)3 * UP_NCOL * (x->C | 1) * 4, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16 *)x->ptr, x->pix_stride, weight, bias, sk, sk_stride, out_nchw, x->C, Hi, Wi, Ho, Wo);
+    } else if (out_nchw) {
         upsample_dw_kernel<true><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x->ptr, x->pix_stride, weight, bias, sk,
                                                                                     sk_stride, out_nchw, 0, B, x->C, Hi, Wi, Ho, Wo);
     } else {
         if (int rc = bf16_view_ok(out, "upsample dw out")) return rc;
         RDFC_REQUIRE(out->C == x->C, "upsample dw: output channel mismatch");
+        if (fast && (size_t)10 * x->C * 4 <= 48 * 1024 && (!sk || (sk_stride % 8 == 0 && ((uintptr_t)sk % 16) == 0)))
+            upsample_dw_nhwc8_kernel<<<grid_for(total / 8), 256, (size_t)10 * x->C * 4, (cudaStream_t)stream>>>(
+                (const __nv_bfloat16 *)x->ptr, x->pix_stride, weight, bias, sk, sk_stride, (__nv_bfloat16 *)out->ptr, out->pix_stride, B, x->C, Hi, Wi, Ho, Wo);
+        else
         upsample_dw_kernel<false><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x->ptr, x->pix_stride, weight, bias, sk,
                                                                                      sk_stride, out->ptr, out->pix_stride, B, x->C, Hi, Wi, Ho, Wo);
     }
