@@ -272,9 +272,8 @@ template <bool kFinal, int kPix, int kMinBlocks>
 __global__ void __launch_bounds__(BAND_THREADS, kMinBlocks)
 nlspn_prop_band_kernel(const float *__restrict__ in, const float *__restrict__ offset, const float *__restrict__ aff,
                        const float *__restrict__ fixp, float *__restrict__ out, float *__restrict__ inter, FuseOut fz, int clamp,
-                       int B, int H, int W, int rows_per_cta, int sub_rows, int halo) {
-    extern __shared__ float band_tile[];
-    const int pitch = W + 4;                         // tile column tc <-> image column tc - 1 (-1 .. W + 2)
+                       int B, int H, int W, int rows_per_cta, int sub_rows, int halo, int pitch) {
+    extern __shared__ float band_tile[];                 // rows of `pitch` floats; tile column tc <-> image column tc - 1 (-1 .. W + 2)
     const long long total = (long long)B * H, P = (long long)H * W;
     long long row = (long long)blockIdx.x * rows_per_cta;
     const long long row_end = row + rows_per_cta < total ? row + rows_per_cta : total;
@@ -355,9 +354,8 @@ __device__ __forceinline__ float2 h2f(uint32_t u) {
 template <bool kFinal>
 __global__ void __launch_bounds__(BAND_THREADS, 4)
 nlspn_prop_packed_kernel(const float *__restrict__ in, const uint4 *__restrict__ pk, const float *__restrict__ fixp,
-                         float *__restrict__ out, FuseOut fz, int clamp, int B, int H, int W, int rows_per_cta, int sub_rows, int halo) {
+                         float *__restrict__ out, FuseOut fz, int clamp, int B, int H, int W, int rows_per_cta, int sub_rows, int halo, int pitch) {
     extern __shared__ float band_tile[];
-    const int pitch = W + 4;
     const long long total = (long long)B * H, P = (long long)H * W;
     long long row = (long long)blockIdx.x * rows_per_cta;
     const long long row_end = row + rows_per_cta < total ? row + rows_per_cta : total;
@@ -380,10 +378,18 @@ nlspn_prop_packed_kernel(const float *__restrict__ in, const uint4 *__restrict__
         const BandView bv{band_tile, im, fix, pitch, ty0, nrows, H, W, Hf, Wf};
         // linear pixel range of the sub-band; the walk starts at the enclosing 32-pixel block so that lane == g % 32
         const long long g0 = (long long)b * P + (long long)y_lo * W, g1 = g0 + (long long)nr * W;
-        for (long long g = (g0 & ~31ll) + threadIdx.x; g < g1; g += BAND_THREADS) {
+        // software pipeline: the three 16-byte loads of the NEXT pixel are in flight while this one is gathered (one pixel per thread and
+        // iteration made every iteration a serial load -> compute chain: ~2.9 us each, the kernel was latency-bound at 0.45 of the HBM peak)
+        long long g = (g0 & ~31ll) + threadIdx.x;
+        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0, n2 = n0;
+        if (g < g1) { const uint4 *p = pk + (g >> 5) * 96 + (g & 31); n0 = ld_stream4(p); n1 = ld_stream4(p + 32); n2 = ld_stream4(p + 64); }
+        for (; g < g1; g += BAND_THREADS) {
+            const uint4 c0 = n0, c1 = n1, c2 = n2;
+            if (g + BAND_THREADS < g1) {
+                const uint4 *p = pk + ((g + BAND_THREADS) >> 5) * 96 + ((g + BAND_THREADS) & 31);
+                n0 = ld_stream4(p); n1 = ld_stream4(p + 32); n2 = ld_stream4(p + 64);
+            }
             if (g < g0) continue;
-            const uint4 *p = pk + (g >> 5) * 96 + (g & 31);
-            const uint4 c0 = ld_stream4(p), c1 = ld_stream4(p + 32), c2 = ld_stream4(p + 64);
             const int pix = (int)(g - (long long)b * P), y = pix / W, x = pix - y * W;
             float dy[9], dx[9], a[9];
             {
@@ -453,12 +459,17 @@ __global__ void fuse_depth_kernel(const float *__restrict__ d1, const float *__r
     }
 }
 
+// Row pitch of the staged band in floats: W + 4 columns, rounded up to a multiple of 32 so that a tap's shared-memory bank depends on
+// its COLUMN only -- lanes are consecutive pixels, so taps whose rows differ from lane to lane (rough offset fields) collide only when two
+// lanes land on the same column, not whenever (row x pitch + column) happens to coincide modulo 32.  RDFC_NLSPN_PITCH32 = 0: W + 4.
+static int band_pitch(int W) { return knob("RDFC_NLSPN_PITCH32", 1) != 0 ? (W + 4 + 31) / 32 * 32 : W + 4; }
+
 // launch geometry of the band kernels: CTAs per SM, rows per CTA, rows per sub-band (what fits the tile), shared memory
 struct BandGeom { int per_sm, rows_per_cta, sub_rows, nctas; size_t smem; bool ok; };
 static BandGeom band_geom(int B, int H, int W, int halo, int per_sm_max) {
     BandGeom g{};
     const long long total = (long long)B * H;
-    const size_t row_bytes = (size_t)(W + 4) * sizeof(float);
+    const size_t row_bytes = (size_t)band_pitch(W) * sizeof(float);
     for (int per_sm = per_sm_max; per_sm >= 1; --per_sm) {
         const size_t cap = (size_t)(220 * 1024) / per_sm - 1024;
         int fit = (int)(cap / row_bytes) - 2 * halo - 3;                 // sub-band rows that fit beside the halo
@@ -584,13 +595,13 @@ static int propagate(const float *feat_init, const float *offset, const float *a
         const bool last = t == prop_time - 1;
         const FuseOut none{nullptr, nullptr, nullptr, nullptr};
         if (band && packed) {
-            if (last) RDFC_CUDA(launch_pdl(nlspn_prop_packed_kernel<true>, g.nctas, BAND_THREADS, g.smem, st, pdl, cur, (const uint4 *)packed, fix, dst, fz, clamp, B, H, W, g.rows_per_cta, g.sub_rows, halo));
-            else RDFC_CUDA(launch_pdl(nlspn_prop_packed_kernel<false>, g.nctas, BAND_THREADS, g.smem, st, pdl, cur, (const uint4 *)packed, fix, dst, none, 0, B, H, W, g.rows_per_cta, g.sub_rows, halo));
+            if (last) RDFC_CUDA(launch_pdl(nlspn_prop_packed_kernel<true>, g.nctas, BAND_THREADS, g.smem, st, pdl, cur, (const uint4 *)packed, fix, dst, fz, clamp, B, H, W, g.rows_per_cta, g.sub_rows, halo, band_pitch(W)));
+            else RDFC_CUDA(launch_pdl(nlspn_prop_packed_kernel<false>, g.nctas, BAND_THREADS, g.smem, st, pdl, cur, (const uint4 *)packed, fix, dst, none, 0, B, H, W, g.rows_per_cta, g.sub_rows, halo, band_pitch(W)));
             RDFC_CHECK_LAUNCH("nlspn_prop_packed_kernel");
         } else if (band) {
 #define RDFC_BAND(FIN, PX, MB, FZ, CL)                                                                                            \
     RDFC_CUDA(launch_pdl(nlspn_prop_band_kernel<FIN, PX, MB>, g.nctas, BAND_THREADS, g.smem, st, pdl, cur, offset, aff, fix, dst, it, \
-                         FZ, CL, B, H, W, g.rows_per_cta, g.sub_rows, halo))
+                         FZ, CL, B, H, W, g.rows_per_cta, g.sub_rows, halo, band_pitch(W)))
             if (pix == 2) { if (last) RDFC_BAND(true, 2, 3, fz, clamp); else RDFC_BAND(false, 2, 3, none, 0); }
             else { if (last) RDFC_BAND(true, 1, 5, fz, clamp); else RDFC_BAND(false, 1, 5, none, 0); }
 #undef RDFC_BAND

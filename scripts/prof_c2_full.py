@@ -7,7 +7,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import bench
 from _synth import synth_inputs
-cfg = bench.CONFIGS["c2"]
+cfg = bench.CONFIGS[os.environ.get("CONFIG", "c2")]
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 dev = torch.device("cuda", 0)
 G = bench.build_product(cfg).to(dev).set_precision("bf16")
@@ -27,6 +27,6 @@ for e in prof.events():
         n = e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:90]
         r = rows.setdefault(n, [0.0, 0]); r[0] += e.device_time; r[1] += 1
 tot = sum(r[0] for r in rows.values())
-print(f"c2 B={B}: {tot/1e3:.2f} ms of GPU kernel time per forward (lanes overlap: wall time is shorter)")
+print(f"{os.environ.get('CONFIG', 'c2')} B={B}: {tot/1e3:.2f} ms of GPU kernel time per forward (lanes overlap: wall time is shorter)")
 for n, (t, c) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:40]:
     print(f"{t/1e3:9.3f} ms {100*t/tot:5.1f}%  x{c:4d}  {n}")
