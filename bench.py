@@ -332,26 +332,18 @@ def main():
 
     def host_batches(n):
         for _ in range(n):
-            yield (rgb_h, depth_h, stem_h)
+            yield (rgb_h, depth_h, stem_h) if cfg["gen"] == "rdfc" else (rgb_h, depth_h)
 
     last = {}
 
     def e2e_run(n):
-        if cfg["gen"] == "rdfc":
-            # G.stream() overlaps the H2D copy of batch i+1 and the D2H read of batch i-1 with the forward of batch i
-            # (the results arrive in pinned host buffers that stream() recycles two batches later; a consumer would use them in place --
-            # an extra 44 MB host memcpy per 32 images here made 8 ranks on one host memory-bound, not the GPUs)
-            for o in G.stream(host_batches(n), outputs=KEYS):
-                for k in KEYS:
-                    last[k] = float(o[k][0, 0, 0, 0])     # host-side read of every returned map
-        else:
-            # RDF-GAN: the module call G(rgb, depth) (guidance network + generator) on batches copied from / to pinned host memory
-            with torch.no_grad():
-                for _ in range(n):
-                    o = G(rgb_h.to(dev, non_blocking=True), depth_h.to(dev, non_blocking=True))
-                    for k, t in zip(KEYS, o):
-                        outs_h[k].copy_(t, non_blocking=True)
-                    torch.cuda.synchronize()
+        # G.stream() overlaps the H2D copy of batch i+1 and the D2H read of batch i-1 with the forward of batch i (RDF-GAN: the ESANet
+        # guidance network runs on the device inside the same pipeline).
+        # (the results arrive in pinned host buffers that stream() recycles two batches later; a consumer would use them in place --
+        # an extra 44 MB host memcpy per 32 images here made 8 ranks on one host memory-bound, not the GPUs)
+        for o in G.stream(host_batches(n), outputs=KEYS):
+            for k in KEYS:
+                last[k] = float(o[k][0, 0, 0, 0])         # host-side read of every returned map
     e2e_run(3)
     barrier()
     t0 = time.perf_counter()

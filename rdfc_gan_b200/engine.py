@@ -662,7 +662,7 @@ class GeneratorEngine:
             plan.run()
             return tuple(t.clone() for t in plan.outputs) if clone else plan.outputs
 
-    def forward_stream(self, batches, device, want=(0, 1, 2, 3, 4)):
+    def forward_stream(self, batches, device, want=(0, 1, 2, 3, 4), pre=None):
         """Pipelined inference over an iterable of HOST batches (stem_in, depth), pinned or not.  Yields, in order, a
         tuple of pinned CPU tensors (the outputs selected by `want`, indices into (d1, c1, d2, c2, pred)).
 
@@ -695,7 +695,9 @@ class GeneratorEngine:
                     ev.synchronize()
                     yield outs
                 cur.wait_event(ev_in)
-                outs_dev = self.forward(sl['stem'], sl['depth'], clone=False)
+                # `pre` (a guidance network) maps the staged first tensor to the stem input on the compute stream; forward() copies its
+                # result into the plan's own input buffer right away, so the network may reuse its output buffer for the next batch
+                outs_dev = self.forward(sl['stem'] if pre is None else pre(sl['stem']), sl['depth'], clone=False)
                 sl['consumed'].record(cur)                     # forward() copied the staging buffers into the plan first
                 if sl['out_d'] is None:
                     sl['out_d'] = [torch.empty_like(outs_dev[k]) for k in want]

@@ -122,15 +122,16 @@ class _GeneratorBase(nn.Module):
 
     _OUTPUTS = ('depth_map_1', 'confidence_map_1', 'depth_map_2', 'confidence_map_2', 'pred_depth')
 
-    def _stream(self, pairs, outputs):
-        """Pipelined inference over HOST (stem input, depth) batches: engine.forward_stream."""
+    def _stream(self, pairs, outputs, pre=None):
+        """Pipelined inference over HOST (stem input, depth) batches: engine.forward_stream.  ``pre``: a device-side map applied to the
+        first tensor of a batch once it is on the GPU (RDF-GAN's guidance network: rgb -> the 40-channel stem input)."""
         want = tuple(self._OUTPUTS.index(k) for k in outputs)
         dev = next(self.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError("rdfc_gan_b200 generators run on CUDA (sm_100a) devices only; move the module first")
         if self.training:
             raise RuntimeError("stream() is an inference API: call .eval()")
-        for res in self.engine().forward_stream(pairs, dev, want):
+        for res in self.engine().forward_stream(pairs, dev, want, pre=pre):
             yield dict(zip(outputs, res))
 
 
@@ -194,12 +195,11 @@ class DCVGANGenerator(_GeneratorBase):
         self._build_tail(ce, cd, de, dd, True, nlspn_configs)               # gd_dec* always exist (:73-76)
 
     def stream(self, batches, outputs=_GeneratorBase._OUTPUTS):
-        """As RDFGenerator.stream for ``(rgb, depth)`` HOST batches; needs ``global_guidance_module`` None / Identity (the stem
-        input is then ``rgb`` itself, e.g. a precomputed 40-channel guidance map): a guidance network runs on the device and
-        belongs in front of ``forward``."""
-        if not (self.global_guidance_module is None or isinstance(self.global_guidance_module, nn.Identity)):
-            raise RuntimeError("stream() needs the guidance map as input (global_guidance_module None or nn.Identity)")
-        return self._stream(((rgb, depth) for rgb, depth in batches), outputs)
+        """As RDFGenerator.stream for ``(rgb, depth)`` HOST batches.  The guidance network (``global_guidance_module``, e.g. this
+        repo's ESANet) runs on the device between the host-to-device copy and the generator, inside the same pipeline."""
+        gm = self.global_guidance_module
+        pre = None if (gm is None or isinstance(gm, nn.Identity)) else gm
+        return self._stream(((rgb, depth) for rgb, depth in batches), outputs, pre=pre)
 
     def forward(self, rgb, depth):
         """rdf_gan_generator.py:233-361 -> (depth_map_1, confidence_map_1, depth_map_2, confidence_map_2, final)"""

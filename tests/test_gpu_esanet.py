@@ -66,6 +66,17 @@ def test_esanet_inside_dcvgan_generator():
         G2.load_state_dict({k: v for k, v in G.state_dict().items() if not k.startswith("global_guidance_module.")})
         ref = G2.cuda().set_precision("bf16")(guidance, depth.cuda())
     assert len(outs) == 5 and all(torch.equal(a, b) for a, b in zip(outs, ref))
+    # the pipelined host API runs the guidance network inside the stream: three host batches, same numbers as the module call
+    keys = ("depth_map_1", "confidence_map_1", "depth_map_2", "confidence_map_2", "pred_depth")
+    rgb2, _, depth2 = synth_inputs(2, 64, 96, seed=5)
+    batches = [(rgb.pin_memory(), depth.pin_memory()), (rgb2.pin_memory(), depth2.pin_memory()), (rgb.pin_memory(), depth.pin_memory())]
+    got = [{k: o[k].clone() for k in keys} for o in G.stream(iter(batches), outputs=keys)]
+    assert len(got) == 3
+    with torch.no_grad():
+        outs2 = G(rgb2.cuda(), depth2.cuda())
+    for i, want in enumerate((outs, outs2, outs)):
+        for k, w in zip(keys, want):
+            assert torch.equal(got[i][k], w.cpu()), (i, k)
 
 
 @pytest.mark.parametrize("case", [(2, 3, 228, 304), (1, 3, 37, 50), (3, 1, 64, 33), (2, 4, 17, 129)])
