@@ -10,7 +10,7 @@ from _synth import synth_inputs
 cfg = bench.CONFIGS[os.environ.get("CONFIG", "c2")]
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 dev = torch.device("cuda", 0)
-G = bench.build_product(cfg).to(dev).set_precision("bf16")
+G = bench.build_product(cfg).to(dev).set_precision(os.environ.get("PRECISION", "bf16"))
 rgb, normal, depth = synth_inputs(B, cfg["H"], cfg["W"], seed=0, Cs=cfg["cs"])
 rgb, normal, depth = rgb.to(dev), normal.to(dev), depth.to(dev)
 with torch.no_grad():
