@@ -131,9 +131,34 @@ __global__ void __launch_bounds__(256) bn_final_kernel(const float *__restrict__
 }
 
 // ---- out = act(x * scale[c] + shift[c] + residual) ---------------------------------------------------------------------
+// kHoist (C / 8 a power of two <= 256, i.e. a divisor of the 256-thread block): a thread's channel group is the same in every iteration
+// of the grid-stride loop, so its eight (scale, shift) pairs are read once and the pixel index advances by an add -- the plain form reads
+// 16 per-channel values through the LSU per 2-3 vector loads of data and divides a 64-bit index per iteration.
+template <bool kHoist>
 __global__ void __launch_bounds__(256) affine_act_kernel(View x, const float *__restrict__ scale, const float *__restrict__ shift, View res,
                                                          float slope, __nv_bfloat16 *__restrict__ out, int out_stride, int C, long long npix) {
     const int cgs = C >> 3;
+    if (kHoist) {
+        const long long tid = (long long)blockIdx.x * 256 + threadIdx.x, T = (long long)gridDim.x * 256;
+        const int c0 = (int)(tid % cgs) * 8;
+        const long long pstep = T / cgs;
+        float sc[8], sh[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { sc[q] = __ldg(scale + c0 + q); sh[q] = __ldg(shift + c0 + q); }
+        for (long long p = tid / cgs; p < npix; p += pstep) {
+            float v[8], r[8];
+            ld8(x.ptr + p * x.stride + c0, v);
+            if (res.ptr) ld8(res.ptr + p * res.stride + c0, r);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float y = fmaf(v[q], sc[q], sh[q]);
+                if (res.ptr) y += r[q];
+                v[q] = fmaxf(y, slope * y);
+            }
+            st8(out + p * out_stride + c0, v);
+        }
+        return;
+    }
     const long long total = npix * cgs;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long p = i / cgs;
@@ -224,15 +249,43 @@ __global__ void __launch_bounds__(256) sum_final_kernel(const float *__restrict_
     }
 }
 
-// dy = gamma * rstd * (dz - sum_dz / N - xhat * sum_dz_xhat / N);  dres = dz
+// dy = gamma * rstd * (dz - sum_dz / N - xhat * sum_dz_xhat / N);  dres = dz.   kHoist: as in affine_act_kernel (same arithmetic order).
+template <bool kHoist>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View dout, View out, View y, const float *__restrict__ mean,
                                                            const float *__restrict__ rstd, const float *__restrict__ gamma,
                                                            const float *__restrict__ sum_dz, const float *__restrict__ sum_dzx, float slope,
                                                            __nv_bfloat16 *__restrict__ dy, int dy_stride, __nv_bfloat16 *__restrict__ dres,
                                                            int dres_stride, int C, long long npix) {
     const int cgs = C >> 3;
-    const long long total = npix * cgs;
     const float invn = 1.f / (float)npix;
+    if (kHoist) {
+        const long long tid = (long long)blockIdx.x * 256 + threadIdx.x, T = (long long)gridDim.x * 256;
+        const int c0 = (int)(tid % cgs) * 8;
+        const long long pstep = T / cgs;
+        float mu[8], rs[8], grs[8], k1[8], sx[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            mu[q] = __ldg(mean + c0 + q); rs[q] = __ldg(rstd + c0 + q); grs[q] = __ldg(gamma + c0 + q) * rs[q];
+            k1[q] = __ldg(sum_dz + c0 + q) * invn; sx[q] = __ldg(sum_dzx + c0 + q);
+        }
+        for (long long p = tid / cgs; p < npix; p += pstep) {
+            float g[8], o[8], v[8], dzv[8];
+            ld8(dout.ptr + p * dout.stride + c0, g);
+            ld8(out.ptr + p * out.stride + c0, o);
+            ld8(y.ptr + p * y.stride + c0, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float dz = g[q] * dact(o[q], slope);
+                const float xh = (v[q] - mu[q]) * rs[q];
+                dzv[q] = dz;
+                v[q] = grs[q] * (dz - k1[q] - xh * sx[q] * invn);
+            }
+            st8(dy + p * dy_stride + c0, v);
+            if (dres) st8(dres + p * dres_stride + c0, dzv);
+        }
+        return;
+    }
+    const long long total = npix * cgs;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long p = i / cgs;
         const int c0 = (int)(i - p * cgs) * 8;
@@ -478,7 +531,10 @@ extern "C" int rdfc_affine_act_forward(const rdfc_view *x, const float *scale, c
     if (residual && residual->ptr) if (int rc = check_view(residual, C, "affine act residual")) return rc;
     const View r = (residual && residual->ptr) ? mk(residual) : View{nullptr, 0};
     const int nblk = (int)min((long long)cdiv(npix * (C / 8), 256), (long long)sm_count() * 16);
-    affine_act_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(mk(x), scale, shift, r, act_slope(act), (__nv_bfloat16 *)out->ptr, out->pix_stride, C, npix);
+    if (256 % (C >> 3) == 0 && knob("RDFC_BN_HOIST", 1) != 0)
+        affine_act_kernel<true><<<nblk, 256, 0, (cudaStream_t)stream>>>(mk(x), scale, shift, r, act_slope(act), (__nv_bfloat16 *)out->ptr, out->pix_stride, C, npix);
+    else
+        affine_act_kernel<false><<<nblk, 256, 0, (cudaStream_t)stream>>>(mk(x), scale, shift, r, act_slope(act), (__nv_bfloat16 *)out->ptr, out->pix_stride, C, npix);
     RDFC_CHECK_LAUNCH("affine_act_kernel");
     return 0;
 }
@@ -503,9 +559,14 @@ extern "C" int rdfc_bn_act_backward(const rdfc_view *dout, const rdfc_view *out,
     sum_final_kernel<<<cdiv(C, 8), 256, 0, st>>>(workspace, C, nblk, sum_dz, sum_dz_xhat);
     RDFC_CHECK_LAUNCH("sum_final_kernel");
     const int ablk = (int)min((long long)cdiv(npix * (C / 8), 256), (long long)sm_count() * 16);
-    bn_bwd_apply_kernel<<<ablk, 256, 0, st>>>(mk(dout), mk(out), mk(y), mean, rstd, gamma, sum_dz, sum_dz_xhat, slope, (__nv_bfloat16 *)dy->ptr,
-                                              dy->pix_stride, (dres && dres->ptr) ? (__nv_bfloat16 *)dres->ptr : nullptr,
-                                              (dres && dres->ptr) ? dres->pix_stride : 0, C, npix);
+    if (256 % (C >> 3) == 0 && knob("RDFC_BN_HOIST", 1) != 0)
+        bn_bwd_apply_kernel<true><<<ablk, 256, 0, st>>>(mk(dout), mk(out), mk(y), mean, rstd, gamma, sum_dz, sum_dz_xhat, slope, (__nv_bfloat16 *)dy->ptr,
+                                                        dy->pix_stride, (dres && dres->ptr) ? (__nv_bfloat16 *)dres->ptr : nullptr,
+                                                        (dres && dres->ptr) ? dres->pix_stride : 0, C, npix);
+    else
+        bn_bwd_apply_kernel<false><<<ablk, 256, 0, st>>>(mk(dout), mk(out), mk(y), mean, rstd, gamma, sum_dz, sum_dz_xhat, slope, (__nv_bfloat16 *)dy->ptr,
+                                                         dy->pix_stride, (dres && dres->ptr) ? (__nv_bfloat16 *)dres->ptr : nullptr,
+                                                         (dres && dres->ptr) ? dres->pix_stride : 0, C, npix);
     RDFC_CHECK_LAUNCH("bn_bwd_apply_kernel");
     return 0;
 }
