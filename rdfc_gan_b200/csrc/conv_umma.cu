@@ -89,6 +89,7 @@ struct Params {
     int dual;                      // two MMA issuer warps (MMA_WARP and MMA2_WARP), each owning a subset of the accumulators
     int pair;                      // cta_group::2: two CTAs (a cluster) work on two pixel tiles with ONE stream of M = 256 MMAs; each
                                    // holds its own A stages and HALF of every filter stage (per-SM shared-memory reads per MMA: 4 KB + N*16 B)
+    int kbs;                       // 1x1 convs: 32-channel k-blocks per A stage (plane j = channels 32 j.. of the same pixels, tap j = its filter block)
     int a_tma, px16, a_plane_bytes, a_tx_bytes;   // a_tx_bytes: bytes the TMA loads of one stage deliver (planes x rows x cols x 64)
     int _pad_tma;   // px16: 16-byte units per staged pixel (4 with TMA: [pixel][64 B]; 1: [cin/8][pixel][16 B])
     const __nv_bfloat16 *in;
@@ -590,14 +591,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
 #endif
                     mbar_expect_tx(full, (uint32_t)P.a_tx_bytes);
                     // input channel of k-block i: plain convs walk the channels; split inputs walk hi, hi again, then lo
-                    int a_ch = i * BK;
+                    int a_ch = i * BK * P.kbs;
                     if (P.split_c) a_ch = a_ch < P.split_c ? a_ch : (a_ch < 2 * P.split_c ? a_ch - P.split_c : a_ch - P.split_c);
                     for (int pl = 0; pl < npl; ++pl) {
                         const Plane &q = P.planes[pl];
                         asm volatile(
                             "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
                                 sA0 + (uint32_t)s * (uint32_t)a_stage_bytes + (uint32_t)pl * plane_b),
-                            "l"(&P.tmap_a), "r"(a_ch), "r"(q.xstep * t.tx0 + q.xoff), "r"(q.ystep * t.ty0 + q.yoff), "r"(t.b), "r"(full)
+                            "l"(&P.tmap_a), "r"(a_ch + (P.kbs > 1 ? pl * BK : 0)), "r"(q.xstep * t.tx0 + q.xoff), "r"(q.ystep * t.ty0 + q.yoff), "r"(t.b), "r"(full)
                             : "memory");
                     }
                     if (++s == sa_n) { s = 0; par ^= 1u; }
@@ -1388,6 +1389,17 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     P.dual = P.a_tma && !P.pair && P.nacc >= 2;
     if (const long long e = knob("RDFC_UMMA_DUAL", KNOB_UNSET); e != KNOB_UNSET) P.dual = P.dual && (int)e != 0;      // development knob
     P.ntiles = (P.pair ? (P.tiles_x * P.tiles_y + 1) / 2 : P.tiles_x * P.tiles_y) * P.B * P.nphases * P.n_tiles_n;   // pair mode: pairs of tiles
+    // 1x1 convs: one tap per A stage means 2 * nacc MMAs per stage against ~500 cycles of barrier / commit / ring overhead in the issuing
+    // warp (role timers).  Stage `kbs` consecutive 32-channel k-blocks at once: k-block j of a stage is "plane" j (the same
+    // pixels, channel coordinate + 32 j) and "tap" j (its block of the packed filters), so the kernel's tap loop walks them inside one stage.
+    P.kbs = 1;
+    if (k1 && P.a_tma && !heads && !stem && !split_c && !P.pair) {
+        const int nkb_total = P.nkb;
+        for (int cand = 3; cand >= 2; --cand)
+            if (nkb_total % cand == 0) { P.kbs = cand; break; }
+        if (const long long e = knob("RDFC_UMMA_KBS", KNOB_UNSET); e != KNOB_UNSET) P.kbs = (e >= 1 && e <= 3 && nkb_total % (int)e == 0) ? (int)e : 1;
+        P.nkb = nkb_total / P.kbs;
+    }
     Phase phases[4] = {};
     int base = 0;
     auto add_plane = [&](int ystep, int yoff, int xstep, int xoff, int rows, int cols) {
@@ -1408,14 +1420,21 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
                         ph.taps[ph.ntaps++] = Tap{pl, ky == 0 ? 1 : 0, kx == 0 ? 1 : 0, ky * 3 + kx};
                     }
             }
+    } else if (d->stride == 1 && P.kbs > 1) {
+        for (int j = 0; j < P.kbs; ++j) {
+            const int pl = add_plane(1, 0, 1, 0, TH, TW);
+            phases[0].taps[phases[0].ntaps++] = Tap{pl, 0, 0, j};
+        }
     } else if (d->stride == 1) {
         const int pl = add_plane(1, -d->pad, 1, -d->pad, TH + d->kh - 1, TW + d->kw - 1);
         Phase &ph = phases[0];
         for (int ky = 0; ky < d->kh; ++ky)
             for (int kx = 0; kx < d->kw; ++kx) ph.taps[ph.ntaps++] = Tap{pl, ky, kx, ky * d->kw + kx};
     } else if (k1) {
-        const int pl = add_plane(2, 0, 2, 0, TH, TW);
-        phases[0].taps[phases[0].ntaps++] = Tap{pl, 0, 0, 0};
+        for (int j = 0; j < P.kbs; ++j) {
+            const int pl = add_plane(2, 0, 2, 0, TH, TW);
+            phases[0].taps[phases[0].ntaps++] = Tap{pl, 0, 0, j};
+        }
     } else {
         // iy = 2*oy - 1 + ky: ky = 1 reads the even-row plane; ky = 0 / 2 read the odd-row plane (rows oy-1 / oy)
         int pl[2][2];
@@ -1453,7 +1472,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
         RDFC_REQUIRE((long long)P.Hi * P.Wi * P.in_stride * 2 < (1ll << 32), "UMMA conv: image too large for 32-bit producer offsets");
         RDFC_REQUIRE(P.npix_pad < (1 << 14), "UMMA conv: staged halo too large for the descriptor LBO field");
     }
-    P.w_kb_stride = (long long)KCH * P.CoutP * 8;
+    P.w_kb_stride = (long long)KCH * P.CoutP * 8 * P.kbs;
     P.b_contig = P.n_tiles_n == 1 && !P.pair;
     for (int z = 0; z < P.nphases; ++z) {
         const Phase &ph = phases[z];
@@ -1474,7 +1493,8 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
                 P.tap_alo[z][tp] = (uint32_t)(q.base + tap.sy * q.cols + tap.sx) | ((uint32_t)P.npix_pad << 16);
                 P.tap_ahi[z][tp] = (uint32_t)q.cols | (1u << 14);
             }
-            P.tap_w[z][tp] = (long long)tap.wtap * P.cin_chunks * P.CoutP * 8;
+            P.tap_w[z][tp] = P.kbs > 1 ? (long long)tap.wtap * KCH * P.CoutP * 8          // "tap" j of a 1x1 stage = the j-th k-block's filter block
+                                       : (long long)tap.wtap * P.cin_chunks * P.CoutP * 8;
         }
     }
     P.tmem_cols = next_pow2_cols(P.nsets * P.nacc * P.bn);
@@ -1482,7 +1502,7 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
 
     // filter taps per B stage: one wait / commit per filter row of a 3x3 conv; the 1/2/2/4-tap phases of a transposed
     // conv and 1x1 convs stream tap by tap
-    P.gtaps = (k3 && !d->transposed) ? 3 : 1;
+    P.gtaps = (k3 && !d->transposed) ? 3 : (P.kbs > 1 ? P.kbs : 1);
     P.vec32 = !heads && ((uintptr_t)d->out.ptr % 32) == 0 && d->out.pix_stride % 16 == 0 &&
               (!P.out2 || (((uintptr_t)P.out2 % 32) == 0 && P.out2_stride % 16 == 0 && P.split % 16 == 0)) &&
               (!d->residual.ptr || (((uintptr_t)d->residual.ptr % 32) == 0 && d->residual.pix_stride % 16 == 0));
