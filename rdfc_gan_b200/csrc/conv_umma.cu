@@ -1026,13 +1026,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                         tc_wait_ld(vb);
                         if (!ok) continue;
                         uint32_t o[8];
+                        // the step's 16 means / rstds / gamma biases / beta biases as 16-byte shared-memory loads (64 scalar loads before)
+                        float mu[16], rs[16], sg[16], sb[16];
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const float4 a = *reinterpret_cast<const float4 *>(s_stat + c0 + 16 * g + 4 * q4);
+                            const float4 b4 = *reinterpret_cast<const float4 *>(s_stat + C + c0 + 16 * g + 4 * q4);
+                            const float4 c4 = *reinterpret_cast<const float4 *>(s_shift + t.n0 + 16 * g + 4 * q4);
+                            const float4 d4 = *reinterpret_cast<const float4 *>(s_shift + t.n0 + half + 16 * g + 4 * q4);
+                            mu[4 * q4] = a.x; mu[4 * q4 + 1] = a.y; mu[4 * q4 + 2] = a.z; mu[4 * q4 + 3] = a.w;
+                            rs[4 * q4] = b4.x; rs[4 * q4 + 1] = b4.y; rs[4 * q4 + 2] = b4.z; rs[4 * q4 + 3] = b4.w;
+                            sg[4 * q4] = c4.x; sg[4 * q4 + 1] = c4.y; sg[4 * q4 + 2] = c4.z; sg[4 * q4 + 3] = c4.w;
+                            sb[4 * q4] = d4.x; sb[4 * q4 + 1] = d4.y; sb[4 * q4 + 2] = d4.z; sb[4 * q4 + 3] = d4.w;
+                        }
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            const int ch = c0 + 16 * g + 2 * q, ng = t.n0 + 16 * g + 2 * q, nb = ng + half;
                             const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&xr[q]));
-                            const float n0v = (xv.x - s_stat[ch]) * s_stat[C + ch], n1v = (xv.y - s_stat[ch + 1]) * s_stat[C + ch + 1];
-                            float g0 = __uint_as_float(vg[2 * q]) + s_shift[ng], g1 = __uint_as_float(vg[2 * q + 1]) + s_shift[ng + 1];
-                            float b0 = __uint_as_float(vb[2 * q]) + s_shift[nb], b1 = __uint_as_float(vb[2 * q + 1]) + s_shift[nb + 1];
+                            const float n0v = (xv.x - mu[2 * q]) * rs[2 * q], n1v = (xv.y - mu[2 * q + 1]) * rs[2 * q + 1];
+                            float g0 = __uint_as_float(vg[2 * q]) + sg[2 * q], g1 = __uint_as_float(vg[2 * q + 1]) + sg[2 * q + 1];
+                            float b0 = __uint_as_float(vb[2 * q]) + sb[2 * q], b1 = __uint_as_float(vb[2 * q + 1]) + sb[2 * q + 1];
                             if (wrow) {
                                 const float2 gwv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gw[q]));
                                 const float2 bwv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&bw[q]));
