@@ -89,6 +89,7 @@ struct Params {
     int dual;                      // two MMA issuer warps (MMA_WARP and MMA2_WARP), each owning a subset of the accumulators
     int pair;                      // cta_group::2: two CTAs (a cluster) work on two pixel tiles with ONE stream of M = 256 MMAs; each
                                    // holds its own A stages and HALF of every filter stage (per-SM shared-memory reads per MMA: 4 KB + N*16 B)
+    int fast9;                     // nacc == 1, gtaps == 9, TMA operands, one phase: the MMA warp issues a stage as one statement (RDFC_UMMA_FAST9)
     int epi_split;                 // one-accumulator tiles: the two epilogue groups share the accumulator's column steps (RDFC_UMMA_EPISPLIT)
     int kbs;                       // 1x1 convs: 32-channel k-blocks per A stage (plane j = channels 32 j.. of the same pixels, tap j = its filter block)
     int a_tma, px16, a_plane_bytes, a_tx_bytes;   // a_tx_bytes: bytes the TMA loads of one stage deliver (planes x rows x cols x 64)
@@ -230,6 +231,72 @@ __device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t
         "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// A whole 9-tap stage of a one-accumulator tile (18 MMAs) as ONE asm statement: no table loads, loops, predicates or dispatch between the MMAs.
+// tlo[t] = tap t's A descriptor low word (without the stage base); filters of tap t sit t * b_tap16 after b_lo.
+__device__ __forceinline__ void tc_mma_stage9(uint32_t d_tmem, const uint32_t (&tlo)[9], uint32_t a_stage_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t acc0, uint32_t b_tap16, uint32_t aks, uint32_t bks) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\t"
+        "setp.ne.b32 p, %15, 0;\n\tsetp.eq.b32 q, 0, 0;\n\t"
+        "add.u32 ta, %1, %10;\n\t"
+        "mov.b32 tb, %12;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, p;\n\t"
+        "add.u32 ta, ta, %17;\n\tadd.u32 tb, tb, %18;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "sub.u32 tb, tb, %18;\n\t"
+        "add.u32 ta, %2, %10;\n\t"
+        "add.u32 tb, tb, %16;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "add.u32 ta, ta, %17;\n\tadd.u32 tb, tb, %18;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "sub.u32 tb, tb, %18;\n\t"
+        "add.u32 ta, %3, %10;\n\t"
+        "add.u32 tb, tb, %16;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "add.u32 ta, ta, %17;\n\tadd.u32 tb, tb, %18;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "sub.u32 tb, tb, %18;\n\t"
+        "add.u32 ta, %4, %10;\n\t"
+        "add.u32 tb, tb, %16;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "add.u32 ta, ta, %17;\n\tadd.u32 tb, tb, %18;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "sub.u32 tb, tb, %18;\n\t"
+        "add.u32 ta, %5, %10;\n\t"
+        "add.u32 tb, tb, %16;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "add.u32 ta, ta, %17;\n\tadd.u32 tb, tb, %18;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "sub.u32 tb, tb, %18;\n\t"
+        "add.u32 ta, %6, %10;\n\t"
+        "add.u32 tb, tb, %16;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "add.u32 ta, ta, %17;\n\tadd.u32 tb, tb, %18;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "sub.u32 tb, tb, %18;\n\t"
+        "add.u32 ta, %7, %10;\n\t"
+        "add.u32 tb, tb, %16;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "add.u32 ta, ta, %17;\n\tadd.u32 tb, tb, %18;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "sub.u32 tb, tb, %18;\n\t"
+        "add.u32 ta, %8, %10;\n\t"
+        "add.u32 tb, tb, %16;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "add.u32 ta, ta, %17;\n\tadd.u32 tb, tb, %18;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "sub.u32 tb, tb, %18;\n\t"
+        "add.u32 ta, %9, %10;\n\t"
+        "add.u32 tb, tb, %16;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "add.u32 ta, ta, %17;\n\tadd.u32 tb, tb, %18;\n\t"
+        "mov.b64 da, {ta, %11};\n\tmov.b64 db, {tb, %13};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %14, q;\n\t"
+        "sub.u32 tb, tb, %18;\n\t"
+        "}"
+        ::"r"(d_tmem), "r"(tlo[0]), "r"(tlo[1]), "r"(tlo[2]), "r"(tlo[3]), "r"(tlo[4]), "r"(tlo[5]), "r"(tlo[6]), "r"(tlo[7]), "r"(tlo[8]), "r"(a_stage_lo),
+          "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc0), "r"(b_tap16), "r"(aks), "r"(bks)
         : "memory");
 }
 __device__ __forceinline__ void tc_mma2_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
@@ -473,6 +540,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
         uint32_t jy16[4], jx8[4];                  // accumulator j: 16 * (rows down) and 8 * (blocks across), decoded once
 #pragma unroll
         for (int j = 0; j < 4; ++j) { jy16[j] = keep(16u * (uint32_t)((j + jb) / nax)); jx8[j] = keep(8u * (uint32_t)P.px16 * (uint32_t)((j + jb) % nax)); }
+        // one accumulator, 9-tap stages, TMA operands, single CTA: the stage is one asm statement over register-resident tap words
+        const bool fast9 = !kPair && keep(P.fast9) != 0;
+        uint32_t tlo9[9], thi9 = 0;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) tlo9[q] = 0;
+        if (fast9) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) tlo9[q] = keep(P.tap_alo[0][q]);
+            thi9 = keep(P.tap_ahi[0][0]);
+        }
         int s = 0, sb = 0, it = 0;
         uint32_t a_par = 0, b_par = 0;
         long long t_acc = 0, t_a = 0, t_b = 0, t_mma = 0, t_commit = 0;
@@ -514,6 +591,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const __grid_con
                     tc_fence_after();
                     if (elect_one()) {
                         const long long _tm0 = DBG_ON ? clock64() : 0;
+                        if (fast9) {
+                            tc_mma_stage9(d_base, tlo9, a_stage_lo, thi9, b_lo, b_hi, idesc, (i | gi) ? 1u : 0u, b_tap16, a_kstep, b_kstep);
+                        } else
                         for (int r3 = 0; r3 < gtaps; r3 += 3) {        // a stage holds 1, 2, 3 or 9 taps: up to three at a time
                         uint2 td[3];
 #pragma unroll
@@ -1568,6 +1648,8 @@ int conv_umma_forward(const rdfc_conv_desc *d, cudaStream_t st, const rdfc_heads
     // when two such stages and two A stages fit.
     if (k3 && !d->transposed && !stem && 2 * a_stage + 2 * 9 * KCH * (P.pair ? P.bn / 2 : P.bn) * 16 + fixed <= budget) P.gtaps = 9;
     if (const long long e = knob("RDFC_UMMA_GTAPS", KNOB_UNSET); e != KNOB_UNSET) P.gtaps = (int)e;    // development knob (1, 3 or 9)
+    // joff of accumulator 0 is 0 (jb = 0): the fast path needs nothing but the tap table
+    P.fast9 = P.gtaps == 9 && P.nacc == 1 && P.a_tma && !P.pair && P.nphases == 1 && !P.dual && knob("RDFC_UMMA_FAST9", 1) != 0;
     const int b_stage = P.gtaps * KCH * (P.pair ? P.bn / 2 : P.bn) * 16;
     // A ring first (>= 2 stages: the producers publish k-block i while k-block i+1 is in flight), then B stages (2..6)
     // the filter stream is latency-bound: bytes in flight per SM = bandwidth x L2 latency (~2000 cycles), so keep
