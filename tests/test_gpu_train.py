@@ -283,3 +283,30 @@ def test_resnet_generator_against_reference(golden_dir):
     assert float((ye.cpu() - torch.from_numpy(gold["out_eval"])).abs().max()) <= 8e-2
     with pytest.raises(RuntimeError):
         G(x.cpu())
+
+
+def test_channel_sliced_views_need_no_copy():
+    """Autograd hands the operands of a channel concatenation back as channel SLICES of one NHWC tensor.  The training ops pass such
+    tensors to the kernels as (pointer, channels, pixel stride) views: the results must be those of contiguous copies, bit for bit."""
+    from rdfc_gan_b200 import _cabi as C
+    from rdfc_gan_b200.train_ops import _dense, _wgrad, bn_act, conv2d_nhwc
+    g = torch.Generator(device="cuda").manual_seed(11)
+    big = torch.randn(2, 21, 35, 192, device="cuda", generator=g).to(BF)
+    xs, gs = big[..., 64:128], big[..., 128:192]                 # two 64-channel slices, pixel stride 192
+    assert not xs.is_contiguous() and C.nhwc_viewable(xs) and _dense(xs) is xs
+    assert not C.nhwc_viewable(big[:, :, ::2]) and _dense(big[:, :, ::2]).is_contiguous()          # a spatial slice still gets copied
+    assert torch.equal(_wgrad(gs, xs, 3, 1), _wgrad(gs.contiguous(), xs.contiguous(), 3, 1))
+    assert torch.equal(_wgrad(gs, xs, 1, 1), _wgrad(gs.contiguous(), xs.contiguous(), 1, 1))
+    w = (torch.randn(64, 64, 3, 3, device="cuda", generator=g) / 24).to(BF).float()
+    assert torch.equal(conv2d_nhwc(xs, w, 3, 1), conv2d_nhwc(xs.contiguous(), w, 3, 1))
+    bn1, bn2 = torch.nn.BatchNorm2d(64).cuda().train(), torch.nn.BatchNorm2d(64).cuda().train()
+    ya = xs.detach().clone().requires_grad_(True)                 # contiguous leaf
+    yb_full = big.detach().clone().requires_grad_(True)
+    oa = bn_act(ya, bn1, gs.contiguous(), C.ACT_RELU)
+    ob = bn_act(yb_full[..., 64:128], bn2, gs, C.ACT_RELU)        # sliced input and sliced residual
+    assert torch.equal(oa, ob)
+    up = torch.randn(oa.shape, device="cuda", generator=g).to(BF)
+    oa.backward(up)
+    ob.backward(up)
+    assert torch.equal(ya.grad, yb_full.grad[..., 64:128]) and torch.equal(bn1.weight.grad, bn2.weight.grad)
+    assert float(yb_full.grad[..., :64].abs().max()) == 0.0
