@@ -119,3 +119,24 @@ def test_esanet_state_dict_matches_reference(golden_dir):
     assert got == want
     with pytest.raises(NotImplementedError):
         ESANetOneModality(pretrained_on_imagenet=False, encoder='resnet50')
+
+
+def test_nhwc_view_descriptors_without_gpu():
+    """_cabi.view / nhwc_viewable: dense NHWC tensors and CHANNEL slices of them become (pointer, channels, pixel stride) views --
+    what the training ops hand to the kernels instead of .contiguous() copies; anything else is refused (host logic only, CPU tensors)."""
+    import torch
+    from rdfc_gan_b200 import _cabi as C
+    big = torch.zeros(2, 5, 7, 192, dtype=torch.bfloat16)
+    v = C.view(big)
+    assert (v.C, v.pix_stride) == (192, 192)
+    sl = big[..., 64:128]
+    assert not sl.is_contiguous() and C.nhwc_viewable(sl)
+    vs = C.view(sl)
+    assert (vs.C, vs.pix_stride) == (64, 192) and vs.ptr == big.data_ptr() + 64 * 2
+    v2 = C.view(big, 32, 16)                                   # explicit channel window of a dense tensor
+    assert (v2.C, v2.pix_stride) == (32, 192) and v2.ptr == big.data_ptr() + 16 * 2
+    assert not C.nhwc_viewable(big[:, :, ::2])                 # spatial slices, permutations and misaligned slices are not views
+    assert not C.nhwc_viewable(big.permute(0, 3, 1, 2))
+    assert not C.nhwc_viewable(big[..., 4:68])                 # 8-byte aligned start: the kernels need 16
+    with pytest.raises(AssertionError):
+        C.view(big[:, :, ::2])
